@@ -1,0 +1,1096 @@
+// engine.cu -- host side of the C-ABI (include/bpp_b200.h): device-resident locus store, batches,
+// staging, launches.  No CPU compute fallback: without a CUDA device every entry point fails
+// through the fatal handler.
+//
+// Reference interfaces mirrored here (file:line relative to /root/reference/src):
+//   locus_create locus.c:622-870, locus_destroy :872, pll_set_tip_states :561, pll_set_tip_clv :596,
+//   pll_set_frequencies :889, pll_set_subst_params :877, locus_update_matrices :2417,
+//   locus_update_partials :2530, locus_root_loglikelihood :2573, pll_update_eigen core_pmatrix.c:239.
+#include "../../include/bpp_b200.h"
+#include "kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+using namespace bppgpu;
+
+// ------------------------------------------------------------------------------------ errors
+static thread_local std::string g_last_error;
+static void (*g_fatal_handler)(const char *) = nullptr;
+
+static void fatal(const char * fmt, ...)
+{
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  if (g_fatal_handler) { g_fatal_handler(buf); return; }
+  fprintf(stderr, "bppgpu: %s\n", buf);     // util.c:30 fatal(): message + exit(1)
+  exit(1);
+}
+
+#define CUDA_CHECK(call)                                                                         \
+  do {                                                                                           \
+    cudaError_t err__ = (call);                                                                  \
+    if (err__ != cudaSuccess)                                                                    \
+      fatal("CUDA error %s at %s:%d: %s", cudaGetErrorName(err__), __FILE__, __LINE__,           \
+            cudaGetErrorString(err__));                                                          \
+  } while (0)
+
+// ------------------------------------------------------------------------------------ arena
+// Slab allocator over cudaMalloc: loci are created once and live for the whole run, so a bump
+// pointer with exact-size reuse of freed blocks is enough (and avoids 10^4-10^5 cudaMalloc calls).
+struct Arena
+{
+  static constexpr size_t kAlign = 256;
+  size_t slab_bytes = (size_t)1 << 30;
+  std::vector<char *> slabs;
+  char * cur = nullptr;
+  size_t cur_left = 0;
+  size_t total = 0;
+  std::multimap<size_t, char *> free_blocks;
+
+  void * alloc(size_t bytes)
+  {
+    bytes = (bytes + kAlign - 1) / kAlign * kAlign;
+    if (bytes == 0) bytes = kAlign;
+    auto it = free_blocks.find(bytes);
+    if (it != free_blocks.end()) { char * p = it->second; free_blocks.erase(it); return p; }
+    if (bytes > cur_left)
+    {
+      size_t sz = std::max(slab_bytes, bytes);
+      char * p = nullptr;
+      cudaError_t err = cudaMalloc(&p, sz);
+      if (err != cudaSuccess)
+      {
+        fatal("Unable to allocate enough memory on the device (%zu bytes): %s", sz, cudaGetErrorString(err));
+        return nullptr;
+      }
+      slabs.push_back(p);
+      total += sz;
+      cur = p; cur_left = sz;
+    }
+    char * r = cur;
+    cur += bytes; cur_left -= bytes;
+    return r;
+  }
+  void release(void * p, size_t bytes)
+  {
+    if (!p) return;
+    bytes = (bytes + kAlign - 1) / kAlign * kAlign;
+    if (bytes == 0) bytes = kAlign;
+    free_blocks.emplace(bytes, (char *)p);
+  }
+  void destroy()
+  {
+    for (char * s : slabs) cudaFree(s);
+    slabs.clear(); free_blocks.clear(); cur = nullptr; cur_left = 0; total = 0;
+  }
+};
+
+// ------------------------------------------------------------------------------------ objects
+struct bppgpu_engine
+{
+  int device = 0;
+  unsigned int math = BPPGPU_MATH_EXACT;
+  cudaStream_t stream = nullptr;
+  Arena arena;
+  std::mutex mu;
+  // device table of LocusDev, indexed by locus id
+  LocusDev * d_loci = nullptr;
+  size_t loci_cap = 0;
+  std::vector<bppgpu_locus *> loci;      // by id (nullptr = free)
+  std::vector<unsigned int> free_ids;
+  unsigned long long launches = 0;
+  int sm_count = 148;
+  size_t smem_optin = 0;
+  // profiling
+  bool profiling = false;
+  double prof_ms[BPPGPU_KERNEL_COUNT] = {0, 0, 0, 0};
+  unsigned long long prof_n[BPPGPU_KERNEL_COUNT] = {0, 0, 0, 0};
+  struct PendingEvent { cudaEvent_t a, b; int kind; };
+  std::vector<PendingEvent> pending;
+  std::vector<cudaEvent_t> event_pool;
+  double log_threshold = 0;
+};
+
+struct bppgpu_locus
+{
+  bppgpu_engine * e = nullptr;
+  unsigned int id = 0;
+  unsigned int dtype = 0, model = 0, tips = 0, clv_buffers = 0, states = 0, sites = 0;
+  unsigned int rate_matrices = 0, prob_matrices = 0, rate_cats = 0, scale_buffers = 0, attributes = 0;
+  LocusDev dev;                        // host copy of the device descriptor
+  // sizes of the arena blocks (for release)
+  size_t b_clv = 0, b_tipdense = 0, b_codes = 0, b_flags = 0, b_pmat = 0, b_scale = 0, b_weights = 0, b_model = 0;
+  size_t b_dip_off = 0, b_dip_map = 0;
+  // host mirrors of the small inputs
+  std::vector<unsigned char> h_codes8;
+  std::vector<unsigned int> h_codes32;
+  std::vector<unsigned char> h_tip_dense_flag;
+  std::vector<double> h_freqs, h_subst, h_rates, h_rate_weights, h_evecs, h_ievecs, h_evals;
+  bool eigen_valid = false;            // locus->eigen_decomp_valid[0]
+  bool codes_dirty = false, model_dirty = false, flags_dirty = false;
+  bppgpu_batch * self_batch = nullptr; // batch of one for the synchronous per-locus API
+};
+
+struct bppgpu_batch
+{
+  bppgpu_engine * e = nullptr;
+  unsigned int n = 0;
+  std::vector<bppgpu_locus *> loci;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int kernel_kind = 0;                 // 0 = 4-state pow2-R kernel, 1 = generic
+  unsigned int RL = 1;                 // lanes per site of the 4-state kernel
+  unsigned int tile_threads = 256;
+  unsigned int n_tiles = 0;
+  // static device tables
+  unsigned int * d_batch_locus = nullptr, * d_tile_locus = nullptr, * d_tile_cell0 = nullptr, * d_tile_first = nullptr;
+  unsigned long long * d_scratch_off = nullptr;
+  unsigned char * d_scratch = nullptr;
+  size_t scratch_bytes = 0;
+  // per-step device inputs (one blob) and outputs
+  char * d_in = nullptr; size_t d_in_cap = 0;
+  char * h_in = nullptr; size_t h_in_cap = 0;       // pinned
+  PlanOp * d_plan = nullptr; size_t plan_cap = 0;
+  unsigned int * d_plan_count = nullptr;
+  double * d_tile_partial = nullptr, * d_lnl = nullptr, * d_lnl_sum = nullptr;
+  double * h_out = nullptr;                         // pinned: n lnl + 1 sum
+  double * d_persite = nullptr; size_t persite_cap = 0;
+  // layout of the staged blob
+  size_t o_mat_off = 0, o_mat_idx = 0, o_mat_bl = 0, o_op_off = 0, o_ops = 0, o_root_clv = 0, o_root_sc = 0;
+  unsigned int total_mats = 0, total_ops = 0;
+  bool staged_mats = false, staged_ops = false, staged_roots = false;
+  cudaEvent_t t0 = nullptr, t1 = nullptr;
+};
+
+// ------------------------------------------------------------------------------------ helpers
+static cudaEvent_t get_event(bppgpu_engine * e)
+{
+  if (!e->event_pool.empty()) { cudaEvent_t ev = e->event_pool.back(); e->event_pool.pop_back(); return ev; }
+  cudaEvent_t ev;
+  CUDA_CHECK(cudaEventCreate(&ev));
+  return ev;
+}
+
+struct ProfScope
+{
+  bppgpu_engine * e; cudaStream_t s; int kind; cudaEvent_t a = nullptr, b = nullptr;
+  ProfScope(bppgpu_engine * e_, cudaStream_t s_, int kind_) : e(e_), s(s_), kind(kind_)
+  {
+    e->launches++;
+    if (e->profiling) { a = get_event(e); b = get_event(e); cudaEventRecord(a, s); }
+  }
+  ~ProfScope()
+  {
+    if (e->profiling) { cudaEventRecord(b, s); e->pending.push_back({a, b, kind}); }
+  }
+};
+
+static void drain_profile(bppgpu_engine * e)
+{
+  for (auto & p : e->pending)
+  {
+    cudaEventSynchronize(p.b);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, p.a, p.b);
+    e->prof_ms[p.kind] += ms; e->prof_n[p.kind]++;
+    e->event_pool.push_back(p.a); e->event_pool.push_back(p.b);
+  }
+  e->pending.clear();
+}
+
+// symmetric eigen-decomposition, cyclic Jacobi.  Used when the host did not hand over its own
+// pll_update_eigen result.  Rows of `vec` are the eigenvectors.
+static void jacobi_eigen(std::vector<double> & a, int n, std::vector<double> & lam, std::vector<double> & vec)
+{
+  vec.assign((size_t)n * n, 0.0);
+  for (int i = 0; i < n; ++i) vec[(size_t)i * n + i] = 1.0;      // columns = eigenvectors during sweeps
+  for (int sweep = 0; sweep < 100; ++sweep)
+  {
+    double off = 0;
+    for (int p = 0; p < n; ++p) for (int q = p + 1; q < n; ++q) off += a[(size_t)p * n + q] * a[(size_t)p * n + q];
+    if (off < 1e-300) break;
+    for (int p = 0; p < n; ++p)
+      for (int q = p + 1; q < n; ++q)
+      {
+        const double apq = a[(size_t)p * n + q];
+        if (std::fabs(apq) < 1e-300) continue;
+        const double app = a[(size_t)p * n + p], aqq = a[(size_t)q * n + q];
+        const double theta = (aqq - app) / (2.0 * apq);
+        const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+        const double c = 1.0 / std::sqrt(t * t + 1.0), s = t * c;
+        for (int k = 0; k < n; ++k)
+        {
+          const double akp = a[(size_t)k * n + p], akq = a[(size_t)k * n + q];
+          a[(size_t)k * n + p] = c * akp - s * akq;
+          a[(size_t)k * n + q] = s * akp + c * akq;
+        }
+        for (int k = 0; k < n; ++k)
+        {
+          const double apk = a[(size_t)p * n + k], aqk = a[(size_t)q * n + k];
+          a[(size_t)p * n + k] = c * apk - s * aqk;
+          a[(size_t)q * n + k] = s * apk + c * aqk;
+        }
+        for (int k = 0; k < n; ++k)
+        {
+          const double vkp = vec[(size_t)k * n + p], vkq = vec[(size_t)k * n + q];
+          vec[(size_t)k * n + p] = c * vkp - s * vkq;
+          vec[(size_t)k * n + q] = s * vkp + c * vkq;
+        }
+      }
+  }
+  lam.resize(n);
+  for (int i = 0; i < n; ++i) lam[i] = a[(size_t)i * n + i];
+  // transpose so that rows are eigenvectors
+  std::vector<double> t((size_t)n * n);
+  for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) t[(size_t)i * n + j] = vec[(size_t)j * n + i];
+  vec.swap(t);
+}
+
+// pll_update_eigen, core_pmatrix.c:239-297 (+ create_ratematrix :186-237): symmetrised rate matrix
+// with mean rate 1; eigenvecs[i][j] = a[i][j]*sqrt(pi_j), inv_eigenvecs[i][j] = a[j][i]/sqrt(pi_i).
+static void host_update_eigen(bppgpu_locus * l)
+{
+  const int S = (int)l->states;
+  const int np = S * (S - 1) / 2;
+  std::vector<double> p(l->h_subst.begin(), l->h_subst.begin() + np);
+  if (p[np - 1] > 0.0) for (int i = 0; i < np; ++i) p[i] /= l->h_subst[np - 1];
+  const std::vector<double> & f = l->h_freqs;
+  std::vector<double> q((size_t)S * S, 0.0);
+  int k = 0;
+  for (int i = 0; i < S; ++i)
+    for (int j = i + 1; j < S; ++j)
+    {
+      const double factor = p[k++];
+      q[(size_t)i * S + j] = q[(size_t)j * S + i] = factor * std::sqrt(f[i] * f[j]);
+      q[(size_t)i * S + i] -= factor * f[j];
+      q[(size_t)j * S + j] -= factor * f[i];
+    }
+  double mean = 0;
+  for (int i = 0; i < S; ++i) mean += f[i] * (-q[(size_t)i * S + i]);
+  for (auto & v : q) v /= mean;
+  std::vector<double> lam, a;
+  jacobi_eigen(q, S, lam, a);
+  l->h_evals = lam;
+  l->h_evecs.assign((size_t)S * S, 0.0);
+  l->h_ievecs.assign((size_t)S * S, 0.0);
+  for (int i = 0; i < S; ++i)
+    for (int j = 0; j < S; ++j)
+    {
+      l->h_evecs[(size_t)i * S + j] = a[(size_t)i * S + j] * std::sqrt(f[j]);
+      l->h_ievecs[(size_t)i * S + j] = a[(size_t)j * S + i] / std::sqrt(f[i]);
+    }
+  l->eigen_valid = true;
+  l->model_dirty = true;
+}
+
+static size_t model_doubles(unsigned S, unsigned R) { return (size_t)S + R + R + 2 * (size_t)S * S + S; }
+
+// push dirty host mirrors (tip codes, dense flags, model block) of a locus to the device
+static void locus_sync(bppgpu_locus * l, cudaStream_t s)
+{
+  if (l->codes_dirty)
+  {
+    if (l->states <= 8)
+      CUDA_CHECK(cudaMemcpyAsync(l->dev.tip_codes, l->h_codes8.data(), l->h_codes8.size(), cudaMemcpyHostToDevice, s));
+    else
+      CUDA_CHECK(cudaMemcpyAsync(l->dev.tip_codes, l->h_codes32.data(), l->h_codes32.size() * 4, cudaMemcpyHostToDevice, s));
+    l->codes_dirty = false;
+  }
+  if (l->flags_dirty)
+  {
+    CUDA_CHECK(cudaMemcpyAsync(l->dev.tip_is_dense, l->h_tip_dense_flag.data(), l->tips, cudaMemcpyHostToDevice, s));
+    l->flags_dirty = false;
+  }
+  if (l->model_dirty)
+  {
+    const unsigned S = l->states, R = l->rate_cats;
+    std::vector<double> blk(model_doubles(S, R));
+    double * w = blk.data();
+    memcpy(w, l->h_freqs.data(), S * 8); w += S;
+    memcpy(w, l->h_rates.data(), R * 8); w += R;
+    memcpy(w, l->h_rate_weights.data(), R * 8); w += R;
+    memcpy(w, l->h_evecs.data(), (size_t)S * S * 8); w += (size_t)S * S;
+    memcpy(w, l->h_ievecs.data(), (size_t)S * S * 8); w += (size_t)S * S;
+    memcpy(w, l->h_evals.data(), S * 8);
+    // pageable source: the copy is staged by the runtime before the call returns
+    CUDA_CHECK(cudaMemcpyAsync(l->dev.freqs, blk.data(), blk.size() * 8, cudaMemcpyHostToDevice, s));
+    l->model_dirty = false;
+  }
+}
+
+static bool model_is_closed_form(const bppgpu_locus * l)
+{
+  return l->dtype == BPPGPU_DATA_DNA && l->model == BPPGPU_DNA_MODEL_JC69;
+}
+
+// ------------------------------------------------------------------------------------ engine API
+extern "C" int bppgpu_device_count(void)
+{
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+extern "C" const char * bppgpu_last_error(void) { return g_last_error.c_str(); }
+extern "C" void bppgpu_set_fatal_handler(void (*handler)(const char *)) { g_fatal_handler = handler; }
+extern "C" const char * bppgpu_version(void) { return "bpp_b200 0.1 (sm_100a)"; }
+
+extern "C" bppgpu_engine * bppgpu_engine_create(int device, unsigned int flags)
+{
+  int n = bppgpu_device_count();
+  if (n <= 0) { fatal("no CUDA device available: the bpp_b200 engine has no CPU fallback"); return nullptr; }
+  if (device < 0 || device >= n) { fatal("invalid device ordinal %d (have %d)", device, n); return nullptr; }
+  CUDA_CHECK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) { fatal("device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor); return nullptr; }
+  bppgpu_engine * e = new bppgpu_engine();
+  e->device = device;
+  e->math = flags & 1u;
+  e->sm_count = prop.multiProcessorCount;
+  e->smem_optin = prop.sharedMemPerBlockOptin;
+  e->log_threshold = std::log(BPPGPU_SCALE_THRESHOLD);      // core_likelihood.c:200 evaluates it with libm
+  CUDA_CHECK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  return e;
+}
+
+extern "C" void bppgpu_engine_destroy(bppgpu_engine * e)
+{
+  if (!e) return;
+  cudaSetDevice(e->device);
+  cudaDeviceSynchronize();
+  std::vector<bppgpu_locus *> ls = e->loci;
+  for (bppgpu_locus * l : ls) if (l) bppgpu_locus_destroy(l);
+  drain_profile(e);
+  for (cudaEvent_t ev : e->event_pool) cudaEventDestroy(ev);
+  if (e->d_loci) cudaFree(e->d_loci);
+  e->arena.destroy();
+  cudaStreamDestroy(e->stream);
+  delete e;
+}
+
+extern "C" int bppgpu_engine_device(const bppgpu_engine * e) { return e->device; }
+extern "C" void bppgpu_engine_set_math(bppgpu_engine * e, unsigned int m) { e->math = m & 1u; }
+extern "C" void bppgpu_engine_synchronize(bppgpu_engine * e) { cudaSetDevice(e->device); CUDA_CHECK(cudaDeviceSynchronize()); }
+extern "C" void * bppgpu_engine_stream(bppgpu_engine * e) { return (void *)e->stream; }
+extern "C" unsigned long long bppgpu_engine_launch_count(const bppgpu_engine * e) { return e->launches; }
+extern "C" unsigned long long bppgpu_engine_bytes_allocated(const bppgpu_engine * e) { return e->arena.total; }
+extern "C" void bppgpu_engine_set_profiling(bppgpu_engine * e, int on) { drain_profile(e); e->profiling = on != 0; }
+extern "C" void bppgpu_engine_reset_profile(bppgpu_engine * e)
+{
+  drain_profile(e);
+  for (int i = 0; i < BPPGPU_KERNEL_COUNT; ++i) { e->prof_ms[i] = 0; e->prof_n[i] = 0; }
+}
+extern "C" void bppgpu_engine_get_profile(bppgpu_engine * e, double * ms, unsigned long long * cnt)
+{
+  drain_profile(e);
+  for (int i = 0; i < BPPGPU_KERNEL_COUNT; ++i) { if (ms) ms[i] = e->prof_ms[i]; if (cnt) cnt[i] = e->prof_n[i]; }
+}
+
+// ------------------------------------------------------------------------------------ locus API
+static void engine_publish_locus(bppgpu_engine * e, bppgpu_locus * l)
+{
+  if (l->id >= e->loci_cap)
+  {
+    size_t ncap = std::max<size_t>(1024, e->loci_cap * 2);
+    while (ncap <= l->id) ncap *= 2;
+    LocusDev * nd = nullptr;
+    CUDA_CHECK(cudaDeviceSynchronize());
+    CUDA_CHECK(cudaMalloc(&nd, ncap * sizeof(LocusDev)));
+    if (e->d_loci)
+    {
+      CUDA_CHECK(cudaMemcpy(nd, e->d_loci, e->loci_cap * sizeof(LocusDev), cudaMemcpyDeviceToDevice));
+      CUDA_CHECK(cudaFree(e->d_loci));
+    }
+    e->d_loci = nd; e->loci_cap = ncap;
+  }
+  CUDA_CHECK(cudaMemcpy(e->d_loci + l->id, &l->dev, sizeof(LocusDev), cudaMemcpyHostToDevice));
+}
+
+extern "C" bppgpu_locus * bppgpu_locus_create(bppgpu_engine * e, unsigned int dtype, unsigned int model,
+                                              unsigned int tips, unsigned int clv_buffers,
+                                              unsigned int states, unsigned int sites,
+                                              unsigned int rate_matrices, unsigned int prob_matrices,
+                                              unsigned int rate_cats, unsigned int scale_buffers,
+                                              unsigned int attributes)
+{
+  if (!e) { fatal("bppgpu_locus_create: no engine"); return nullptr; }
+  if (states == 0 || states > 32) { fatal("unsupported number of states %u", states); return nullptr; }
+  if (rate_matrices != 1) { fatal("rate_matrices must be 1 (method.c:4143)"); return nullptr; }
+  if (sites == 0 || tips < 2 || rate_cats == 0) { fatal("invalid locus dimensions"); return nullptr; }
+  std::lock_guard<std::mutex> lock(e->mu);
+  CUDA_CHECK(cudaSetDevice(e->device));
+  bppgpu_locus * l = new bppgpu_locus();
+  l->e = e;
+  l->dtype = dtype; l->model = model; l->tips = tips; l->clv_buffers = clv_buffers; l->states = states;
+  l->sites = sites; l->rate_matrices = rate_matrices; l->prob_matrices = prob_matrices;
+  l->rate_cats = rate_cats; l->scale_buffers = scale_buffers; l->attributes = attributes;
+  const size_t S = states, R = rate_cats, P = sites;
+  const size_t clv_doubles = P * R * S;
+  LocusDev & d = l->dev;
+  memset(&d, 0, sizeof(d));
+  l->b_clv = clv_buffers * clv_doubles * 8;
+  l->b_codes = (size_t)tips * P * (S <= 8 ? 1 : 4);
+  l->b_flags = tips;
+  l->b_pmat = (size_t)prob_matrices * R * S * S * 8;
+  l->b_scale = (size_t)scale_buffers * P * 4;
+  l->b_weights = P * 4;
+  l->b_model = model_doubles(states, rate_cats) * 8;
+  d.clv = (double *)e->arena.alloc(l->b_clv);
+  d.tip_codes = e->arena.alloc(l->b_codes);
+  d.tip_is_dense = (unsigned char *)e->arena.alloc(l->b_flags);
+  d.pmat = (double *)e->arena.alloc(l->b_pmat);
+  d.scale = scale_buffers ? (unsigned int *)e->arena.alloc(l->b_scale) : nullptr;
+  d.weights = (unsigned int *)e->arena.alloc(l->b_weights);
+  double * m = (double *)e->arena.alloc(l->b_model);
+  d.freqs = m; d.rates = m + S; d.rate_weights = d.rates + R; d.eigenvecs = d.rate_weights + R;
+  d.inv_eigenvecs = d.eigenvecs + S * S; d.eigenvals = d.inv_eigenvecs + S * S;
+  d.clv_stride = clv_doubles;
+  d.tips = tips; d.sites = sites; d.states = states; d.rate_cats = rate_cats;
+  d.clv_buffers = clv_buffers; d.prob_matrices = prob_matrices; d.scale_buffers = scale_buffers;
+  d.model_kind = model_is_closed_form(l) ? 0 : 1;
+  // zero what the reference zeroes (locus.c:745-755,765-771,859-867); weights default to 1 (:852)
+  CUDA_CHECK(cudaMemsetAsync(d.clv, 0, l->b_clv, e->stream));
+  CUDA_CHECK(cudaMemsetAsync(d.pmat, 0, l->b_pmat, e->stream));
+  if (d.scale) CUDA_CHECK(cudaMemsetAsync(d.scale, 0, l->b_scale, e->stream));
+  CUDA_CHECK(cudaMemsetAsync(d.tip_codes, 0, l->b_codes, e->stream));
+  CUDA_CHECK(cudaMemsetAsync(d.tip_is_dense, 0, l->b_flags, e->stream));
+  {
+    std::vector<unsigned int> ones(P, 1u);
+    CUDA_CHECK(cudaMemcpyAsync(d.weights, ones.data(), P * 4, cudaMemcpyHostToDevice, e->stream));
+    CUDA_CHECK(cudaStreamSynchronize(e->stream));
+  }
+  if (S <= 8) l->h_codes8.assign((size_t)tips * P, 0); else l->h_codes32.assign((size_t)tips * P, 0);
+  l->h_tip_dense_flag.assign(tips, 0);
+  l->h_freqs.assign(S, 0.0);                       // zero like locus.c:826 until pll_set_frequencies
+  l->h_subst.assign(S * (S - 1) / 2, 0.0);
+  l->h_rates.assign(R, 1.0);
+  l->h_rate_weights.assign(R, 1.0 / (double)R);    // locus.c:845-848
+  l->h_evecs.assign(S * S, 0.0); l->h_ievecs.assign(S * S, 0.0); l->h_evals.assign(S, 0.0);
+  l->model_dirty = true;
+  if (!e->free_ids.empty()) { l->id = e->free_ids.back(); e->free_ids.pop_back(); e->loci[l->id] = l; }
+  else { l->id = (unsigned)e->loci.size(); e->loci.push_back(l); }
+  engine_publish_locus(e, l);
+  return l;
+}
+
+extern "C" void bppgpu_locus_destroy(bppgpu_locus * l)
+{
+  if (!l) return;
+  bppgpu_engine * e = l->e;
+  if (l->self_batch) { bppgpu_batch * b = l->self_batch; l->self_batch = nullptr; bppgpu_batch_destroy(b); }
+  std::lock_guard<std::mutex> lock(e->mu);
+  cudaSetDevice(e->device);
+  cudaDeviceSynchronize();
+  Arena & a = e->arena;
+  a.release(l->dev.clv, l->b_clv);
+  a.release(l->dev.tip_dense, l->b_tipdense);
+  a.release(l->dev.tip_codes, l->b_codes);
+  a.release(l->dev.tip_is_dense, l->b_flags);
+  a.release(l->dev.pmat, l->b_pmat);
+  a.release(l->dev.scale, l->b_scale);
+  a.release(l->dev.weights, l->b_weights);
+  a.release(l->dev.freqs, l->b_model);
+  a.release(l->dev.dip_off, l->b_dip_off);
+  a.release(l->dev.dip_map, l->b_dip_map);
+  e->loci[l->id] = nullptr;
+  e->free_ids.push_back(l->id);
+  delete l;
+}
+
+extern "C" int bppgpu_set_tip_states(bppgpu_locus * l, unsigned int tip, const unsigned int * map, const char * seq)
+{
+  if (tip >= l->tips) { fatal("tip index %u out of range", tip); return BPPGPU_FAILURE; }
+  const size_t P = l->sites;
+  for (size_t i = 0; i < P; ++i)
+  {
+    const unsigned int c = map[(int)(unsigned char)seq[i]];
+    if (c == 0) { fatal("Illegal state code in tip \"%c\"", seq[i]); return BPPGPU_FAILURE; }   // locus.c:538
+    if (l->states <= 8) l->h_codes8[tip * P + i] = (unsigned char)c; else l->h_codes32[tip * P + i] = c;
+  }
+  l->codes_dirty = true;
+  if (l->h_tip_dense_flag[tip]) { l->h_tip_dense_flag[tip] = 0; l->flags_dirty = true; }
+  return BPPGPU_SUCCESS;
+}
+
+extern "C" int bppgpu_set_tip_clv(bppgpu_locus * l, unsigned int tip, const double * clv, int padding)
+{
+  (void)padding;                                   // states_padded == states
+  if (tip >= l->tips) { fatal("tip index %u out of range", tip); return BPPGPU_FAILURE; }
+  const size_t P = l->sites, S = l->states, R = l->rate_cats;
+  bool binary = true;
+  for (size_t i = 0; i < P * S && binary; ++i) binary = (clv[i] == 0.0 || clv[i] == 1.0);
+  if (binary)
+  {
+    bool nonzero = true;
+    for (size_t i = 0; i < P; ++i)
+    {
+      unsigned int c = 0;
+      for (size_t j = 0; j < S; ++j) if (clv[i * S + j] == 1.0) c |= 1u << j;
+      if (!c) nonzero = false;
+      if (S <= 8) l->h_codes8[tip * P + i] = (unsigned char)c; else l->h_codes32[tip * P + i] = c;
+    }
+    (void)nonzero;                                 // an all-zero tip vector is legal here (lnL = -inf)
+    l->codes_dirty = true;
+    if (l->h_tip_dense_flag[tip]) { l->h_tip_dense_flag[tip] = 0; l->flags_dirty = true; }
+    return BPPGPU_SUCCESS;
+  }
+  bppgpu_engine * e = l->e;
+  std::lock_guard<std::mutex> lock(e->mu);
+  CUDA_CHECK(cudaSetDevice(e->device));
+  if (!l->dev.tip_dense)
+  {
+    l->b_tipdense = (size_t)l->tips * P * R * S * 8;
+    l->dev.tip_dense = (double *)e->arena.alloc(l->b_tipdense);
+    engine_publish_locus(e, l);
+  }
+  std::vector<double> full(P * R * S);             // replicate over categories, locus.c:609-616
+  for (size_t i = 0; i < P; ++i) for (size_t r = 0; r < R; ++r) memcpy(&full[(i * R + r) * S], clv + i * S, S * 8);
+  CUDA_CHECK(cudaMemcpy(l->dev.tip_dense + (size_t)tip * P * R * S, full.data(), full.size() * 8, cudaMemcpyHostToDevice));
+  l->h_tip_dense_flag[tip] = 1; l->flags_dirty = true;
+  return BPPGPU_SUCCESS;
+}
+
+extern "C" void bppgpu_set_pattern_weights(bppgpu_locus * l, const unsigned int * w)
+{
+  CUDA_CHECK(cudaSetDevice(l->e->device));
+  CUDA_CHECK(cudaMemcpy(l->dev.weights, w, (size_t)l->sites * 4, cudaMemcpyHostToDevice));
+}
+extern "C" void bppgpu_set_frequencies(bppgpu_locus * l, unsigned int idx, const double * f)
+{
+  if (idx != 0) { fatal("freqs_index must be 0"); return; }
+  l->h_freqs.assign(f, f + l->states); l->eigen_valid = false; l->model_dirty = true;   // locus.c:889-897
+}
+extern "C" void bppgpu_set_subst_params(bppgpu_locus * l, unsigned int idx, const double * p)
+{
+  if (idx != 0) { fatal("params_index must be 0"); return; }
+  l->h_subst.assign(p, p + l->states * (l->states - 1) / 2); l->eigen_valid = false;    // locus.c:877-887
+}
+extern "C" void bppgpu_set_category_rates(bppgpu_locus * l, const double * r)
+{
+  l->h_rates.assign(r, r + l->rate_cats); l->model_dirty = true;
+}
+extern "C" void bppgpu_set_category_weights(bppgpu_locus * l, const double * w)
+{
+  l->h_rate_weights.assign(w, w + l->rate_cats); l->model_dirty = true;
+}
+extern "C" void bppgpu_set_eigen(bppgpu_locus * l, unsigned int idx, const double * ev, const double * iev, const double * lam)
+{
+  if (idx != 0) { fatal("params_index must be 0"); return; }
+  const size_t S = l->states;
+  l->h_evecs.assign(ev, ev + S * S); l->h_ievecs.assign(iev, iev + S * S); l->h_evals.assign(lam, lam + S);
+  l->eigen_valid = true; l->model_dirty = true;
+}
+extern "C" void bppgpu_get_eigen(bppgpu_locus * l, unsigned int idx, double * ev, double * iev, double * lam)
+{
+  (void)idx;
+  if (!l->eigen_valid) host_update_eigen(l);
+  const size_t S = l->states;
+  memcpy(ev, l->h_evecs.data(), S * S * 8); memcpy(iev, l->h_ievecs.data(), S * S * 8); memcpy(lam, l->h_evals.data(), S * 8);
+}
+
+extern "C" int bppgpu_set_diploid(bppgpu_locus * l, unsigned int unphased, const unsigned long * cnt,
+                                  const unsigned long * mapping, unsigned long maplen)
+{
+  bppgpu_engine * e = l->e;
+  std::lock_guard<std::mutex> lock(e->mu);
+  CUDA_CHECK(cudaSetDevice(e->device));
+  std::vector<unsigned long long> off(unphased + 1, 0), mp(maplen);
+  for (unsigned int i = 0; i < unphased; ++i) off[i + 1] = off[i] + cnt[i];
+  if (off[unphased] != maplen) { fatal("diploid mapping length mismatch"); return BPPGPU_FAILURE; }
+  for (unsigned long i = 0; i < maplen; ++i) mp[i] = mapping[i];
+  e->arena.release(l->dev.dip_off, l->b_dip_off); e->arena.release(l->dev.dip_map, l->b_dip_map);
+  l->b_dip_off = off.size() * 8; l->b_dip_map = std::max<size_t>(8, mp.size() * 8);
+  l->dev.dip_off = (unsigned long long *)e->arena.alloc(l->b_dip_off);
+  l->dev.dip_map = (unsigned long long *)e->arena.alloc(l->b_dip_map);
+  CUDA_CHECK(cudaMemcpy(l->dev.dip_off, off.data(), off.size() * 8, cudaMemcpyHostToDevice));
+  if (!mp.empty()) CUDA_CHECK(cudaMemcpy(l->dev.dip_map, mp.data(), mp.size() * 8, cudaMemcpyHostToDevice));
+  l->dev.unphased = unphased;
+  engine_publish_locus(e, l);
+  return BPPGPU_SUCCESS;
+}
+
+// ------------------------------------------------------------------------------------ batch
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static void batch_launch_cfg(bppgpu_batch * b)
+{
+  // all loci of a batch share states / rate_cats (checked at creation)
+  const bppgpu_locus * l0 = b->loci[0];
+  const unsigned R = l0->rate_cats;
+  const bool pow2 = (R & (R - 1)) == 0 && R <= 32;
+  if (l0->states == 4 && pow2) { b->kernel_kind = 0; b->RL = R; }
+  else { b->kernel_kind = 1; b->RL = 1; }
+  // tile size: 256 cells for big loci, 128 for small ones (fewer idle lanes in the last tile)
+  size_t cells = 0;
+  for (auto * l : b->loci) cells += (size_t)l->sites * (b->kernel_kind == 0 ? R : 1);
+  const size_t mean = cells / b->n;
+  if (b->kernel_kind == 0) b->tile_threads = mean >= 512 ? 256 : 128;
+  else b->tile_threads = 128;
+}
+
+extern "C" bppgpu_batch * bppgpu_batch_create(bppgpu_engine * e, unsigned int n, bppgpu_locus * const * loci)
+{
+  if (!e || n == 0) { fatal("bppgpu_batch_create: empty batch"); return nullptr; }
+  CUDA_CHECK(cudaSetDevice(e->device));
+  bppgpu_batch * b = new bppgpu_batch();
+  b->e = e; b->n = n; b->loci.assign(loci, loci + n);
+  for (unsigned i = 0; i < n; ++i)
+  {
+    if (!loci[i] || loci[i]->e != e) { fatal("batch locus %u belongs to another engine", i); delete b; return nullptr; }
+    if (loci[i]->states != loci[0]->states || loci[i]->rate_cats != loci[0]->rate_cats)
+    { fatal("all loci of a batch must share states and rate_cats"); delete b; return nullptr; }
+  }
+  CUDA_CHECK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+  b->own_stream = true;
+  batch_launch_cfg(b);
+  std::vector<unsigned int> ids(n), tile_locus, tile_cell0, tile_first(n + 1, 0);
+  std::vector<unsigned long long> soff(n);
+  size_t sbytes = 0;
+  for (unsigned i = 0; i < n; ++i)
+  {
+    const bppgpu_locus * l = loci[i];
+    ids[i] = l->id;
+    const unsigned cells = l->sites * (b->kernel_kind == 0 ? b->RL : 1);
+    tile_first[i] = (unsigned)tile_locus.size();
+    for (unsigned c = 0; c < cells; c += b->tile_threads) { tile_locus.push_back(i); tile_cell0.push_back(c); }
+    soff[i] = sbytes; sbytes += align_up(l->clv_buffers, 16);
+  }
+  tile_first[n] = (unsigned)tile_locus.size();
+  b->n_tiles = (unsigned)tile_locus.size();
+  b->scratch_bytes = sbytes;
+  CUDA_CHECK(cudaMalloc(&b->d_batch_locus, n * 4));
+  CUDA_CHECK(cudaMalloc(&b->d_tile_locus, b->n_tiles * 4));
+  CUDA_CHECK(cudaMalloc(&b->d_tile_cell0, b->n_tiles * 4));
+  CUDA_CHECK(cudaMalloc(&b->d_tile_first, (n + 1) * 4));
+  CUDA_CHECK(cudaMalloc(&b->d_scratch_off, n * 8));
+  CUDA_CHECK(cudaMalloc(&b->d_scratch, std::max<size_t>(16, sbytes)));
+  CUDA_CHECK(cudaMalloc(&b->d_plan_count, n * 4));
+  CUDA_CHECK(cudaMalloc(&b->d_tile_partial, b->n_tiles * 8));
+  CUDA_CHECK(cudaMalloc(&b->d_lnl, (n + 1) * 8));
+  b->d_lnl_sum = b->d_lnl + n;
+  CUDA_CHECK(cudaHostAlloc(&b->h_out, (n + 1) * 8, cudaHostAllocDefault));
+  CUDA_CHECK(cudaMemcpy(b->d_batch_locus, ids.data(), n * 4, cudaMemcpyHostToDevice));
+  CUDA_CHECK(cudaMemcpy(b->d_tile_locus, tile_locus.data(), b->n_tiles * 4, cudaMemcpyHostToDevice));
+  CUDA_CHECK(cudaMemcpy(b->d_tile_cell0, tile_cell0.data(), b->n_tiles * 4, cudaMemcpyHostToDevice));
+  CUDA_CHECK(cudaMemcpy(b->d_tile_first, tile_first.data(), (n + 1) * 4, cudaMemcpyHostToDevice));
+  CUDA_CHECK(cudaMemcpy(b->d_scratch_off, soff.data(), n * 8, cudaMemcpyHostToDevice));
+  CUDA_CHECK(cudaMemset(b->d_plan_count, 0, n * 4));
+  CUDA_CHECK(cudaMemset(b->d_tile_partial, 0, b->n_tiles * 8));
+  CUDA_CHECK(cudaEventCreate(&b->t0));
+  CUDA_CHECK(cudaEventCreate(&b->t1));
+  return b;
+}
+
+extern "C" void bppgpu_batch_destroy(bppgpu_batch * b)
+{
+  if (!b) return;
+  cudaSetDevice(b->e->device);
+  cudaStreamSynchronize(b->stream);
+  drain_profile(b->e);
+  cudaFree(b->d_batch_locus); cudaFree(b->d_tile_locus); cudaFree(b->d_tile_cell0); cudaFree(b->d_tile_first);
+  cudaFree(b->d_scratch_off); cudaFree(b->d_scratch); cudaFree(b->d_plan_count); cudaFree(b->d_tile_partial);
+  cudaFree(b->d_lnl); cudaFree(b->d_in); cudaFree(b->d_plan); cudaFree(b->d_persite);
+  cudaFreeHost(b->h_out); cudaFreeHost(b->h_in);
+  cudaEventDestroy(b->t0); cudaEventDestroy(b->t1);
+  if (b->own_stream) cudaStreamDestroy(b->stream);
+  delete b;
+}
+
+extern "C" unsigned int bppgpu_batch_size(const bppgpu_batch * b) { return b->n; }
+extern "C" void * bppgpu_batch_lnl_sum_dev(bppgpu_batch * b) { return (void *)b->d_lnl_sum; }
+extern "C" void * bppgpu_batch_stream(bppgpu_batch * b) { return (void *)b->stream; }
+extern "C" void bppgpu_batch_synchronize(bppgpu_batch * b) { CUDA_CHECK(cudaStreamSynchronize(b->stream)); }
+extern "C" void bppgpu_batch_timer_start(bppgpu_batch * b) { CUDA_CHECK(cudaEventRecord(b->t0, b->stream)); }
+extern "C" double bppgpu_batch_timer_stop_ms(bppgpu_batch * b)
+{
+  CUDA_CHECK(cudaEventRecord(b->t1, b->stream));
+  CUDA_CHECK(cudaEventSynchronize(b->t1));
+  float ms = 0;
+  CUDA_CHECK(cudaEventElapsedTime(&ms, b->t0, b->t1));
+  return ms;
+}
+
+// Stage the inputs of one step into the pinned blob and copy it to the device in ONE transfer.
+// Any of the three groups may be absent (nullptr counts).
+static int batch_stage(bppgpu_batch * b, const unsigned int * mcounts, const unsigned int * midx, const double * mbl,
+                       const unsigned int * ocounts, const bppgpu_partial_op * ops,
+                       const unsigned int * rclv, const int * rsc)
+{
+  bppgpu_engine * e = b->e;
+  CUDA_CHECK(cudaSetDevice(e->device));
+  const unsigned n = b->n;
+  size_t tm = 0, to = 0;
+  if (mcounts) for (unsigned i = 0; i < n; ++i) tm += mcounts[i];
+  if (ocounts) for (unsigned i = 0; i < n; ++i) to += ocounts[i];
+  size_t off = 0;
+  b->o_mat_off = off; off = align_up(off + (n + 1) * 4, 16);
+  b->o_mat_idx = off; off = align_up(off + tm * 4, 16);
+  b->o_mat_bl = off;  off = align_up(off + tm * 8, 16);
+  b->o_op_off = off;  off = align_up(off + (n + 1) * 4, 16);
+  b->o_ops = off;     off = align_up(off + to * sizeof(bppgpu_partial_op), 16);
+  b->o_root_clv = off; off = align_up(off + n * 4, 16);
+  b->o_root_sc = off;  off = align_up(off + n * 4, 16);
+  if (off > b->h_in_cap)
+  {
+    CUDA_CHECK(cudaStreamSynchronize(b->stream));
+    if (b->h_in) cudaFreeHost(b->h_in);
+    if (b->d_in) cudaFree(b->d_in);
+    b->h_in_cap = b->d_in_cap = off + off / 4;
+    CUDA_CHECK(cudaHostAlloc(&b->h_in, b->h_in_cap, cudaHostAllocDefault));
+    CUDA_CHECK(cudaMalloc(&b->d_in, b->d_in_cap));
+  }
+  if (to + n > b->plan_cap)
+  {
+    CUDA_CHECK(cudaStreamSynchronize(b->stream));
+    if (b->d_plan) cudaFree(b->d_plan);
+    b->plan_cap = (to + n) + (to + n) / 4;
+    CUDA_CHECK(cudaMalloc(&b->d_plan, b->plan_cap * sizeof(PlanOp)));
+  }
+  // the previous step's blob may still be in flight on the stream
+  CUDA_CHECK(cudaStreamSynchronize(b->stream));
+  unsigned int * moff = (unsigned int *)(b->h_in + b->o_mat_off);
+  unsigned int * ooff = (unsigned int *)(b->h_in + b->o_op_off);
+  moff[0] = 0; ooff[0] = 0;
+  for (unsigned i = 0; i < n; ++i)
+  {
+    moff[i + 1] = moff[i] + (mcounts ? mcounts[i] : 0);
+    ooff[i + 1] = ooff[i] + (ocounts ? ocounts[i] : 0);
+  }
+  if (tm) { memcpy(b->h_in + b->o_mat_idx, midx, tm * 4); memcpy(b->h_in + b->o_mat_bl, mbl, tm * 8); }
+  if (to) memcpy(b->h_in + b->o_ops, ops, to * sizeof(bppgpu_partial_op));
+  if (rclv)
+  {
+    memcpy(b->h_in + b->o_root_clv, rclv, n * 4);
+    if (rsc) memcpy(b->h_in + b->o_root_sc, rsc, n * 4);
+    else { int * p = (int *)(b->h_in + b->o_root_sc); for (unsigned i = 0; i < n; ++i) p[i] = -1; }
+  }
+  b->total_mats = (unsigned)tm; b->total_ops = (unsigned)to;
+  b->staged_mats = mcounts != nullptr; b->staged_ops = ocounts != nullptr; b->staged_roots = rclv != nullptr;
+  CUDA_CHECK(cudaMemcpyAsync(b->d_in, b->h_in, off, cudaMemcpyHostToDevice, b->stream));
+  return BPPGPU_SUCCESS;
+}
+
+static void batch_sync_loci(bppgpu_batch * b, bool need_eigen)
+{
+  for (bppgpu_locus * l : b->loci)
+  {
+    if (need_eigen && !l->eigen_valid && !model_is_closed_form(l)) host_update_eigen(l);   // locus.c:2462-2476
+    if (l->codes_dirty || l->model_dirty || l->flags_dirty) locus_sync(l, b->stream);
+  }
+}
+
+template <int RL>
+static void launch_tree_s4(bppgpu_batch * b, const TreeParams & prm, size_t smem)
+{
+  bppgpu_engine * e = b->e;
+  if (e->math == BPPGPU_MATH_EXACT)
+  {
+    CUDA_CHECK(cudaFuncSetAttribute(tree_kernel_s4<RL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tree_kernel_s4<RL, true><<<b->n_tiles, b->tile_threads, smem, b->stream>>>(prm);
+  }
+  else
+  {
+    CUDA_CHECK(cudaFuncSetAttribute(tree_kernel_s4<RL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tree_kernel_s4<RL, false><<<b->n_tiles, b->tile_threads, smem, b->stream>>>(prm);
+  }
+}
+
+// launches: [pmatrix] [plan + tree (+ finish)] on the batch stream, using the staged blob
+static int batch_run(bppgpu_batch * b, bool do_mats, bool do_tree, bool want_root, double * persite, int persite_mode)
+{
+  bppgpu_engine * e = b->e;
+  CUDA_CHECK(cudaSetDevice(e->device));
+  const unsigned n = b->n;
+  batch_sync_loci(b, do_mats);
+  const unsigned int * d_mat_off = (const unsigned int *)(b->d_in + b->o_mat_off);
+  const unsigned int * d_mat_idx = (const unsigned int *)(b->d_in + b->o_mat_idx);
+  const double * d_mat_bl = (const double *)(b->d_in + b->o_mat_bl);
+  const unsigned int * d_op_off = (const unsigned int *)(b->d_in + b->o_op_off);
+  const RawOp * d_ops = (const RawOp *)(b->d_in + b->o_ops);
+  const unsigned int * d_root_clv = (const unsigned int *)(b->d_in + b->o_root_clv);
+  const int * d_root_sc = (const int *)(b->d_in + b->o_root_sc);
+
+  if (do_mats && b->total_mats)
+  {
+    ProfScope ps(e, b->stream, BPPGPU_KERNEL_PMATRIX);
+    const unsigned S = b->loci[0]->states;
+    if (S > 8)
+    {
+      const size_t sm = (2 * (size_t)S * S + S) * 8;
+      pmatrix_kernel_wide<<<n, 128, sm, b->stream>>>(e->d_loci, b->d_batch_locus, d_mat_off, d_mat_idx, d_mat_bl);
+    }
+    else
+      pmatrix_kernel<<<n, 64, 0, b->stream>>>(e->d_loci, b->d_batch_locus, d_mat_off, d_mat_idx, d_mat_bl);
+    CUDA_CHECK(cudaGetLastError());
+  }
+  if (!do_tree) return BPPGPU_SUCCESS;
+
+  // stack slots: enough for any binary tree of this batch in recursive post-order is its height;
+  // cap by shared memory, the plan falls back to HBM re-reads beyond that
+  int slots = 0;
+  if (b->kernel_kind == 0)
+  {
+    unsigned maxT = 0;
+    for (auto * l : b->loci) maxT = std::max(maxT, l->tips);
+    slots = 1; while ((1u << slots) < maxT) ++slots;      // ceil(log2 T)
+    slots = std::min(slots, 6);
+  }
+  {
+    ProfScope ps(e, b->stream, BPPGPU_KERNEL_PLAN);
+    plan_kernel<<<(n + 127) / 128, 128, 0, b->stream>>>(e->d_loci, b->d_batch_locus, n, d_op_off, d_ops, d_root_clv,
+                                                       d_root_sc, want_root ? 1 : 0, b->d_plan, b->d_plan_count,
+                                                       b->d_scratch, b->d_scratch_off, slots);
+    CUDA_CHECK(cudaGetLastError());
+  }
+  TreeParams prm;
+  prm.loci = e->d_loci; prm.batch_locus = b->d_batch_locus; prm.tile_locus = b->d_tile_locus;
+  prm.tile_cell0 = b->d_tile_cell0; prm.op_off = d_op_off; prm.plan = b->d_plan; prm.plan_count = b->d_plan_count;
+  prm.tile_partial = want_root ? b->d_tile_partial : nullptr;
+  prm.persite = persite; prm.persite_mode = persite_mode; prm.n_slots = slots;
+  prm.log_threshold = e->log_threshold;
+  {
+    ProfScope ps(e, b->stream, BPPGPU_KERNEL_TREE);
+    if (b->kernel_kind == 0)
+    {
+      const unsigned RL = b->RL, nt = b->tile_threads;
+      size_t smem = TREE_CHUNK * sizeof(PlanOp) + (size_t)TREE_CHUNK * 2 * RL * PM_STRIDE * 8 +
+                    (size_t)slots * nt * (32 + 4) + 32 * 8 + 16;
+      switch (RL)
+      {
+        case 1: launch_tree_s4<1>(b, prm, smem); break;
+        case 2: launch_tree_s4<2>(b, prm, smem); break;
+        case 4: launch_tree_s4<4>(b, prm, smem); break;
+        case 8: launch_tree_s4<8>(b, prm, smem); break;
+        case 16: launch_tree_s4<16>(b, prm, smem); break;
+        case 32: launch_tree_s4<32>(b, prm, smem); break;
+        default: fatal("internal: RL=%u", RL); return BPPGPU_FAILURE;
+      }
+    }
+    else
+    {
+      if (e->math == BPPGPU_MATH_EXACT) tree_kernel_generic<true><<<b->n_tiles, b->tile_threads, 0, b->stream>>>(prm);
+      else tree_kernel_generic<false><<<b->n_tiles, b->tile_threads, 0, b->stream>>>(prm);
+    }
+    CUDA_CHECK(cudaGetLastError());
+  }
+  if (want_root)
+  {
+    ProfScope ps(e, b->stream, BPPGPU_KERNEL_FINISH);
+    finish_kernel<<<1, 1024, 0, b->stream>>>(b->d_tile_partial, b->d_tile_first, n, b->d_lnl, b->d_lnl_sum);
+    CUDA_CHECK(cudaGetLastError());
+  }
+  return BPPGPU_SUCCESS;
+}
+
+static int batch_collect(bppgpu_batch * b, double * lnl_out, double * sum_out)
+{
+  CUDA_CHECK(cudaSetDevice(b->e->device));
+  CUDA_CHECK(cudaMemcpyAsync(b->h_out, b->d_lnl, (b->n + 1) * 8, cudaMemcpyDeviceToHost, b->stream));
+  CUDA_CHECK(cudaStreamSynchronize(b->stream));
+  if (lnl_out) memcpy(lnl_out, b->h_out, b->n * 8);
+  if (sum_out) *sum_out = b->h_out[b->n];
+  return BPPGPU_SUCCESS;
+}
+
+extern "C" int bppgpu_batch_update_matrices(bppgpu_batch * b, const unsigned int * counts,
+                                            const unsigned int * idx, const double * bl)
+{
+  if (!batch_stage(b, counts, idx, bl, nullptr, nullptr, nullptr, nullptr)) return BPPGPU_FAILURE;
+  if (!batch_run(b, true, false, false, nullptr, 0)) return BPPGPU_FAILURE;
+  CUDA_CHECK(cudaStreamSynchronize(b->stream));
+  return BPPGPU_SUCCESS;
+}
+
+extern "C" int bppgpu_batch_update_partials(bppgpu_batch * b, const unsigned int * counts, const bppgpu_partial_op * ops)
+{
+  if (!batch_stage(b, nullptr, nullptr, nullptr, counts, ops, nullptr, nullptr)) return BPPGPU_FAILURE;
+  if (!batch_run(b, false, true, false, nullptr, 0)) return BPPGPU_FAILURE;
+  CUDA_CHECK(cudaStreamSynchronize(b->stream));
+  return BPPGPU_SUCCESS;
+}
+
+extern "C" int bppgpu_batch_root_loglikelihood(bppgpu_batch * b, const unsigned int * rclv, const int * rsc, double * out)
+{
+  if (!batch_stage(b, nullptr, nullptr, nullptr, nullptr, nullptr, rclv, rsc)) return BPPGPU_FAILURE;
+  if (!batch_run(b, false, true, true, nullptr, 0)) return BPPGPU_FAILURE;
+  return batch_collect(b, out, nullptr);
+}
+
+extern "C" int bppgpu_batch_stage(bppgpu_batch * b, const unsigned int * mc, const unsigned int * mi, const double * mb,
+                                  const unsigned int * oc, const bppgpu_partial_op * ops,
+                                  const unsigned int * rclv, const int * rsc)
+{
+  return batch_stage(b, mc, mi, mb, oc, ops, rclv, rsc);
+}
+
+extern "C" int bppgpu_batch_run(bppgpu_batch * b)
+{
+  return batch_run(b, b->staged_mats, b->staged_ops || b->staged_roots, b->staged_roots, nullptr, 0);
+}
+
+extern "C" int bppgpu_batch_collect(bppgpu_batch * b, double * lnl_out, double * sum_out)
+{
+  return batch_collect(b, lnl_out, sum_out);
+}
+
+extern "C" int bppgpu_batch_full_pass(bppgpu_batch * b, const unsigned int * mc, const unsigned int * mi, const double * mb,
+                                      const unsigned int * oc, const bppgpu_partial_op * ops,
+                                      const unsigned int * rclv, const int * rsc, double * lnl_out, double * sum_out)
+{
+  if (!batch_stage(b, mc, mi, mb, oc, ops, rclv, rsc)) return BPPGPU_FAILURE;
+  if (!batch_run(b, mc != nullptr, true, rclv != nullptr, nullptr, 0)) return BPPGPU_FAILURE;
+  return batch_collect(b, lnl_out, sum_out);
+}
+
+// ------------------------------------------------------------------------------------ per-locus synchronous seam
+static bppgpu_batch * self_batch(bppgpu_locus * l)
+{
+  if (!l->self_batch)
+  {
+    bppgpu_locus * arr[1] = { l };
+    l->self_batch = bppgpu_batch_create(l->e, 1, arr);
+  }
+  return l->self_batch;
+}
+
+extern "C" int bppgpu_update_matrices(bppgpu_locus * l, unsigned int count, const unsigned int * idx, const double * bl)
+{
+  for (unsigned i = 0; i < count; ++i)
+    if (idx[i] >= l->prob_matrices) { fatal("pmatrix index %u out of range", idx[i]); return BPPGPU_FAILURE; }
+  return bppgpu_batch_update_matrices(self_batch(l), &count, idx, bl);
+}
+
+extern "C" int bppgpu_update_partials(bppgpu_locus * l, unsigned int count, const bppgpu_partial_op * ops)
+{
+  const unsigned nb = l->tips + l->clv_buffers;
+  for (unsigned i = 0; i < count; ++i)
+  {
+    const bppgpu_partial_op & o = ops[i];
+    if (o.parent_clv_index < l->tips || o.parent_clv_index >= nb || o.left_clv_index >= nb || o.right_clv_index >= nb ||
+        o.left_pmatrix_index >= l->prob_matrices || o.right_pmatrix_index >= l->prob_matrices ||
+        o.parent_scaler_index >= (int)l->scale_buffers || o.left_scaler_index >= (int)l->scale_buffers ||
+        o.right_scaler_index >= (int)l->scale_buffers)
+    { fatal("update_partials: op %u has an index out of range", i); return BPPGPU_FAILURE; }
+  }
+  return bppgpu_batch_update_partials(self_batch(l), &count, ops);
+}
+
+static void ensure_persite(bppgpu_batch * b, size_t n)
+{
+  if (n > b->persite_cap)
+  {
+    CUDA_CHECK(cudaStreamSynchronize(b->stream));
+    if (b->d_persite) cudaFree(b->d_persite);
+    CUDA_CHECK(cudaMalloc(&b->d_persite, n * 8));
+    b->persite_cap = n;
+  }
+}
+
+extern "C" double bppgpu_root_loglikelihood(bppgpu_locus * l, unsigned int root_clv, int root_sc, double * persite)
+{
+  bppgpu_batch * b = self_batch(l);
+  double out = 0;
+  if (!batch_stage(b, nullptr, nullptr, nullptr, nullptr, nullptr, &root_clv, &root_sc)) return NAN;
+  if (persite) ensure_persite(b, l->sites);
+  if (!batch_run(b, false, true, true, persite ? b->d_persite : nullptr, 1)) return NAN;
+  batch_collect(b, &out, nullptr);
+  if (persite) CUDA_CHECK(cudaMemcpy(persite, b->d_persite, (size_t)l->sites * 8, cudaMemcpyDeviceToHost));
+  return out;
+}
+
+extern "C" int bppgpu_root_likelihood_vector(bppgpu_locus * l, unsigned int root_clv, double * persite_lh)
+{
+  bppgpu_batch * b = self_batch(l);
+  int none = -1;
+  if (!batch_stage(b, nullptr, nullptr, nullptr, nullptr, nullptr, &root_clv, &none)) return BPPGPU_FAILURE;
+  ensure_persite(b, l->sites);
+  if (!batch_run(b, false, true, true, b->d_persite, 2)) return BPPGPU_FAILURE;
+  CUDA_CHECK(cudaStreamSynchronize(b->stream));
+  CUDA_CHECK(cudaMemcpy(persite_lh, b->d_persite, (size_t)l->sites * 8, cudaMemcpyDeviceToHost));
+  return BPPGPU_SUCCESS;
+}
+
+extern "C" double bppgpu_root_loglikelihood_diploid(bppgpu_locus * l, unsigned int root_clv)
+{
+  if (!l->dev.dip_off) { fatal("locus has no diploid mapping"); return NAN; }
+  bppgpu_batch * b = self_batch(l);
+  int none = -1;
+  if (!batch_stage(b, nullptr, nullptr, nullptr, nullptr, nullptr, &root_clv, &none)) return NAN;
+  ensure_persite(b, l->sites);
+  if (!batch_run(b, false, true, true, b->d_persite, 2)) return NAN;
+  {
+    ProfScope ps(b->e, b->stream, BPPGPU_KERNEL_FINISH);
+    diploid_kernel<<<1, 256, 0, b->stream>>>(b->e->d_loci, l->id, b->d_persite, b->d_lnl_sum);
+    CUDA_CHECK(cudaGetLastError());
+  }
+  double out = 0;
+  CUDA_CHECK(cudaMemcpyAsync(b->h_out, b->d_lnl_sum, 8, cudaMemcpyDeviceToHost, b->stream));
+  CUDA_CHECK(cudaStreamSynchronize(b->stream));
+  out = b->h_out[0];
+  return out;
+}
+
+// ------------------------------------------------------------------------------------ raw buffers
+extern "C" int bppgpu_get_clv(bppgpu_locus * l, unsigned int clv_index, double * out)
+{
+  CUDA_CHECK(cudaSetDevice(l->e->device));
+  const size_t P = l->sites, R = l->rate_cats, S = l->states, nd = P * R * S;
+  if (clv_index >= l->tips + l->clv_buffers) { fatal("clv index out of range"); return BPPGPU_FAILURE; }
+  if (l->self_batch) CUDA_CHECK(cudaStreamSynchronize(l->self_batch->stream));
+  if (clv_index >= l->tips)
+  {
+    CUDA_CHECK(cudaMemcpy(out, l->dev.clv + (size_t)(clv_index - l->tips) * nd, nd * 8, cudaMemcpyDeviceToHost));
+    return BPPGPU_SUCCESS;
+  }
+  if (l->h_tip_dense_flag[clv_index])
+  {
+    CUDA_CHECK(cudaMemcpy(out, l->dev.tip_dense + (size_t)clv_index * nd, nd * 8, cudaMemcpyDeviceToHost));
+    return BPPGPU_SUCCESS;
+  }
+  for (size_t i = 0; i < P; ++i)          // expand the packed tip like set_tipclv, locus.c:540-555
+  {
+    const unsigned int c = (S <= 8) ? l->h_codes8[clv_index * P + i] : l->h_codes32[clv_index * P + i];
+    for (size_t r = 0; r < R; ++r) for (size_t j = 0; j < S; ++j) out[(i * R + r) * S + j] = (double)((c >> j) & 1u);
+  }
+  return BPPGPU_SUCCESS;
+}
+
+extern "C" int bppgpu_get_pmatrix(bppgpu_locus * l, unsigned int idx, double * out)
+{
+  CUDA_CHECK(cudaSetDevice(l->e->device));
+  if (idx >= l->prob_matrices) { fatal("pmatrix index out of range"); return BPPGPU_FAILURE; }
+  const size_t nd = (size_t)l->rate_cats * l->states * l->states;
+  CUDA_CHECK(cudaMemcpy(out, l->dev.pmat + idx * nd, nd * 8, cudaMemcpyDeviceToHost));
+  return BPPGPU_SUCCESS;
+}
+
+extern "C" int bppgpu_set_pmatrix(bppgpu_locus * l, unsigned int idx, const double * in)
+{
+  CUDA_CHECK(cudaSetDevice(l->e->device));
+  if (idx >= l->prob_matrices) { fatal("pmatrix index out of range"); return BPPGPU_FAILURE; }
+  const size_t nd = (size_t)l->rate_cats * l->states * l->states;
+  CUDA_CHECK(cudaMemcpy(l->dev.pmat + idx * nd, in, nd * 8, cudaMemcpyHostToDevice));
+  return BPPGPU_SUCCESS;
+}
+
+extern "C" int bppgpu_get_scaler(bppgpu_locus * l, unsigned int idx, unsigned int * out)
+{
+  CUDA_CHECK(cudaSetDevice(l->e->device));
+  if (idx >= l->scale_buffers) { fatal("scaler index out of range"); return BPPGPU_FAILURE; }
+  CUDA_CHECK(cudaMemcpy(out, l->dev.scale + (size_t)idx * l->sites, (size_t)l->sites * 4, cudaMemcpyDeviceToHost));
+  return BPPGPU_SUCCESS;
+}

@@ -1,0 +1,62 @@
+"""Shared test helpers (CPU side)."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from bpp_b200 import synth  # noqa: E402
+from oracle import felsenstein as F  # noqa: E402
+from oracle import refbind  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def char_map(states):
+    return synth.iupac_nt_map() if states == 4 else synth.aa_map()
+
+
+def ref_set_from_workload(w, arch=refbind.ARCH_AVX2):
+    """Load a synth.Workload into the compiled reference (oracle/_ref)."""
+    model = {"JC69": refbind.MODEL_JC69, "GTR": refbind.MODEL_GTR, "LG": refbind.AA_MODEL_LG}[w.model]
+    rs = refbind.RefSet(w.n_loci, w.states, w.rate_cats, w.scaling, model=model, arch=arch)
+    for i in range(w.n_loci):
+        rs.create(i, w.tips, w.sites)
+        for t in range(w.tips):
+            rs.set_tip_states(i, t, w.tip_chars[i, t].tobytes())
+        rs.set_weights(i, w.weights[i])
+        if w.model == "JC69":
+            # locus_set_frequencies_and_rates (locus.c:899) sets pi = 1/4 for JC69
+            rs.set_model(i, freqs=w.freqs[i], rates=w.rates)
+        else:
+            rs.set_model(i, freqs=w.freqs[i], subst=w.subst[i], rates=w.rates)
+        rs.set_tree(i, w.left[i], w.right[i], w.times[i], float(w.rate_mui[i]))
+    return rs
+
+
+def lg_tables():
+    d = np.load(os.path.join(GOLDEN, "lg_model.npz"))
+    return d["rates"], d["freqs"]
+
+
+def rel_err(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    den = np.maximum(np.abs(b), 1e-300)
+    return float(np.max(np.abs(a - b) / den)) if a.size else 0.0
+
+
+def load_case(name):
+    """A golden case as (Workload, dict of reference outputs)."""
+    d = np.load(os.path.join(GOLDEN, "case_%s.npz" % name))
+    n, T, P, S, R, sc = [int(x) for x in d["meta"]]
+    w = synth.Workload(name, n, T, P, S, R, str(d["model"]), bool(sc), d["left"], d["right"], d["times"],
+                       d["rate_mui"], d["tip_chars"], d["weights"], d["freqs"], d["subst"], d["rates"])
+    return w, d
+
+
+GOLDEN_CASES = ["jc69_r1", "gtr_g4_scale", "gtr_g4", "lg_g4", "jc69_deep_scale", "gtr_g4_deep_scale",
+                "lg_g4_deep_scale"]

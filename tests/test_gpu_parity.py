@@ -1,0 +1,302 @@
+"""GPU: parity of the CUDA path (through the C-ABI) with the oracle and the reference fixtures.
+
+Bars (BASELINE.json north_star): per-locus lnL relative error <= 1e-10 against the reference;
+scalers (integers) exactly equal; 4-state CLVs BIT-IDENTICAL to the reference's AVX kernels
+when both sides use the same P-matrices (math="exact").
+"""
+import numpy as np
+import pytest
+
+from helpers import F, GOLDEN_CASES, char_map, lg_tables, load_case, rel_err, synth
+
+pytestmark = pytest.mark.gpu
+
+LNL_RTOL = 1e-10
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from bpp_b200 import engine
+    e = engine.Engine(0, math="exact")
+    yield e
+    e.close()
+
+
+def _load(eng, w):
+    from bpp_b200 import engine
+    loci, trees = engine.load_workload(eng, w)
+    return loci, trees, engine.Batch(eng, loci)
+
+
+def _free(loci, batch):
+    batch.destroy()
+    for l in loci:
+        l.destroy()
+
+
+@pytest.mark.parametrize("math", ["exact", "fma"])
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_full_pass_lnl_matches_reference_fixture(eng, name, math):
+    w, d = load_case(name)
+    eng.set_math(math)
+    loci, trees, batch = _load(eng, w)
+    lnl, total = batch.full_pass(trees.full_pass_step())
+    eng.set_math("exact")
+    assert rel_err(lnl, d["lnl"]) <= LNL_RTOL, (name, lnl, d["lnl"])
+    assert abs(total - d["lnl"].sum()) <= LNL_RTOL * abs(total)
+    _free(loci, batch)
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_clv_scaler_pmatrix_match_reference_fixture(eng, name):
+    w, d = load_case(name)
+    T = w.tips
+    loci, trees, batch = _load(eng, w)
+    batch.full_pass(trees.full_pass_step())
+    l = loci[0]
+    tol = 1e-9 if w.states == 20 else 1e-11
+    for k, n in enumerate(range(T, 2 * T - 1)):
+        assert rel_err(l.get_clv(n), d["l0_clv"][k]) < tol, (name, n)
+        if w.scaling:
+            assert np.array_equal(l.get_scaler(n - T), d["l0_scaler"][k]), (name, n)
+    if "l0_pmat" in d:
+        for n in range(2 * T - 2):
+            assert np.max(np.abs(l.get_pmatrix(n) - d["l0_pmat"][n])) < 1e-14
+    _free(loci, batch)
+
+
+@pytest.mark.parametrize("name", ["jc69_r1", "gtr_g4_scale", "gtr_g4"])
+def test_clv_bit_exact_with_reference_pmatrices(eng, name):
+    """Upload the reference's own P-matrices: every inner CLV, scaler and the per-site lnL must be
+    bit-identical to --arch avx/avx2 (core_partials_avx.c:368-531, core_likelihood_avx.c:98-157)."""
+    w, d = load_case(name)
+    T = w.tips
+    loci, trees, batch = _load(eng, w)
+    l = loci[0]
+    for n in range(2 * T - 2):
+        l.set_pmatrix(n, d["l0_pmat"][n])
+    mc, mi, mb, oc, ops, rc, rs = trees.full_pass_step()
+    ops0 = ops[:T - 1]
+    l.update_partials(ops0)
+    for k, n in enumerate(range(T, 2 * T - 1)):
+        assert np.array_equal(l.get_clv(n), d["l0_clv"][k]), (name, n)
+        if w.scaling:
+            assert np.array_equal(l.get_scaler(n - T), d["l0_scaler"][k])
+    lnl, persite = l.root_loglikelihood(int(rc[0]), int(rs[0]), persite=True)
+    assert np.allclose(persite, d["l0_persite"], rtol=4e-16, atol=0)       # CUDA log vs glibc log: <= 1 ulp
+    assert abs(lnl - d["lnl"][0]) <= 1e-13 * abs(lnl)
+    _free(loci, batch)
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_mixing_step_with_index_flips(eng, name):
+    """prop_mixing_update_gtrees (prop_mixing.c:52-220): scale ages, flip every index to the spare
+    buffers, recompute; then flip back (rejection) and read the untouched old lnL again."""
+    w, d = load_case(name)
+    loci, trees, batch = _load(eng, w)
+    lnl0, _ = batch.full_pass(trees.full_pass_step())
+    old_root = trees.clv_index[:, trees.root].copy()
+    old_sc = trees.scaler_index[:, trees.root].copy()
+    trees.times = trees.times * float(d["mix_c"])
+    trees.flip_pmatrix()
+    trees.flip_clv()
+    lnl1, _ = batch.full_pass(trees.full_pass_step())
+    assert rel_err(lnl1, d["lnl_mix"]) <= LNL_RTOL
+    # rejection: the old buffers still hold the old state
+    again = batch.root_loglikelihood(old_root, old_sc)
+    assert np.array_equal(again, lnl0)
+    _free(loci, batch)
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(tips=8, sites=1000, states=4, rate_cats=1, model="JC69"),                  # config-2 shape
+    dict(tips=16, sites=1000, states=4, rate_cats=4, model="GTR", scaling=True),     # config-3 shape
+    dict(tips=8, sites=500, states=20, rate_cats=4, model="LG"),                     # config-4 shape
+    dict(tips=2, sites=1, states=4, rate_cats=1, model="JC69"),                      # smallest legal locus
+    dict(tips=3, sites=257, states=4, rate_cats=2, model="GTR"),                     # ragged last tile
+    dict(tips=7, sites=300, states=4, rate_cats=3, model="GTR", rates=[0.2, 0.9, 1.9]),   # R not a power of 2
+    dict(tips=33, sites=129, states=4, rate_cats=8, model="GTR", scaling=True, rates=list(np.linspace(0.1, 3, 8))),
+])
+def test_against_oracle_seeded(eng, cfg):
+    cfg = dict(cfg)
+    rates = cfg.pop("rates", None)
+    w = synth.make_workload("seeded", n_loci=12, seed=4242, lg=lg_tables(),
+                            **{**cfg, "rate_cats": cfg["rate_cats"] if rates is None else 1})
+    if rates is not None:
+        w.rate_cats = len(rates)
+        w.rates = np.array(rates, dtype=np.float64)
+    loci, trees, batch = _load(eng, w)
+    lnl, _ = batch.full_pass(trees.full_pass_step())
+    cm = char_map(w.states)
+    step = 1 if w.states == 4 else 4
+    for i in range(0, w.n_loci, step):
+        ref = F.locus_from_workload(w, i, cm).full_pass()
+        assert abs(lnl[i] - ref) <= LNL_RTOL * abs(ref), (i, lnl[i], ref)
+    _free(loci, batch)
+
+
+def test_ragged_batch_of_different_loci(eng):
+    """Loci of one batch may differ in tips and sites (real data do, SURVEY 7 hard part 6)."""
+    from bpp_b200 import engine
+    shapes = [(4, 10), (9, 513), (2, 3), (17, 256), (5, 255), (8, 1)]
+    loci, steps, refs = [], [], []
+    cm = char_map(4)
+    for k, (T, P) in enumerate(shapes):
+        w = synth.make_workload("rag%d" % k, n_loci=1, tips=T, sites=P, states=4, rate_cats=4, model="GTR",
+                                scaling=True, seed=100 + k)
+        ls, tr = engine.load_workload(eng, w)
+        loci += ls
+        steps.append(tr.full_pass_step())
+        refs.append(F.locus_from_workload(w, 0, cm).full_pass())
+    batch = engine.Batch(eng, loci)
+    step = tuple(np.concatenate([s[j] for s in steps]) for j in range(7))
+    lnl, total = batch.full_pass(step)
+    assert rel_err(lnl, refs) <= LNL_RTOL
+    assert abs(total - float(np.sum(refs))) <= LNL_RTOL * abs(total)
+    _free(loci, batch)
+
+
+def test_partial_update_root_path(eng):
+    """gene-tree age move (gtree.c:5437-5467): change one node age, update 2-3 P-matrices and the
+    CLVs on the path node -> root only; unchanged siblings are read from HBM."""
+    from bpp_b200 import engine
+    w = synth.make_workload("path", n_loci=5, tips=12, sites=77, states=4, rate_cats=4, model="GTR",
+                            scaling=True, seed=77)
+    loci, trees, batch = _load(eng, w)
+    batch.full_pass(trees.full_pass_step())
+    cm = char_map(4)
+    T = w.tips
+    for i, l in enumerate(loci):
+        o = F.locus_from_workload(w, i, cm)
+        o.full_pass()
+        node = T + 1 + (i % (T - 3))
+        kids = [o.left[node - T], o.right[node - T]]
+        lo = max(o.times[kids[0]], o.times[kids[1]])
+        hi = o.times[o.parent[node]]
+        newt = lo + 0.37 * (hi - lo)
+        o.times[node] = newt
+        trees.times[i, node] = newt
+        touched = kids + [node]
+        path = []
+        n = node
+        while n >= 0:
+            path.append(n)
+            n = o.parent[n]
+        # oracle side
+        for n in touched:
+            o.flip_pmatrix(n)
+        o.update_matrices(touched)
+        for n in path:
+            o.flip_clv(n)
+        o.update_partials(path)
+        ref = o.root_loglikelihood()
+        # device side: same index arithmetic on the host, indices passed down
+        e2 = 2 * T - 2
+        for n in touched:
+            trees.pmatrix_index[i, n] = (e2 + trees.pmatrix_index[i, n]) % (2 * e2)
+        bl = [(trees.times[i, trees.parent[i, n]] - trees.times[i, n]) * trees.rate_mui[i] for n in touched]
+        l.update_matrices([trees.pmatrix_index[i, n] for n in touched], bl)
+        for n in path:
+            trees.clv_index[i, n] = T + (trees.clv_index[i, n] - 1) % (2 * T - 2)
+            trees.scaler_index[i, n] = (T + trees.scaler_index[i, n] - 1) % (2 * T - 2)
+        ops = np.zeros(len(path), dtype=engine.OP_DTYPE)
+        for k, n in enumerate(path):
+            a, b = trees.left[i, n - T], trees.right[i, n - T]
+            ops[k] = (trees.clv_index[i, n], trees.clv_index[i, a], trees.clv_index[i, b],
+                      trees.pmatrix_index[i, a], trees.pmatrix_index[i, b],
+                      trees.scaler_index[i, n], trees.scaler_index[i, a], trees.scaler_index[i, b])
+        l.update_partials(ops)
+        got = l.root_loglikelihood(int(trees.clv_index[i, trees.root]), int(trees.scaler_index[i, trees.root]))
+        assert abs(got - ref) <= LNL_RTOL * abs(ref), (i, got, ref)
+    _free(loci, batch)
+
+
+def test_dense_tip_clv_and_likelihood_vector_and_diploid(eng):
+    """pll_set_tip_clv with non-0/1 values (locus.c:596), pll_core_root_likelihood_vector
+    (core_likelihood.c:214) and the diploid phase-mean branch (locus.c:2586-2615)."""
+    from bpp_b200 import engine
+    rng = np.random.default_rng(3)
+    T, P, R = 6, 41, 4
+    w = synth.make_workload("dense", n_loci=1, tips=T, sites=P, states=4, rate_cats=R, model="GTR", seed=31)
+    loci, trees, batch = _load(eng, w)
+    l = loci[0]
+    o = F.locus_from_workload(w, 0, char_map(4))
+    vals = rng.uniform(0.05, 1.0, size=(P, 4))
+    l.set_tip_clv(2, vals)
+    o.set_tip_values(2, vals)
+    onehot = np.eye(4)[rng.integers(0, 4, size=P)]
+    l.set_tip_clv(4, onehot)                      # 0/1 values are re-packed
+    o.set_tip_values(4, onehot)
+    lnl, _ = batch.full_pass(trees.full_pass_step())
+    ref = o.full_pass()
+    assert abs(lnl[0] - ref) <= LNL_RTOL * abs(ref)
+    assert np.array_equal(l.get_clv(2).reshape(P, R, 4)[:, 1, :], vals)
+    lh = l.root_likelihood_vector(int(trees.clv_index[0, trees.root]))
+    assert rel_err(lh, o.root_likelihood_vector()) <= 1e-13
+    # diploid: unphased sites map to 1, 2 or 4 phase resolutions
+    counts, mapping = [], []
+    k = 0
+    while k < P:
+        c = min([1, 2, 4][len(counts) % 3], P - k)
+        counts.append(c)
+        mapping += list(range(k, k + c))
+        k += c
+    l.set_diploid(counts, mapping)
+    got = l.root_loglikelihood_diploid(int(trees.clv_index[0, trees.root]))
+    want = F.diploid_loglikelihood(o.root_likelihood_vector(), counts, mapping, o.weights)
+    assert abs(got - want) <= LNL_RTOL * abs(want)
+    _free(loci, batch)
+
+
+def test_zero_branch_and_minus_infinity(eng):
+    """bl < 1e-100 -> identity P (core_pmatrix.c:738-743); incompatible tips across zero-length
+    branches give term == 0 -> lnL = -inf like the reference (method.c:4302)."""
+    from bpp_b200 import engine
+    cm = char_map(4)
+    l = engine.Locus.create_like_bpp(eng, 2, 3, 4, 1, False)
+    l.set_tip_states(0, cm, b"AAC")
+    l.set_tip_states(1, cm, b"AGC")
+    l.set_frequencies(np.full(4, 0.25))
+    l.update_matrices([0, 1], [0.0, 1e-101])
+    assert np.array_equal(l.get_pmatrix(0), np.eye(4).ravel())
+    assert np.array_equal(l.get_pmatrix(1), np.eye(4).ravel())
+    ops = np.zeros(1, dtype=engine.OP_DTYPE)
+    ops[0] = (2, 0, 1, 0, 1, -1, -1, -1)
+    l.update_partials(ops)
+    v, persite = l.root_loglikelihood(2, -1, persite=True)
+    assert v == -np.inf and np.isfinite(persite[0]) and persite[1] == -np.inf
+    l.destroy()
+
+
+def test_illegal_state_code_is_fatal(eng):
+    from bpp_b200 import engine
+    l = engine.Locus.create_like_bpp(eng, 2, 4, 4, 1, False)
+    with pytest.raises(engine.BppGpuError, match="Illegal state code"):
+        l.set_tip_states(0, char_map(4), b"AC!T")
+    l.destroy()
+
+
+def test_staged_run_is_idempotent_and_deterministic(eng):
+    """stage once, run twice: identical bits (fixed-order reductions, no float atomics)."""
+    w = synth.make_workload("idem", n_loci=40, tips=8, sites=300, states=4, rate_cats=4, model="GTR", seed=9)
+    loci, trees, batch = _load(eng, w)
+    batch.stage(trees.full_pass_step())
+    batch.run()
+    a, ta = batch.collect()
+    batch.run()
+    b, tb = batch.collect()
+    assert np.array_equal(a, b) and ta == tb
+    _free(loci, batch)
+
+
+def test_linearity_in_pattern_weights_full_size_property(eng):
+    """Size-independent property at a BASELINE-sized locus count per launch: lnL is linear in the
+    pattern weights, so doubling every weight doubles every per-locus lnL exactly (power of two)."""
+    w = synth.make_workload("lin", n_loci=300, tips=8, sites=1000, states=4, rate_cats=1, model="JC69", seed=21)
+    loci, trees, batch = _load(eng, w)
+    a, _ = batch.full_pass(trees.full_pass_step())
+    for i, l in enumerate(loci):
+        l.set_pattern_weights(w.weights[i] * 2)
+    b, _ = batch.full_pass(trees.full_pass_step())
+    assert np.array_equal(b, 2 * a)
+    _free(loci, batch)
