@@ -1,0 +1,153 @@
+// common.cuh -- shared device-side types of the sm_100a Felsenstein-pruning engine.
+//
+// Reference semantics (file:line relative to /root/reference/src):
+//   P-matrix   locus.c:2325-2415 (JC69 closed form), core_pmatrix.c:674-783 (eigen form)
+//   CLV update core_partials.c:585-756; association order of core_partials_avx.c:368-531
+//   root lnL   core_likelihood.c:24-212, core_likelihood_avx.c:98-157; vector form :214-408
+//
+// Data layout in HBM (per locus; CLVs in the reference's order so a CLV is P*R*S contiguous doubles):
+//   clv[buffer][pattern][cat][state]     pmat[idx][cat][row = parent state][col = child state]
+//   scale[buffer][pattern] (u32)         weights[pattern] (u32)
+//   tips, 4 states : 4-bit state masks, 8 tips per u32 word: tipwords[pattern][tip/8] >> 4*(tip%8)
+//   tips, >4 states: u32 masks tip_codes[tip][pattern]
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace bppgpu {
+
+struct LocusDev
+{
+  double * clv;                 // inner buffers; buffer b (= clv_index - tips) at clv + b*clv_stride
+  double * tip_dense;           // dense tip CLVs (pll_set_tip_clv with non-0/1 values) or nullptr
+  void * tip_codes;             // packed tip state masks (layout above)
+  unsigned char * tip_is_dense; // [tips]
+  double * pmat;                // idx at pmat + idx*R*S*S
+  unsigned int * scale;         // buffer s at scale + s*sites
+  unsigned int * weights;       // [sites]
+  double * freqs;               // [S]
+  double * rates;               // [R]
+  double * rate_weights;        // [R]
+  double * eigenvecs;           // [S*S]
+  double * inv_eigenvecs;       // [S*S]
+  double * eigenvals;           // [S]
+  unsigned long long * dip_off; // diploid CSR offsets [unphased+1] or nullptr
+  unsigned long long * dip_map; // diploid mapping
+  unsigned long long clv_stride;
+  unsigned int tips, sites, states, rate_cats;
+  unsigned int clv_buffers, prob_matrices, scale_buffers, model_kind;   // model_kind 0 = JC69, 1 = eigen
+  unsigned int unphased, tip_words;                                     // tip_words = ceil(tips/8) (4 states)
+};
+
+// operand kinds of a planned pruning step
+enum : unsigned { SRC_TIP_PACKED = 0, SRC_TIP_DENSE = 1, SRC_HBM = 2, SRC_SLOT = 3, SRC_PREV = 4 };
+enum : unsigned { CTL_SPILL_MASK = 0xFFu, CTL_ROOT = 1u << 8, CTL_EVAL_ONLY = 1u << 9 };
+
+struct PlanOp                   // 48 bytes, uniform per CTA
+{
+  unsigned int dst;             // inner buffer index of the parent
+  unsigned int lsrc, rsrc;      // kind << 28 | index
+  unsigned int lpm, rpm;        // pmatrix indices
+  int dsc, lsc, rsc;            // scaler buffer indices or -1
+  unsigned int ctl;             // bits 0-7 spill slot + 1 (0 = none); CTL_ROOT; CTL_EVAL_ONLY
+  int root_sc;                  // scaler buffer of the root for CTL_EVAL_ONLY
+  unsigned int pad[2];
+};
+
+struct RawOp                    // == bppgpu_partial_op
+{
+  unsigned int parent, left, right, lpm, rpm;
+  int psc, lsc, rsc;
+};
+
+// ---- staged per-locus block of the 4-state tree kernel (built by plan_kernel_blocks) ----------
+// [LocusHdr 128 B][rate_weights RL doubles, padded to 16 B][chunk 0][chunk 1]...
+// chunk = [PlanOp ops[TREE_CHUNK]][double P[TREE_CHUNK][2][RL][PM_STRIDE]]
+constexpr int TREE_CHUNK = 16;      // ops per staged chunk
+constexpr int PM_STRIDE  = 18;      // doubles per (child, cat) matrix in shared memory (16 + 2 pad: the
+                                    // RL categories of a site land in different banks)
+struct LocusHdr
+{
+  double * clv;
+  double * tip_dense;
+  unsigned int * scale;
+  const unsigned int * tipwords;
+  unsigned long long clv_stride;
+  unsigned int sites, nops, tip_words, n_chunks;
+  double freqs[4];
+  double pad[5];
+};
+static_assert(sizeof(LocusHdr) == 128, "LocusHdr must be 128 bytes");
+
+__host__ __device__ inline size_t rw_bytes(unsigned RL) { return ((size_t)RL * 8 + 15) & ~(size_t)15; }
+__host__ __device__ inline size_t chunk_bytes(unsigned RL)
+{
+  return (size_t)TREE_CHUNK * sizeof(PlanOp) + (size_t)TREE_CHUNK * 2 * RL * PM_STRIDE * 8;
+}
+__host__ __device__ inline size_t block_bytes(unsigned RL, unsigned nops_max)
+{
+  const unsigned nc = (nops_max + TREE_CHUNK - 1) / TREE_CHUNK;
+  return sizeof(LocusHdr) + rw_bytes(RL) + (size_t)(nc ? nc : 1) * chunk_bytes(RL);
+}
+
+// one tile of blockDim cells (cell = pattern*RL + cat) of one locus; static per batch
+struct TileDesc
+{
+  const unsigned int * tipwords;   // the locus' packed tips
+  const unsigned int * weights;    // the locus' pattern weights
+  unsigned int locus;              // batch-local locus
+  unsigned int cell0;              // first cell of the tile
+  unsigned int tip_words;
+  unsigned int ncell;              // sites * RL
+};
+static_assert(sizeof(TileDesc) == 32, "TileDesc must be 32 bytes");
+
+struct TreeParams
+{
+  const LocusDev * loci;
+  const unsigned int * batch_locus;
+  const unsigned int * tile_locus;    // generic kernel: batch-local locus of each tile
+  const unsigned int * tile_cell0;    // generic kernel: first pattern of each tile
+  const unsigned int * op_off;
+  const PlanOp * plan;                // generic kernel: flat plan
+  const unsigned int * plan_count;
+  const TileDesc * tiles;             // 4-state kernel
+  const unsigned char * blocks;       // 4-state kernel: staged per-locus blocks
+  const unsigned long long * blk_off; // byte offset of each locus' block
+  unsigned int n_tiles;
+  double * tile_partial;              // per-tile weighted site-lnL sums
+  double * persite;                   // optional per-site output of the (single) locus, or nullptr
+  int persite_mode;                   // 1 = weighted site lnL, 2 = site likelihood (vector form)
+  int n_slots;                        // shared-memory stack slots per thread
+  double log_threshold;               // log(PLL_SCALE_THRESHOLD) as the host libm evaluates it
+};
+
+#define BPPGPU_SCALE_FACTOR    115792089237316195423570985008687907853269984665640564039457584007913129639936.0
+#define BPPGPU_SCALE_THRESHOLD (1.0 / BPPGPU_SCALE_FACTOR)
+
+// ----------------------------------------------------------------------------- memory helpers
+__device__ __forceinline__ void ld256_nc(const double * p, double & a, double & b, double & c, double & d)
+{
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];"
+               : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+}
+// coherent variant: a CLV written earlier in the same kernel by the same thread may be re-read
+__device__ __forceinline__ void ld256(const double * p, double & a, double & b, double & c, double & d)
+{
+  asm volatile("ld.global.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];"
+               : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p) : "memory");
+}
+__device__ __forceinline__ void st256(double * p, double a, double b, double c, double d)
+{
+  asm volatile("st.global.L1::no_allocate.v4.f64 [%0], {%1,%2,%3,%4};"
+               :: "l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void * smem_dst, const void * gsrc)
+{
+  const unsigned int s = (unsigned int)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(s), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+}  // namespace bppgpu

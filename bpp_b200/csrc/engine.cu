@@ -7,7 +7,12 @@
 //   pll_set_frequencies :889, pll_set_subst_params :877, locus_update_matrices :2417,
 //   locus_update_partials :2530, locus_root_loglikelihood :2573, pll_update_eigen core_pmatrix.c:239.
 #include "../../include/bpp_b200.h"
-#include "kernels.cuh"
+#include "common.cuh"
+#include "pmatrix.cuh"
+#include "plan.cuh"
+#include "tree_s4.cuh"
+#include "tree_generic.cuh"
+#include "reduce.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -135,8 +140,7 @@ struct bppgpu_locus
   size_t b_clv = 0, b_tipdense = 0, b_codes = 0, b_flags = 0, b_pmat = 0, b_scale = 0, b_weights = 0, b_model = 0;
   size_t b_dip_off = 0, b_dip_map = 0;
   // host mirrors of the small inputs
-  std::vector<unsigned char> h_codes8;
-  std::vector<unsigned int> h_codes32;
+  std::vector<unsigned int> h_codes;    // 4 states: [pattern][tip/8] nibbles; else [tip][pattern] masks
   std::vector<unsigned char> h_tip_dense_flag;
   std::vector<double> h_freqs, h_subst, h_rates, h_rate_weights, h_evecs, h_ievecs, h_evals;
   bool eigen_valid = false;            // locus->eigen_decomp_valid[0]
@@ -163,13 +167,16 @@ struct bppgpu_batch
   // per-step device inputs (one blob) and outputs
   char * d_in = nullptr; size_t d_in_cap = 0;
   char * h_in = nullptr; size_t h_in_cap = 0;       // pinned
-  PlanOp * d_plan = nullptr; size_t plan_cap = 0;
+  PlanOp * d_plan = nullptr; size_t plan_cap = 0;   // generic kernel: flat plan
+  unsigned char * d_blocks = nullptr; size_t blocks_cap = 0;   // 4-state kernel: staged per-locus blocks
+  TileDesc * d_tiles = nullptr;
   unsigned int * d_plan_count = nullptr;
+  int grid = 0; size_t tree_smem = 0; int slots = 0;
   double * d_tile_partial = nullptr, * d_lnl = nullptr, * d_lnl_sum = nullptr;
   double * h_out = nullptr;                         // pinned: n lnl + 1 sum
   double * d_persite = nullptr; size_t persite_cap = 0;
   // layout of the staged blob
-  size_t o_mat_off = 0, o_mat_idx = 0, o_mat_bl = 0, o_op_off = 0, o_ops = 0, o_root_clv = 0, o_root_sc = 0;
+  size_t o_mat_off = 0, o_mat_idx = 0, o_mat_bl = 0, o_op_off = 0, o_ops = 0, o_root_clv = 0, o_root_sc = 0, o_blk_off = 0;
   unsigned int total_mats = 0, total_ops = 0;
   bool staged_mats = false, staged_ops = false, staged_roots = false;
   cudaEvent_t t0 = nullptr, t1 = nullptr;
@@ -296,6 +303,22 @@ static void host_update_eigen(bppgpu_locus * l)
   l->model_dirty = true;
 }
 
+static inline void set_code(bppgpu_locus * l, unsigned tip, size_t site, unsigned int c)
+{
+  if (l->states == 4)
+  {
+    unsigned int & w = l->h_codes[site * l->dev.tip_words + (tip >> 3)];
+    const unsigned sh = (tip & 7u) * 4;
+    w = (w & ~(0xFu << sh)) | ((c & 0xFu) << sh);
+  }
+  else l->h_codes[(size_t)tip * l->sites + site] = c;
+}
+static inline unsigned int get_code(const bppgpu_locus * l, unsigned tip, size_t site)
+{
+  if (l->states == 4) return (l->h_codes[site * l->dev.tip_words + (tip >> 3)] >> ((tip & 7u) * 4)) & 0xFu;
+  return l->h_codes[(size_t)tip * l->sites + site];
+}
+
 static size_t model_doubles(unsigned S, unsigned R) { return (size_t)S + R + R + 2 * (size_t)S * S + S; }
 
 // push dirty host mirrors (tip codes, dense flags, model block) of a locus to the device
@@ -303,10 +326,7 @@ static void locus_sync(bppgpu_locus * l, cudaStream_t s)
 {
   if (l->codes_dirty)
   {
-    if (l->states <= 8)
-      CUDA_CHECK(cudaMemcpyAsync(l->dev.tip_codes, l->h_codes8.data(), l->h_codes8.size(), cudaMemcpyHostToDevice, s));
-    else
-      CUDA_CHECK(cudaMemcpyAsync(l->dev.tip_codes, l->h_codes32.data(), l->h_codes32.size() * 4, cudaMemcpyHostToDevice, s));
+    CUDA_CHECK(cudaMemcpyAsync(l->dev.tip_codes, l->h_codes.data(), l->h_codes.size() * 4, cudaMemcpyHostToDevice, s));
     l->codes_dirty = false;
   }
   if (l->flags_dirty)
@@ -428,7 +448,7 @@ extern "C" bppgpu_locus * bppgpu_locus_create(bppgpu_engine * e, unsigned int dt
                                               unsigned int attributes)
 {
   if (!e) { fatal("bppgpu_locus_create: no engine"); return nullptr; }
-  if (states == 0 || states > 32) { fatal("unsupported number of states %u", states); return nullptr; }
+  if (states < 2 || states > 32) { fatal("unsupported number of states %u", states); return nullptr; }
   if (rate_matrices != 1) { fatal("rate_matrices must be 1 (method.c:4143)"); return nullptr; }
   if (sites == 0 || tips < 2 || rate_cats == 0) { fatal("invalid locus dimensions"); return nullptr; }
   std::lock_guard<std::mutex> lock(e->mu);
@@ -443,7 +463,8 @@ extern "C" bppgpu_locus * bppgpu_locus_create(bppgpu_engine * e, unsigned int dt
   LocusDev & d = l->dev;
   memset(&d, 0, sizeof(d));
   l->b_clv = clv_buffers * clv_doubles * 8;
-  l->b_codes = (size_t)tips * P * (S <= 8 ? 1 : 4);
+  const size_t TW = (tips + 7) / 8;
+  l->b_codes = (S == 4) ? P * TW * 4 : (size_t)tips * P * 4;
   l->b_flags = tips;
   l->b_pmat = (size_t)prob_matrices * R * S * S * 8;
   l->b_scale = (size_t)scale_buffers * P * 4;
@@ -462,6 +483,7 @@ extern "C" bppgpu_locus * bppgpu_locus_create(bppgpu_engine * e, unsigned int dt
   d.tips = tips; d.sites = sites; d.states = states; d.rate_cats = rate_cats;
   d.clv_buffers = clv_buffers; d.prob_matrices = prob_matrices; d.scale_buffers = scale_buffers;
   d.model_kind = model_is_closed_form(l) ? 0 : 1;
+  d.tip_words = (unsigned)TW;
   // zero what the reference zeroes (locus.c:745-755,765-771,859-867); weights default to 1 (:852)
   CUDA_CHECK(cudaMemsetAsync(d.clv, 0, l->b_clv, e->stream));
   CUDA_CHECK(cudaMemsetAsync(d.pmat, 0, l->b_pmat, e->stream));
@@ -473,7 +495,7 @@ extern "C" bppgpu_locus * bppgpu_locus_create(bppgpu_engine * e, unsigned int dt
     CUDA_CHECK(cudaMemcpyAsync(d.weights, ones.data(), P * 4, cudaMemcpyHostToDevice, e->stream));
     CUDA_CHECK(cudaStreamSynchronize(e->stream));
   }
-  if (S <= 8) l->h_codes8.assign((size_t)tips * P, 0); else l->h_codes32.assign((size_t)tips * P, 0);
+  l->h_codes.assign(l->b_codes / 4, 0);
   l->h_tip_dense_flag.assign(tips, 0);
   l->h_freqs.assign(S, 0.0);                       // zero like locus.c:826 until pll_set_frequencies
   l->h_subst.assign(S * (S - 1) / 2, 0.0);
@@ -519,7 +541,7 @@ extern "C" int bppgpu_set_tip_states(bppgpu_locus * l, unsigned int tip, const u
   {
     const unsigned int c = map[(int)(unsigned char)seq[i]];
     if (c == 0) { fatal("Illegal state code in tip \"%c\"", seq[i]); return BPPGPU_FAILURE; }   // locus.c:538
-    if (l->states <= 8) l->h_codes8[tip * P + i] = (unsigned char)c; else l->h_codes32[tip * P + i] = c;
+    set_code(l, tip, i, c);
   }
   l->codes_dirty = true;
   if (l->h_tip_dense_flag[tip]) { l->h_tip_dense_flag[tip] = 0; l->flags_dirty = true; }
@@ -535,15 +557,12 @@ extern "C" int bppgpu_set_tip_clv(bppgpu_locus * l, unsigned int tip, const doub
   for (size_t i = 0; i < P * S && binary; ++i) binary = (clv[i] == 0.0 || clv[i] == 1.0);
   if (binary)
   {
-    bool nonzero = true;
-    for (size_t i = 0; i < P; ++i)
+    for (size_t i = 0; i < P; ++i)                 // an all-zero tip vector is legal here (lnL = -inf)
     {
       unsigned int c = 0;
       for (size_t j = 0; j < S; ++j) if (clv[i * S + j] == 1.0) c |= 1u << j;
-      if (!c) nonzero = false;
-      if (S <= 8) l->h_codes8[tip * P + i] = (unsigned char)c; else l->h_codes32[tip * P + i] = c;
+      set_code(l, tip, i, c);
     }
-    (void)nonzero;                                 // an all-zero tip vector is legal here (lnL = -inf)
     l->codes_dirty = true;
     if (l->h_tip_dense_flag[tip]) { l->h_tip_dense_flag[tip] = 0; l->flags_dirty = true; }
     return BPPGPU_SUCCESS;
@@ -658,6 +677,7 @@ extern "C" bppgpu_batch * bppgpu_batch_create(bppgpu_engine * e, unsigned int n,
   b->own_stream = true;
   batch_launch_cfg(b);
   std::vector<unsigned int> ids(n), tile_locus, tile_cell0, tile_first(n + 1, 0);
+  std::vector<TileDesc> tiles;
   std::vector<unsigned long long> soff(n);
   size_t sbytes = 0;
   for (unsigned i = 0; i < n; ++i)
@@ -666,7 +686,17 @@ extern "C" bppgpu_batch * bppgpu_batch_create(bppgpu_engine * e, unsigned int n,
     ids[i] = l->id;
     const unsigned cells = l->sites * (b->kernel_kind == 0 ? b->RL : 1);
     tile_first[i] = (unsigned)tile_locus.size();
-    for (unsigned c = 0; c < cells; c += b->tile_threads) { tile_locus.push_back(i); tile_cell0.push_back(c); }
+    for (unsigned c = 0; c < cells; c += b->tile_threads)
+    {
+      tile_locus.push_back(i); tile_cell0.push_back(c);
+      if (b->kernel_kind == 0)
+      {
+        TileDesc td;
+        td.tipwords = (const unsigned int *)l->dev.tip_codes; td.weights = l->dev.weights;
+        td.locus = i; td.cell0 = c; td.tip_words = l->dev.tip_words; td.ncell = cells;
+        tiles.push_back(td);
+      }
+    }
     soff[i] = sbytes; sbytes += align_up(l->clv_buffers, 16);
   }
   tile_first[n] = (unsigned)tile_locus.size();
@@ -688,6 +718,11 @@ extern "C" bppgpu_batch * bppgpu_batch_create(bppgpu_engine * e, unsigned int n,
   CUDA_CHECK(cudaMemcpy(b->d_tile_cell0, tile_cell0.data(), b->n_tiles * 4, cudaMemcpyHostToDevice));
   CUDA_CHECK(cudaMemcpy(b->d_tile_first, tile_first.data(), (n + 1) * 4, cudaMemcpyHostToDevice));
   CUDA_CHECK(cudaMemcpy(b->d_scratch_off, soff.data(), n * 8, cudaMemcpyHostToDevice));
+  if (b->kernel_kind == 0)
+  {
+    CUDA_CHECK(cudaMalloc(&b->d_tiles, tiles.size() * sizeof(TileDesc)));
+    CUDA_CHECK(cudaMemcpy(b->d_tiles, tiles.data(), tiles.size() * sizeof(TileDesc), cudaMemcpyHostToDevice));
+  }
   CUDA_CHECK(cudaMemset(b->d_plan_count, 0, n * 4));
   CUDA_CHECK(cudaMemset(b->d_tile_partial, 0, b->n_tiles * 8));
   CUDA_CHECK(cudaEventCreate(&b->t0));
@@ -704,6 +739,7 @@ extern "C" void bppgpu_batch_destroy(bppgpu_batch * b)
   cudaFree(b->d_batch_locus); cudaFree(b->d_tile_locus); cudaFree(b->d_tile_cell0); cudaFree(b->d_tile_first);
   cudaFree(b->d_scratch_off); cudaFree(b->d_scratch); cudaFree(b->d_plan_count); cudaFree(b->d_tile_partial);
   cudaFree(b->d_lnl); cudaFree(b->d_in); cudaFree(b->d_plan); cudaFree(b->d_persite);
+  cudaFree(b->d_blocks); cudaFree(b->d_tiles);
   cudaFreeHost(b->h_out); cudaFreeHost(b->h_in);
   cudaEventDestroy(b->t0); cudaEventDestroy(b->t1);
   if (b->own_stream) cudaStreamDestroy(b->stream);
@@ -744,6 +780,7 @@ static int batch_stage(bppgpu_batch * b, const unsigned int * mcounts, const uns
   b->o_ops = off;     off = align_up(off + to * sizeof(bppgpu_partial_op), 16);
   b->o_root_clv = off; off = align_up(off + n * 4, 16);
   b->o_root_sc = off;  off = align_up(off + n * 4, 16);
+  b->o_blk_off = off;  off = align_up(off + (size_t)(n + 1) * 8, 16);
   if (off > b->h_in_cap)
   {
     CUDA_CHECK(cudaStreamSynchronize(b->stream));
@@ -753,7 +790,7 @@ static int batch_stage(bppgpu_batch * b, const unsigned int * mcounts, const uns
     CUDA_CHECK(cudaHostAlloc(&b->h_in, b->h_in_cap, cudaHostAllocDefault));
     CUDA_CHECK(cudaMalloc(&b->d_in, b->d_in_cap));
   }
-  if (to + n > b->plan_cap)
+  if (b->kernel_kind == 1 && to + n > b->plan_cap)
   {
     CUDA_CHECK(cudaStreamSynchronize(b->stream));
     if (b->d_plan) cudaFree(b->d_plan);
@@ -765,10 +802,21 @@ static int batch_stage(bppgpu_batch * b, const unsigned int * mcounts, const uns
   unsigned int * moff = (unsigned int *)(b->h_in + b->o_mat_off);
   unsigned int * ooff = (unsigned int *)(b->h_in + b->o_op_off);
   moff[0] = 0; ooff[0] = 0;
+  unsigned long long * boff = (unsigned long long *)(b->h_in + b->o_blk_off);
+  boff[0] = 0;
   for (unsigned i = 0; i < n; ++i)
   {
     moff[i + 1] = moff[i] + (mcounts ? mcounts[i] : 0);
     ooff[i + 1] = ooff[i] + (ocounts ? ocounts[i] : 0);
+    // one spare op per locus for a root that the list does not produce (CTL_EVAL_ONLY)
+    boff[i + 1] = boff[i] + block_bytes(b->RL, (ocounts ? ocounts[i] : 0) + 1);
+  }
+  if (b->kernel_kind == 0 && boff[n] > b->blocks_cap)
+  {
+    CUDA_CHECK(cudaStreamSynchronize(b->stream));
+    if (b->d_blocks) cudaFree(b->d_blocks);
+    b->blocks_cap = boff[n] + boff[n] / 4;
+    CUDA_CHECK(cudaMalloc(&b->d_blocks, b->blocks_cap));
   }
   if (tm) { memcpy(b->h_in + b->o_mat_idx, midx, tm * 4); memcpy(b->h_in + b->o_mat_bl, mbl, tm * 8); }
   if (to) memcpy(b->h_in + b->o_ops, ops, to * sizeof(bppgpu_partial_op));
@@ -793,20 +841,31 @@ static void batch_sync_loci(bppgpu_batch * b, bool need_eigen)
   }
 }
 
-template <int RL>
-static void launch_tree_s4(bppgpu_batch * b, const TreeParams & prm, size_t smem)
+static size_t tree_s4_smem(unsigned RL, int slots, unsigned nthr)
+{
+  return sizeof(LocusHdr) + rw_bytes(RL) + chunk_bytes(RL) + 4 * sizeof(TileDesc) + 32 * 8 +
+         (size_t)slots * nthr * (32 + 4);
+}
+
+// persistent launch: as many CTAs as fit on the device at once, each walks a contiguous tile range
+template <int RL, bool EXACT>
+static void launch_tree_s4_impl(bppgpu_batch * b, const TreeParams & prm)
 {
   bppgpu_engine * e = b->e;
-  if (e->math == BPPGPU_MATH_EXACT)
-  {
-    CUDA_CHECK(cudaFuncSetAttribute(tree_kernel_s4<RL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    tree_kernel_s4<RL, true><<<b->n_tiles, b->tile_threads, smem, b->stream>>>(prm);
-  }
-  else
-  {
-    CUDA_CHECK(cudaFuncSetAttribute(tree_kernel_s4<RL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    tree_kernel_s4<RL, false><<<b->n_tiles, b->tile_threads, smem, b->stream>>>(prm);
-  }
+  const size_t smem = tree_s4_smem(RL, prm.n_slots, b->tile_threads);
+  CUDA_CHECK(cudaFuncSetAttribute(tree_kernel_s4<RL, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tree_kernel_s4<RL, EXACT>, (int)b->tile_threads, smem));
+  if (per_sm < 1) { fatal("tree kernel does not fit on an SM (smem %zu)", smem); return; }
+  const unsigned grid = std::min<unsigned>(b->n_tiles, (unsigned)(per_sm * e->sm_count));
+  tree_kernel_s4<RL, EXACT><<<grid, b->tile_threads, smem, b->stream>>>(prm);
+}
+
+template <int RL>
+static void launch_tree_s4(bppgpu_batch * b, const TreeParams & prm)
+{
+  if (b->e->math == BPPGPU_MATH_EXACT) launch_tree_s4_impl<RL, true>(b, prm);
+  else launch_tree_s4_impl<RL, false>(b, prm);
 }
 
 // launches: [pmatrix] [plan + tree (+ finish)] on the batch stream, using the staged blob
@@ -839,26 +898,34 @@ static int batch_run(bppgpu_batch * b, bool do_mats, bool do_tree, bool want_roo
   }
   if (!do_tree) return BPPGPU_SUCCESS;
 
-  // stack slots: enough for any binary tree of this batch in recursive post-order is its height;
-  // cap by shared memory, the plan falls back to HBM re-reads beyond that
+  // shared-memory stack slots per thread: ceil(log2 T) covers balanced trees in recursive post-order;
+  // beyond that the plan falls back to re-reading the child from HBM (still correct)
   int slots = 0;
   if (b->kernel_kind == 0)
   {
     unsigned maxT = 0;
     for (auto * l : b->loci) maxT = std::max(maxT, l->tips);
-    slots = 1; while ((1u << slots) < maxT) ++slots;      // ceil(log2 T)
+    slots = 1; while ((1u << slots) < maxT) ++slots;
     slots = std::min(slots, 6);
   }
+  const unsigned long long * d_blk_off = (const unsigned long long *)(b->d_in + b->o_blk_off);
   {
     ProfScope ps(e, b->stream, BPPGPU_KERNEL_PLAN);
-    plan_kernel<<<(n + 127) / 128, 128, 0, b->stream>>>(e->d_loci, b->d_batch_locus, n, d_op_off, d_ops, d_root_clv,
-                                                       d_root_sc, want_root ? 1 : 0, b->d_plan, b->d_plan_count,
-                                                       b->d_scratch, b->d_scratch_off, slots);
+    if (b->kernel_kind == 0)
+      plan_kernel_blocks<<<(n * 32 + 127) / 128, 128, 0, b->stream>>>(
+          e->d_loci, b->d_batch_locus, n, d_op_off, d_ops, d_root_clv, d_root_sc, want_root ? 1 : 0,
+          b->d_blocks, d_blk_off, b->d_plan_count, b->d_scratch, b->d_scratch_off, slots, b->RL);
+    else
+      plan_kernel_flat<<<(n + 127) / 128, 128, 0, b->stream>>>(
+          e->d_loci, b->d_batch_locus, n, d_op_off, d_ops, d_root_clv, d_root_sc, want_root ? 1 : 0,
+          b->d_plan, b->d_plan_count, b->d_scratch, b->d_scratch_off);
     CUDA_CHECK(cudaGetLastError());
   }
   TreeParams prm;
+  memset(&prm, 0, sizeof(prm));
   prm.loci = e->d_loci; prm.batch_locus = b->d_batch_locus; prm.tile_locus = b->d_tile_locus;
   prm.tile_cell0 = b->d_tile_cell0; prm.op_off = d_op_off; prm.plan = b->d_plan; prm.plan_count = b->d_plan_count;
+  prm.tiles = b->d_tiles; prm.blocks = b->d_blocks; prm.blk_off = d_blk_off; prm.n_tiles = b->n_tiles;
   prm.tile_partial = want_root ? b->d_tile_partial : nullptr;
   prm.persite = persite; prm.persite_mode = persite_mode; prm.n_slots = slots;
   prm.log_threshold = e->log_threshold;
@@ -866,18 +933,15 @@ static int batch_run(bppgpu_batch * b, bool do_mats, bool do_tree, bool want_roo
     ProfScope ps(e, b->stream, BPPGPU_KERNEL_TREE);
     if (b->kernel_kind == 0)
     {
-      const unsigned RL = b->RL, nt = b->tile_threads;
-      size_t smem = TREE_CHUNK * sizeof(PlanOp) + (size_t)TREE_CHUNK * 2 * RL * PM_STRIDE * 8 +
-                    (size_t)slots * nt * (32 + 4) + 32 * 8 + 16;
-      switch (RL)
+      switch (b->RL)
       {
-        case 1: launch_tree_s4<1>(b, prm, smem); break;
-        case 2: launch_tree_s4<2>(b, prm, smem); break;
-        case 4: launch_tree_s4<4>(b, prm, smem); break;
-        case 8: launch_tree_s4<8>(b, prm, smem); break;
-        case 16: launch_tree_s4<16>(b, prm, smem); break;
-        case 32: launch_tree_s4<32>(b, prm, smem); break;
-        default: fatal("internal: RL=%u", RL); return BPPGPU_FAILURE;
+        case 1: launch_tree_s4<1>(b, prm); break;
+        case 2: launch_tree_s4<2>(b, prm); break;
+        case 4: launch_tree_s4<4>(b, prm); break;
+        case 8: launch_tree_s4<8>(b, prm); break;
+        case 16: launch_tree_s4<16>(b, prm); break;
+        case 32: launch_tree_s4<32>(b, prm); break;
+        default: fatal("internal: RL=%u", b->RL); return BPPGPU_FAILURE;
       }
     }
     else
@@ -1063,7 +1127,7 @@ extern "C" int bppgpu_get_clv(bppgpu_locus * l, unsigned int clv_index, double *
   }
   for (size_t i = 0; i < P; ++i)          // expand the packed tip like set_tipclv, locus.c:540-555
   {
-    const unsigned int c = (S <= 8) ? l->h_codes8[clv_index * P + i] : l->h_codes32[clv_index * P + i];
+    const unsigned int c = get_code(l, clv_index, i);
     for (size_t r = 0; r < R; ++r) for (size_t j = 0; j < S; ++j) out[(i * R + r) * S + j] = (double)((c >> j) & 1u);
   }
   return BPPGPU_SUCCESS;

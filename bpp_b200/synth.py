@@ -151,7 +151,7 @@ def random_trees(rng, n, tips, dt_lo=0.0005, dt_hi=0.025):
 
 
 def make_workload(name, n_loci, tips, sites, states=4, rate_cats=1, model="JC69", scaling=False,
-                  seed=SEED, ambiguity=0.02, dt_lo=0.0005, dt_hi=0.025, lg=None):
+                  seed=SEED, ambiguity=0.02, dt_lo=0.0005, dt_hi=0.025, lg=None, rates=None):
     rng = np.random.Generator(np.random.PCG64(seed))
     left, right, times = random_trees(rng, n_loci, tips, dt_lo, dt_hi)
     alpha = np.frombuffer(NT_ALPHABET if states == 4 else AA_ALPHABET, dtype=np.uint8)
@@ -176,12 +176,15 @@ def make_workload(name, n_loci, tips, sites, states=4, rate_cats=1, model="JC69"
         freqs = np.tile(np.asarray(lg[1], dtype=np.float64), (n_loci, 1))
     else:
         raise ValueError(model)
-    if rate_cats == 1:
+    if rates is not None:
+        rates = np.array(rates, dtype=np.float64)
+        assert rates.size == rate_cats
+    elif rate_cats == 1:
         rates = np.ones(1)
     elif rate_cats == 4:
         rates = GAMMA4_ALPHA_0_5.copy()
     else:
-        raise ValueError("synthetic workloads use 1 or 4 rate categories")
+        raise ValueError("pass rates= for rate_cats other than 1 or 4")
     return Workload(name, n_loci, tips, sites, states, rate_cats, model, scaling, left, right, times,
                     np.ones(n_loci), np.ascontiguousarray(chars), weights, freqs, subst, rates, seed)
 

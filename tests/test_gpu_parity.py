@@ -113,18 +113,12 @@ def test_mixing_step_with_index_flips(eng, name):
     dict(tips=16, sites=1000, states=4, rate_cats=4, model="GTR", scaling=True),     # config-3 shape
     dict(tips=8, sites=500, states=20, rate_cats=4, model="LG"),                     # config-4 shape
     dict(tips=2, sites=1, states=4, rate_cats=1, model="JC69"),                      # smallest legal locus
-    dict(tips=3, sites=257, states=4, rate_cats=2, model="GTR"),                     # ragged last tile
+    dict(tips=3, sites=257, states=4, rate_cats=2, model="GTR", rates=[0.4, 1.6]),   # ragged last tile
     dict(tips=7, sites=300, states=4, rate_cats=3, model="GTR", rates=[0.2, 0.9, 1.9]),   # R not a power of 2
     dict(tips=33, sites=129, states=4, rate_cats=8, model="GTR", scaling=True, rates=list(np.linspace(0.1, 3, 8))),
 ])
 def test_against_oracle_seeded(eng, cfg):
-    cfg = dict(cfg)
-    rates = cfg.pop("rates", None)
-    w = synth.make_workload("seeded", n_loci=12, seed=4242, lg=lg_tables(),
-                            **{**cfg, "rate_cats": cfg["rate_cats"] if rates is None else 1})
-    if rates is not None:
-        w.rate_cats = len(rates)
-        w.rates = np.array(rates, dtype=np.float64)
+    w = synth.make_workload("seeded", n_loci=12, seed=4242, lg=lg_tables(), **cfg)
     loci, trees, batch = _load(eng, w)
     lnl, _ = batch.full_pass(trees.full_pass_step())
     cm = char_map(w.states)
