@@ -41,15 +41,15 @@ struct LocusDev
 
 // operand kinds of a planned pruning step
 enum : unsigned { SRC_TIP_PACKED = 0, SRC_TIP_DENSE = 1, SRC_HBM = 2, SRC_SLOT = 3, SRC_PREV = 4 };
-enum : unsigned { CTL_SPILL_MASK = 0xFFu, CTL_ROOT = 1u << 8, CTL_EVAL_ONLY = 1u << 9 };
+enum : unsigned { CTL_ROOT = 1u << 8, CTL_EVAL_ONLY = 1u << 9 };
 
-struct PlanOp                   // 48 bytes, uniform per CTA
+struct PlanOp                   // flat plan of the generic kernel, 48 bytes
 {
   unsigned int dst;             // inner buffer index of the parent
   unsigned int lsrc, rsrc;      // kind << 28 | index
   unsigned int lpm, rpm;        // pmatrix indices
   int dsc, lsc, rsc;            // scaler buffer indices or -1
-  unsigned int ctl;             // bits 0-7 spill slot + 1 (0 = none); CTL_ROOT; CTL_EVAL_ONLY
+  unsigned int ctl;             // CTL_ROOT; CTL_EVAL_ONLY
   int root_sc;                  // scaler buffer of the root for CTL_EVAL_ONLY
   unsigned int pad[2];
 };
@@ -62,32 +62,72 @@ struct RawOp                    // == bppgpu_partial_op
 
 // ---- staged per-locus block of the 4-state tree kernel (built by plan_kernel_blocks) ----------
 // [LocusHdr 128 B][rate_weights RL doubles, padded to 16 B][chunk 0][chunk 1]...
-// chunk = [PlanOp ops[TREE_CHUNK]][double P[TREE_CHUNK][2][RL][PM_STRIDE]]
+// chunk = [ChunkHdr 16 B][OpRec ops[TREE_CHUNK]][double Pup[TREE_CHUNK][RL][PM_STRIDE]]
+//         [double tipP[lut_cap(RL)][RL][PM_STRIDE]]
+// Pup[k]  = P-matrix of the edge ABOVE the node op k computes (the consumer's lpm/rpm);
+// tipP[s] = P-matrix of the edge above the packed tip child that was given LUT slot s.
+constexpr int TREE_NT    = 256;     // threads (= cells) per tile of the 4-state kernel
 constexpr int TREE_CHUNK = 16;      // ops per staged chunk
-constexpr int PM_STRIDE  = 18;      // doubles per (child, cat) matrix in shared memory (16 + 2 pad: the
-                                    // RL categories of a site land in different banks)
+constexpr int PM_STRIDE  = 18;      // doubles per (matrix, cat) in shared memory (16 + 2 pad: the RL
+                                    // categories of a site land in different banks)
+constexpr int LUT_ROW    = 6;       // doubles per state-mask row of a tip lookup table (4 + 2 pad: the
+                                    // one-hot masks 1,2,4,8 and 15 fall into different bank groups)
+constexpr int LUT_CAT    = 16 * LUT_ROW + 2;   // doubles per (tip child, cat) table
+__host__ __device__ constexpr int lut_cap(int RL) { return RL <= 2 ? 32 : (64 / RL); }   // tip children per chunk
+
+struct ChunkHdr { unsigned int nops, ntips, pad0, pad1; };
+
+// pre-decoded op of the 4-state kernel (64 bytes = 4 x uint4, uniform per CTA).
+// Operand A is never the register-resident X; operand B may be (B_PREV).
+enum : unsigned { OP_PARK = 1u << 0, OP_ROOT = 1u << 1, OP_EVAL = 1u << 2, OP_PUSH = 1u << 3, OP_BPREV = 1u << 4,
+                  OP_SCALE = 1u << 5 };
+struct OpRec
+{
+  unsigned int ctl;             // OP_* flags
+  unsigned int dst_cell;        // parent buffer offset in cells (32-byte units): dst * sites * RL
+  unsigned int a_kind, a_p0;    // packed tip: p0 = word index, p1 = nibble shift, p2 = LUT offset (16-byte units)
+  unsigned int a_p1, a_p2;      // slot: p0 = slot; hbm / dense tip: p0 = buffer or tip, p1 = pmatrix, p2 = scaler (int)
+  unsigned int b_kind, b_p0;
+  unsigned int b_p1, b_p2;
+  int dsc;                      // parent scaler buffer or -1
+  int root_sc;                  // root scaler buffer for OP_EVAL
+  unsigned int park_slot;       // OP_PARK: slot that receives the register X before this op runs
+  unsigned int up_pm;           // planner: pmatrix of the edge above dst (OP_PUSH)
+  unsigned int a_pm, b_pm;      // planner: pmatrix of the edges above A and B (tip tables)
+};
+static_assert(sizeof(OpRec) == 64, "OpRec must be 64 bytes");
+
 struct LocusHdr
 {
   double * clv;
   double * tip_dense;
   unsigned int * scale;
   const unsigned int * tipwords;
+  const double * pmat;
   unsigned long long clv_stride;
   unsigned int sites, nops, tip_words, n_chunks;
   double freqs[4];
-  double pad[5];
+  double pad[4];
 };
 static_assert(sizeof(LocusHdr) == 128, "LocusHdr must be 128 bytes");
 
 __host__ __device__ inline size_t rw_bytes(unsigned RL) { return ((size_t)RL * 8 + 15) & ~(size_t)15; }
 __host__ __device__ inline size_t chunk_bytes(unsigned RL)
 {
-  return (size_t)TREE_CHUNK * sizeof(PlanOp) + (size_t)TREE_CHUNK * 2 * RL * PM_STRIDE * 8;
+  return sizeof(ChunkHdr) + (size_t)TREE_CHUNK * sizeof(OpRec) + (size_t)TREE_CHUNK * RL * PM_STRIDE * 8 +
+         (size_t)lut_cap((int)RL) * RL * PM_STRIDE * 8;
+}
+// upper bound on the chunks of a list of nops ops: a chunk closes after TREE_CHUNK ops or when the
+// next op's tip children no longer fit its lookup tables
+__host__ __device__ inline unsigned int max_chunks(unsigned RL, unsigned nops)
+{
+  const unsigned cap = (unsigned)lut_cap((int)RL);
+  const unsigned m = cap / 2 < (unsigned)TREE_CHUNK ? (cap / 2 ? cap / 2 : 1) : (unsigned)TREE_CHUNK;
+  return (nops + m - 1) / m + 1;
 }
 __host__ __device__ inline size_t block_bytes(unsigned RL, unsigned nops_max)
 {
-  const unsigned nc = (nops_max + TREE_CHUNK - 1) / TREE_CHUNK;
-  return sizeof(LocusHdr) + rw_bytes(RL) + (size_t)(nc ? nc : 1) * chunk_bytes(RL);
+  return sizeof(LocusHdr) + rw_bytes(RL) + (size_t)max_chunks(RL, nops_max) * chunk_bytes(RL);
 }
 
 // one tile of blockDim cells (cell = pattern*RL + cat) of one locus; static per batch
@@ -113,7 +153,7 @@ struct TreeParams
   const unsigned int * plan_count;
   const TileDesc * tiles;             // 4-state kernel
   const unsigned char * blocks;       // 4-state kernel: staged per-locus blocks
-  const unsigned long long * blk_off; // byte offset of each locus' block
+  const unsigned long long * tile_blk;// byte offset of the block of each tile's locus (written by the planner)
   unsigned int n_tiles;
   double * tile_partial;              // per-tile weighted site-lnL sums
   double * persite;                   // optional per-site output of the (single) locus, or nullptr

@@ -170,6 +170,7 @@ struct bppgpu_batch
   PlanOp * d_plan = nullptr; size_t plan_cap = 0;   // generic kernel: flat plan
   unsigned char * d_blocks = nullptr; size_t blocks_cap = 0;   // 4-state kernel: staged per-locus blocks
   TileDesc * d_tiles = nullptr;
+  unsigned long long * d_tile_blk = nullptr;        // per tile: {block offset, 0}, written by the planner
   unsigned int * d_plan_count = nullptr;
   int grid = 0; size_t tree_smem = 0; int slots = 0;
   double * d_tile_partial = nullptr, * d_lnl = nullptr, * d_lnl_sum = nullptr;
@@ -650,15 +651,15 @@ static void batch_launch_cfg(bppgpu_batch * b)
   // all loci of a batch share states / rate_cats (checked at creation)
   const bppgpu_locus * l0 = b->loci[0];
   const unsigned R = l0->rate_cats;
-  const bool pow2 = (R & (R - 1)) == 0 && R <= 32;
+  const bool pow2 = (R & (R - 1)) == 0 && R <= 8;
   if (l0->states == 4 && pow2) { b->kernel_kind = 0; b->RL = R; }
   else { b->kernel_kind = 1; b->RL = 1; }
   // tile size: 256 cells for big loci, 128 for small ones (fewer idle lanes in the last tile)
   size_t cells = 0;
   for (auto * l : b->loci) cells += (size_t)l->sites * (b->kernel_kind == 0 ? R : 1);
   const size_t mean = cells / b->n;
-  if (b->kernel_kind == 0) b->tile_threads = mean >= 512 ? 256 : 128;
-  else b->tile_threads = 128;
+  (void)mean;
+  b->tile_threads = b->kernel_kind == 0 ? TREE_NT : 128;
 }
 
 extern "C" bppgpu_batch * bppgpu_batch_create(bppgpu_engine * e, unsigned int n, bppgpu_locus * const * loci)
@@ -697,7 +698,7 @@ extern "C" bppgpu_batch * bppgpu_batch_create(bppgpu_engine * e, unsigned int n,
         tiles.push_back(td);
       }
     }
-    soff[i] = sbytes; sbytes += align_up(l->clv_buffers, 16);
+    soff[i] = sbytes; sbytes += align_up((size_t)l->clv_buffers * 5, 16);
   }
   tile_first[n] = (unsigned)tile_locus.size();
   b->n_tiles = (unsigned)tile_locus.size();
@@ -722,6 +723,7 @@ extern "C" bppgpu_batch * bppgpu_batch_create(bppgpu_engine * e, unsigned int n,
   {
     CUDA_CHECK(cudaMalloc(&b->d_tiles, tiles.size() * sizeof(TileDesc)));
     CUDA_CHECK(cudaMemcpy(b->d_tiles, tiles.data(), tiles.size() * sizeof(TileDesc), cudaMemcpyHostToDevice));
+    CUDA_CHECK(cudaMalloc(&b->d_tile_blk, tiles.size() * 16));
   }
   CUDA_CHECK(cudaMemset(b->d_plan_count, 0, n * 4));
   CUDA_CHECK(cudaMemset(b->d_tile_partial, 0, b->n_tiles * 8));
@@ -739,7 +741,7 @@ extern "C" void bppgpu_batch_destroy(bppgpu_batch * b)
   cudaFree(b->d_batch_locus); cudaFree(b->d_tile_locus); cudaFree(b->d_tile_cell0); cudaFree(b->d_tile_first);
   cudaFree(b->d_scratch_off); cudaFree(b->d_scratch); cudaFree(b->d_plan_count); cudaFree(b->d_tile_partial);
   cudaFree(b->d_lnl); cudaFree(b->d_in); cudaFree(b->d_plan); cudaFree(b->d_persite);
-  cudaFree(b->d_blocks); cudaFree(b->d_tiles);
+  cudaFree(b->d_blocks); cudaFree(b->d_tiles); cudaFree(b->d_tile_blk);
   cudaFreeHost(b->h_out); cudaFreeHost(b->h_in);
   cudaEventDestroy(b->t0); cudaEventDestroy(b->t1);
   if (b->own_stream) cudaStreamDestroy(b->stream);
@@ -841,24 +843,18 @@ static void batch_sync_loci(bppgpu_batch * b, bool need_eigen)
   }
 }
 
-static size_t tree_s4_smem(unsigned RL, int slots, unsigned nthr)
-{
-  return sizeof(LocusHdr) + rw_bytes(RL) + chunk_bytes(RL) + 4 * sizeof(TileDesc) + 32 * 8 +
-         (size_t)slots * nthr * (32 + 4);
-}
-
 // persistent launch: as many CTAs as fit on the device at once, each walks a contiguous tile range
 template <int RL, bool EXACT>
 static void launch_tree_s4_impl(bppgpu_batch * b, const TreeParams & prm)
 {
   bppgpu_engine * e = b->e;
-  const size_t smem = tree_s4_smem(RL, prm.n_slots, b->tile_threads);
+  const size_t smem = S4Layout<RL>::bytes(prm.n_slots);
   CUDA_CHECK(cudaFuncSetAttribute(tree_kernel_s4<RL, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
-  CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tree_kernel_s4<RL, EXACT>, (int)b->tile_threads, smem));
+  CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tree_kernel_s4<RL, EXACT>, TREE_NT, smem));
   if (per_sm < 1) { fatal("tree kernel does not fit on an SM (smem %zu)", smem); return; }
   const unsigned grid = std::min<unsigned>(b->n_tiles, (unsigned)(per_sm * e->sm_count));
-  tree_kernel_s4<RL, EXACT><<<grid, b->tile_threads, smem, b->stream>>>(prm);
+  tree_kernel_s4<RL, EXACT><<<grid, TREE_NT, smem, b->stream>>>(prm);
 }
 
 template <int RL>
@@ -914,18 +910,19 @@ static int batch_run(bppgpu_batch * b, bool do_mats, bool do_tree, bool want_roo
     if (b->kernel_kind == 0)
       plan_kernel_blocks<<<(n * 32 + 127) / 128, 128, 0, b->stream>>>(
           e->d_loci, b->d_batch_locus, n, d_op_off, d_ops, d_root_clv, d_root_sc, want_root ? 1 : 0,
-          b->d_blocks, d_blk_off, b->d_plan_count, b->d_scratch, b->d_scratch_off, slots, b->RL);
+          b->d_blocks, d_blk_off, b->d_tile_first, b->d_tile_blk, b->d_plan_count, b->d_scratch, b->d_scratch_off,
+          slots, b->RL);
     else
       plan_kernel_flat<<<(n + 127) / 128, 128, 0, b->stream>>>(
           e->d_loci, b->d_batch_locus, n, d_op_off, d_ops, d_root_clv, d_root_sc, want_root ? 1 : 0,
-          b->d_plan, b->d_plan_count, b->d_scratch, b->d_scratch_off);
+          b->d_plan, b->d_plan_count);
     CUDA_CHECK(cudaGetLastError());
   }
   TreeParams prm;
   memset(&prm, 0, sizeof(prm));
   prm.loci = e->d_loci; prm.batch_locus = b->d_batch_locus; prm.tile_locus = b->d_tile_locus;
   prm.tile_cell0 = b->d_tile_cell0; prm.op_off = d_op_off; prm.plan = b->d_plan; prm.plan_count = b->d_plan_count;
-  prm.tiles = b->d_tiles; prm.blocks = b->d_blocks; prm.blk_off = d_blk_off; prm.n_tiles = b->n_tiles;
+  prm.tiles = b->d_tiles; prm.blocks = b->d_blocks; prm.tile_blk = b->d_tile_blk; prm.n_tiles = b->n_tiles;
   prm.tile_partial = want_root ? b->d_tile_partial : nullptr;
   prm.persite = persite; prm.persite_mode = persite_mode; prm.n_slots = slots;
   prm.log_threshold = e->log_threshold;
@@ -939,8 +936,6 @@ static int batch_run(bppgpu_batch * b, bool do_mats, bool do_tree, bool want_roo
         case 2: launch_tree_s4<2>(b, prm); break;
         case 4: launch_tree_s4<4>(b, prm); break;
         case 8: launch_tree_s4<8>(b, prm); break;
-        case 16: launch_tree_s4<16>(b, prm); break;
-        case 32: launch_tree_s4<32>(b, prm); break;
         default: fatal("internal: RL=%u", b->RL); return BPPGPU_FAILURE;
       }
     }

@@ -1,104 +1,81 @@
 // plan.cuh -- turn a locus' post-ordered op list (the traversal locus_update_partials walks,
-// locus.c:2530-2571) into a stack-machine program: a child produced earlier in the same list is
-// taken from a register (SRC_PREV) or a shared-memory slot (SRC_SLOT) instead of being re-read
-// from HBM; everything else is a packed tip, a dense tip or an HBM-resident CLV.
+// locus.c:2530-2571) into a stack-machine program.
+//
+// A child produced earlier in the same list is taken from a register (the previous op's result)
+// or a shared-memory slot instead of being re-read from HBM; everything else is a packed tip, a
+// dense tip or an HBM-resident CLV.
+//
+// 4-state blocks use the PUSH model: what travels in the register / slot is not the child's CLV c
+// but X = P_edge . c, computed once right after c is produced (the op gets OP_PUSH and the
+// P-matrix of the edge above it).  Packed tip children get a per-edge 16-entry lookup table of
+// X = P_edge . bits(mask); the planner hands out the table slots and closes a chunk when the
+// next op's tables would not fit.
 #pragma once
 #include "common.cuh"
 
 namespace bppgpu {
 
-// Sequential planner (one thread per locus).  emit(k, op) stores op k; returns the op count
-// (n, or n+1 when a CTL_EVAL_ONLY op for a root that this list does not produce is appended).
-template <class Emit>
-__device__ __forceinline__ unsigned int plan_locus(const LocusDev & L, const RawOp * __restrict__ o, unsigned int n,
-                                                   unsigned int rootc, int rootsc, bool want_root,
-                                                   unsigned char * __restrict__ loc, int max_slots, bool allow_prev,
-                                                   Emit emit)
-{
-  const unsigned int T = L.tips;
-  for (unsigned int k = 0; k < n; ++k)
-  {
-    loc[o[k].parent - T] = 0;
-    if (o[k].left >= T) loc[o[k].left - T] = 0;
-    if (o[k].right >= T) loc[o[k].right - T] = 0;
-  }
-  unsigned int free_slots = (max_slots >= 32) ? 0xFFFFFFFFu : ((1u << max_slots) - 1u);
-  unsigned int prev = 0xFFFFFFFFu;
-  bool root_done = false;
-  for (unsigned int k = 0; k < n; ++k)
-  {
-    const RawOp r = o[k];
-    PlanOp q;
-    q.dst = r.parent - T; q.lpm = r.lpm; q.rpm = r.rpm;
-    q.dsc = r.psc; q.lsc = r.lsc; q.rsc = r.rsc; q.ctl = 0; q.root_sc = -1; q.pad[0] = q.pad[1] = 0;
-    unsigned int src[2]; unsigned int consumed_slots = 0; bool uses_prev = false;
-    const unsigned int child[2] = { r.left, r.right };
-    for (int c = 0; c < 2; ++c)
-    {
-      const unsigned int idx = child[c];
-      if (idx < T) src[c] = ((L.tip_is_dense[idx] ? SRC_TIP_DENSE : SRC_TIP_PACKED) << 28) | idx;
-      else
-      {
-        const unsigned int b = idx - T;
-        if (allow_prev && b == prev && !uses_prev) { src[c] = (SRC_PREV << 28); uses_prev = true; }
-        else if (loc[b]) { src[c] = (SRC_SLOT << 28) | (unsigned)(loc[b] - 1); consumed_slots |= 1u << (loc[b] - 1); loc[b] = 0; }
-        else src[c] = (SRC_HBM << 28) | b;
-      }
-    }
-    // the previous result is not consumed by this op: park it in a free slot (else it stays HBM-only)
-    if (prev != 0xFFFFFFFFu && !uses_prev && free_slots)
-    {
-      const int s = __ffs(free_slots) - 1;
-      free_slots &= ~(1u << s);
-      loc[prev] = (unsigned char)(s + 1);
-      q.ctl |= (unsigned)(s + 1);
-    }
-    free_slots |= consumed_slots;
-    q.lsrc = src[0]; q.rsrc = src[1];
-    if (want_root && r.parent == rootc) { q.ctl |= CTL_ROOT; q.root_sc = r.psc; root_done = true; }
-    emit(k, q);
-    prev = q.dst;
-  }
-  if (want_root && !root_done)
-  {
-    PlanOp q;
-    q.dst = 0; q.lpm = q.rpm = 0; q.dsc = -1; q.rsc = -1; q.rsrc = 0; q.pad[0] = q.pad[1] = 0;
-    q.lsc = rootsc; q.root_sc = rootsc;
-    q.ctl = CTL_EVAL_ONLY | CTL_ROOT;
-    if (rootc < T) q.lsrc = ((L.tip_is_dense[rootc] ? SRC_TIP_DENSE : SRC_TIP_PACKED) << 28) | rootc;
-    else q.lsrc = (SRC_HBM << 28) | (rootc - T);       // not produced by this list: HBM-resident
-    emit(n, q);
-    return n + 1;
-  }
-  return n;
-}
-
-// flat plan for the generic kernel: plan + op_off[bl] + bl, one spare entry per locus
+// ---------------------------------------------------------------- flat plan (generic kernel)
+// plan + op_off[bl] + bl, one spare entry per locus; every operand comes from HBM
 __global__ void plan_kernel_flat(const LocusDev * __restrict__ loci, const unsigned int * __restrict__ batch_locus,
                                  unsigned int n_loci, const unsigned int * __restrict__ op_off,
                                  const RawOp * __restrict__ ops, const unsigned int * __restrict__ root_clv,
                                  const int * __restrict__ root_sc, int want_root,
-                                 PlanOp * __restrict__ plan, unsigned int * __restrict__ plan_count,
-                                 unsigned char * __restrict__ scratch, const unsigned long long * __restrict__ scratch_off)
+                                 PlanOp * __restrict__ plan, unsigned int * __restrict__ plan_count)
 {
   const unsigned int bl = blockIdx.x * blockDim.x + threadIdx.x;
   if (bl >= n_loci) return;
   const LocusDev & L = loci[batch_locus[bl]];
   const unsigned int first = op_off[bl], n = op_off[bl + 1] - first;
+  const RawOp * o = ops + first;
   PlanOp * p = plan + first + bl;
-  plan_count[bl] = plan_locus(L, ops + first, n, want_root ? root_clv[bl] : 0xFFFFFFFFu, want_root ? root_sc[bl] : -1,
-                              want_root != 0, scratch + scratch_off[bl], 0, false,
-                              [p](unsigned int k, const PlanOp & q) { p[k] = q; });
+  const unsigned int T = L.tips;
+  const unsigned int rootc = want_root ? root_clv[bl] : 0xFFFFFFFFu;
+  bool root_done = false;
+  auto classify = [&](unsigned int idx) -> unsigned int
+  {
+    if (idx < T) return ((L.tip_is_dense[idx] ? SRC_TIP_DENSE : SRC_TIP_PACKED) << 28) | idx;
+    return (SRC_HBM << 28) | (idx - T);
+  };
+  for (unsigned int k = 0; k < n; ++k)
+  {
+    const RawOp r = o[k];
+    PlanOp q;
+    q.dst = r.parent - T; q.lpm = r.lpm; q.rpm = r.rpm; q.dsc = r.psc; q.lsc = r.lsc; q.rsc = r.rsc;
+    q.ctl = 0; q.root_sc = -1; q.pad[0] = q.pad[1] = 0;
+    q.lsrc = classify(r.left); q.rsrc = classify(r.right);
+    if (want_root && r.parent == rootc) { q.ctl |= CTL_ROOT; q.root_sc = r.psc; root_done = true; }
+    p[k] = q;
+  }
+  unsigned int cnt = n;
+  if (want_root && !root_done)
+  {
+    PlanOp q;
+    q.dst = 0; q.lpm = q.rpm = 0; q.dsc = -1; q.rsc = -1; q.rsrc = 0; q.pad[0] = q.pad[1] = 0;
+    q.lsc = root_sc[bl]; q.root_sc = root_sc[bl];
+    q.ctl = CTL_EVAL_ONLY | CTL_ROOT;
+    q.lsrc = classify(rootc);
+    p[n] = q;
+    cnt = n + 1;
+  }
+  plan_count[bl] = cnt;
 }
 
-// staged blocks for the 4-state kernel: one WARP per locus; lane 0 plans, all lanes gather the
-// P-matrices of every op into the block in the kernel's shared-memory layout
+// ---------------------------------------------------------------- staged blocks (4-state kernel)
+// One WARP per locus: lane 0 plans sequentially, then all lanes gather the P-matrices the kernel
+// needs (Pup of every pushed op, tipP of every packed tip child) into the block, already in the
+// kernel's padded shared-memory layout, and publish the block offset of every tile of the locus.
+// scratch per locus: [unsigned int where[clv_buffers]]: byte offset (within the block) of the OpRec
+// that produced the buffer and still holds its X in a slot, 0 = HBM only; [unsigned char slot_of[clv_buffers]].
+struct Operand { unsigned int kind, p0, p1, p2, pm; };
+
 __global__ void __launch_bounds__(128)
 plan_kernel_blocks(const LocusDev * __restrict__ loci, const unsigned int * __restrict__ batch_locus,
                    unsigned int n_loci, const unsigned int * __restrict__ op_off,
                    const RawOp * __restrict__ ops, const unsigned int * __restrict__ root_clv,
                    const int * __restrict__ root_sc, int want_root,
                    unsigned char * __restrict__ blocks, const unsigned long long * __restrict__ blk_off,
+                   const unsigned int * __restrict__ tile_first, unsigned long long * __restrict__ tile_blk,
                    unsigned int * __restrict__ plan_count,
                    unsigned char * __restrict__ scratch, const unsigned long long * __restrict__ scratch_off,
                    int max_slots, unsigned int RL)
@@ -108,39 +85,170 @@ plan_kernel_blocks(const LocusDev * __restrict__ loci, const unsigned int * __re
   if (bl >= n_loci) return;
   const LocusDev & L = loci[batch_locus[bl]];
   const unsigned int first = op_off[bl], n = op_off[bl + 1] - first;
+  const RawOp * __restrict__ o = ops + first;
   unsigned char * blk = blocks + blk_off[bl];
   const size_t cb = chunk_bytes(RL);
-  unsigned char * chunks = blk + sizeof(LocusHdr) + rw_bytes(RL);
-  unsigned int cnt = 0;
+  const unsigned int chunks0 = (unsigned int)(sizeof(LocusHdr) + rw_bytes(RL));
+  const unsigned int cap = (unsigned int)lut_cap((int)RL);
+  const unsigned int lut_unit = RL * (LUT_CAT / 2);      // 16-byte units per tip table set
+  const unsigned int T = L.tips;
+  unsigned int n_chunks = 0, cnt = 0;
+
+  for (unsigned int t = tile_first[bl] + lane; t < tile_first[bl + 1]; t += 32) { tile_blk[2 * (size_t)t] = blk_off[bl]; tile_blk[2 * (size_t)t + 1] = 0; }
+
   if (lane == 0)
   {
-    cnt = plan_locus(L, ops + first, n, want_root ? root_clv[bl] : 0xFFFFFFFFu, want_root ? root_sc[bl] : -1,
-                     want_root != 0, scratch + scratch_off[bl], max_slots, true,
-                     [chunks, cb](unsigned int k, const PlanOp & q)
-                     { reinterpret_cast<PlanOp *>(chunks + (size_t)(k / TREE_CHUNK) * cb)[k % TREE_CHUNK] = q; });
+    unsigned int * where = reinterpret_cast<unsigned int *>(scratch + scratch_off[bl]);
+    unsigned char * slot_of = reinterpret_cast<unsigned char *>(where + L.clv_buffers);
+    for (unsigned int k = 0; k < n; ++k)
+    {
+      where[o[k].parent - T] = 0;
+      if (o[k].left >= T) where[o[k].left - T] = 0;
+      if (o[k].right >= T) where[o[k].right - T] = 0;
+    }
+    const unsigned int rootc = want_root ? root_clv[bl] : 0xFFFFFFFFu;
+    unsigned int free_slots = (max_slots >= 32) ? 0xFFFFFFFFu : ((1u << max_slots) - 1u);
+    unsigned int prev = 0xFFFFFFFFu;        // buffer whose X sits in the register, or none
+    unsigned int prev_off = 0;              // block offset of the op that produced it
+    bool root_done = false;
+    unsigned int c_idx = 0, c_nops = 0, c_ntips = 0;
+    auto close_chunk = [&]()
+    {
+      ChunkHdr * h = reinterpret_cast<ChunkHdr *>(blk + chunks0 + (size_t)c_idx * cb);
+      h->nops = c_nops; h->ntips = c_ntips; h->pad0 = h->pad1 = 0;
+      ++c_idx; c_nops = 0; c_ntips = 0;
+    };
+    const unsigned int cells_per_buf = L.sites * RL;
+    for (unsigned int k = 0; k < n; ++k)
+    {
+      const RawOp r = o[k];
+      const unsigned int child[2] = { r.left, r.right };
+      unsigned int ntip = 0;
+      for (int c = 0; c < 2; ++c) if (child[c] < T && !L.tip_is_dense[child[c]]) ++ntip;
+      if (c_nops == (unsigned)TREE_CHUNK || c_ntips + ntip > cap) close_chunk();
+      Operand opd[2];
+      int prev_child = -1;
+      unsigned int consumed_slots = 0;
+      for (int c = 0; c < 2; ++c)
+      {
+        const unsigned int idx = child[c];
+        Operand & q = opd[c];
+        q.pm = c ? r.rpm : r.lpm; q.p0 = q.p1 = q.p2 = 0;
+        if (idx < T)
+        {
+          if (L.tip_is_dense[idx]) { q.kind = SRC_TIP_DENSE; q.p0 = idx; q.p1 = q.pm; q.p2 = 0xFFFFFFFFu; }
+          else { q.kind = SRC_TIP_PACKED; q.p0 = idx >> 3; q.p1 = (idx & 7u) * 4; q.p2 = c_ntips * lut_unit; ++c_ntips; }
+        }
+        else
+        {
+          const unsigned int b = idx - T;
+          if (b == prev && prev_child < 0)
+          {
+            q.kind = SRC_PREV; prev_child = c;
+            OpRec * prod = reinterpret_cast<OpRec *>(blk + prev_off);
+            prod->ctl |= OP_PUSH; prod->up_pm = q.pm;
+          }
+          else if (where[b])
+          {
+            const unsigned int s = slot_of[b];
+            q.kind = SRC_SLOT; q.p0 = s; consumed_slots |= 1u << s;
+            OpRec * prod = reinterpret_cast<OpRec *>(blk + where[b]);
+            prod->ctl |= OP_PUSH; prod->up_pm = q.pm;
+            where[b] = 0;
+          }
+          else { q.kind = SRC_HBM; q.p0 = b; q.p1 = q.pm; q.p2 = (unsigned int)(c ? r.rsc : r.lsc); }
+        }
+      }
+      OpRec q;
+      q.ctl = 0; q.dst_cell = (r.parent - T) * cells_per_buf; q.dsc = r.psc; q.root_sc = -1;
+      q.park_slot = 0; q.up_pm = 0;
+      if (r.psc >= 0) q.ctl |= OP_SCALE;
+      // the previous result is not consumed by this op: park its X in a free slot, else it is
+      // dropped (its consumer re-reads the CLV from HBM and applies P itself)
+      if (prev != 0xFFFFFFFFu && prev_child < 0 && free_slots)
+      {
+        const int s = __ffs(free_slots) - 1;
+        free_slots &= ~(1u << s);
+        where[prev] = prev_off; slot_of[prev] = (unsigned char)s;
+        q.ctl |= OP_PARK; q.park_slot = (unsigned)s;
+      }
+      free_slots |= consumed_slots;
+      // operand A is never the register X (the product is commutative)
+      const Operand & A = opd[prev_child == 0 ? 1 : 0];
+      const Operand & B = opd[prev_child == 0 ? 0 : 1];
+      q.a_kind = A.kind; q.a_p0 = A.p0; q.a_p1 = A.p1; q.a_p2 = A.p2; q.a_pm = A.pm;
+      q.b_kind = B.kind; q.b_p0 = B.p0; q.b_p1 = B.p1; q.b_p2 = B.p2; q.b_pm = B.pm;
+      if (prev_child >= 0) q.ctl |= OP_BPREV;
+      if (want_root && r.parent == rootc) { q.ctl |= OP_ROOT; q.root_sc = r.psc; root_done = true; }
+      const unsigned int off = chunks0 + (unsigned int)((size_t)c_idx * cb) + (unsigned int)sizeof(ChunkHdr) +
+                               c_nops * (unsigned int)sizeof(OpRec);
+      *reinterpret_cast<OpRec *>(blk + off) = q;
+      ++c_nops;
+      prev = r.parent - T; prev_off = off;
+    }
+    cnt = n;
+    if (want_root && !root_done)
+    {
+      if (c_nops == (unsigned)TREE_CHUNK) close_chunk();
+      OpRec q;
+      memset(&q, 0, sizeof(q));
+      q.ctl = OP_EVAL | OP_ROOT; q.dsc = -1; q.root_sc = root_sc[bl];
+      if (rootc < T)
+      {
+        if (L.tip_is_dense[rootc]) { q.a_kind = SRC_TIP_DENSE; q.a_p0 = rootc; }
+        else { q.a_kind = SRC_TIP_PACKED; q.a_p0 = rootc >> 3; q.a_p1 = (rootc & 7u) * 4; }
+      }
+      else { q.a_kind = SRC_HBM; q.a_p0 = rootc - T; q.a_p2 = (unsigned int)root_sc[bl]; }
+      const unsigned int off = chunks0 + (unsigned int)((size_t)c_idx * cb) + (unsigned int)sizeof(ChunkHdr) +
+                               c_nops * (unsigned int)sizeof(OpRec);
+      *reinterpret_cast<OpRec *>(blk + off) = q;
+      ++c_nops;
+      cnt = n + 1;
+    }
+    if (c_nops) close_chunk();
+    n_chunks = c_idx;
     LocusHdr * H = reinterpret_cast<LocusHdr *>(blk);
     H->clv = L.clv; H->tip_dense = L.tip_dense; H->scale = L.scale;
-    H->tipwords = reinterpret_cast<const unsigned int *>(L.tip_codes);
+    H->tipwords = reinterpret_cast<const unsigned int *>(L.tip_codes); H->pmat = L.pmat;
     H->clv_stride = L.clv_stride; H->sites = L.sites; H->nops = cnt; H->tip_words = L.tip_words;
-    H->n_chunks = (cnt + TREE_CHUNK - 1) / TREE_CHUNK;
+    H->n_chunks = n_chunks;
     for (int j = 0; j < 4; ++j) H->freqs[j] = L.freqs[j];
     plan_count[bl] = cnt;
   }
-  cnt = __shfl_sync(0xFFFFFFFFu, cnt, 0);
+  n_chunks = __shfl_sync(0xFFFFFFFFu, n_chunks, 0);
   __syncwarp();
   double * rw = reinterpret_cast<double *>(blk + sizeof(LocusHdr));
   for (unsigned int j = lane; j < RL; j += 32) rw[j] = L.rate_weights[j];
-  // gather: element e -> (op k, child c, cat r, entry x)
-  const unsigned int per_op = 2 * RL * 16;
-  for (unsigned int e = lane; e < cnt * per_op; e += 32)
+  // gather: per chunk, per op: Pup (if pushed) and the tipP of its packed tip children
+  const unsigned int mat = RL * 16;                     // doubles per matrix
+  for (unsigned int c = 0; c < n_chunks; ++c)
   {
-    const unsigned int k = e / per_op, w = e % per_op;
-    const unsigned int c = w / (RL * 16), r = (w / 16) % RL, x = w & 15u;
-    unsigned char * ch = chunks + (size_t)(k / TREE_CHUNK) * cb;
-    const PlanOp & q = reinterpret_cast<const PlanOp *>(ch)[k % TREE_CHUNK];
-    if (q.ctl & CTL_EVAL_ONLY) continue;
-    double * P = reinterpret_cast<double *>(ch + TREE_CHUNK * sizeof(PlanOp));
-    P[(((k % TREE_CHUNK) * 2 + c) * RL + r) * PM_STRIDE + x] = L.pmat[((size_t)(c ? q.rpm : q.lpm) * RL + r) * 16 + x];
+    unsigned char * ch = blk + chunks0 + (size_t)c * cb;
+    const ChunkHdr hdr = *reinterpret_cast<const ChunkHdr *>(ch);
+    const OpRec * cops = reinterpret_cast<const OpRec *>(ch + sizeof(ChunkHdr));
+    double * Pup = reinterpret_cast<double *>(ch + sizeof(ChunkHdr) + TREE_CHUNK * sizeof(OpRec));
+    double * tipP = Pup + (size_t)TREE_CHUNK * RL * PM_STRIDE;
+    for (unsigned int e = lane; e < hdr.nops * 3 * mat; e += 32)
+    {
+      const unsigned int k = e / (3 * mat), w = e % (3 * mat);
+      const unsigned int which = w / mat, r = (w / 16) % RL, x = w & 15u;
+      const OpRec & q = cops[k];
+      if (q.ctl & OP_EVAL) continue;
+      if (which == 0)
+      {
+        if (q.ctl & OP_PUSH) Pup[((size_t)k * RL + r) * PM_STRIDE + x] = L.pmat[((size_t)q.up_pm * RL + r) * 16 + x];
+      }
+      else
+      {
+        const unsigned int kind = which == 1 ? q.a_kind : q.b_kind;
+        if (kind == SRC_TIP_PACKED)
+        {
+          const unsigned int s = (which == 1 ? q.a_p2 : q.b_p2) / lut_unit;
+          const unsigned int pm = which == 1 ? q.a_pm : q.b_pm;
+          tipP[((size_t)s * RL + r) * PM_STRIDE + x] = L.pmat[((size_t)pm * RL + r) * 16 + x];
+        }
+      }
+    }
   }
 }
 
