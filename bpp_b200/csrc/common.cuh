@@ -78,24 +78,28 @@ __host__ __device__ constexpr int lut_cap(int RL) { return RL <= 2 ? 32 : (64 / 
 struct ChunkHdr { unsigned int nops, ntips, pad0, pad1; };
 
 // pre-decoded op of the 4-state kernel (64 bytes = 4 x uint4, uniform per CTA).
-// Operand A is never the register-resident X; operand B may be (B_PREV).
-enum : unsigned { OP_PARK = 1u << 0, OP_ROOT = 1u << 1, OP_EVAL = 1u << 2, OP_PUSH = 1u << 3, OP_BPREV = 1u << 4,
-                  OP_SCALE = 1u << 5 };
+// Operand A is never the register-resident X; operand B may be (OP_BPREV).
+//   fast operands: packed tip whose word is register-resident (tip < 16) or a stack slot:
+//     sel = mask (15 tip / 0 slot) | word index << 4 | nibble shift << 8
+//     off = tip: lookup-table offset; slot: stack offset (uint4 units, relative to the thread's base)
+//   cold operands (HBM-resident CLV, dense tip, tip >= 16): kind / p0 / pm / sc
+enum : unsigned { OP_ROOT = 1u << 0, OP_EVAL = 1u << 1, OP_PUSH = 1u << 2, OP_BPREV = 1u << 3, OP_SCALE = 1u << 4,
+                  OP_PARKA = 1u << 5,       // after the push, park X in stack slot park_off
+                  OP_AKIND_SHIFT = 8, OP_BKIND_SHIFT = 12 };
 struct OpRec
 {
-  unsigned int ctl;             // OP_* flags
+  unsigned int ctl;             // OP_* flags | a_kind << 8 | b_kind << 12
   unsigned int dst_cell;        // parent buffer offset in cells (32-byte units): dst * sites * RL
-  unsigned int a_kind, a_p0;    // packed tip: p0 = word index, p1 = nibble shift, p2 = LUT offset (16-byte units)
-  unsigned int a_p1, a_p2;      // slot: p0 = slot; hbm / dense tip: p0 = buffer or tip, p1 = pmatrix, p2 = scaler (int)
-  unsigned int b_kind, b_p0;
-  unsigned int b_p1, b_p2;
-  int dsc;                      // parent scaler buffer or -1
-  int root_sc;                  // root scaler buffer for OP_EVAL
-  unsigned int park_slot;       // OP_PARK: slot that receives the register X before this op runs
-  unsigned int up_pm;           // planner: pmatrix of the edge above dst (OP_PUSH)
-  unsigned int a_pm, b_pm;      // planner: pmatrix of the edges above A and B (tip tables)
+  unsigned int a_sel, a_off;
+  unsigned int b_sel, b_off;
+  int dsc;                      // parent scaler buffer or -1 (OP_EVAL: the root's scaler buffer)
+  unsigned int park_off;        // OP_PARKA: stack offset of the slot
+  unsigned int a_p0, a_pm; int a_sc; unsigned int up_pm;     // up_pm: pmatrix of the edge above dst (OP_PUSH)
+  unsigned int b_p0, b_pm; int b_sc; unsigned int pad;
 };
 static_assert(sizeof(OpRec) == 64, "OpRec must be 64 bytes");
+
+enum : unsigned { HDR_FAST = 1u };   // every op of the locus uses fast operands only
 
 struct LocusHdr
 {
@@ -107,7 +111,8 @@ struct LocusHdr
   unsigned long long clv_stride;
   unsigned int sites, nops, tip_words, n_chunks;
   double freqs[4];
-  double pad[4];
+  unsigned int flags, pad0;
+  double pad[3];
 };
 static_assert(sizeof(LocusHdr) == 128, "LocusHdr must be 128 bytes");
 
@@ -139,7 +144,7 @@ struct TileDesc
   unsigned int cell0;              // first cell of the tile
   unsigned int tip_words;
   unsigned int ncell;              // sites * RL
-};
+};                                 // a tile covers TREE_NT * CPT cells: thread tid owns cells cell0 + tid + j*TREE_NT
 static_assert(sizeof(TileDesc) == 32, "TileDesc must be 32 bytes");
 
 struct TreeParams
@@ -158,7 +163,7 @@ struct TreeParams
   double * tile_partial;              // per-tile weighted site-lnL sums
   double * persite;                   // optional per-site output of the (single) locus, or nullptr
   int persite_mode;                   // 1 = weighted site lnL, 2 = site likelihood (vector form)
-  int n_slots;                        // shared-memory stack slots per thread
+  int n_slots;                        // shared-memory stack slots per cell
   double log_threshold;               // log(PLL_SCALE_THRESHOLD) as the host libm evaluates it
 };
 

@@ -157,6 +157,7 @@ struct bppgpu_batch
   bool own_stream = false;
   int kernel_kind = 0;                 // 0 = 4-state pow2-R kernel, 1 = generic
   unsigned int RL = 1;                 // lanes per site of the 4-state kernel
+  unsigned int cpt = 1;                // cells per thread of the 4-state kernel
   unsigned int tile_threads = 256;
   unsigned int n_tiles = 0;
   // static device tables
@@ -658,7 +659,7 @@ static void batch_launch_cfg(bppgpu_batch * b)
   size_t cells = 0;
   for (auto * l : b->loci) cells += (size_t)l->sites * (b->kernel_kind == 0 ? R : 1);
   const size_t mean = cells / b->n;
-  (void)mean;
+  b->cpt = (b->kernel_kind == 0 && mean >= 2 * TREE_NT) ? 2 : 1;
   b->tile_threads = b->kernel_kind == 0 ? TREE_NT : 128;
 }
 
@@ -687,7 +688,7 @@ extern "C" bppgpu_batch * bppgpu_batch_create(bppgpu_engine * e, unsigned int n,
     ids[i] = l->id;
     const unsigned cells = l->sites * (b->kernel_kind == 0 ? b->RL : 1);
     tile_first[i] = (unsigned)tile_locus.size();
-    for (unsigned c = 0; c < cells; c += b->tile_threads)
+    for (unsigned c = 0; c < cells; c += b->tile_threads * b->cpt)
     {
       tile_locus.push_back(i); tile_cell0.push_back(c);
       if (b->kernel_kind == 0)
@@ -844,24 +845,25 @@ static void batch_sync_loci(bppgpu_batch * b, bool need_eigen)
 }
 
 // persistent launch: as many CTAs as fit on the device at once, each walks a contiguous tile range
-template <int RL, bool EXACT>
+template <int RL, bool EXACT, int CPT>
 static void launch_tree_s4_impl(bppgpu_batch * b, const TreeParams & prm)
 {
   bppgpu_engine * e = b->e;
-  const size_t smem = S4Layout<RL>::bytes(prm.n_slots);
-  CUDA_CHECK(cudaFuncSetAttribute(tree_kernel_s4<RL, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const size_t smem = S4Layout<RL, CPT>::bytes(prm.n_slots);
+  CUDA_CHECK(cudaFuncSetAttribute(tree_kernel_s4<RL, EXACT, CPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
-  CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tree_kernel_s4<RL, EXACT>, TREE_NT, smem));
+  CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tree_kernel_s4<RL, EXACT, CPT>, TREE_NT, smem));
   if (per_sm < 1) { fatal("tree kernel does not fit on an SM (smem %zu)", smem); return; }
   const unsigned grid = std::min<unsigned>(b->n_tiles, (unsigned)(per_sm * e->sm_count));
-  tree_kernel_s4<RL, EXACT><<<grid, TREE_NT, smem, b->stream>>>(prm);
+  tree_kernel_s4<RL, EXACT, CPT><<<grid, TREE_NT, smem, b->stream>>>(prm);
 }
 
 template <int RL>
 static void launch_tree_s4(bppgpu_batch * b, const TreeParams & prm)
 {
-  if (b->e->math == BPPGPU_MATH_EXACT) launch_tree_s4_impl<RL, true>(b, prm);
-  else launch_tree_s4_impl<RL, false>(b, prm);
+  const bool exact = b->e->math == BPPGPU_MATH_EXACT;
+  if (b->cpt == 2) { if (exact) launch_tree_s4_impl<RL, true, 2>(b, prm); else launch_tree_s4_impl<RL, false, 2>(b, prm); }
+  else { if (exact) launch_tree_s4_impl<RL, true, 1>(b, prm); else launch_tree_s4_impl<RL, false, 1>(b, prm); }
 }
 
 // launches: [pmatrix] [plan + tree (+ finish)] on the batch stream, using the staged blob
@@ -902,7 +904,7 @@ static int batch_run(bppgpu_batch * b, bool do_mats, bool do_tree, bool want_roo
     unsigned maxT = 0;
     for (auto * l : b->loci) maxT = std::max(maxT, l->tips);
     slots = 1; while ((1u << slots) < maxT) ++slots;
-    slots = std::min(slots, 6);
+    slots = std::min(std::max(slots - 1, 1), 6);
   }
   const unsigned long long * d_blk_off = (const unsigned long long *)(b->d_in + b->o_blk_off);
   {
@@ -911,7 +913,7 @@ static int batch_run(bppgpu_batch * b, bool do_mats, bool do_tree, bool want_roo
       plan_kernel_blocks<<<(n * 32 + 127) / 128, 128, 0, b->stream>>>(
           e->d_loci, b->d_batch_locus, n, d_op_off, d_ops, d_root_clv, d_root_sc, want_root ? 1 : 0,
           b->d_blocks, d_blk_off, b->d_tile_first, b->d_tile_blk, b->d_plan_count, b->d_scratch, b->d_scratch_off,
-          slots, b->RL);
+          slots, b->RL, b->cpt);
     else
       plan_kernel_flat<<<(n + 127) / 128, 128, 0, b->stream>>>(
           e->d_loci, b->d_batch_locus, n, d_op_off, d_ops, d_root_clv, d_root_sc, want_root ? 1 : 0,

@@ -67,7 +67,7 @@ __global__ void plan_kernel_flat(const LocusDev * __restrict__ loci, const unsig
 // kernel's padded shared-memory layout, and publish the block offset of every tile of the locus.
 // scratch per locus: [unsigned int where[clv_buffers]]: byte offset (within the block) of the OpRec
 // that produced the buffer and still holds its X in a slot, 0 = HBM only; [unsigned char slot_of[clv_buffers]].
-struct Operand { unsigned int kind, p0, p1, p2, pm; };
+struct Operand { unsigned int kind, sel, off, p0, pm; int sc; };
 
 __global__ void __launch_bounds__(128)
 plan_kernel_blocks(const LocusDev * __restrict__ loci, const unsigned int * __restrict__ batch_locus,
@@ -78,7 +78,7 @@ plan_kernel_blocks(const LocusDev * __restrict__ loci, const unsigned int * __re
                    const unsigned int * __restrict__ tile_first, unsigned long long * __restrict__ tile_blk,
                    unsigned int * __restrict__ plan_count,
                    unsigned char * __restrict__ scratch, const unsigned long long * __restrict__ scratch_off,
-                   int max_slots, unsigned int RL)
+                   int max_slots, unsigned int RL, unsigned int cpt)
 {
   const unsigned int bl = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const unsigned int lane = threadIdx.x & 31u;
@@ -90,11 +90,16 @@ plan_kernel_blocks(const LocusDev * __restrict__ loci, const unsigned int * __re
   const size_t cb = chunk_bytes(RL);
   const unsigned int chunks0 = (unsigned int)(sizeof(LocusHdr) + rw_bytes(RL));
   const unsigned int cap = (unsigned int)lut_cap((int)RL);
-  const unsigned int lut_unit = RL * (LUT_CAT / 2);      // 16-byte units per tip table set
+  const unsigned int lut_unit = RL * (LUT_CAT / 2);      // uint4 units per tip table set
+  const unsigned int slot_unit = 2 * cpt * TREE_NT;      // uint4 units per stack slot
   const unsigned int T = L.tips;
   unsigned int n_chunks = 0, cnt = 0;
 
-  for (unsigned int t = tile_first[bl] + lane; t < tile_first[bl + 1]; t += 32) { tile_blk[2 * (size_t)t] = blk_off[bl]; tile_blk[2 * (size_t)t + 1] = 0; }
+  for (unsigned int t = tile_first[bl] + lane; t < tile_first[bl + 1]; t += 32)
+  {
+    tile_blk[2 * (size_t)t] = blk_off[bl];
+    tile_blk[2 * (size_t)t + 1] = 0;
+  }
 
   if (lane == 0)
   {
@@ -110,7 +115,7 @@ plan_kernel_blocks(const LocusDev * __restrict__ loci, const unsigned int * __re
     unsigned int free_slots = (max_slots >= 32) ? 0xFFFFFFFFu : ((1u << max_slots) - 1u);
     unsigned int prev = 0xFFFFFFFFu;        // buffer whose X sits in the register, or none
     unsigned int prev_off = 0;              // block offset of the op that produced it
-    bool root_done = false;
+    bool root_done = false, fast = true;
     unsigned int c_idx = 0, c_nops = 0, c_ntips = 0;
     auto close_chunk = [&]()
     {
@@ -133,11 +138,18 @@ plan_kernel_blocks(const LocusDev * __restrict__ loci, const unsigned int * __re
       {
         const unsigned int idx = child[c];
         Operand & q = opd[c];
-        q.pm = c ? r.rpm : r.lpm; q.p0 = q.p1 = q.p2 = 0;
+        q.pm = c ? r.rpm : r.lpm; q.sel = q.off = q.p0 = 0; q.sc = -1;
         if (idx < T)
         {
-          if (L.tip_is_dense[idx]) { q.kind = SRC_TIP_DENSE; q.p0 = idx; q.p1 = q.pm; q.p2 = 0xFFFFFFFFu; }
-          else { q.kind = SRC_TIP_PACKED; q.p0 = idx >> 3; q.p1 = (idx & 7u) * 4; q.p2 = c_ntips * lut_unit; ++c_ntips; }
+          q.p0 = idx;
+          if (L.tip_is_dense[idx]) { q.kind = SRC_TIP_DENSE; fast = false; }
+          else
+          {
+            q.kind = SRC_TIP_PACKED;
+            q.sel = 15u | ((idx >> 3) << 4) | (((idx & 7u) * 4) << 8);
+            q.off = c_ntips * lut_unit; ++c_ntips;
+            if (idx >= 16) fast = false;
+          }
         }
         else
         {
@@ -151,35 +163,36 @@ plan_kernel_blocks(const LocusDev * __restrict__ loci, const unsigned int * __re
           else if (where[b])
           {
             const unsigned int s = slot_of[b];
-            q.kind = SRC_SLOT; q.p0 = s; consumed_slots |= 1u << s;
+            q.kind = SRC_SLOT; q.p0 = s; q.off = s * slot_unit; consumed_slots |= 1u << s;
             OpRec * prod = reinterpret_cast<OpRec *>(blk + where[b]);
             prod->ctl |= OP_PUSH; prod->up_pm = q.pm;
             where[b] = 0;
           }
-          else { q.kind = SRC_HBM; q.p0 = b; q.p1 = q.pm; q.p2 = (unsigned int)(c ? r.rsc : r.lsc); }
+          else { q.kind = SRC_HBM; q.p0 = b; q.sc = c ? r.rsc : r.lsc; fast = false; }
         }
       }
-      OpRec q;
-      q.ctl = 0; q.dst_cell = (r.parent - T) * cells_per_buf; q.dsc = r.psc; q.root_sc = -1;
-      q.park_slot = 0; q.up_pm = 0;
-      if (r.psc >= 0) q.ctl |= OP_SCALE;
-      // the previous result is not consumed by this op: park its X in a free slot, else it is
-      // dropped (its consumer re-reads the CLV from HBM and applies P itself)
+      // the previous result is not consumed by this op: its producer parks X in a free slot right after
+      // the push; without a free slot it is dropped (the consumer re-reads the CLV from HBM)
       if (prev != 0xFFFFFFFFu && prev_child < 0 && free_slots)
       {
         const int s = __ffs(free_slots) - 1;
         free_slots &= ~(1u << s);
         where[prev] = prev_off; slot_of[prev] = (unsigned char)s;
-        q.ctl |= OP_PARK; q.park_slot = (unsigned)s;
+        OpRec * prod = reinterpret_cast<OpRec *>(blk + prev_off);
+        prod->ctl |= OP_PARKA; prod->park_off = (unsigned)s * slot_unit;
       }
       free_slots |= consumed_slots;
       // operand A is never the register X (the product is commutative)
       const Operand & A = opd[prev_child == 0 ? 1 : 0];
       const Operand & B = opd[prev_child == 0 ? 0 : 1];
-      q.a_kind = A.kind; q.a_p0 = A.p0; q.a_p1 = A.p1; q.a_p2 = A.p2; q.a_pm = A.pm;
-      q.b_kind = B.kind; q.b_p0 = B.p0; q.b_p1 = B.p1; q.b_p2 = B.p2; q.b_pm = B.pm;
+      OpRec q;
+      q.ctl = (A.kind << OP_AKIND_SHIFT) | (B.kind << OP_BKIND_SHIFT);
+      q.dst_cell = (r.parent - T) * cells_per_buf; q.dsc = r.psc; q.park_off = 0; q.up_pm = 0; q.pad = 0;
+      q.a_sel = A.sel; q.a_off = A.off; q.a_p0 = A.p0; q.a_pm = A.pm; q.a_sc = A.sc;
+      q.b_sel = B.sel; q.b_off = B.off; q.b_p0 = B.p0; q.b_pm = B.pm; q.b_sc = B.sc;
+      if (r.psc >= 0) q.ctl |= OP_SCALE;
       if (prev_child >= 0) q.ctl |= OP_BPREV;
-      if (want_root && r.parent == rootc) { q.ctl |= OP_ROOT; q.root_sc = r.psc; root_done = true; }
+      if (want_root && r.parent == rootc) { q.ctl |= OP_ROOT; root_done = true; }
       const unsigned int off = chunks0 + (unsigned int)((size_t)c_idx * cb) + (unsigned int)sizeof(ChunkHdr) +
                                c_nops * (unsigned int)sizeof(OpRec);
       *reinterpret_cast<OpRec *>(blk + off) = q;
@@ -192,13 +205,17 @@ plan_kernel_blocks(const LocusDev * __restrict__ loci, const unsigned int * __re
       if (c_nops == (unsigned)TREE_CHUNK) close_chunk();
       OpRec q;
       memset(&q, 0, sizeof(q));
-      q.ctl = OP_EVAL | OP_ROOT; q.dsc = -1; q.root_sc = root_sc[bl];
+      unsigned int kind;
+      q.dsc = root_sc[bl]; q.a_sc = root_sc[bl];
       if (rootc < T)
       {
-        if (L.tip_is_dense[rootc]) { q.a_kind = SRC_TIP_DENSE; q.a_p0 = rootc; }
-        else { q.a_kind = SRC_TIP_PACKED; q.a_p0 = rootc >> 3; q.a_p1 = (rootc & 7u) * 4; }
+        q.a_p0 = rootc;
+        if (L.tip_is_dense[rootc]) kind = SRC_TIP_DENSE;
+        else { kind = SRC_TIP_PACKED; q.a_sel = 15u | ((rootc >> 3) << 4) | (((rootc & 7u) * 4) << 8); }
       }
-      else { q.a_kind = SRC_HBM; q.a_p0 = rootc - T; q.a_p2 = (unsigned int)root_sc[bl]; }
+      else { kind = SRC_HBM; q.a_p0 = rootc - T; }
+      q.ctl = OP_EVAL | OP_ROOT | (kind << OP_AKIND_SHIFT);
+      fast = false;
       const unsigned int off = chunks0 + (unsigned int)((size_t)c_idx * cb) + (unsigned int)sizeof(ChunkHdr) +
                                c_nops * (unsigned int)sizeof(OpRec);
       *reinterpret_cast<OpRec *>(blk + off) = q;
@@ -211,7 +228,7 @@ plan_kernel_blocks(const LocusDev * __restrict__ loci, const unsigned int * __re
     H->clv = L.clv; H->tip_dense = L.tip_dense; H->scale = L.scale;
     H->tipwords = reinterpret_cast<const unsigned int *>(L.tip_codes); H->pmat = L.pmat;
     H->clv_stride = L.clv_stride; H->sites = L.sites; H->nops = cnt; H->tip_words = L.tip_words;
-    H->n_chunks = n_chunks;
+    H->n_chunks = n_chunks; H->flags = (fast && n_chunks == 1) ? HDR_FAST : 0u; H->pad0 = 0;
     for (int j = 0; j < 4; ++j) H->freqs[j] = L.freqs[j];
     plan_count[bl] = cnt;
   }
@@ -240,10 +257,10 @@ plan_kernel_blocks(const LocusDev * __restrict__ loci, const unsigned int * __re
       }
       else
       {
-        const unsigned int kind = which == 1 ? q.a_kind : q.b_kind;
+        const unsigned int kind = (q.ctl >> (which == 1 ? OP_AKIND_SHIFT : OP_BKIND_SHIFT)) & 15u;
         if (kind == SRC_TIP_PACKED)
         {
-          const unsigned int s = (which == 1 ? q.a_p2 : q.b_p2) / lut_unit;
+          const unsigned int s = (which == 1 ? q.a_off : q.b_off) / lut_unit;
           const unsigned int pm = which == 1 ? q.a_pm : q.b_pm;
           tipP[((size_t)s * RL + r) * PM_STRIDE + x] = L.pmat[((size_t)pm * RL + r) * 16 + x];
         }

@@ -1,20 +1,24 @@
 // tree_s4.cuh -- the hot kernel: tree-fused Felsenstein pruning for 4 states.
 //
-// One persistent CTA walks a contiguous range of tiles; a tile is TREE_NT cells
+// One persistent CTA walks a contiguous range of tiles; a tile is TREE_NT*CPT cells
 // (cell = pattern*RL + cat, RL = rate categories, a power of two <= 8 so that the RL lanes of a site
-// sit in one warp) of one locus.  For its tile a thread executes the locus' WHOLE planned op list as
-// a stack machine over TRANSFORMED vectors X = P_edge . clv:
+// sit in one warp) of one locus; thread tid owns the CPT cells cell0 + tid + j*TREE_NT (same category).
+// For its cells a thread executes the locus' WHOLE planned op list as a stack machine over
+// TRANSFORMED vectors X = P_edge . clv:
 //   - a packed tip child (4 bits per tip and site, fetched one tile ahead, kept in registers) is one
 //     shared-memory lookup  X = LUT_edge[mask]  (16 masks x 4 doubles per edge and category, built
 //     per staged chunk from the edge's P-matrix);
 //   - an inner child produced earlier in the list is the register-resident X of the previous op or a
 //     shared-memory stack slot -- it is never re-read from HBM;
 //   - parent = X_a * X_b (4 multiplies), stored once with a 256-bit store, then pushed through the
-//     P-matrix of the edge above it (the only 4x4 mat-vec of the op);
+//     P-matrix of the edge above it (the only 4x4 mat-vec of the op; its 16 shared-memory words are
+//     loaded once for the thread's CPT cells);
 //   - per-site rescaling and the root's site log-likelihoods are fused into the same pass.
 // The per-locus program (header, ops, P-matrices) is a contiguous block built by plan_kernel_blocks;
 // the block of the NEXT locus is copied with cp.async into the second stage buffer while the current
 // tile computes, and tile descriptors run two tiles ahead in a small ring.
+// Loci whose ops all use fast operands (HDR_FAST) run tile_fast; anything else (HBM-resident
+// children of partial updates, dense tips, more than 16 tips, root-only evaluation) runs tile_general.
 // HBM traffic per locus is the compulsory (T-1) CLV writes + packed tips + weights + the block
 // (SURVEY.md 8d "B_min").
 //
@@ -32,8 +36,7 @@
 
 namespace bppgpu {
 
-// all views alias the dynamic shared memory; indexing them with integers (no generic pointers)
-// keeps the address arithmetic out of the instruction stream
+// all views alias the dynamic shared memory
 extern __shared__ uint4 s4[];
 extern __shared__ double s8[];
 extern __shared__ unsigned int s1[];
@@ -73,38 +76,11 @@ __device__ __forceinline__ Vec4 matvec_s4(const unsigned int p, const double v0,
   return x;
 }
 
-// cold path: child CLV resident in HBM (partial updates, stack overflow) or a dense tip: load it and
-// apply the edge's P-matrix straight from global memory (L1-cached).  kind/p0/p1/p2 as in OpRec.
-template <int RL, bool EXACT>
-__device__ __noinline__ Vec4 fetch_global(const LocusHdr * H, unsigned int kind, unsigned int p0, unsigned int p1,
-                                          unsigned int p2, unsigned int cell, unsigned int pattern, unsigned int cat,
-                                          unsigned int * sc)
-{
-  double v0, v1, v2, v3;
-  if (kind == SRC_TIP_DENSE) ld256_nc(H->tip_dense + (size_t)p0 * H->clv_stride + (size_t)cell * 4, v0, v1, v2, v3);
-  else ld256(H->clv + (size_t)p0 * H->clv_stride + (size_t)cell * 4, v0, v1, v2, v3);
-  *sc = (kind == SRC_HBM && (int)p2 >= 0) ? H->scale[(size_t)p2 * H->sites + pattern] : 0u;
-  const double2 * __restrict__ p = reinterpret_cast<const double2 *>(H->pmat + ((size_t)p1 * RL + cat) * 16);
-  Vec4 x;
-  x.a = dot4<EXACT>(__ldg(p + 0), __ldg(p + 1), v0, v1, v2, v3);
-  x.b = dot4<EXACT>(__ldg(p + 2), __ldg(p + 3), v0, v1, v2, v3);
-  x.c = dot4<EXACT>(__ldg(p + 4), __ldg(p + 5), v0, v1, v2, v3);
-  x.d = dot4<EXACT>(__ldg(p + 6), __ldg(p + 7), v0, v1, v2, v3);
-  return x;
-}
-
-// cold path: tip word beyond the two register-resident ones (more than 16 tips)
-__device__ __noinline__ unsigned int fetch_tipword(const LocusHdr * H, unsigned int pattern, unsigned int wi)
-{
-  return __ldg(H->tipwords + (size_t)pattern * H->tip_words + wi);
-}
-
-template <int RL>
+template <int RL, int CPT>
 struct S4Layout               // everything in uint4 (16-byte) units
 {
   static constexpr unsigned RW16 = (unsigned)((((size_t)RL * 8 + 15) & ~(size_t)15) / 16);
   static constexpr unsigned CAP = (unsigned)lut_cap(RL);
-  static constexpr unsigned HDR = 0;
   static constexpr unsigned RW = 8;
   static constexpr unsigned CH = RW + RW16;                       // ChunkHdr
   static constexpr unsigned OPS = CH + 1;                         // OpRec[TREE_CHUNK]
@@ -115,20 +91,355 @@ struct S4Layout               // everything in uint4 (16-byte) units
   static constexpr unsigned LUT = 2 * STAGE;                      // [CAP][RL] x 49
   static constexpr unsigned RING = LUT + CAP * RL * 49;           // 4 x (TileDesc 2 + blk 1)
   static constexpr unsigned RED = RING + 12;                      // 32 doubles
-  static constexpr unsigned STACK = RED + 16;                     // [slots][2][TREE_NT] uint4, then [slots][TREE_NT] u32
+  static constexpr unsigned STACK = RED + 16;                     // [slots][CPT*TREE_NT][2] uint4, then [slots][CPT*TREE_NT] u32
+  static constexpr unsigned SLOT = 2 * CPT * TREE_NT;             // uint4 per slot
   __host__ __device__ static constexpr size_t bytes(int slots)
   {
-    return (size_t)STACK * 16 + (size_t)slots * (2 * TREE_NT * 16 + TREE_NT * 4);
+    return (size_t)STACK * 16 + (size_t)slots * ((size_t)SLOT * 16 + CPT * TREE_NT * 4);
   }
 };
 
+// everything a tile function needs to know about the thread's cells
+template <int CPT>
+struct TileCtx
+{
+  unsigned int sb;               // stage buffer base (uint4 units)
+  unsigned int sst1;             // u32 index of the scaler stack
+  unsigned int cat;
+  unsigned int cell[CPT];        // clamped cell index
+  bool valid[CPT];
+  unsigned int tw0[CPT], tw1[CPT], wgt[CPT];
+};
+
+// ------------------------------------------------------------------------------------------------
+// fast path: every operand is a register-resident packed tip, a stack slot or the previous X
+// ------------------------------------------------------------------------------------------------
+template <int RL, bool EXACT, int CPT>
+__device__ __forceinline__ double tile_fast(const TreeParams & prm, const TileCtx<CPT> & tc)
+{
+  using Lay = S4Layout<RL, CPT>;
+  const unsigned int tid = threadIdx.x, lane = tid & 31u;
+  const unsigned int sb = tc.sb;
+  const LocusHdr * H = reinterpret_cast<const LocusHdr *>(&s4[sb]);
+  const unsigned int lut_t = Lay::LUT + tc.cat * 49;
+  const unsigned int stk_t = Lay::STACK + tid * 2;
+  const unsigned int pup_t = sb + Lay::PUP + tc.cat * 9;
+  const unsigned int ops = sb + Lay::OPS;
+  const unsigned int cn = s1[(sb + Lay::CH) * 4];
+  unsigned char * const clv0 = reinterpret_cast<unsigned char *>(H->clv);
+  const unsigned int sites = H->sites;
+
+  double x[CPT][4];
+  unsigned int psc[CPT];
+  double site_sum = 0.0;
+#pragma unroll
+  for (int j = 0; j < CPT; ++j) { x[j][0] = x[j][1] = x[j][2] = x[j][3] = 0.0; psc[j] = 0; }
+
+  for (unsigned int k = 0; k < cn; ++k)
+  {
+    const uint4 w0 = s4[ops + 4 * k], w1 = s4[ops + 4 * k + 1];
+    const unsigned int ctl = w0.x;
+    double o[CPT][4];
+    unsigned int osc[CPT];
+    // ---- operand A (tip lookup or stack slot), then the product with B
+    {
+      const unsigned int amask = w0.z & 15u, ash = (w0.z >> 8) & 31u;
+      const bool aw1 = (w0.z & 16u) != 0;
+      const unsigned int bmask = w1.x & 15u, bsh = (w1.x >> 8) & 31u;
+      const bool bw1 = (w1.x & 16u) != 0;
+#pragma unroll
+      for (int j = 0; j < CPT; ++j)
+      {
+        const unsigned int wa = aw1 ? tc.tw1[j] : tc.tw0[j];
+        const unsigned int ia = (amask ? lut_t : stk_t + j * (2 * TREE_NT)) + w0.w + ((wa >> ash) & amask) * 3;
+        const double2 a0 = as_d2(s4[ia]), a1 = as_d2(s4[ia + 1]);
+        if (ctl & OP_BPREV)
+        {
+          o[j][0] = __dmul_rn(x[j][0], a0.x); o[j][1] = __dmul_rn(x[j][1], a0.y);
+          o[j][2] = __dmul_rn(x[j][2], a1.x); o[j][3] = __dmul_rn(x[j][3], a1.y);
+        }
+        else
+        {
+          const unsigned int wb = bw1 ? tc.tw1[j] : tc.tw0[j];
+          const unsigned int ib = (bmask ? lut_t : stk_t + j * (2 * TREE_NT)) + w1.y + ((wb >> bsh) & bmask) * 3;
+          const double2 b0 = as_d2(s4[ib]), b1 = as_d2(s4[ib + 1]);
+          o[j][0] = __dmul_rn(a0.x, b0.x); o[j][1] = __dmul_rn(a0.y, b0.y);
+          o[j][2] = __dmul_rn(a1.x, b1.x); o[j][3] = __dmul_rn(a1.y, b1.y);
+        }
+        osc[j] = 0;
+      }
+    }
+    // ---- per-site scaling (core_partials.c:720,739-754)
+    if (ctl & OP_SCALE)
+    {
+      const uint4 w2 = s4[ops + 4 * k + 2], w3 = s4[ops + 4 * k + 3];
+      const bool a_slot = ((ctl >> OP_AKIND_SHIFT) & 15u) == SRC_SLOT, b_slot = ((ctl >> OP_BKIND_SHIFT) & 15u) == SRC_SLOT;
+#pragma unroll
+      for (int j = 0; j < CPT; ++j)
+      {
+        unsigned int sc = 0;
+        if (a_slot) sc += s1[tc.sst1 + w2.x * (CPT * TREE_NT) + j * TREE_NT + tid];
+        if (ctl & OP_BPREV) sc += psc[j];
+        else if (b_slot) sc += s1[tc.sst1 + w3.x * (CPT * TREE_NT) + j * TREE_NT + tid];
+        unsigned int below = (o[j][0] < BPPGPU_SCALE_THRESHOLD) & (o[j][1] < BPPGPU_SCALE_THRESHOLD) &
+                             (o[j][2] < BPPGPU_SCALE_THRESHOLD) & (o[j][3] < BPPGPU_SCALE_THRESHOLD);
+#pragma unroll
+        for (int dd = 1; dd < RL; dd <<= 1) below &= __shfl_xor_sync(0xFFFFFFFFu, below, dd);
+        if (below)
+        {
+          o[j][0] = __dmul_rn(o[j][0], BPPGPU_SCALE_FACTOR); o[j][1] = __dmul_rn(o[j][1], BPPGPU_SCALE_FACTOR);
+          o[j][2] = __dmul_rn(o[j][2], BPPGPU_SCALE_FACTOR); o[j][3] = __dmul_rn(o[j][3], BPPGPU_SCALE_FACTOR);
+          sc += 1;
+        }
+        osc[j] = sc;
+        if (tc.valid[j] && tc.cat == 0) H->scale[(size_t)(int)w1.z * sites + tc.cell[j] / RL] = sc;
+      }
+    }
+    // ---- the CLV goes to HBM exactly once
+#pragma unroll
+    for (int j = 0; j < CPT; ++j)
+      if (tc.valid[j])
+        st256(reinterpret_cast<double *>(clv0 + (((size_t)w0.y + tc.cell[j]) << 5)), o[j][0], o[j][1], o[j][2], o[j][3]);
+    // ---- push through the edge above: this X is what the parent's op consumes
+    if (ctl & OP_PUSH)
+    {
+      const unsigned int p = pup_t + k * (RL * 9);
+#pragma unroll
+      for (int h = 0; h < 4; ++h)
+      {
+        const double2 pa = as_d2(s4[p + 2 * h]), pb = as_d2(s4[p + 2 * h + 1]);
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) x[j][h] = dot4<EXACT>(pa, pb, o[j][0], o[j][1], o[j][2], o[j][3]);
+      }
+#pragma unroll
+      for (int j = 0; j < CPT; ++j) psc[j] = osc[j];
+      if (ctl & OP_PARKA)
+      {
+        const unsigned int po = w1.w;
+#pragma unroll
+        for (int j = 0; j < CPT; ++j)
+        {
+          s4[stk_t + j * (2 * TREE_NT) + po] = as_u4(x[j][0], x[j][1]);
+          s4[stk_t + j * (2 * TREE_NT) + po + 1] = as_u4(x[j][2], x[j][3]);
+          if (ctl & OP_SCALE) s1[tc.sst1 + (po / Lay::SLOT) * (CPT * TREE_NT) + j * TREE_NT + tid] = psc[j];
+        }
+      }
+    }
+    if (ctl & OP_ROOT)
+    {
+      const double f0 = H->freqs[0], f1 = H->freqs[1], f2 = H->freqs[2], f3 = H->freqs[3];
+#pragma unroll
+      for (int j = 0; j < CPT; ++j)
+      {
+        const double tr = __dadd_rn(__dadd_rn(__dmul_rn(f0, o[j][0]), __dmul_rn(f1, o[j][1])),
+                                    __dadd_rn(__dmul_rn(f2, o[j][2]), __dmul_rn(f3, o[j][3])));
+        double term = 0.0;
+#pragma unroll
+        for (int r = 0; r < RL; ++r)
+        {
+          const double v = __shfl_sync(0xFFFFFFFFu, tr, (lane & ~(unsigned)(RL - 1)) + r);
+          term = __dadd_rn(term, __dmul_rn(v, s8[(sb + Lay::RW) * 2 + r]));
+        }
+        double s;
+        if (prm.persite_mode == 2) s = term;
+        else
+        {
+          s = log(term);
+          if (osc[j]) s = __dadd_rn(s, __dmul_rn((double)osc[j], prm.log_threshold));
+          s = __dmul_rn(s, (double)tc.wgt[j]);
+        }
+        if (tc.valid[j] && tc.cat == 0)
+        {
+          site_sum += s;
+          if (prm.persite) prm.persite[tc.cell[j] / RL] = s;
+        }
+      }
+    }
+  }
+  return site_sum;
+}
+
+// ------------------------------------------------------------------------------------------------
+// general path: any operand kind, any number of chunks; one cell at a time, correctness first
+// ------------------------------------------------------------------------------------------------
 template <int RL, bool EXACT>
-__global__ void __launch_bounds__(TREE_NT, 3)
+__device__ __forceinline__ Vec4 load_global_x(const LocusHdr * H, unsigned int kind, unsigned int p0, unsigned int pm,
+                                              int scidx, unsigned int cell, unsigned int cat, unsigned int & sc)
+{
+  double v0, v1, v2, v3;
+  if (kind == SRC_TIP_DENSE) ld256_nc(H->tip_dense + (size_t)p0 * H->clv_stride + (size_t)cell * 4, v0, v1, v2, v3);
+  else ld256(H->clv + (size_t)p0 * H->clv_stride + (size_t)cell * 4, v0, v1, v2, v3);
+  sc = (kind == SRC_HBM && scidx >= 0) ? H->scale[(size_t)scidx * H->sites + cell / RL] : 0u;
+  const double2 * __restrict__ p = reinterpret_cast<const double2 *>(H->pmat + ((size_t)pm * RL + cat) * 16);
+  Vec4 x;
+  x.a = dot4<EXACT>(__ldg(p + 0), __ldg(p + 1), v0, v1, v2, v3);
+  x.b = dot4<EXACT>(__ldg(p + 2), __ldg(p + 3), v0, v1, v2, v3);
+  x.c = dot4<EXACT>(__ldg(p + 4), __ldg(p + 5), v0, v1, v2, v3);
+  x.d = dot4<EXACT>(__ldg(p + 6), __ldg(p + 7), v0, v1, v2, v3);
+  return x;
+}
+
+// One chunk of ops for cell slot j of the thread.  X / psc persist across chunks in xs / pscs.
+template <int RL, bool EXACT, int CPT>
+__device__ __noinline__ double chunk_general(const TreeParams prm, unsigned int sb, unsigned int sst1, unsigned int j,
+                                             unsigned int cell, bool valid, unsigned int cat, unsigned int tw0,
+                                             unsigned int tw1, unsigned int wgt, double * xs, unsigned int * pscs)
+{
+  using Lay = S4Layout<RL, CPT>;
+  const unsigned int tid = threadIdx.x, lane = tid & 31u;
+  const LocusHdr * H = reinterpret_cast<const LocusHdr *>(&s4[sb]);
+  const unsigned int pattern = cell / RL;
+  const unsigned int lut_t = Lay::LUT + cat * 49;
+  const unsigned int stk_t = Lay::STACK + tid * 2 + j * (2 * TREE_NT);
+  const unsigned int ops = sb + Lay::OPS;
+  const unsigned int cn = s1[(sb + Lay::CH) * 4];
+  double x0 = xs[0], x1 = xs[1], x2 = xs[2], x3 = xs[3];
+  unsigned int psc = *pscs;
+  double site_sum = 0.0;
+
+  for (unsigned int k = 0; k < cn; ++k)
+  {
+    const uint4 w0 = s4[ops + 4 * k], w1 = s4[ops + 4 * k + 1], w2 = s4[ops + 4 * k + 2], w3 = s4[ops + 4 * k + 3];
+    const unsigned int ctl = w0.x;
+    auto tipmask = [&](unsigned int sel, unsigned int tip) -> unsigned int
+    {
+      unsigned int word = (sel & 16u) ? tw1 : tw0;
+      if (tip >= 16) word = __ldg(H->tipwords + (size_t)pattern * H->tip_words + (tip >> 3));
+      return (word >> ((tip & 7u) * 4)) & 15u;
+    };
+    auto fetch = [&](unsigned int kind, unsigned int sel, unsigned int off, unsigned int p0, unsigned int pm, int scidx,
+                     unsigned int & sc) -> Vec4
+    {
+      Vec4 r;
+      if (kind == SRC_TIP_PACKED)
+      {
+        const unsigned int li = lut_t + off + tipmask(sel, p0) * 3;
+        const double2 u = as_d2(s4[li]), w = as_d2(s4[li + 1]);
+        r.a = u.x; r.b = u.y; r.c = w.x; r.d = w.y; sc = 0;
+      }
+      else if (kind == SRC_SLOT)
+      {
+        const double2 u = as_d2(s4[stk_t + off]), w = as_d2(s4[stk_t + off + 1]);
+        r.a = u.x; r.b = u.y; r.c = w.x; r.d = w.y;
+        sc = s1[sst1 + p0 * (CPT * TREE_NT) + j * TREE_NT + tid];
+      }
+      else r = load_global_x<RL, EXACT>(H, kind, p0, pm, scidx, cell, cat, sc);
+      return r;
+    };
+    const unsigned int akind = (ctl >> OP_AKIND_SHIFT) & 15u, bkind = (ctl >> OP_BKIND_SHIFT) & 15u;
+    double o0, o1, o2, o3;
+    unsigned int osc = 0;
+    if (ctl & OP_EVAL)
+    {
+      // root CLV that this list did not produce: read it (no P applied)
+      if (akind == SRC_TIP_PACKED)
+      {
+        const unsigned int mask = tipmask(w0.z, w2.x);
+        o0 = (double)(mask & 1u); o1 = (double)((mask >> 1) & 1u); o2 = (double)((mask >> 2) & 1u); o3 = (double)((mask >> 3) & 1u);
+      }
+      else if (akind == SRC_TIP_DENSE) ld256_nc(H->tip_dense + (size_t)w2.x * H->clv_stride + (size_t)cell * 4, o0, o1, o2, o3);
+      else
+      {
+        ld256(H->clv + (size_t)w2.x * H->clv_stride + (size_t)cell * 4, o0, o1, o2, o3);
+        if ((int)w1.z >= 0) osc = H->scale[(size_t)(int)w1.z * H->sites + pattern];
+      }
+    }
+    else
+    {
+      unsigned int asc = 0, bsc = 0;
+      const Vec4 a = fetch(akind, w0.z, w0.w, w2.x, w2.y, (int)w2.z, asc);
+      if (ctl & OP_BPREV)
+      {
+        o0 = __dmul_rn(x0, a.a); o1 = __dmul_rn(x1, a.b); o2 = __dmul_rn(x2, a.c); o3 = __dmul_rn(x3, a.d);
+        bsc = psc;
+      }
+      else
+      {
+        const Vec4 b = fetch(bkind, w1.x, w1.y, w3.x, w3.y, (int)w3.z, bsc);
+        o0 = __dmul_rn(a.a, b.a); o1 = __dmul_rn(a.b, b.b); o2 = __dmul_rn(a.c, b.c); o3 = __dmul_rn(a.d, b.d);
+      }
+      if (ctl & OP_SCALE)
+      {
+        osc = asc + bsc;
+        unsigned int below = (o0 < BPPGPU_SCALE_THRESHOLD) & (o1 < BPPGPU_SCALE_THRESHOLD) &
+                             (o2 < BPPGPU_SCALE_THRESHOLD) & (o3 < BPPGPU_SCALE_THRESHOLD);
+#pragma unroll
+        for (int dd = 1; dd < RL; dd <<= 1) below &= __shfl_xor_sync(0xFFFFFFFFu, below, dd);
+        if (below)
+        {
+          o0 = __dmul_rn(o0, BPPGPU_SCALE_FACTOR); o1 = __dmul_rn(o1, BPPGPU_SCALE_FACTOR);
+          o2 = __dmul_rn(o2, BPPGPU_SCALE_FACTOR); o3 = __dmul_rn(o3, BPPGPU_SCALE_FACTOR);
+          osc += 1;
+        }
+        if (valid && cat == 0) H->scale[(size_t)(int)w1.z * H->sites + pattern] = osc;
+      }
+      if (valid) st256(H->clv + (((size_t)w0.y + cell) << 2), o0, o1, o2, o3);
+      if (ctl & OP_PUSH)
+      {
+        const Vec4 x = matvec_s4<EXACT>(sb + Lay::PUP + (k * RL + cat) * 9, o0, o1, o2, o3);
+        x0 = x.a; x1 = x.b; x2 = x.c; x3 = x.d; psc = osc;
+        if (ctl & OP_PARKA)
+        {
+          s4[stk_t + w1.w] = as_u4(x0, x1);
+          s4[stk_t + w1.w + 1] = as_u4(x2, x3);
+          s1[sst1 + (w1.w / Lay::SLOT) * (CPT * TREE_NT) + j * TREE_NT + tid] = psc;
+        }
+      }
+    }
+    if (ctl & OP_ROOT)
+    {
+      const double tr = __dadd_rn(__dadd_rn(__dmul_rn(H->freqs[0], o0), __dmul_rn(H->freqs[1], o1)),
+                                  __dadd_rn(__dmul_rn(H->freqs[2], o2), __dmul_rn(H->freqs[3], o3)));
+      double term = 0.0;
+#pragma unroll
+      for (int r = 0; r < RL; ++r)
+      {
+        const double v = __shfl_sync(0xFFFFFFFFu, tr, (lane & ~(unsigned)(RL - 1)) + r);
+        term = __dadd_rn(term, __dmul_rn(v, s8[(sb + Lay::RW) * 2 + r]));
+      }
+      unsigned int rsc = osc;
+      if (ctl & OP_EVAL) rsc = ((int)w1.z >= 0) ? osc : 0;
+      double s;
+      if (prm.persite_mode == 2) s = term;
+      else
+      {
+        s = log(term);
+        if (rsc) s = __dadd_rn(s, __dmul_rn((double)rsc, prm.log_threshold));
+        s = __dmul_rn(s, (double)wgt);
+      }
+      if (valid && cat == 0)
+      {
+        site_sum += s;
+        if (prm.persite) prm.persite[pattern] = s;
+      }
+    }
+  }
+  xs[0] = x0; xs[1] = x1; xs[2] = x2; xs[3] = x3; *pscs = psc;
+  return site_sum;
+}
+
+// LUT[s][cat][mask] = P_tip-edge . bits(mask), same operation order as the mat-vec
+template <int RL, bool EXACT, int CPT>
+__device__ __forceinline__ void build_lut(unsigned int sb)
+{
+  using Lay = S4Layout<RL, CPT>;
+  const unsigned int entries = s1[(sb + Lay::CH) * 4 + 1] * RL * 16;       // ChunkHdr.ntips
+  for (unsigned int e = threadIdx.x; e < entries; e += TREE_NT)
+  {
+    const unsigned int mask = e & 15u, sc = e >> 4;      // sc = slot*RL + cat
+    const Vec4 v = matvec_s4<EXACT>(sb + Lay::TIPP + sc * 9, (double)(mask & 1u), (double)((mask >> 1) & 1u),
+                                    (double)((mask >> 2) & 1u), (double)((mask >> 3) & 1u));
+    s4[Lay::LUT + sc * 49 + mask * 3] = as_u4(v.a, v.b);
+    s4[Lay::LUT + sc * 49 + mask * 3 + 1] = as_u4(v.c, v.d);
+  }
+}
+
+template <int RL, bool EXACT, int CPT>
+__global__ void __launch_bounds__(TREE_NT, CPT == 1 ? 3 : 2)
 tree_kernel_s4(const TreeParams prm)
 {
-  using Lay = S4Layout<RL>;
+  using Lay = S4Layout<RL, CPT>;
   const unsigned int tid = threadIdx.x, lane = tid & 31u;
-  const unsigned int SST1 = (Lay::STACK + (unsigned)prm.n_slots * 2 * TREE_NT) * 4;      // u32 index of the scaler stack
 
   const unsigned int t_begin = (unsigned int)(((unsigned long long)prm.n_tiles * blockIdx.x) / gridDim.x);
   const unsigned int t_end = (unsigned int)(((unsigned long long)prm.n_tiles * (blockIdx.x + 1)) / gridDim.x);
@@ -148,6 +459,18 @@ tree_kernel_s4(const TreeParams prm)
     const uint4 * src = reinterpret_cast<const uint4 *>(prm.blocks + blk);
     for (unsigned int w = tid; w < Lay::STAGE; w += TREE_NT) cp_async16(&s4[buf * Lay::STAGE + w], src + w);
   };
+  auto load_tips = [&](const TileDesc & d, unsigned int * tw0, unsigned int * tw1, unsigned int * wgt)
+  {
+#pragma unroll
+    for (int j = 0; j < CPT; ++j)
+    {
+      const unsigned int craw = d.cell0 + tid + j * TREE_NT;
+      const unsigned int pat = (craw < d.ncell ? craw : d.ncell - 1) / RL;
+      tw0[j] = __ldg(d.tipwords + (size_t)pat * d.tip_words);
+      tw1[j] = (d.tip_words > 1) ? __ldg(d.tipwords + (size_t)pat * d.tip_words + 1) : 0u;
+      wgt[j] = __ldg(d.weights + pat);
+    }
+  };
 
   ring_fetch(t_begin);
   ring_fetch(t_begin + 1);
@@ -155,16 +478,10 @@ tree_kernel_s4(const TreeParams prm)
   cp_async_wait_all();
   __syncthreads();
 
-  // tips / weight of the first tile
-  unsigned int tw0 = 0, tw1 = 0, wgt = 0;
-  {
-    const TileDesc d = *reinterpret_cast<const TileDesc *>(&s4[Lay::RING + (t_begin & 3u) * 3]);
-    const unsigned int craw = d.cell0 + tid;
-    const unsigned int pat = (craw < d.ncell ? craw : d.ncell - 1) / RL;
-    tw0 = __ldg(d.tipwords + (size_t)pat * d.tip_words);
-    if (d.tip_words > 1) tw1 = __ldg(d.tipwords + (size_t)pat * d.tip_words + 1);
-    wgt = __ldg(d.weights + pat);
-  }
+  TileCtx<CPT> tc;
+  tc.sst1 = (Lay::STACK + (unsigned)prm.n_slots * Lay::SLOT) * 4;
+  load_tips(*reinterpret_cast<const TileDesc *>(&s4[Lay::RING + (t_begin & 3u) * 3]), tc.tw0, tc.tw1, tc.wgt);
+
   unsigned int buf = 0;
   unsigned int staged_locus = 0xFFFFFFFFu;      // locus whose header + chunk 0 + LUT are valid in stage[buf]
   unsigned int prefetched_locus = 0xFFFFFFFFu;  // locus whose block is (being) copied into stage[buf ^ 1]
@@ -174,7 +491,7 @@ tree_kernel_s4(const TreeParams prm)
     const unsigned int rs = Lay::RING + (t & 3u) * 3;
     const TileDesc d = *reinterpret_cast<const TileDesc *>(&s4[rs]);
     const unsigned long long blk = *reinterpret_cast<const unsigned long long *>(&s4[rs + 2]);
-    bool build_lut = false;
+    // ---- make the locus block current: either it was prefetched into the other buffer, or load it now
     if (d.locus != staged_locus)
     {
       if (d.locus == prefetched_locus) buf ^= 1u;          // landed: wait_all + barrier at the end of the last tile
@@ -186,24 +503,23 @@ tree_kernel_s4(const TreeParams prm)
         __syncthreads();
       }
       prefetched_locus = 0xFFFFFFFFu;
-      build_lut = true;
+      build_lut<RL, EXACT, CPT>(buf * Lay::STAGE);
+      __syncthreads();
+      staged_locus = d.locus;
     }
     // ---- prefetch: tips/weight of tile t+1 -> registers; block of the next locus -> other stage buffer;
     //      descriptor of tile t+2 -> ring
-    unsigned int ntw0 = 0, ntw1 = 0, nwgt = 0;
+    unsigned int ntw0[CPT], ntw1[CPT], nwgt[CPT];
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) { ntw0[j] = ntw1[j] = nwgt[j] = 0; }
     if (t + 1 < t_end)
     {
       const unsigned int rn = Lay::RING + ((t + 1) & 3u) * 3;
       const TileDesc dn = *reinterpret_cast<const TileDesc *>(&s4[rn]);
-      const unsigned int craw = dn.cell0 + tid;
-      const unsigned int pat = (craw < dn.ncell ? craw : dn.ncell - 1) / RL;
-      ntw0 = __ldg(dn.tipwords + (size_t)pat * dn.tip_words);
-      if (dn.tip_words > 1) ntw1 = __ldg(dn.tipwords + (size_t)pat * dn.tip_words + 1);
-      nwgt = __ldg(dn.weights + pat);
+      load_tips(dn, ntw0, ntw1, nwgt);
       if (dn.locus != d.locus && dn.locus != prefetched_locus)
       {
-        const unsigned long long nblk = *reinterpret_cast<const unsigned long long *>(&s4[rn + 2]);
-        stage_fetch(buf ^ 1u, nblk);
+        stage_fetch(buf ^ 1u, *reinterpret_cast<const unsigned long long *>(&s4[rn + 2]));
         prefetched_locus = dn.locus;
       }
     }
@@ -212,179 +528,50 @@ tree_kernel_s4(const TreeParams prm)
 
     const unsigned int sb = buf * Lay::STAGE;
     const LocusHdr * H = reinterpret_cast<const LocusHdr *>(&s4[sb]);
-
-    const unsigned int ncell = d.ncell;
-    const unsigned int cell_raw = d.cell0 + tid;
-    const bool valid = cell_raw < ncell;
-    const unsigned int cell = valid ? cell_raw : ncell - 1;
-    const unsigned int pattern = cell / RL;
-    const unsigned int cat = cell % RL;
-    const unsigned int lut_t = Lay::LUT + cat * 49;
-    const unsigned int stk_t = Lay::STACK + tid;
-
-    double x0 = 0, x1 = 0, x2 = 0, x3 = 0;    // X of the previous op's result
-    unsigned int psc = 0;
-    double site_val = 0.0;
-    const unsigned int n_chunks = H->n_chunks;
-    unsigned char * const clv_cell = reinterpret_cast<unsigned char *>(H->clv) + ((size_t)cell << 5);
-
-    for (unsigned int c = 0; c < n_chunks; ++c)
+    tc.sb = sb;
+    tc.cat = (d.cell0 + tid) % RL;
+#pragma unroll
+    for (int j = 0; j < CPT; ++j)
     {
-      if (c > 0)
-      {
-        // trees with more ops than one chunk holds: later chunks are staged in place, synchronously
-        __syncthreads();
-        const uint4 * src = reinterpret_cast<const uint4 *>(prm.blocks + blk) + Lay::CH + (size_t)c * Lay::CHUNK;
-        for (unsigned int w = tid; w < Lay::CHUNK; w += TREE_NT) s4[sb + Lay::CH + w] = __ldg(src + w);
-        __syncthreads();
-        build_lut = true;
-      }
-      if (build_lut)
-      {
-        // LUT[s][cat][mask] = P_tip-edge . bits(mask), same operation order as the mat-vec
-        const unsigned int entries = s1[(sb + Lay::CH) * 4 + 1] * RL * 16;       // ChunkHdr.ntips
-        for (unsigned int e = tid; e < entries; e += TREE_NT)
-        {
-          const unsigned int mask = e & 15u, sc = e >> 4;      // sc = slot*RL + cat
-          const Vec4 v = matvec_s4<EXACT>(sb + Lay::TIPP + sc * 9, (double)(mask & 1u), (double)((mask >> 1) & 1u),
-                                          (double)((mask >> 2) & 1u), (double)((mask >> 3) & 1u));
-          s4[Lay::LUT + sc * 49 + mask * 3] = as_u4(v.a, v.b);
-          s4[Lay::LUT + sc * 49 + mask * 3 + 1] = as_u4(v.c, v.d);
-        }
-        __syncthreads();
-        build_lut = false;
-        staged_locus = (c == 0) ? d.locus : 0xFFFFFFFFu;     // a later chunk overwrote chunk 0
-      }
-      const unsigned int cn = s1[(sb + Lay::CH) * 4];         // ChunkHdr.nops
-      const unsigned int ops = sb + Lay::OPS;
-      const unsigned int pup_t = sb + Lay::PUP + cat * 9;
+      const unsigned int craw = d.cell0 + tid + j * TREE_NT;
+      tc.valid[j] = craw < d.ncell;
+      tc.cell[j] = tc.valid[j] ? craw : d.ncell - 1;
+    }
 
-      for (unsigned int k = 0; k < cn; ++k)
-      {
-        const uint4 w0 = s4[ops + 4 * k], w1 = s4[ops + 4 * k + 1], w2 = s4[ops + 4 * k + 2];
-        const unsigned int ctl = w0.x;
-        if (ctl & OP_PARK)
-        {
-          const unsigned int ps = s1[(ops + 4 * k + 3) * 4];
-          s4[stk_t + ps * (2 * TREE_NT)] = as_u4(x0, x1);
-          s4[stk_t + ps * (2 * TREE_NT) + TREE_NT] = as_u4(x2, x3);
-          s1[SST1 + ps * TREE_NT + tid] = psc;
-        }
-        // X of an operand that is not the register-resident previous result
-        auto fetch = [&](unsigned int kind, unsigned int p0, unsigned int p1, unsigned int p2, unsigned int & sc) -> Vec4
-        {
-          Vec4 r;
-          if (kind == SRC_TIP_PACKED)
-          {
-            unsigned int word = p0 ? tw1 : tw0;
-            if (p0 >= 2) word = fetch_tipword(H, pattern, p0);
-            const unsigned int mask = (word >> p1) & 15u;
-            const unsigned int li = lut_t + p2 + mask * 3;
-            const double2 u = as_d2(s4[li]), w = as_d2(s4[li + 1]);
-            r.a = u.x; r.b = u.y; r.c = w.x; r.d = w.y; sc = 0;
-          }
-          else if (kind == SRC_SLOT)
-          {
-            const double2 u = as_d2(s4[stk_t + p0 * (2 * TREE_NT)]), w = as_d2(s4[stk_t + p0 * (2 * TREE_NT) + TREE_NT]);
-            r.a = u.x; r.b = u.y; r.c = w.x; r.d = w.y; sc = s1[SST1 + p0 * TREE_NT + tid];
-          }
-          else r = fetch_global<RL, EXACT>(H, kind, p0, p1, p2, cell, pattern, cat, &sc);
-          return r;
-        };
-
-        double o0, o1, o2, o3;
-        unsigned int osc = 0;
-        if (ctl & OP_EVAL)
-        {
-          // root CLV that this list did not produce: read it (no P applied)
-          const unsigned int kind = w0.z, p0 = w0.w;
-          if (kind == SRC_TIP_PACKED)
-          {
-            unsigned int word = p0 ? tw1 : tw0;
-            if (p0 >= 2) word = fetch_tipword(H, pattern, p0);
-            const unsigned int mask = (word >> w1.x) & 15u;
-            o0 = (double)(mask & 1u); o1 = (double)((mask >> 1) & 1u); o2 = (double)((mask >> 2) & 1u); o3 = (double)((mask >> 3) & 1u);
-          }
-          else if (kind == SRC_TIP_DENSE) ld256_nc(H->tip_dense + (size_t)p0 * H->clv_stride + (size_t)cell * 4, o0, o1, o2, o3);
-          else
-          {
-            ld256(H->clv + (size_t)p0 * H->clv_stride + (size_t)cell * 4, o0, o1, o2, o3);
-            if ((int)w1.y >= 0) osc = H->scale[(size_t)w1.y * H->sites + pattern];
-          }
-        }
-        else
-        {
-          unsigned int asc = 0, bsc = 0;
-          const Vec4 a = fetch(w0.z, w0.w, w1.x, w1.y, asc);
-          if (ctl & OP_BPREV)
-          {
-            o0 = __dmul_rn(x0, a.a); o1 = __dmul_rn(x1, a.b); o2 = __dmul_rn(x2, a.c); o3 = __dmul_rn(x3, a.d);
-            bsc = psc;
-          }
-          else
-          {
-            const Vec4 b = fetch(w1.z, w1.w, w2.x, w2.y, bsc);
-            o0 = __dmul_rn(a.a, b.a); o1 = __dmul_rn(a.b, b.b); o2 = __dmul_rn(a.c, b.c); o3 = __dmul_rn(a.d, b.d);
-          }
-          // ---- per-site scaling (core_partials.c:720,739-754)
-          if (ctl & OP_SCALE)
-          {
-            osc = asc + bsc;
-            unsigned int below = (o0 < BPPGPU_SCALE_THRESHOLD) & (o1 < BPPGPU_SCALE_THRESHOLD) &
-                                 (o2 < BPPGPU_SCALE_THRESHOLD) & (o3 < BPPGPU_SCALE_THRESHOLD);
+    double site_sum;
+    if (H->flags & HDR_FAST) site_sum = tile_fast<RL, EXACT, CPT>(prm, tc);
+    else
+    {
+      // general path: chunk by chunk (later chunks are staged in place, synchronously), cell by cell
+      double xs[CPT][4];
+      unsigned int pscs[CPT];
 #pragma unroll
-            for (int dd = 1; dd < RL; dd <<= 1) below &= __shfl_xor_sync(0xFFFFFFFFu, below, dd);
-            if (below)
-            {
-              o0 = __dmul_rn(o0, BPPGPU_SCALE_FACTOR); o1 = __dmul_rn(o1, BPPGPU_SCALE_FACTOR);
-              o2 = __dmul_rn(o2, BPPGPU_SCALE_FACTOR); o3 = __dmul_rn(o3, BPPGPU_SCALE_FACTOR);
-              osc += 1;
-            }
-            if (valid && cat == 0) H->scale[(size_t)(int)w2.z * H->sites + pattern] = osc;
-          }
-          if (valid) st256(reinterpret_cast<double *>(clv_cell + ((size_t)w0.y << 5)), o0, o1, o2, o3);
-          // ---- push through the edge above: this X is what the parent's op consumes
-          if (ctl & OP_PUSH)
-          {
-            const Vec4 x = matvec_s4<EXACT>(pup_t + k * (RL * 9), o0, o1, o2, o3);
-            x0 = x.a; x1 = x.b; x2 = x.c; x3 = x.d; psc = osc;
-          }
-        }
-
-        if (ctl & OP_ROOT)
+      for (int j = 0; j < CPT; ++j) { xs[j][0] = xs[j][1] = xs[j][2] = xs[j][3] = 0.0; pscs[j] = 0; }
+      site_sum = 0.0;
+      const unsigned int n_chunks = H->n_chunks;
+      for (unsigned int c = 0; c < n_chunks; ++c)
+      {
+        if (c > 0)
         {
-          const double tr = __dadd_rn(__dadd_rn(__dmul_rn(H->freqs[0], o0), __dmul_rn(H->freqs[1], o1)),
-                                      __dadd_rn(__dmul_rn(H->freqs[2], o2), __dmul_rn(H->freqs[3], o3)));
-          double term = 0.0;
-#pragma unroll
-          for (int j = 0; j < RL; ++j)
-          {
-            const double v = __shfl_sync(0xFFFFFFFFu, tr, (lane & ~(unsigned)(RL - 1)) + j);
-            term = __dadd_rn(term, __dmul_rn(v, s8[(sb + Lay::RW) * 2 + j]));
-          }
-          unsigned int rsc = osc;
-          if (ctl & OP_EVAL) rsc = ((int)w2.w >= 0) ? osc : 0;
-          double s;
-          if (prm.persite_mode == 2) s = term;
-          else
-          {
-            s = log(term);
-            if (rsc) s = __dadd_rn(s, __dmul_rn((double)rsc, prm.log_threshold));
-            s = __dmul_rn(s, (double)wgt);
-          }
-          if (valid && cat == 0)
-          {
-            site_val = s;
-            if (prm.persite) prm.persite[pattern] = s;
-          }
+          __syncthreads();
+          const uint4 * src = reinterpret_cast<const uint4 *>(prm.blocks + blk) + Lay::CH + (size_t)c * Lay::CHUNK;
+          for (unsigned int w = tid; w < Lay::CHUNK; w += TREE_NT) s4[sb + Lay::CH + w] = __ldg(src + w);
+          __syncthreads();
+          build_lut<RL, EXACT, CPT>(sb);
+          __syncthreads();
+          staged_locus = 0xFFFFFFFFu;          // chunk 0 is gone
         }
+#pragma unroll
+        for (int j = 0; j < CPT; ++j)
+          site_sum += chunk_general<RL, EXACT, CPT>(prm, sb, tc.sst1, j, tc.cell[j], tc.valid[j], tc.cat, tc.tw0[j],
+                                                    tc.tw1[j], tc.wgt[j], xs[j], &pscs[j]);
       }
     }
 
     // ---- deterministic tile reduction of the weighted site lnL values
     if (prm.tile_partial)
     {
-      double v = site_val;
+      double v = site_sum;
 #pragma unroll
       for (int dd = 16; dd > 0; dd >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, dd);
       if (lane == 0) s8[Lay::RED * 2 + (t & 1u) * 16 + (tid >> 5)] = v;
@@ -397,7 +584,8 @@ tree_kernel_s4(const TreeParams prm)
       for (unsigned int w = 0; w < (TREE_NT >> 5); ++w) acc += s8[Lay::RED * 2 + (t & 1u) * 16 + w];
       prm.tile_partial[t] = acc;
     }
-    tw0 = ntw0; tw1 = ntw1; wgt = nwgt;
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) { tc.tw0[j] = ntw0[j]; tc.tw1[j] = ntw1[j]; tc.wgt[j] = nwgt[j]; }
   }
 }
 
