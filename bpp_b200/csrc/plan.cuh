@@ -65,8 +65,9 @@ __global__ void plan_kernel_flat(const LocusDev * __restrict__ loci, const unsig
 // One WARP per locus: lane 0 plans sequentially, then all lanes gather the P-matrices the kernel
 // needs (Pup of every pushed op, tipP of every packed tip child) into the block, already in the
 // kernel's padded shared-memory layout, and publish the block offset of every tile of the locus.
-// scratch per locus: [unsigned int where[clv_buffers]]: byte offset (within the block) of the OpRec
-// that produced the buffer and still holds its X in a slot, 0 = HBM only; [unsigned char slot_of[clv_buffers]].
+// scratch per locus (global memory, only for loci too big for the shared-memory path):
+// [unsigned int where[clv_buffers]]: 1 + op slot of the OpRec that produced the buffer and still holds its X
+// in a stack slot, 0 = HBM only; [unsigned char slot_of[clv_buffers]].
 struct Operand { unsigned int kind, sel, off, p0, pm; int sc; };
 
 __global__ void __launch_bounds__(128)
@@ -85,7 +86,7 @@ plan_kernel_blocks(const LocusDev * __restrict__ loci, const unsigned int * __re
   if (bl >= n_loci) return;
   const LocusDev & L = loci[batch_locus[bl]];
   const unsigned int first = op_off[bl], n = op_off[bl + 1] - first;
-  const RawOp * __restrict__ o = ops + first;
+  const RawOp * o = ops + first;
   unsigned char * blk = blocks + blk_off[bl];
   const size_t cb = chunk_bytes(RL);
   const unsigned int chunks0 = (unsigned int)(sizeof(LocusHdr) + rw_bytes(RL));
@@ -95,6 +96,26 @@ plan_kernel_blocks(const LocusDev * __restrict__ loci, const unsigned int * __re
   const unsigned int T = L.tips;
   unsigned int n_chunks = 0, cnt = 0;
 
+  // small loci (the common case) are planned entirely in shared memory: raw ops, the producer map and
+  // the OpRecs under construction; the block in HBM is written once, coalesced, at the end
+  constexpr unsigned int SM_OPS = 2 * TREE_CHUNK, SM_BUF = 64;
+  __shared__ __align__(16) RawOp s_raw[4][SM_OPS];
+  __shared__ __align__(16) OpRec s_rec[4][SM_OPS];
+  __shared__ unsigned int s_where[4][SM_BUF];
+  __shared__ unsigned char s_slot[4][SM_BUF];
+  const unsigned int wib = threadIdx.x >> 5;
+  // every closed chunk holds >= m ops, so a list of n (+1 eval-only) ops needs <= n/m + 1 chunks
+  const unsigned int m_ops = (cap / 2 < (unsigned)TREE_CHUNK) ? (cap / 2 ? cap / 2 : 1u) : (unsigned)TREE_CHUNK;
+  const bool small = (n + 1 <= SM_OPS) && (L.clv_buffers <= SM_BUF) && (n / m_ops + 1 <= SM_OPS / TREE_CHUNK);
+  if (small)
+  {
+    const uint4 * src = reinterpret_cast<const uint4 *>(o);
+    uint4 * dst = reinterpret_cast<uint4 *>(s_raw[wib]);
+    for (unsigned int w = lane; w < n * 2; w += 32) dst[w] = src[w];
+    __syncwarp();
+    o = s_raw[wib];
+  }
+
   for (unsigned int t = tile_first[bl] + lane; t < tile_first[bl + 1]; t += 32)
   {
     tile_blk[2 * (size_t)t] = blk_off[bl];
@@ -103,8 +124,14 @@ plan_kernel_blocks(const LocusDev * __restrict__ loci, const unsigned int * __re
 
   if (lane == 0)
   {
-    unsigned int * where = reinterpret_cast<unsigned int *>(scratch + scratch_off[bl]);
-    unsigned char * slot_of = reinterpret_cast<unsigned char *>(where + L.clv_buffers);
+    unsigned int * where = small ? s_where[wib] : reinterpret_cast<unsigned int *>(scratch + scratch_off[bl]);
+    unsigned char * slot_of = small ? s_slot[wib] : reinterpret_cast<unsigned char *>(where + L.clv_buffers);
+    // OpRec r (global op slot c_idx*TREE_CHUNK + c_nops) lives in shared memory or directly in the block
+    auto rec_at = [&](unsigned int r) -> OpRec *
+    {
+      if (small) return &s_rec[wib][r];
+      return reinterpret_cast<OpRec *>(blk + chunks0 + (size_t)(r / TREE_CHUNK) * cb + sizeof(ChunkHdr)) + (r % TREE_CHUNK);
+    };
     for (unsigned int k = 0; k < n; ++k)
     {
       where[o[k].parent - T] = 0;
@@ -114,7 +141,7 @@ plan_kernel_blocks(const LocusDev * __restrict__ loci, const unsigned int * __re
     const unsigned int rootc = want_root ? root_clv[bl] : 0xFFFFFFFFu;
     unsigned int free_slots = (max_slots >= 32) ? 0xFFFFFFFFu : ((1u << max_slots) - 1u);
     unsigned int prev = 0xFFFFFFFFu;        // buffer whose X sits in the register, or none
-    unsigned int prev_off = 0;              // block offset of the op that produced it
+    unsigned int prev_off = 0;              // global op slot of the op that produced it
     bool root_done = false, fast = true;
     unsigned int c_idx = 0, c_nops = 0, c_ntips = 0;
     auto close_chunk = [&]()
@@ -157,14 +184,14 @@ plan_kernel_blocks(const LocusDev * __restrict__ loci, const unsigned int * __re
           if (b == prev && prev_child < 0)
           {
             q.kind = SRC_PREV; prev_child = c;
-            OpRec * prod = reinterpret_cast<OpRec *>(blk + prev_off);
+            OpRec * prod = rec_at(prev_off);
             prod->ctl |= OP_PUSH; prod->up_pm = q.pm;
           }
           else if (where[b])
           {
             const unsigned int s = slot_of[b];
             q.kind = SRC_SLOT; q.p0 = s; q.off = s * slot_unit; consumed_slots |= 1u << s;
-            OpRec * prod = reinterpret_cast<OpRec *>(blk + where[b]);
+            OpRec * prod = rec_at(where[b] - 1);
             prod->ctl |= OP_PUSH; prod->up_pm = q.pm;
             where[b] = 0;
           }
@@ -177,8 +204,8 @@ plan_kernel_blocks(const LocusDev * __restrict__ loci, const unsigned int * __re
       {
         const int s = __ffs(free_slots) - 1;
         free_slots &= ~(1u << s);
-        where[prev] = prev_off; slot_of[prev] = (unsigned char)s;
-        OpRec * prod = reinterpret_cast<OpRec *>(blk + prev_off);
+        where[prev] = prev_off + 1; slot_of[prev] = (unsigned char)s;
+        OpRec * prod = rec_at(prev_off);
         prod->ctl |= OP_PARKA; prod->park_off = (unsigned)s * slot_unit;
       }
       free_slots |= consumed_slots;
@@ -193,11 +220,10 @@ plan_kernel_blocks(const LocusDev * __restrict__ loci, const unsigned int * __re
       if (r.psc >= 0) q.ctl |= OP_SCALE;
       if (prev_child >= 0) q.ctl |= OP_BPREV;
       if (want_root && r.parent == rootc) { q.ctl |= OP_ROOT; root_done = true; }
-      const unsigned int off = chunks0 + (unsigned int)((size_t)c_idx * cb) + (unsigned int)sizeof(ChunkHdr) +
-                               c_nops * (unsigned int)sizeof(OpRec);
-      *reinterpret_cast<OpRec *>(blk + off) = q;
+      const unsigned int rix = c_idx * TREE_CHUNK + c_nops;
+      *rec_at(rix) = q;
       ++c_nops;
-      prev = r.parent - T; prev_off = off;
+      prev = r.parent - T; prev_off = rix;
     }
     cnt = n;
     if (want_root && !root_done)
@@ -216,9 +242,7 @@ plan_kernel_blocks(const LocusDev * __restrict__ loci, const unsigned int * __re
       else { kind = SRC_HBM; q.a_p0 = rootc - T; }
       q.ctl = OP_EVAL | OP_ROOT | (kind << OP_AKIND_SHIFT);
       fast = false;
-      const unsigned int off = chunks0 + (unsigned int)((size_t)c_idx * cb) + (unsigned int)sizeof(ChunkHdr) +
-                               c_nops * (unsigned int)sizeof(OpRec);
-      *reinterpret_cast<OpRec *>(blk + off) = q;
+      *rec_at(c_idx * TREE_CHUNK + c_nops) = q;
       ++c_nops;
       cnt = n + 1;
     }
@@ -234,6 +258,16 @@ plan_kernel_blocks(const LocusDev * __restrict__ loci, const unsigned int * __re
   }
   n_chunks = __shfl_sync(0xFFFFFFFFu, n_chunks, 0);
   __syncwarp();
+  if (small)
+  {
+    // OpRecs: shared -> block, 16 bytes per lane and step
+    for (unsigned int w = lane; w < n_chunks * TREE_CHUNK * 4; w += 32)
+    {
+      const unsigned int r = w >> 2;
+      uint4 * dst = reinterpret_cast<uint4 *>(blk + chunks0 + (size_t)(r / TREE_CHUNK) * cb + sizeof(ChunkHdr)) + (r % TREE_CHUNK) * 4 + (w & 3u);
+      *dst = reinterpret_cast<const uint4 *>(s_rec[wib])[w];
+    }
+  }
   double * rw = reinterpret_cast<double *>(blk + sizeof(LocusHdr));
   for (unsigned int j = lane; j < RL; j += 32) rw[j] = L.rate_weights[j];
   // gather: per chunk, per op: Pup (if pushed) and the tipP of its packed tip children
@@ -242,7 +276,7 @@ plan_kernel_blocks(const LocusDev * __restrict__ loci, const unsigned int * __re
   {
     unsigned char * ch = blk + chunks0 + (size_t)c * cb;
     const ChunkHdr hdr = *reinterpret_cast<const ChunkHdr *>(ch);
-    const OpRec * cops = reinterpret_cast<const OpRec *>(ch + sizeof(ChunkHdr));
+    const OpRec * cops = small ? &s_rec[wib][c * TREE_CHUNK] : reinterpret_cast<const OpRec *>(ch + sizeof(ChunkHdr));
     double * Pup = reinterpret_cast<double *>(ch + sizeof(ChunkHdr) + TREE_CHUNK * sizeof(OpRec));
     double * tipP = Pup + (size_t)TREE_CHUNK * RL * PM_STRIDE;
     for (unsigned int e = lane; e < hdr.nops * 3 * mat; e += 32)

@@ -38,6 +38,7 @@ namespace bppgpu {
 
 // all views alias the dynamic shared memory
 extern __shared__ uint4 s4[];
+extern __shared__ double2 sd2[];
 extern __shared__ double s8[];
 extern __shared__ unsigned int s1[];
 
@@ -152,20 +153,18 @@ __device__ __forceinline__ double tile_fast(const TreeParams & prm, const TileCt
       {
         const unsigned int wa = aw1 ? tc.tw1[j] : tc.tw0[j];
         const unsigned int ia = (amask ? lut_t : stk_t + j * (2 * TREE_NT)) + w0.w + ((wa >> ash) & amask) * 3;
-        const double2 a0 = as_d2(s4[ia]), a1 = as_d2(s4[ia + 1]);
-        if (ctl & OP_BPREV)
+        const double2 a0 = sd2[ia], a1 = sd2[ia + 1];
+        if (!(ctl & OP_BPREV))
         {
-          o[j][0] = __dmul_rn(x[j][0], a0.x); o[j][1] = __dmul_rn(x[j][1], a0.y);
-          o[j][2] = __dmul_rn(x[j][2], a1.x); o[j][3] = __dmul_rn(x[j][3], a1.y);
-        }
-        else
-        {
+          // operand B is not the register X: load it INTO the X registers (they are dead: a pushed X
+          // is consumed by exactly one op, and that op has OP_BPREV)
           const unsigned int wb = bw1 ? tc.tw1[j] : tc.tw0[j];
           const unsigned int ib = (bmask ? lut_t : stk_t + j * (2 * TREE_NT)) + w1.y + ((wb >> bsh) & bmask) * 3;
-          const double2 b0 = as_d2(s4[ib]), b1 = as_d2(s4[ib + 1]);
-          o[j][0] = __dmul_rn(a0.x, b0.x); o[j][1] = __dmul_rn(a0.y, b0.y);
-          o[j][2] = __dmul_rn(a1.x, b1.x); o[j][3] = __dmul_rn(a1.y, b1.y);
+          const double2 b0 = sd2[ib], b1 = sd2[ib + 1];
+          x[j][0] = b0.x; x[j][1] = b0.y; x[j][2] = b1.x; x[j][3] = b1.y;
         }
+        o[j][0] = __dmul_rn(x[j][0], a0.x); o[j][1] = __dmul_rn(x[j][1], a0.y);
+        o[j][2] = __dmul_rn(x[j][2], a1.x); o[j][3] = __dmul_rn(x[j][3], a1.y);
         osc[j] = 0;
       }
     }
@@ -207,7 +206,7 @@ __device__ __forceinline__ double tile_fast(const TreeParams & prm, const TileCt
 #pragma unroll
       for (int h = 0; h < 4; ++h)
       {
-        const double2 pa = as_d2(s4[p + 2 * h]), pb = as_d2(s4[p + 2 * h + 1]);
+        const double2 pa = sd2[p + 2 * h], pb = sd2[p + 2 * h + 1];
 #pragma unroll
         for (int j = 0; j < CPT; ++j) x[j][h] = dot4<EXACT>(pa, pb, o[j][0], o[j][1], o[j][2], o[j][3]);
       }
@@ -219,8 +218,8 @@ __device__ __forceinline__ double tile_fast(const TreeParams & prm, const TileCt
 #pragma unroll
         for (int j = 0; j < CPT; ++j)
         {
-          s4[stk_t + j * (2 * TREE_NT) + po] = as_u4(x[j][0], x[j][1]);
-          s4[stk_t + j * (2 * TREE_NT) + po + 1] = as_u4(x[j][2], x[j][3]);
+          sd2[stk_t + j * (2 * TREE_NT) + po] = make_double2(x[j][0], x[j][1]);
+          sd2[stk_t + j * (2 * TREE_NT) + po + 1] = make_double2(x[j][2], x[j][3]);
           if (ctl & OP_SCALE) s1[tc.sst1 + (po / Lay::SLOT) * (CPT * TREE_NT) + j * TREE_NT + tid] = psc[j];
         }
       }
