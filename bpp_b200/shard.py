@@ -1,0 +1,24 @@
+"""Multi-GPU sharding of the likelihood path: loci are independent, so each rank owns a contiguous
+range of loci and the only exchange is one all-reduce of the lnL sums per step.
+
+Mirrors the reference's thread partition load_balance_none (threads.c:234-263: loci/threads each,
+the remainder handed out one by one to the first threads) and the master's post-barrier sum of the
+per-thread lnacceptance (threads.c:583-590)."""
+
+
+def locus_range(n_loci, world, rank):
+    """(first, count) of the loci owned by `rank` out of `world` ranks."""
+    per, rem = divmod(n_loci, world)
+    first = rank * per + min(rank, rem)
+    return first, per + (1 if rank < rem else 0)
+
+
+def allreduce_sum(values, group=None):
+    """Sum a small float64 vector over the ranks (NCCL on GPUs, gloo in the CPU tests); identity
+    when torch.distributed is not initialised."""
+    import torch
+    import torch.distributed as dist
+    t = values if isinstance(values, torch.Tensor) else torch.tensor(values, dtype=torch.float64)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t
