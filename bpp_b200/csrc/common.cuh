@@ -37,6 +37,10 @@ struct LocusDev
   unsigned int tips, sites, states, rate_cats;
   unsigned int clv_buffers, prob_matrices, scale_buffers, model_kind;   // model_kind 0 = JC69, 1 = eigen
   unsigned int unphased, tip_words;                                     // tip_words = ceil(tips/8) (4 states)
+  // > 4 states: column ids of the tips (0..S-1 = one-hot state, S.. = ambiguity mask colmask[id-S])
+  unsigned char * tip_cols;     // [tips][sites]
+  unsigned int * colmask;       // [4] ambiguity masks
+  unsigned int n_ext_cols, pad1;
 };
 
 // operand kinds of a planned pruning step

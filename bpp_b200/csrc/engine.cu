@@ -11,6 +11,7 @@
 #include "pmatrix.cuh"
 #include "plan.cuh"
 #include "tree_s4.cuh"
+#include "tree_s20.cuh"
 #include "tree_generic.cuh"
 #include "reduce.cuh"
 
@@ -141,6 +142,11 @@ struct bppgpu_locus
   size_t b_dip_off = 0, b_dip_map = 0;
   // host mirrors of the small inputs
   std::vector<unsigned int> h_codes;    // 4 states: [pattern][tip/8] nibbles; else [tip][pattern] masks
+  std::vector<unsigned char> h_cols;    // > 4 states: [tip][pattern] column ids
+  unsigned int h_colmask[4] = {0, 0, 0, 0};
+  unsigned int n_ext_cols = 0;
+  bool col_overflow = false;            // more than 4 distinct ambiguity masks: generic kernel only
+  size_t b_cols = 0, b_colmask = 0;
   std::vector<unsigned char> h_tip_dense_flag;
   std::vector<double> h_freqs, h_subst, h_rates, h_rate_weights, h_evecs, h_ievecs, h_evals;
   bool eigen_valid = false;            // locus->eigen_decomp_valid[0]
@@ -155,7 +161,7 @@ struct bppgpu_batch
   std::vector<bppgpu_locus *> loci;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
-  int kernel_kind = 0;                 // 0 = 4-state pow2-R kernel, 1 = generic
+  int kernel_kind = 0;                 // 0 = 4-state kernel, 1 = generic fallback, 2 = 20-state DMMA kernel
   unsigned int RL = 1;                 // lanes per site of the 4-state kernel
   unsigned int cpt = 1;                // cells per thread of the 4-state kernel
   unsigned int tile_threads = 256;
@@ -313,7 +319,23 @@ static inline void set_code(bppgpu_locus * l, unsigned tip, size_t site, unsigne
     const unsigned sh = (tip & 7u) * 4;
     w = (w & ~(0xFu << sh)) | ((c & 0xFu) << sh);
   }
-  else l->h_codes[(size_t)tip * l->sites + site] = c;
+  else
+  {
+    l->h_codes[(size_t)tip * l->sites + site] = c;
+    // column id for the tensor-core path: one-hot -> state, else one of up to 4 ambiguity columns
+    unsigned int col = 0xFF;
+    if (c && !(c & (c - 1))) col = (unsigned int)__builtin_ctz(c);
+    else
+    {
+      for (unsigned int x = 0; x < l->n_ext_cols; ++x) if (l->h_colmask[x] == c) col = l->states + x;
+      if (col == 0xFF)
+      {
+        if (l->n_ext_cols < 4) { l->h_colmask[l->n_ext_cols] = c; col = l->states + l->n_ext_cols; ++l->n_ext_cols; }
+        else { l->col_overflow = true; col = 0; }
+      }
+    }
+    l->h_cols[(size_t)tip * l->sites + site] = (unsigned char)col;
+  }
 }
 static inline unsigned int get_code(const bppgpu_locus * l, unsigned tip, size_t site)
 {
@@ -329,6 +351,16 @@ static void locus_sync(bppgpu_locus * l, cudaStream_t s)
   if (l->codes_dirty)
   {
     CUDA_CHECK(cudaMemcpyAsync(l->dev.tip_codes, l->h_codes.data(), l->h_codes.size() * 4, cudaMemcpyHostToDevice, s));
+    if (l->dev.tip_cols)
+    {
+      CUDA_CHECK(cudaMemcpyAsync(l->dev.tip_cols, l->h_cols.data(), l->h_cols.size(), cudaMemcpyHostToDevice, s));
+      CUDA_CHECK(cudaMemcpyAsync(l->dev.colmask, l->h_colmask, sizeof(l->h_colmask), cudaMemcpyHostToDevice, s));
+      if (l->dev.n_ext_cols != l->n_ext_cols)
+      {
+        l->dev.n_ext_cols = l->n_ext_cols;
+        CUDA_CHECK(cudaMemcpyAsync(l->e->d_loci + l->id, &l->dev, sizeof(LocusDev), cudaMemcpyHostToDevice, s));
+      }
+    }
     l->codes_dirty = false;
   }
   if (l->flags_dirty)
@@ -474,6 +506,13 @@ extern "C" bppgpu_locus * bppgpu_locus_create(bppgpu_engine * e, unsigned int dt
   l->b_model = model_doubles(states, rate_cats) * 8;
   d.clv = (double *)e->arena.alloc(l->b_clv);
   d.tip_codes = e->arena.alloc(l->b_codes);
+  if (S != 4)
+  {
+    l->b_cols = (size_t)tips * P; l->b_colmask = 16;
+    d.tip_cols = (unsigned char *)e->arena.alloc(l->b_cols);
+    d.colmask = (unsigned int *)e->arena.alloc(l->b_colmask);
+    l->h_cols.assign(l->b_cols, 0);
+  }
   d.tip_is_dense = (unsigned char *)e->arena.alloc(l->b_flags);
   d.pmat = (double *)e->arena.alloc(l->b_pmat);
   d.scale = scale_buffers ? (unsigned int *)e->arena.alloc(l->b_scale) : nullptr;
@@ -523,6 +562,8 @@ extern "C" void bppgpu_locus_destroy(bppgpu_locus * l)
   a.release(l->dev.clv, l->b_clv);
   a.release(l->dev.tip_dense, l->b_tipdense);
   a.release(l->dev.tip_codes, l->b_codes);
+  a.release(l->dev.tip_cols, l->b_cols);
+  a.release(l->dev.colmask, l->b_colmask);
   a.release(l->dev.tip_is_dense, l->b_flags);
   a.release(l->dev.pmat, l->b_pmat);
   a.release(l->dev.scale, l->b_scale);
@@ -653,14 +694,17 @@ static void batch_launch_cfg(bppgpu_batch * b)
   const bppgpu_locus * l0 = b->loci[0];
   const unsigned R = l0->rate_cats;
   const bool pow2 = (R & (R - 1)) == 0 && R <= 8;
+  bool overflow = false;
+  for (auto * l : b->loci) overflow = overflow || l->col_overflow;
   if (l0->states == 4 && pow2) { b->kernel_kind = 0; b->RL = R; }
+  else if (l0->states == S20 && pow2 && !overflow) { b->kernel_kind = 2; b->RL = R; }
   else { b->kernel_kind = 1; b->RL = 1; }
-  // tile size: 256 cells for big loci, 128 for small ones (fewer idle lanes in the last tile)
   size_t cells = 0;
-  for (auto * l : b->loci) cells += (size_t)l->sites * (b->kernel_kind == 0 ? R : 1);
+  for (auto * l : b->loci) cells += (size_t)l->sites * (b->kernel_kind != 1 ? R : 1);
   const size_t mean = cells / b->n;
+  // 4-state kernel: 2 cells per thread once the loci are big enough to fill such tiles
   b->cpt = (b->kernel_kind == 0 && mean >= 2 * TREE_NT) ? 2 : 1;
-  b->tile_threads = b->kernel_kind == 0 ? TREE_NT : 128;
+  b->tile_threads = b->kernel_kind != 1 ? TREE_NT : 128;
 }
 
 extern "C" bppgpu_batch * bppgpu_batch_create(bppgpu_engine * e, unsigned int n, bppgpu_locus * const * loci)
@@ -686,9 +730,10 @@ extern "C" bppgpu_batch * bppgpu_batch_create(bppgpu_engine * e, unsigned int n,
   {
     const bppgpu_locus * l = loci[i];
     ids[i] = l->id;
-    const unsigned cells = l->sites * (b->kernel_kind == 0 ? b->RL : 1);
+    const unsigned cells = l->sites * (b->kernel_kind != 1 ? b->RL : 1);
     tile_first[i] = (unsigned)tile_locus.size();
-    for (unsigned c = 0; c < cells; c += b->tile_threads * b->cpt)
+    const unsigned tile_cells = b->kernel_kind == 2 ? (unsigned)S20_TILE : b->tile_threads * b->cpt;
+    for (unsigned c = 0; c < cells; c += tile_cells)
     {
       tile_locus.push_back(i); tile_cell0.push_back(c);
       if (b->kernel_kind == 0)
@@ -726,6 +771,7 @@ extern "C" bppgpu_batch * bppgpu_batch_create(bppgpu_engine * e, unsigned int n,
     CUDA_CHECK(cudaMemcpy(b->d_tiles, tiles.data(), tiles.size() * sizeof(TileDesc), cudaMemcpyHostToDevice));
     CUDA_CHECK(cudaMalloc(&b->d_tile_blk, tiles.size() * 16));
   }
+  if (b->kernel_kind == 2) CUDA_CHECK(cudaMalloc(&b->d_tile_blk, (size_t)b->n_tiles * 16));
   CUDA_CHECK(cudaMemset(b->d_plan_count, 0, n * 4));
   CUDA_CHECK(cudaMemset(b->d_tile_partial, 0, b->n_tiles * 8));
   CUDA_CHECK(cudaEventCreate(&b->t0));
@@ -812,9 +858,10 @@ static int batch_stage(bppgpu_batch * b, const unsigned int * mcounts, const uns
     moff[i + 1] = moff[i] + (mcounts ? mcounts[i] : 0);
     ooff[i + 1] = ooff[i] + (ocounts ? ocounts[i] : 0);
     // one spare op per locus for a root that the list does not produce (CTL_EVAL_ONLY)
-    boff[i + 1] = boff[i] + block_bytes(b->RL, (ocounts ? ocounts[i] : 0) + 1);
+    const unsigned nmax = (ocounts ? ocounts[i] : 0) + 1;
+    boff[i + 1] = boff[i] + (b->kernel_kind == 2 ? align_up(block20_bytes(b->RL, nmax), 256) : block_bytes(b->RL, nmax));
   }
-  if (b->kernel_kind == 0 && boff[n] > b->blocks_cap)
+  if (b->kernel_kind != 1 && boff[n] > b->blocks_cap)
   {
     CUDA_CHECK(cudaStreamSynchronize(b->stream));
     if (b->d_blocks) cudaFree(b->d_blocks);
@@ -866,6 +913,19 @@ static void launch_tree_s4(bppgpu_batch * b, const TreeParams & prm)
   else { if (exact) launch_tree_s4_impl<RL, true, 1>(b, prm); else launch_tree_s4_impl<RL, false, 1>(b, prm); }
 }
 
+template <int RL>
+static void launch_tree_s20(bppgpu_batch * b, const TreeParams & prm)
+{
+  bppgpu_engine * e = b->e;
+  const size_t smem = s20_smem_bytes<RL>(prm.n_slots);
+  CUDA_CHECK(cudaFuncSetAttribute(tree_kernel_s20<RL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tree_kernel_s20<RL>, TREE_NT, smem));
+  if (per_sm < 1) { fatal("20-state tree kernel does not fit on an SM (smem %zu)", smem); return; }
+  const unsigned grid = std::min<unsigned>(b->n_tiles, (unsigned)(per_sm * e->sm_count));
+  tree_kernel_s20<RL><<<grid, TREE_NT, smem, b->stream>>>(prm);
+}
+
 // launches: [pmatrix] [plan + tree (+ finish)] on the batch stream, using the staged blob
 static int batch_run(bppgpu_batch * b, bool do_mats, bool do_tree, bool want_root, double * persite, int persite_mode)
 {
@@ -899,12 +959,19 @@ static int batch_run(bppgpu_batch * b, bool do_mats, bool do_tree, bool want_roo
   // shared-memory stack slots per thread: ceil(log2 T) covers balanced trees in recursive post-order;
   // beyond that the plan falls back to re-reading the child from HBM (still correct)
   int slots = 0;
-  if (b->kernel_kind == 0)
+  if (b->kernel_kind == 2)
+    for (auto * l : b->loci)
+      if (l->col_overflow)
+      {
+        fatal("a locus of this batch has more than 4 distinct ambiguity codes; create the batch after the tip states are set");
+        return BPPGPU_FAILURE;
+      }
+  if (b->kernel_kind != 1)
   {
     unsigned maxT = 0;
     for (auto * l : b->loci) maxT = std::max(maxT, l->tips);
     slots = 1; while ((1u << slots) < maxT) ++slots;
-    slots = std::min(std::max(slots - 1, 1), 6);
+    slots = std::min(std::max(slots - 1, 1), b->kernel_kind == 2 ? 3 : 6);   // bounded by shared memory
   }
   const unsigned long long * d_blk_off = (const unsigned long long *)(b->d_in + b->o_blk_off);
   {
@@ -914,6 +981,11 @@ static int batch_run(bppgpu_batch * b, bool do_mats, bool do_tree, bool want_roo
           e->d_loci, b->d_batch_locus, n, d_op_off, d_ops, d_root_clv, d_root_sc, want_root ? 1 : 0,
           b->d_blocks, d_blk_off, b->d_tile_first, b->d_tile_blk, b->d_plan_count, b->d_scratch, b->d_scratch_off,
           slots, b->RL, b->cpt);
+    else if (b->kernel_kind == 2)
+      plan_kernel_blocks20<<<(n * 32 + 127) / 128, 128, 0, b->stream>>>(
+          e->d_loci, b->d_batch_locus, n, d_op_off, d_ops, d_root_clv, d_root_sc, want_root ? 1 : 0,
+          b->d_blocks, d_blk_off, b->d_tile_first, b->d_tile_blk, b->d_plan_count, b->d_scratch, b->d_scratch_off,
+          slots, b->RL);
     else
       plan_kernel_flat<<<(n + 127) / 128, 128, 0, b->stream>>>(
           e->d_loci, b->d_batch_locus, n, d_op_off, d_ops, d_root_clv, d_root_sc, want_root ? 1 : 0,
@@ -938,6 +1010,17 @@ static int batch_run(bppgpu_batch * b, bool do_mats, bool do_tree, bool want_roo
         case 2: launch_tree_s4<2>(b, prm); break;
         case 4: launch_tree_s4<4>(b, prm); break;
         case 8: launch_tree_s4<8>(b, prm); break;
+        default: fatal("internal: RL=%u", b->RL); return BPPGPU_FAILURE;
+      }
+    }
+    else if (b->kernel_kind == 2)
+    {
+      switch (b->RL)
+      {
+        case 1: launch_tree_s20<1>(b, prm); break;
+        case 2: launch_tree_s20<2>(b, prm); break;
+        case 4: launch_tree_s20<4>(b, prm); break;
+        case 8: launch_tree_s20<8>(b, prm); break;
         default: fatal("internal: RL=%u", b->RL); return BPPGPU_FAILURE;
       }
     }
