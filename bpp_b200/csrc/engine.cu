@@ -8,7 +8,6 @@
 //   locus_update_partials :2530, locus_root_loglikelihood :2573, pll_update_eigen core_pmatrix.c:239.
 #include "../../include/bpp_b200.h"
 #include "common.cuh"
-#include "pmatrix.cuh"
 #include "plan.cuh"
 #include "tree_s4.cuh"
 #include "tree_s20.cuh"
@@ -180,7 +179,8 @@ struct bppgpu_batch
   unsigned long long * d_tile_blk = nullptr;        // per tile: {block offset, 0}, written by the planner
   unsigned int * d_plan_count = nullptr;
   int grid = 0; size_t tree_smem = 0; int slots = 0;
-  double * d_tile_partial = nullptr, * d_lnl = nullptr, * d_lnl_sum = nullptr;
+  double * d_tile_partial = nullptr, * d_lnl = nullptr, * d_lnl_sum = nullptr, * d_block_sums = nullptr;
+  unsigned int * d_counter = nullptr;
   double * h_out = nullptr;                         // pinned: n lnl + 1 sum
   double * d_persite = nullptr; size_t persite_cap = 0;
   // layout of the staged blob
@@ -759,6 +759,9 @@ extern "C" bppgpu_batch * bppgpu_batch_create(bppgpu_engine * e, unsigned int n,
   CUDA_CHECK(cudaMalloc(&b->d_tile_partial, b->n_tiles * 8));
   CUDA_CHECK(cudaMalloc(&b->d_lnl, (n + 1) * 8));
   b->d_lnl_sum = b->d_lnl + n;
+  CUDA_CHECK(cudaMalloc(&b->d_block_sums, ((n + 255) / 256) * 8));
+  CUDA_CHECK(cudaMalloc(&b->d_counter, 4));
+  CUDA_CHECK(cudaMemset(b->d_counter, 0, 4));
   CUDA_CHECK(cudaHostAlloc(&b->h_out, (n + 1) * 8, cudaHostAllocDefault));
   CUDA_CHECK(cudaMemcpy(b->d_batch_locus, ids.data(), n * 4, cudaMemcpyHostToDevice));
   CUDA_CHECK(cudaMemcpy(b->d_tile_locus, tile_locus.data(), b->n_tiles * 4, cudaMemcpyHostToDevice));
@@ -788,7 +791,7 @@ extern "C" void bppgpu_batch_destroy(bppgpu_batch * b)
   cudaFree(b->d_batch_locus); cudaFree(b->d_tile_locus); cudaFree(b->d_tile_cell0); cudaFree(b->d_tile_first);
   cudaFree(b->d_scratch_off); cudaFree(b->d_scratch); cudaFree(b->d_plan_count); cudaFree(b->d_tile_partial);
   cudaFree(b->d_lnl); cudaFree(b->d_in); cudaFree(b->d_plan); cudaFree(b->d_persite);
-  cudaFree(b->d_blocks); cudaFree(b->d_tiles); cudaFree(b->d_tile_blk);
+  cudaFree(b->d_blocks); cudaFree(b->d_tiles); cudaFree(b->d_tile_blk); cudaFree(b->d_block_sums); cudaFree(b->d_counter);
   cudaFreeHost(b->h_out); cudaFreeHost(b->h_in);
   cudaEventDestroy(b->t0); cudaEventDestroy(b->t1);
   if (b->own_stream) cudaStreamDestroy(b->stream);
@@ -941,14 +944,16 @@ static int batch_run(bppgpu_batch * b, bool do_mats, bool do_tree, bool want_roo
   const unsigned int * d_root_clv = (const unsigned int *)(b->d_in + b->o_root_clv);
   const int * d_root_sc = (const int *)(b->d_in + b->o_root_sc);
 
-  if (do_mats && b->total_mats)
+  // 4-state batches doing matrices and partials in one call build the P-matrices inside the planner
+  const bool fuse_mats = do_mats && do_tree && b->kernel_kind == 0 && b->total_mats;
+  if (do_mats && b->total_mats && !fuse_mats)
   {
     ProfScope ps(e, b->stream, BPPGPU_KERNEL_PMATRIX);
     const unsigned S = b->loci[0]->states;
     if (S > 8)
     {
-      const size_t sm = (2 * (size_t)S * S + S) * 8;
-      pmatrix_kernel_wide<<<n, 128, sm, b->stream>>>(e->d_loci, b->d_batch_locus, d_mat_off, d_mat_idx, d_mat_bl);
+      const size_t sm = 3 * (size_t)S * S * 8;
+      pmatrix_kernel_wide<<<dim3(n, 8), 128, sm, b->stream>>>(e->d_loci, b->d_batch_locus, d_mat_off, d_mat_idx, d_mat_bl);
     }
     else
       pmatrix_kernel<<<n, 64, 0, b->stream>>>(e->d_loci, b->d_batch_locus, d_mat_off, d_mat_idx, d_mat_bl);
@@ -971,7 +976,11 @@ static int batch_run(bppgpu_batch * b, bool do_mats, bool do_tree, bool want_roo
     unsigned maxT = 0;
     for (auto * l : b->loci) maxT = std::max(maxT, l->tips);
     slots = 1; while ((1u << slots) < maxT) ++slots;
-    slots = std::min(std::max(slots - 1, 1), b->kernel_kind == 2 ? 3 : 6);   // bounded by shared memory
+    slots = std::min(std::max(slots - 1, 1), 6);
+    // 20 states: a parked X costs 3.4 kB of shared memory per warp and slot, which would push the
+    // P-matrices (read through L1) out of the SM; re-reading the child's CLV (an L2 hit) and redoing one
+    // DMMA mat-vec is cheaper, so nothing is parked
+    if (b->kernel_kind == 2) slots = 0;
   }
   const unsigned long long * d_blk_off = (const unsigned long long *)(b->d_in + b->o_blk_off);
   {
@@ -980,7 +989,7 @@ static int batch_run(bppgpu_batch * b, bool do_mats, bool do_tree, bool want_roo
       plan_kernel_blocks<<<(n * 32 + 127) / 128, 128, 0, b->stream>>>(
           e->d_loci, b->d_batch_locus, n, d_op_off, d_ops, d_root_clv, d_root_sc, want_root ? 1 : 0,
           b->d_blocks, d_blk_off, b->d_tile_first, b->d_tile_blk, b->d_plan_count, b->d_scratch, b->d_scratch_off,
-          slots, b->RL, b->cpt);
+          slots, b->RL, b->cpt, fuse_mats ? d_mat_off : nullptr, d_mat_idx, d_mat_bl);
     else if (b->kernel_kind == 2)
       plan_kernel_blocks20<<<(n * 32 + 127) / 128, 128, 0, b->stream>>>(
           e->d_loci, b->d_batch_locus, n, d_op_off, d_ops, d_root_clv, d_root_sc, want_root ? 1 : 0,
@@ -1034,7 +1043,8 @@ static int batch_run(bppgpu_batch * b, bool do_mats, bool do_tree, bool want_roo
   if (want_root)
   {
     ProfScope ps(e, b->stream, BPPGPU_KERNEL_FINISH);
-    finish_kernel<<<1, 1024, 0, b->stream>>>(b->d_tile_partial, b->d_tile_first, n, b->d_lnl, b->d_lnl_sum);
+    finish_kernel<<<(n + 255) / 256, 256, 0, b->stream>>>(b->d_tile_partial, b->d_tile_first, n, b->d_lnl, b->d_lnl_sum,
+                                                          b->d_block_sums, b->d_counter);
     CUDA_CHECK(cudaGetLastError());
   }
   return BPPGPU_SUCCESS;

@@ -12,6 +12,7 @@
 // next op's tables would not fit.
 #pragma once
 #include "common.cuh"
+#include "pmatrix.cuh"
 
 namespace bppgpu {
 
@@ -79,12 +80,26 @@ plan_kernel_blocks(const LocusDev * __restrict__ loci, const unsigned int * __re
                    const unsigned int * __restrict__ tile_first, unsigned long long * __restrict__ tile_blk,
                    unsigned int * __restrict__ plan_count,
                    unsigned char * __restrict__ scratch, const unsigned long long * __restrict__ scratch_off,
-                   int max_slots, unsigned int RL, unsigned int cpt)
+                   int max_slots, unsigned int RL, unsigned int cpt,
+                   const unsigned int * __restrict__ mat_off, const unsigned int * __restrict__ mat_idx,
+                   const double * __restrict__ mat_bl)
 {
   const unsigned int bl = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const unsigned int lane = threadIdx.x & 31u;
   if (bl >= n_loci) return;
   const LocusDev & L = loci[batch_locus[bl]];
+  // fused P-matrix build (mat_off != nullptr): the warp computes its locus' matrices first; the gather
+  // below reads them back after the __syncwarp() that orders the warp's global writes
+  if (mat_off)
+  {
+    const unsigned int mfirst = mat_off[bl], mcount = mat_off[bl + 1] - mfirst;
+    for (unsigned int t = lane; t < mcount * RL * 4; t += 32)
+    {
+      const unsigned int j = t & 3u, n = (t >> 2) % RL, m = t / (4 * RL);
+      pmatrix_row(L, mat_idx[mfirst + m], mat_bl[mfirst + m], n, j);
+    }
+    __syncwarp();
+  }
   const unsigned int first = op_off[bl], n = op_off[bl + 1] - first;
   const RawOp * o = ops + first;
   unsigned char * blk = blocks + blk_off[bl];
