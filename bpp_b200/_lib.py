@@ -89,7 +89,7 @@ def load():
         "bppgpu_update_partials": (i, [vp, u, opp]),
         "bppgpu_root_loglikelihood": (d, [vp, u, i, dp]),
         "bppgpu_root_likelihood_vector": (i, [vp, u, dp]),
-        "bppgpu_set_diploid": (i, [vp, u, C.POINTER(C.c_ulong), C.POINTER(C.c_ulong), C.c_ulong]),
+        "bppgpu_set_diploid": (i, [vp, u, C.POINTER(C.c_ulong), C.POINTER(C.c_ulong), C.c_ulong, up]),
         "bppgpu_root_loglikelihood_diploid": (d, [vp, u]),
         "bppgpu_get_clv": (i, [vp, u, dp]),
         "bppgpu_get_pmatrix": (i, [vp, u, dp]),

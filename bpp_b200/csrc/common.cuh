@@ -41,6 +41,7 @@ struct LocusDev
   unsigned char * tip_cols;     // [tips][sites]
   unsigned int * colmask;       // [4] ambiguity masks
   unsigned int n_ext_cols, pad1;
+  unsigned int * dip_weights;   // diploid loci: weights of the unphased sites [unphased]
 };
 
 // operand kinds of a planned pruning step

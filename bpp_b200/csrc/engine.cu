@@ -138,7 +138,7 @@ struct bppgpu_locus
   LocusDev dev;                        // host copy of the device descriptor
   // sizes of the arena blocks (for release)
   size_t b_clv = 0, b_tipdense = 0, b_codes = 0, b_flags = 0, b_pmat = 0, b_scale = 0, b_weights = 0, b_model = 0;
-  size_t b_dip_off = 0, b_dip_map = 0;
+  size_t b_dip_off = 0, b_dip_map = 0, b_dip_w = 0;
   // host mirrors of the small inputs
   std::vector<unsigned int> h_codes;    // 4 states: [pattern][tip/8] nibbles; else [tip][pattern] masks
   std::vector<unsigned char> h_cols;    // > 4 states: [tip][pattern] column ids
@@ -571,6 +571,7 @@ extern "C" void bppgpu_locus_destroy(bppgpu_locus * l)
   a.release(l->dev.freqs, l->b_model);
   a.release(l->dev.dip_off, l->b_dip_off);
   a.release(l->dev.dip_map, l->b_dip_map);
+  a.release(l->dev.dip_weights, l->b_dip_w);
   e->loci[l->id] = nullptr;
   e->free_ids.push_back(l->id);
   delete l;
@@ -665,7 +666,7 @@ extern "C" void bppgpu_get_eigen(bppgpu_locus * l, unsigned int idx, double * ev
 }
 
 extern "C" int bppgpu_set_diploid(bppgpu_locus * l, unsigned int unphased, const unsigned long * cnt,
-                                  const unsigned long * mapping, unsigned long maplen)
+                                  const unsigned long * mapping, unsigned long maplen, const unsigned int * weights)
 {
   bppgpu_engine * e = l->e;
   std::lock_guard<std::mutex> lock(e->mu);
@@ -675,6 +676,10 @@ extern "C" int bppgpu_set_diploid(bppgpu_locus * l, unsigned int unphased, const
   if (off[unphased] != maplen) { fatal("diploid mapping length mismatch"); return BPPGPU_FAILURE; }
   for (unsigned long i = 0; i < maplen; ++i) mp[i] = mapping[i];
   e->arena.release(l->dev.dip_off, l->b_dip_off); e->arena.release(l->dev.dip_map, l->b_dip_map);
+  e->arena.release(l->dev.dip_weights, l->b_dip_w);
+  l->b_dip_w = std::max<size_t>(4, (size_t)unphased * 4);
+  l->dev.dip_weights = (unsigned int *)e->arena.alloc(l->b_dip_w);
+  CUDA_CHECK(cudaMemcpy(l->dev.dip_weights, weights, (size_t)unphased * 4, cudaMemcpyHostToDevice));
   l->b_dip_off = off.size() * 8; l->b_dip_map = std::max<size_t>(8, mp.size() * 8);
   l->dev.dip_off = (unsigned long long *)e->arena.alloc(l->b_dip_off);
   l->dev.dip_map = (unsigned long long *)e->arena.alloc(l->b_dip_map);

@@ -69,7 +69,7 @@ diploid_kernel(const LocusDev * __restrict__ loci, unsigned int locus_id, const 
     double mean = 0.0;
     for (unsigned long long k = a; k < b; ++k) mean = __dadd_rn(mean, lh[L.dip_map[k]]);
     mean = mean / (double)(b - a);
-    acc += __dmul_rn(log(mean), (double)L.weights[i]);
+    acc += __dmul_rn(log(mean), (double)L.dip_weights[i]);
   }
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, d);

@@ -197,11 +197,15 @@ class Locus:
         self.L.bppgpu_get_eigen(self.h, 0, _dp(a), _dp(b), _dp(c))
         return a, b, c
 
-    def set_diploid(self, resolution_count, mapping):
+    def set_diploid(self, resolution_count, mapping, unphased_weights):
+        """diploid.c / method.c:4172-4193: phase-resolution counts and mapping of the unphased sites and
+        THEIR weights (unphased_length entries, which may differ from `sites`)."""
         rc = np.ascontiguousarray(resolution_count, dtype=np.uint64)
         mp = np.ascontiguousarray(mapping, dtype=np.uint64)
+        uw = _u32(unphased_weights)
+        assert uw.size == rc.size
         ul = C.POINTER(C.c_ulong)
-        r = self.L.bppgpu_set_diploid(self.h, len(rc), rc.ctypes.data_as(ul), mp.ctypes.data_as(ul), len(mp))
+        r = self.L.bppgpu_set_diploid(self.h, len(rc), rc.ctypes.data_as(ul), mp.ctypes.data_as(ul), len(mp), _up(uw))
         _lib.check()
         return r
 

@@ -144,7 +144,8 @@ int  bppgpu_root_likelihood_vector(bppgpu_locus * l, unsigned int root_clv_index
    mean over phase resolutions, log, weight, sum */
 int  bppgpu_set_diploid(bppgpu_locus * l, unsigned int unphased_length,
                         const unsigned long * resolution_count, const unsigned long * mapping,
-                        unsigned long mapping_length);
+                        unsigned long mapping_length,
+                        const unsigned int * unphased_weights);   /* unphased_length weights, method.c:4185-4193 */
 double bppgpu_root_loglikelihood_diploid(bppgpu_locus * l, unsigned int root_clv_index);
 
 /* raw buffer access (debug printers output.c:26-96, parity tests, kernel-seam use) */

@@ -60,3 +60,28 @@ def load_case(name):
 
 GOLDEN_CASES = ["jc69_r1", "gtr_g4_scale", "gtr_g4", "lg_g4", "jc69_deep_scale", "gtr_g4_deep_scale",
                 "lg_g4_deep_scale"]
+
+
+def frogs_fixture():
+    return np.load(os.path.join(GOLDEN, "frogs_A00.npz"))
+
+
+def frogs_oracle_locus(d, k):
+    """Locus k of the frogs A00 fixture (real data as the reference's init() saw it) as an OracleLocus."""
+    p = "l%d_" % k
+    tips, sites, states, cats = [int(x) for x in d[p + "dims"][:4]]
+    o = F.OracleLocus(tips, sites, states, cats, scaling=False, model="JC69")
+    nodes = d[p + "nodes"]
+    nn = 2 * tips - 1
+    left, right = np.zeros(tips - 1, dtype=np.int64), np.zeros(tips - 1, dtype=np.int64)
+    times = np.zeros(nn)
+    for row, tl in zip(nodes, d[p + "time_length"]):
+        idx = int(row[0])
+        times[idx] = tl[0]
+        if row[1] >= 0:
+            left[idx - tips], right[idx - tips] = row[1], row[2]
+    o.set_tree(left, right, times, 1.0)
+    for t in range(tips):
+        o.set_tip_masks(t, d[p + "tip_masks"][t].astype(np.uint32))
+    o.set_model(freqs=d[p + "freqs"], rates=d[p + "rates"])
+    return o

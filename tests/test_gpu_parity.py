@@ -235,9 +235,10 @@ def test_dense_tip_clv_and_likelihood_vector_and_diploid(eng):
         counts.append(c)
         mapping += list(range(k, k + c))
         k += c
-    l.set_diploid(counts, mapping)
+    uw = rng.integers(1, 4, size=len(counts)).astype(np.uint32)
+    l.set_diploid(counts, mapping, uw)
     got = l.root_loglikelihood_diploid(int(trees.clv_index[0, trees.root]))
-    want = F.diploid_loglikelihood(o.root_likelihood_vector(), counts, mapping, o.weights)
+    want = F.diploid_loglikelihood(o.root_likelihood_vector(), counts, mapping, uw)
     assert abs(got - want) <= LNL_RTOL * abs(want)
     _free(loci, batch)
 
@@ -294,3 +295,43 @@ def test_linearity_in_pattern_weights_full_size_property(eng):
     b, _ = batch.full_pass(trees.full_pass_step())
     assert np.array_equal(b, 2 * a)
     _free(loci, batch)
+
+
+def test_frogs_real_data_diploid(eng):
+    """BASELINE.json config 1 (frogs A00): 5 real, ragged, diploid loci (42-60 sequences, 22-102
+    patterns) through update_matrices -> update_partials -> likelihood vector -> device-side phase
+    mean.  log-L0 = -7320.932289 as printed by the reference."""
+    from bpp_b200 import engine
+    from helpers import frogs_fixture
+    d = frogs_fixture()
+    total = 0.0
+    for k in range(int(d["n_loci"])):
+        p = "l%d_" % k
+        T, P, S, R = [int(x) for x in d[p + "dims"][:4]]
+        l = engine.Locus.create_like_bpp(eng, T, P, S, R, False, engine.DNA_MODEL_JC69)
+        for t in range(T):
+            l.set_tip_clv(t, ((d[p + "tip_masks"][t][:, None] >> np.arange(4)) & 1).astype(np.float64))
+        l.set_frequencies(d[p + "freqs"])
+        l.set_category_rates(d[p + "rates"])
+        l.set_diploid(d[p + "resolution_count"], d[p + "mapping"], d[p + "weights"])
+        nodes, tl = d[p + "nodes"], d[p + "time_length"]
+        by_idx = {int(r[0]): (r, t) for r, t in zip(nodes, tl)}
+        edges = [i for i in by_idx if by_idx[i][0][3] >= 0]
+        l.update_matrices([int(by_idx[i][0][6]) for i in edges], [by_idx[i][1][1] for i in edges])
+        # post-order = reversed pre-order of the inner nodes (children before parents)
+        inner = [int(r[0]) for r in nodes if r[1] >= 0][::-1]
+        ops = np.zeros(len(inner), dtype=engine.OP_DTYPE)
+        for j, i in enumerate(inner):
+            r = by_idx[i][0]
+            a, b = by_idx[int(r[1])][0], by_idx[int(r[2])][0]
+            ops[j] = (r[4], a[4], b[4], a[6], b[6], -1, -1, -1)
+        l.update_partials(ops)
+        root = int(nodes[0][4])
+        assert rel_err(l.get_clv(root), d[p + "root_clv"]) < 1e-10
+        lh = l.root_likelihood_vector(root)
+        assert np.allclose(lh, d[p + "likelihood_vector"], rtol=1e-10, atol=0)
+        lnl = l.root_loglikelihood_diploid(root)
+        assert abs(lnl - float(d[p + "logl"])) <= LNL_RTOL * abs(lnl)
+        total += lnl
+        l.destroy()
+    assert abs(total - (-7320.932289)) < 5e-6
