@@ -45,7 +45,9 @@ struct LocusDev
 };
 
 // operand kinds of a planned pruning step
-enum : unsigned { SRC_TIP_PACKED = 0, SRC_TIP_DENSE = 1, SRC_HBM = 2, SRC_SLOT = 3, SRC_PREV = 4 };
+enum : unsigned { SRC_TIP_PACKED = 0, SRC_TIP_DENSE = 1, SRC_HBM = 2, SRC_SLOT = 3, SRC_PREV = 4,
+                  SRC_HBML = 5 };   // HBM-resident CLV produced by an op of the same staged chunk: its edge's
+                                    // P-matrix is the producer's Pup, already in shared memory (4-state fast path)
 enum : unsigned { CTL_ROOT = 1u << 8, CTL_EVAL_ONLY = 1u << 9 };
 
 struct PlanOp                   // flat plan of the generic kernel, 48 bytes

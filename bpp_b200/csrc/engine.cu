@@ -118,7 +118,7 @@ struct bppgpu_engine
   std::vector<unsigned int> free_ids;
   unsigned long long launches = 0;
   int sm_count = 148;
-  size_t smem_optin = 0;
+  size_t smem_optin = 0, smem_per_sm = 0;
   // profiling
   bool profiling = false;
   double prof_ms[BPPGPU_KERNEL_COUNT] = {0, 0, 0, 0};
@@ -416,6 +416,7 @@ extern "C" bppgpu_engine * bppgpu_engine_create(int device, unsigned int flags)
   e->math = flags & 1u;
   e->sm_count = prop.multiProcessorCount;
   e->smem_optin = prop.sharedMemPerBlockOptin;
+  e->smem_per_sm = prop.sharedMemPerMultiprocessor;
   e->log_threshold = std::log(BPPGPU_SCALE_THRESHOLD);      // core_likelihood.c:200 evaluates it with libm
   CUDA_CHECK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
   return e;
@@ -899,7 +900,17 @@ static void batch_sync_loci(bppgpu_batch * b, bool need_eigen)
   }
 }
 
-// persistent launch: as many CTAs as fit on the device at once, each walks a contiguous tile range
+// persistent launch: as many CTAs as fit on the device at once, each walks a contiguous tile range.
+// The stack-slot count is a performance knob only (a value that finds no slot is re-read from L2), so it
+// is lowered until two CTAs fit on an SM.
+template <int RL, bool EXACT, int CPT>
+static int tree_s4_slots(bppgpu_batch * b, int wanted)
+{
+  int slots = wanted;
+  while (slots > 1 && 2 * (S4Layout<RL, CPT>::bytes(slots) + 1024) > b->e->smem_per_sm) --slots;
+  return slots;
+}
+
 template <int RL, bool EXACT, int CPT>
 static void launch_tree_s4_impl(bppgpu_batch * b, const TreeParams & prm)
 {
@@ -986,6 +997,22 @@ static int batch_run(bppgpu_batch * b, bool do_mats, bool do_tree, bool want_roo
     // P-matrices (read through L1) out of the SM; re-reading the child's CLV (an L2 hit) and redoing one
     // DMMA mat-vec is cheaper, so nothing is parked
     if (b->kernel_kind == 2) slots = 0;
+    if (b->kernel_kind == 0)
+    {
+      const int w = slots;
+      switch (b->RL * 10 + b->cpt)
+      {
+        case 11: slots = tree_s4_slots<1, true, 1>(b, w); break;
+        case 12: slots = tree_s4_slots<1, true, 2>(b, w); break;
+        case 21: slots = tree_s4_slots<2, true, 1>(b, w); break;
+        case 22: slots = tree_s4_slots<2, true, 2>(b, w); break;
+        case 41: slots = tree_s4_slots<4, true, 1>(b, w); break;
+        case 42: slots = tree_s4_slots<4, true, 2>(b, w); break;
+        case 81: slots = tree_s4_slots<8, true, 1>(b, w); break;
+        case 82: slots = tree_s4_slots<8, true, 2>(b, w); break;
+        default: break;
+      }
+    }
   }
   const unsigned long long * d_blk_off = (const unsigned long long *)(b->d_in + b->o_blk_off);
   {

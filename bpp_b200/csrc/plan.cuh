@@ -118,6 +118,10 @@ plan_kernel_blocks(const LocusDev * __restrict__ loci, const unsigned int * __re
   __shared__ __align__(16) OpRec s_rec[4][SM_OPS];
   __shared__ unsigned int s_where[4][SM_BUF];
   __shared__ unsigned char s_slot[4][SM_BUF];
+  __shared__ unsigned char s_prod[4][SM_BUF];       // 1 + op slot that produced the buffer in this list
+  __shared__ unsigned char s_order[4][SM_OPS];      // evaluation order (Sethi-Ullman)
+  __shared__ signed char s_kid[4][SM_OPS][2];       // producing op of the left / right child, or -1
+  __shared__ unsigned char s_need[4][SM_OPS];
   const unsigned int wib = threadIdx.x >> 5;
   // every closed chunk holds >= m ops, so a list of n (+1 eval-only) ops needs <= n/m + 1 chunks
   const unsigned int m_ops = (cap / 2 < (unsigned)TREE_CHUNK) ? (cap / 2 ? cap / 2 : 1u) : (unsigned)TREE_CHUNK;
@@ -153,6 +157,63 @@ plan_kernel_blocks(const LocusDev * __restrict__ loci, const unsigned int * __re
       if (o[k].left >= T) where[o[k].left - T] = 0;
       if (o[k].right >= T) where[o[k].right - T] = 0;
     }
+    // Evaluation order.  Any order that respects the dependencies gives bit-identical results, so small
+    // lists are re-ordered Sethi-Ullman style (the child subtree that needs more parked values first):
+    // a balanced tree of T tips then needs log2(T)-1 stack slots instead of up to T/3 in the caller's
+    // left-first post-order.
+    unsigned char * order = s_order[wib];
+    unsigned char * prodmap = s_prod[wib];
+    if (small)
+    {
+      signed char (*kid)[2] = s_kid[wib];
+      unsigned char * need = s_need[wib];
+      unsigned int consumed = 0;
+      for (unsigned int k = 0; k < n; ++k)
+      {
+        prodmap[o[k].parent - T] = 0;
+        if (o[k].left >= T) prodmap[o[k].left - T] = 0;
+        if (o[k].right >= T) prodmap[o[k].right - T] = 0;
+      }
+      for (unsigned int k = 0; k < n; ++k)
+      {
+        int c0 = -1, c1 = -1;
+        if (o[k].left >= T && prodmap[o[k].left - T]) c0 = prodmap[o[k].left - T] - 1;
+        if (o[k].right >= T && prodmap[o[k].right - T]) c1 = prodmap[o[k].right - T] - 1;
+        if (c0 >= 0 && (consumed >> c0) & 1u) c0 = -1;      // a value is pushed to one consumer only
+        if (c1 >= 0 && ((consumed >> c1) & 1u || c1 == c0)) c1 = -1;
+        kid[k][0] = (signed char)c0; kid[k][1] = (signed char)c1;
+        if (c0 >= 0) consumed |= 1u << c0;
+        if (c1 >= 0) consumed |= 1u << c1;
+        const unsigned int n0 = c0 >= 0 ? need[c0] : 0u, n1 = c1 >= 0 ? need[c1] : 0u;
+        need[k] = (unsigned char)((c0 >= 0 && c1 >= 0) ? max(max(n0, n1), 1u + min(n0, n1)) : max(n0, n1));
+        prodmap[o[k].parent - T] = (unsigned char)(k + 1);
+      }
+      // post-order DFS from every list root (ops nobody in the list consumes), bigger need first
+      unsigned int emitted = 0;
+      unsigned char stack[SM_OPS];
+      unsigned int done = 0;
+      for (unsigned int root = 0; root < n; ++root)
+      {
+        if ((consumed >> root) & 1u) continue;
+        int sp = 0;
+        stack[sp++] = (unsigned char)root;
+        while (sp > 0)
+        {
+          const unsigned int k = stack[sp - 1];
+          const int c0 = kid[k][0], c1 = kid[k][1];
+          const bool p0 = c0 >= 0 && !((done >> c0) & 1u), p1 = c1 >= 0 && !((done >> c1) & 1u);
+          if (p0 || p1)
+          {
+            int nxt;
+            if (p0 && p1) nxt = need[c0] >= need[c1] ? c0 : c1;
+            else nxt = p0 ? c0 : c1;
+            stack[sp++] = (unsigned char)nxt;
+          }
+          else { order[emitted++] = (unsigned char)k; done |= 1u << k; --sp; }
+        }
+      }
+      for (unsigned int k = 0; k < n; ++k) prodmap[o[k].parent - T] = 0;      // reused below: op slot of the producer
+    }
     const unsigned int rootc = want_root ? root_clv[bl] : 0xFFFFFFFFu;
     unsigned int free_slots = (max_slots >= 32) ? 0xFFFFFFFFu : ((1u << max_slots) - 1u);
     unsigned int prev = 0xFFFFFFFFu;        // buffer whose X sits in the register, or none
@@ -166,9 +227,9 @@ plan_kernel_blocks(const LocusDev * __restrict__ loci, const unsigned int * __re
       ++c_idx; c_nops = 0; c_ntips = 0;
     };
     const unsigned int cells_per_buf = L.sites * RL;
-    for (unsigned int k = 0; k < n; ++k)
+    for (unsigned int kk = 0; kk < n; ++kk)
     {
-      const RawOp r = o[k];
+      const RawOp r = o[small ? (unsigned int)order[kk] : kk];
       const unsigned int child[2] = { r.left, r.right };
       unsigned int ntip = 0;
       for (int c = 0; c < 2; ++c) if (child[c] < T && !L.tip_is_dense[child[c]]) ++ntip;
@@ -210,7 +271,18 @@ plan_kernel_blocks(const LocusDev * __restrict__ loci, const unsigned int * __re
             prod->ctl |= OP_PUSH; prod->up_pm = q.pm;
             where[b] = 0;
           }
-          else { q.kind = SRC_HBM; q.p0 = b; q.sc = c ? r.rsc : r.lsc; fast = false; }
+          else
+          {
+            q.kind = SRC_HBM; q.p0 = b; q.sc = c ? r.rsc : r.lsc;
+            // produced by an op of the chunk being filled: the fast path re-reads the CLV (an L2 hit)
+            // and applies the producer's Pup, which is staged with this chunk
+            if (small && prodmap[b] && (unsigned)(prodmap[b] - 1) / TREE_CHUNK == c_idx)
+            {
+              q.kind = SRC_HBML; q.off = (unsigned)(prodmap[b] - 1) % TREE_CHUNK;
+              OpRec * prod = rec_at(prodmap[b] - 1);
+              prod->ctl |= OP_PUSH; prod->up_pm = q.pm;
+            }
+          }
         }
       }
       // the previous result is not consumed by this op: its producer parks X in a free slot right after
@@ -224,9 +296,12 @@ plan_kernel_blocks(const LocusDev * __restrict__ loci, const unsigned int * __re
         prod->ctl |= OP_PARKA; prod->park_off = (unsigned)s * slot_unit;
       }
       free_slots |= consumed_slots;
-      // operand A is never the register X (the product is commutative)
-      const Operand & A = opd[prev_child == 0 ? 1 : 0];
-      const Operand & B = opd[prev_child == 0 ? 0 : 1];
+      // operand A is never the register X (the product is commutative); a re-read CLV must be A
+      int ia = prev_child == 0 ? 1 : 0;
+      if (prev_child < 0 && opd[1].kind == SRC_HBML && opd[0].kind != SRC_HBML) ia = 1;
+      const Operand & A = opd[ia];
+      const Operand & B = opd[1 - ia];
+      if (A.kind == SRC_HBM || B.kind == SRC_HBM || B.kind == SRC_HBML) fast = false;
       OpRec q;
       q.ctl = (A.kind << OP_AKIND_SHIFT) | (B.kind << OP_BKIND_SHIFT);
       q.dst_cell = (r.parent - T) * cells_per_buf; q.dsc = r.psc; q.park_off = 0; q.up_pm = 0; q.pad = 0;
@@ -239,6 +314,7 @@ plan_kernel_blocks(const LocusDev * __restrict__ loci, const unsigned int * __re
       *rec_at(rix) = q;
       ++c_nops;
       prev = r.parent - T; prev_off = rix;
+      if (small) prodmap[r.parent - T] = (unsigned char)(rix + 1);
     }
     cnt = n;
     if (want_root && !root_done)

@@ -89,7 +89,8 @@ struct S4Layout               // everything in uint4 (16-byte) units
   static constexpr unsigned TIPP = PUP + TREE_CHUNK * RL * 9;     // [CAP][RL] x 9
   static constexpr unsigned STAGE = TIPP + CAP * RL * 9;          // one stage buffer
   static constexpr unsigned CHUNK = STAGE - CH;                   // chunk size
-  static constexpr unsigned LUT = 2 * STAGE;                      // [CAP][RL] x 49
+  static constexpr unsigned NSTAGE = RL >= 4 ? 1 : 2;             // double-buffered staging only where shared memory allows
+  static constexpr unsigned LUT = NSTAGE * STAGE;                 // [CAP][RL] x 49
   static constexpr unsigned RING = LUT + CAP * RL * 49;           // 4 x (TileDesc 2 + blk 1)
   static constexpr unsigned RED = RING + 12;                      // 32 doubles
   static constexpr unsigned STACK = RED + 16;                     // [slots][CPT*TREE_NT][2] uint4, then [slots][CPT*TREE_NT] u32
@@ -148,12 +149,29 @@ __device__ __forceinline__ double tile_fast(const TreeParams & prm, const TileCt
       const bool aw1 = (w0.z & 16u) != 0;
       const unsigned int bmask = w1.x & 15u, bsh = (w1.x >> 8) & 31u;
       const bool bw1 = (w1.x & 16u) != 0;
+      const bool a_hbml = ((ctl >> OP_AKIND_SHIFT) & 15u) == SRC_HBML;
+      unsigned int a_cell0 = 0;
+      if (a_hbml) a_cell0 = s1[(ops + 4 * k + 2) * 4] * (sites * RL);      // a_p0 = buffer index
 #pragma unroll
       for (int j = 0; j < CPT; ++j)
       {
-        const unsigned int wa = aw1 ? tc.tw1[j] : tc.tw0[j];
-        const unsigned int ia = (amask ? lut_t : stk_t + j * (2 * TREE_NT)) + w0.w + ((wa >> ash) & amask) * 3;
-        const double2 a0 = sd2[ia], a1 = sd2[ia + 1];
+        double2 a0, a1;
+        if (a_hbml)
+        {
+          // child CLV written earlier in this pass by this very thread but no longer on chip: re-read it
+          // (an L2 hit) and apply its edge's P-matrix, the producer's Pup of this chunk
+          double v0, v1, v2, v3;
+          ld256(reinterpret_cast<const double *>(clv0 + (((size_t)a_cell0 + tc.cell[j]) << 5)), v0, v1, v2, v3);
+          const unsigned int pa = pup_t + w0.w * (RL * 9);
+          a0.x = dot4<EXACT>(sd2[pa + 0], sd2[pa + 1], v0, v1, v2, v3); a0.y = dot4<EXACT>(sd2[pa + 2], sd2[pa + 3], v0, v1, v2, v3);
+          a1.x = dot4<EXACT>(sd2[pa + 4], sd2[pa + 5], v0, v1, v2, v3); a1.y = dot4<EXACT>(sd2[pa + 6], sd2[pa + 7], v0, v1, v2, v3);
+        }
+        else
+        {
+          const unsigned int wa = aw1 ? tc.tw1[j] : tc.tw0[j];
+          const unsigned int ia = (amask ? lut_t : stk_t + j * (2 * TREE_NT)) + w0.w + ((wa >> ash) & amask) * 3;
+          a0 = sd2[ia]; a1 = sd2[ia + 1];
+        }
         if (!(ctl & OP_BPREV))
         {
           // operand B is not the register X: load it INTO the X registers (they are dead: a pushed X
@@ -178,6 +196,7 @@ __device__ __forceinline__ double tile_fast(const TreeParams & prm, const TileCt
       {
         unsigned int sc = 0;
         if (a_slot) sc += s1[tc.sst1 + w2.x * (CPT * TREE_NT) + j * TREE_NT + tid];
+        if (((ctl >> OP_AKIND_SHIFT) & 15u) == SRC_HBML && (int)w2.z >= 0) sc += H->scale[(size_t)(int)w2.z * sites + tc.cell[j] / RL];
         if (ctl & OP_BPREV) sc += psc[j];
         else if (b_slot) sc += s1[tc.sst1 + w3.x * (CPT * TREE_NT) + j * TREE_NT + tid];
         unsigned int below = (o[j][0] < BPPGPU_SCALE_THRESHOLD) & (o[j][1] < BPPGPU_SCALE_THRESHOLD) &
@@ -325,7 +344,9 @@ __device__ __noinline__ double chunk_general(const TreeParams prm, unsigned int 
       else r = load_global_x<RL, EXACT>(H, kind, p0, pm, scidx, cell, cat, sc);
       return r;
     };
-    const unsigned int akind = (ctl >> OP_AKIND_SHIFT) & 15u, bkind = (ctl >> OP_BKIND_SHIFT) & 15u;
+    unsigned int akind = (ctl >> OP_AKIND_SHIFT) & 15u, bkind = (ctl >> OP_BKIND_SHIFT) & 15u;
+    if (akind == SRC_HBML) akind = SRC_HBM;          // the general path applies P from global memory
+    if (bkind == SRC_HBML) bkind = SRC_HBM;
     double o0, o1, o2, o3;
     unsigned int osc = 0;
     if (ctl & OP_EVAL)
@@ -516,7 +537,7 @@ tree_kernel_s4(const TreeParams prm)
       const unsigned int rn = Lay::RING + ((t + 1) & 3u) * 3;
       const TileDesc dn = *reinterpret_cast<const TileDesc *>(&s4[rn]);
       load_tips(dn, ntw0, ntw1, nwgt);
-      if (dn.locus != d.locus && dn.locus != prefetched_locus)
+      if (Lay::NSTAGE == 2 && dn.locus != d.locus && dn.locus != prefetched_locus)
       {
         stage_fetch(buf ^ 1u, *reinterpret_cast<const unsigned long long *>(&s4[rn + 2]));
         prefetched_locus = dn.locus;
