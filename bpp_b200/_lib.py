@@ -14,7 +14,7 @@ SYMBOLS = [
     "bppgpu_device_count", "bppgpu_engine_create", "bppgpu_engine_destroy", "bppgpu_engine_device",
     "bppgpu_engine_set_math", "bppgpu_engine_synchronize", "bppgpu_engine_stream",
     "bppgpu_engine_launch_count", "bppgpu_engine_bytes_allocated", "bppgpu_last_error",
-    "bppgpu_set_fatal_handler", "bppgpu_version", "bppgpu_engine_set_profiling",
+    "bppgpu_set_fatal_handler", "bppgpu_version", "bppgpu_host_alloc", "bppgpu_host_free", "bppgpu_engine_set_profiling",
     "bppgpu_engine_get_profile", "bppgpu_engine_reset_profile",
     "bppgpu_locus_create", "bppgpu_locus_destroy", "bppgpu_set_tip_states", "bppgpu_set_tip_clv",
     "bppgpu_set_pattern_weights", "bppgpu_set_frequencies", "bppgpu_set_subst_params",
@@ -71,6 +71,8 @@ def load():
         "bppgpu_last_error": (C.c_char_p, []),
         "bppgpu_set_fatal_handler": (None, [vp]),
         "bppgpu_version": (C.c_char_p, []),
+        "bppgpu_host_alloc": (vp, [C.c_size_t]),
+        "bppgpu_host_free": (None, [vp]),
         "bppgpu_engine_set_profiling": (None, [vp, i]),
         "bppgpu_engine_get_profile": (None, [vp, dp, C.POINTER(ull)]),
         "bppgpu_engine_reset_profile": (None, [vp]),

@@ -877,19 +877,55 @@ static int batch_stage(bppgpu_batch * b, const unsigned int * mcounts, const uns
     b->blocks_cap = boff[n] + boff[n] / 4;
     CUDA_CHECK(cudaMalloc(&b->d_blocks, b->blocks_cap));
   }
-  if (tm) { memcpy(b->h_in + b->o_mat_idx, midx, tm * 4); memcpy(b->h_in + b->o_mat_bl, mbl, tm * 8); }
-  if (to) memcpy(b->h_in + b->o_ops, ops, to * sizeof(bppgpu_partial_op));
+  // the three offset tables are built here; the caller's arrays go to the device directly when they live in
+  // pinned memory (bppgpu_host_alloc / cudaHostRegister), otherwise through the pinned blob
+  auto is_pinned = [](const void * p) -> bool
+  {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+  };
+  auto put = [&](size_t dst, const void * src, size_t bytes)
+  {
+    if (!bytes) return;
+    const void * from = src;
+    if (!is_pinned(src)) { memcpy(b->h_in + dst, src, bytes); from = b->h_in + dst; }
+    CUDA_CHECK(cudaMemcpyAsync(b->d_in + dst, from, bytes, cudaMemcpyHostToDevice, b->stream));
+  };
+  CUDA_CHECK(cudaMemcpyAsync(b->d_in + b->o_mat_off, b->h_in + b->o_mat_off, (n + 1) * 4, cudaMemcpyHostToDevice, b->stream));
+  CUDA_CHECK(cudaMemcpyAsync(b->d_in + b->o_op_off, b->h_in + b->o_op_off, (n + 1) * 4, cudaMemcpyHostToDevice, b->stream));
+  CUDA_CHECK(cudaMemcpyAsync(b->d_in + b->o_blk_off, b->h_in + b->o_blk_off, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, b->stream));
+  if (tm) { put(b->o_mat_idx, midx, tm * 4); put(b->o_mat_bl, mbl, tm * 8); }
+  if (to) put(b->o_ops, ops, to * sizeof(bppgpu_partial_op));
   if (rclv)
   {
-    memcpy(b->h_in + b->o_root_clv, rclv, n * 4);
-    if (rsc) memcpy(b->h_in + b->o_root_sc, rsc, n * 4);
-    else { int * p = (int *)(b->h_in + b->o_root_sc); for (unsigned i = 0; i < n; ++i) p[i] = -1; }
+    put(b->o_root_clv, rclv, n * 4);
+    if (rsc) put(b->o_root_sc, rsc, n * 4);
+    else
+    {
+      int * p = (int *)(b->h_in + b->o_root_sc);
+      for (unsigned i = 0; i < n; ++i) p[i] = -1;
+      CUDA_CHECK(cudaMemcpyAsync(b->d_in + b->o_root_sc, p, n * 4, cudaMemcpyHostToDevice, b->stream));
+    }
   }
   b->total_mats = (unsigned)tm; b->total_ops = (unsigned)to;
   b->staged_mats = mcounts != nullptr; b->staged_ops = ocounts != nullptr; b->staged_roots = rclv != nullptr;
-  CUDA_CHECK(cudaMemcpyAsync(b->d_in, b->h_in, off, cudaMemcpyHostToDevice, b->stream));
   return BPPGPU_SUCCESS;
 }
+
+extern "C" void * bppgpu_host_alloc(size_t bytes)
+{
+  void * p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess)
+  {
+    cudaGetLastError();
+    fatal("Unable to allocate %zu bytes of pinned host memory", bytes);
+    return nullptr;
+  }
+  return p;
+}
+
+extern "C" void bppgpu_host_free(void * p) { if (p) cudaFreeHost(p); }
 
 static void batch_sync_loci(bppgpu_batch * b, bool need_eigen)
 {

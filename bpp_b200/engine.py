@@ -57,6 +57,33 @@ def _i32(a):
     return np.ascontiguousarray(a, dtype=np.int32)
 
 
+class PinnedArray:
+    """A numpy array backed by pinned host memory of the library (bppgpu_host_alloc): step inputs kept
+    in such arrays are copied H2D without an intermediate staging copy."""
+
+    def __init__(self, like):
+        L = _lib.load()
+        a = np.ascontiguousarray(like)
+        self._L, self.ptr = L, L.bppgpu_host_alloc(max(1, a.nbytes))
+        _lib.check()
+        buf = (C.c_char * max(1, a.nbytes)).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=a.dtype, count=a.size).reshape(a.shape)
+        self.array[...] = a
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            self._L.bppgpu_host_free(self.ptr)
+            self.ptr = None
+
+
+def pin_step(step):
+    """Copy the 7 arrays of a full-pass step into pinned memory; returns (pinned step tuple, holders)."""
+    dt = [np.uint32, np.uint32, np.float64, np.uint32, OP_DTYPE, np.uint32, np.int32]
+    holders = [PinnedArray(np.ascontiguousarray(a, dtype=t)) for a, t in zip(step, dt)]
+    return tuple(h.array for h in holders), holders
+
+
 def device_count():
     return _lib.load().bppgpu_device_count()
 

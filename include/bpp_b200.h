@@ -24,6 +24,8 @@
 #ifndef BPP_B200_H
 #define BPP_B200_H
 
+#include <stddef.h>
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -81,6 +83,11 @@ unsigned long long bppgpu_engine_bytes_allocated(const bppgpu_engine * e);
 const char * bppgpu_last_error(void);
 void bppgpu_set_fatal_handler(void (*handler)(const char * msg));
 const char * bppgpu_version(void);
+
+/* pinned host memory: step arrays (branch lengths, ops, indices ...) that live here are copied to the
+   device straight from the caller's buffers, anything else is staged through an internal pinned blob */
+void * bppgpu_host_alloc(size_t bytes);
+void   bppgpu_host_free(void * p);
 
 /* per-kernel device timers (CUDA events on the launching stream), for bench.py's roofline */
 #define BPPGPU_KERNEL_PMATRIX 0

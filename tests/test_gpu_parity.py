@@ -335,3 +335,19 @@ def test_frogs_real_data_diploid(eng):
         total += lnl
         l.destroy()
     assert abs(total - (-7320.932289)) < 5e-6
+
+
+def test_pinned_step_inputs_give_identical_results(eng):
+    """Step arrays kept in pinned memory (bppgpu_host_alloc) go to the device without the staging
+    copy; the result must be bit-identical to the pageable path."""
+    from bpp_b200 import engine
+    w = synth.make_workload("pin", n_loci=30, tips=9, sites=301, states=4, rate_cats=4, model="GTR", scaling=True, seed=5)
+    loci, trees, batch = _load(eng, w)
+    step = trees.full_pass_step()
+    a, ta = batch.full_pass(step)
+    pstep, holders = engine.pin_step(step)
+    b, tb = batch.full_pass(pstep)
+    assert np.array_equal(a, b) and ta == tb
+    for h in holders:
+        h.free()
+    _free(loci, batch)
