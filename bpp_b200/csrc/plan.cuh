@@ -62,6 +62,238 @@ __global__ void plan_kernel_flat(const LocusDev * __restrict__ loci, const unsig
   plan_count[bl] = cnt;
 }
 
+
+// ---------------------------------------------------------------- lane-parallel planner (lists of <= 32 ops)
+// lane k owns op k.  Producer / consumer links, Sethi-Ullman needs, subtree sizes and evaluation
+// positions are computed with warp shuffles; only the slot / chunk bookkeeping walks the positions
+// one by one (uniformly, ~20 instructions per op).  Produces exactly the program the serial planner
+// below produces for the same evaluation order.
+struct SmallPlanOut { unsigned int n_chunks, cnt; bool fast; };
+
+__device__ __forceinline__ SmallPlanOut
+plan_small_parallel(const LocusDev & L, const RawOp * o, unsigned int n, unsigned int rootc, int rootsc, bool want_root,
+                    unsigned char * blk, unsigned int chunks0, size_t cb, unsigned int cap, unsigned int lut_unit,
+                    unsigned int slot_unit, int max_slots, unsigned int RL, OpRec * rec,
+                    unsigned char * s_order, unsigned int * s_push)
+{
+  const unsigned int FULL = 0xFFFFFFFFu;
+  const unsigned int lane = threadIdx.x & 31u;
+  const unsigned int T = L.tips;
+  const bool act = lane < n;
+  RawOp r;
+  if (act) r = o[lane];
+  else { r.parent = 0xFFFFFFFFu; r.left = r.right = 0; r.lpm = r.rpm = 0; r.psc = r.lsc = r.rsc = -1; }
+  const unsigned int child[2] = { r.left, r.right };
+  bool tip[2], dense[2];
+#pragma unroll
+  for (int c = 0; c < 2; ++c)
+  {
+    tip[c] = act && child[c] < T;
+    dense[c] = tip[c] && L.tip_is_dense[child[c]] != 0;
+  }
+  // producer of each inner child: the latest earlier op that writes that buffer
+  int kid[2] = { -1, -1 };
+  for (unsigned int j = 0; j < n; ++j)
+  {
+    const unsigned int pj = __shfl_sync(FULL, r.parent, j);
+    if (act && j < lane)
+    {
+      if (!tip[0] && pj == child[0]) kid[0] = (int)j;
+      if (!tip[1] && pj == child[1]) kid[1] = (int)j;
+    }
+  }
+  if (kid[1] == kid[0]) kid[1] = -1;
+  // consumer of each op: the first op that takes its result (a pushed value has one consumer)
+  int par = -1;
+  for (unsigned int k2 = 0; k2 < n; ++k2)
+  {
+    const int a0 = __shfl_sync(FULL, kid[0], k2), a1 = __shfl_sync(FULL, kid[1], k2);
+    if (par < 0 && (a0 == (int)lane || a1 == (int)lane)) par = (int)k2;
+  }
+#pragma unroll
+  for (int c = 0; c < 2; ++c)
+  {
+    const int pk = __shfl_sync(FULL, par, kid[c] >= 0 ? kid[c] : 0);
+    if (kid[c] >= 0 && pk != (int)lane) kid[c] = -1;
+  }
+  // Sethi-Ullman need and subtree size, bottom-up in index order (producers precede consumers)
+  unsigned int need = 0, sz = 1;
+  for (unsigned int it = 0; it < n; ++it)
+  {
+    const unsigned int n0 = __shfl_sync(FULL, need, kid[0] >= 0 ? kid[0] : 0), n1 = __shfl_sync(FULL, need, kid[1] >= 0 ? kid[1] : 0);
+    const unsigned int s0 = __shfl_sync(FULL, sz, kid[0] >= 0 ? kid[0] : 0), s1 = __shfl_sync(FULL, sz, kid[1] >= 0 ? kid[1] : 0);
+    if (lane == it)
+    {
+      const unsigned int m0 = kid[0] >= 0 ? n0 : 0u, m1 = kid[1] >= 0 ? n1 : 0u;
+      need = (kid[0] >= 0 && kid[1] >= 0) ? max(max(m0, m1), 1u + min(m0, m1)) : max(m0, m1);
+      sz = 1u + (kid[0] >= 0 ? s0 : 0u) + (kid[1] >= 0 ? s1 : 0u);
+    }
+  }
+  int fk;                                       // the kid evaluated first: the one that needs more
+  {
+    const unsigned int n0 = __shfl_sync(FULL, need, kid[0] >= 0 ? kid[0] : 0), n1 = __shfl_sync(FULL, need, kid[1] >= 0 ? kid[1] : 0);
+    fk = (kid[0] >= 0 && kid[1] >= 0) ? (n0 >= n1 ? kid[0] : kid[1]) : (kid[0] >= 0 ? kid[0] : kid[1]);
+  }
+  // evaluation positions: list roots in index order, then top-down (consumers have larger indices)
+  const bool is_root = act && par < 0;
+  unsigned int start = 0;
+  for (unsigned int j = 0; j < n; ++j)
+  {
+    const unsigned int rj = __shfl_sync(FULL, is_root ? sz : 0u, j);
+    if (is_root && j < lane) start += rj;
+  }
+  for (int it = (int)n - 1; it >= 0; --it)
+  {
+    const unsigned int st = __shfl_sync(FULL, start, it);
+    const int fkk = __shfl_sync(FULL, fk, it);
+    const unsigned int szf = __shfl_sync(FULL, sz, fkk >= 0 ? fkk : 0);
+    if (par == it) start = st + ((int)lane == fkk ? 0u : szf);
+  }
+  const unsigned int pos = start + sz - 1;
+  if (act) s_order[pos] = (unsigned char)lane;
+  s_push[lane] = 0;
+  __syncwarp();
+  // slots and chunks, position by position (uniform control flow)
+  unsigned int ntip = 0;
+#pragma unroll
+  for (int c = 0; c < 2; ++c) if (tip[c] && !dense[c]) ++ntip;
+  unsigned int free_slots = (max_slots >= 32) ? FULL : ((1u << max_slots) - 1u);
+  unsigned int c_idx = 0, c_nops = 0, c_ntips = 0;
+  int myslot = -1;
+  unsigned int mychunk = 0, myidx = 0, mylut = 0;
+  for (unsigned int p = 0; p < n; ++p)
+  {
+    const unsigned int k = s_order[p];
+    if (p > 0)
+    {
+      const unsigned int kp = s_order[p - 1];
+      const int cons = __shfl_sync(FULL, par, kp);
+      if (cons >= 0 && cons != (int)k && free_slots)
+      {
+        const int s = __ffs(free_slots) - 1;
+        free_slots &= ~(1u << s);
+        if (lane == kp) myslot = s;
+      }
+    }
+    const int k0 = __shfl_sync(FULL, kid[0], k), k1 = __shfl_sync(FULL, kid[1], k);
+    const int s0 = __shfl_sync(FULL, myslot, k0 >= 0 ? k0 : 0), s1 = __shfl_sync(FULL, myslot, k1 >= 0 ? k1 : 0);
+    if (k0 >= 0 && s0 >= 0) free_slots |= 1u << s0;
+    if (k1 >= 0 && s1 >= 0) free_slots |= 1u << s1;
+    const unsigned int ntk = __shfl_sync(FULL, ntip, k);
+    if (c_nops == (unsigned)TREE_CHUNK || c_ntips + ntk > cap)
+    {
+      if (lane == 0)
+      {
+        ChunkHdr * h = reinterpret_cast<ChunkHdr *>(blk + chunks0 + (size_t)c_idx * cb);
+        h->nops = c_nops; h->ntips = c_ntips; h->pad0 = h->pad1 = 0;
+      }
+      ++c_idx; c_nops = 0; c_ntips = 0;
+    }
+    if (lane == k) { mychunk = c_idx; myidx = c_nops; mylut = c_ntips; }
+    ++c_nops; c_ntips += ntk;
+  }
+  // operands
+  const unsigned int cells_per_buf = L.sites * RL;
+  unsigned int okind[2], osel[2], ooff[2], op0[2], opm[2]; int osc[2];
+  int prev_child = -1;
+  bool op_fast = true;
+  unsigned int lutn = mylut;
+#pragma unroll
+  for (int c = 0; c < 2; ++c)
+  {
+    const int kc = kid[c] >= 0 ? kid[c] : 0;
+    const unsigned int kpos = __shfl_sync(FULL, pos, kc);
+    const int kslot = __shfl_sync(FULL, myslot, kc);
+    const unsigned int kchunk = __shfl_sync(FULL, mychunk, kc), kidx = __shfl_sync(FULL, myidx, kc);
+    opm[c] = c ? r.rpm : r.lpm; osel[c] = ooff[c] = op0[c] = 0; osc[c] = -1; okind[c] = SRC_HBM;
+    if (!act) continue;
+    if (tip[c])
+    {
+      op0[c] = child[c];
+      if (dense[c]) { okind[c] = SRC_TIP_DENSE; op_fast = false; }
+      else
+      {
+        okind[c] = SRC_TIP_PACKED;
+        osel[c] = 15u | ((child[c] >> 3) << 4) | (((child[c] & 7u) * 4) << 8);
+        ooff[c] = lutn * lut_unit; ++lutn;
+        if (child[c] >= 16) op_fast = false;
+      }
+    }
+    else if (kid[c] >= 0 && kpos + 1 == pos && prev_child < 0) { okind[c] = SRC_PREV; prev_child = c; s_push[kid[c]] = opm[c] + 1; }
+    else if (kid[c] >= 0 && kslot >= 0) { okind[c] = SRC_SLOT; op0[c] = (unsigned)kslot; ooff[c] = (unsigned)kslot * slot_unit; s_push[kid[c]] = opm[c] + 1; }
+    else
+    {
+      op0[c] = child[c] - T; osc[c] = c ? r.rsc : r.lsc;
+      if (kid[c] >= 0 && kchunk == mychunk) { okind[c] = SRC_HBML; ooff[c] = kidx; s_push[kid[c]] = opm[c] + 1; }
+    }
+  }
+  __syncwarp();
+  const bool root_done = __ballot_sync(FULL, act && want_root && r.parent == rootc) != 0;
+  if (act)
+  {
+    int ia = prev_child == 0 ? 1 : 0;
+    if (prev_child < 0 && okind[1] == SRC_HBML && okind[0] != SRC_HBML) ia = 1;
+    const int ib = 1 - ia;
+    if (okind[ia] == SRC_HBM || okind[ib] == SRC_HBM || okind[ib] == SRC_HBML) op_fast = false;
+    OpRec q;
+    q.ctl = (okind[ia] << OP_AKIND_SHIFT) | (okind[ib] << OP_BKIND_SHIFT);
+    q.dst_cell = (r.parent - T) * cells_per_buf; q.dsc = r.psc; q.pad = 0;
+    q.a_sel = osel[ia]; q.a_off = ooff[ia]; q.a_p0 = op0[ia]; q.a_pm = opm[ia]; q.a_sc = osc[ia];
+    q.b_sel = osel[ib]; q.b_off = ooff[ib]; q.b_p0 = op0[ib]; q.b_pm = opm[ib]; q.b_sc = osc[ib];
+    q.park_off = 0; q.up_pm = 0;
+    if (r.psc >= 0) q.ctl |= OP_SCALE;
+    if (prev_child >= 0) q.ctl |= OP_BPREV;
+    if (want_root && r.parent == rootc) q.ctl |= OP_ROOT;
+    if (s_push[lane]) { q.ctl |= OP_PUSH; q.up_pm = s_push[lane] - 1; }
+    if (myslot >= 0) { q.ctl |= OP_PARKA; q.park_off = (unsigned)myslot * slot_unit; }
+    rec[mychunk * TREE_CHUNK + myidx] = q;
+  }
+  bool fast = __ballot_sync(FULL, !act || op_fast) == FULL;
+  unsigned int cnt = n;
+  if (want_root && !root_done)
+  {
+    if (c_nops == (unsigned)TREE_CHUNK)
+    {
+      if (lane == 0)
+      {
+        ChunkHdr * h = reinterpret_cast<ChunkHdr *>(blk + chunks0 + (size_t)c_idx * cb);
+        h->nops = c_nops; h->ntips = c_ntips; h->pad0 = h->pad1 = 0;
+      }
+      ++c_idx; c_nops = 0; c_ntips = 0;
+    }
+    if (lane == 0)
+    {
+      OpRec q;
+      memset(&q, 0, sizeof(q));
+      unsigned int kind;
+      q.dsc = rootsc; q.a_sc = rootsc;
+      if (rootc < T)
+      {
+        q.a_p0 = rootc;
+        if (L.tip_is_dense[rootc]) kind = SRC_TIP_DENSE;
+        else { kind = SRC_TIP_PACKED; q.a_sel = 15u | ((rootc >> 3) << 4) | (((rootc & 7u) * 4) << 8); }
+      }
+      else { kind = SRC_HBM; q.a_p0 = rootc - T; }
+      q.ctl = OP_EVAL | OP_ROOT | (kind << OP_AKIND_SHIFT);
+      rec[c_idx * TREE_CHUNK + c_nops] = q;
+    }
+    ++c_nops; cnt = n + 1; fast = false;
+  }
+  if (c_nops)
+  {
+    if (lane == 0)
+    {
+      ChunkHdr * h = reinterpret_cast<ChunkHdr *>(blk + chunks0 + (size_t)c_idx * cb);
+      h->nops = c_nops; h->ntips = c_ntips; h->pad0 = h->pad1 = 0;
+    }
+    ++c_idx;
+  }
+  __syncwarp();
+  SmallPlanOut out;
+  out.n_chunks = c_idx; out.cnt = cnt; out.fast = fast && c_idx == 1;
+  return out;
+}
+
 // ---------------------------------------------------------------- staged blocks (4-state kernel)
 // One WARP per locus: lane 0 plans sequentially, then all lanes gather the P-matrices the kernel
 // needs (Pup of every pushed op, tipP of every packed tip child) into the block, already in the
@@ -93,10 +325,10 @@ plan_kernel_blocks(const LocusDev * __restrict__ loci, const unsigned int * __re
   if (mat_off)
   {
     const unsigned int mfirst = mat_off[bl], mcount = mat_off[bl + 1] - mfirst;
-    for (unsigned int t = lane; t < mcount * RL * 4; t += 32)
+    for (unsigned int t = lane; t < mcount * RL; t += 32)
     {
-      const unsigned int j = t & 3u, n = (t >> 2) % RL, m = t / (4 * RL);
-      pmatrix_row(L, mat_idx[mfirst + m], mat_bl[mfirst + m], n, j);
+      const unsigned int n = t % RL, m = t / RL;
+      pmatrix_full4(L, mat_idx[mfirst + m], mat_bl[mfirst + m], n);
     }
     __syncwarp();
   }
@@ -141,7 +373,24 @@ plan_kernel_blocks(const LocusDev * __restrict__ loci, const unsigned int * __re
     tile_blk[2 * (size_t)t + 1] = 0;
   }
 
-  if (lane == 0)
+  if (small)
+  {
+    const SmallPlanOut sp = plan_small_parallel(L, o, n, want_root ? root_clv[bl] : 0xFFFFFFFFu, want_root ? root_sc[bl] : -1,
+                                                want_root != 0, blk, chunks0, cb, cap, lut_unit, slot_unit, max_slots, RL,
+                                                s_rec[wib], s_order[wib], s_where[wib]);
+    n_chunks = sp.n_chunks; cnt = sp.cnt;
+    if (lane == 0)
+    {
+      LocusHdr * H = reinterpret_cast<LocusHdr *>(blk);
+      H->clv = L.clv; H->tip_dense = L.tip_dense; H->scale = L.scale;
+      H->tipwords = reinterpret_cast<const unsigned int *>(L.tip_codes); H->pmat = L.pmat;
+      H->clv_stride = L.clv_stride; H->sites = L.sites; H->nops = cnt; H->tip_words = L.tip_words;
+      H->n_chunks = n_chunks; H->flags = sp.fast ? HDR_FAST : 0u; H->pad0 = 0;
+      for (int j = 0; j < 4; ++j) H->freqs[j] = L.freqs[j];
+      plan_count[bl] = cnt;
+    }
+  }
+  else if (lane == 0)
   {
     unsigned int * where = small ? s_where[wib] : reinterpret_cast<unsigned int *>(scratch + scratch_off[bl]);
     unsigned char * slot_of = small ? s_slot[wib] : reinterpret_cast<unsigned char *>(where + L.clv_buffers);
@@ -361,8 +610,9 @@ plan_kernel_blocks(const LocusDev * __restrict__ loci, const unsigned int * __re
   }
   double * rw = reinterpret_cast<double *>(blk + sizeof(LocusHdr));
   for (unsigned int j = lane; j < RL; j += 32) rw[j] = L.rate_weights[j];
-  // gather: per chunk, per op: Pup (if pushed) and the tipP of its packed tip children
-  const unsigned int mat = RL * 16;                     // doubles per matrix
+  // gather: per chunk, per op: Pup (if pushed) and the tipP of its packed tip children.  A matrix set is
+  // RL*8 double2; `per` lanes copy one set, so a warp moves 32/per sets per step.
+  const unsigned int per = RL * 8;                      // double2 per (op, which) matrix set
   for (unsigned int c = 0; c < n_chunks; ++c)
   {
     unsigned char * ch = blk + chunks0 + (size_t)c * cb;
@@ -370,26 +620,29 @@ plan_kernel_blocks(const LocusDev * __restrict__ loci, const unsigned int * __re
     const OpRec * cops = small ? &s_rec[wib][c * TREE_CHUNK] : reinterpret_cast<const OpRec *>(ch + sizeof(ChunkHdr));
     double * Pup = reinterpret_cast<double *>(ch + sizeof(ChunkHdr) + TREE_CHUNK * sizeof(OpRec));
     double * tipP = Pup + (size_t)TREE_CHUNK * RL * PM_STRIDE;
-    for (unsigned int e = lane; e < hdr.nops * 3 * mat; e += 32)
+    const unsigned int total = hdr.nops * 3 * per;
+    for (unsigned int idx = lane; idx < total; idx += 32)
     {
-      const unsigned int k = e / (3 * mat), w = e % (3 * mat);
-      const unsigned int which = w / mat, r = (w / 16) % RL, x = w & 15u;
+      const unsigned int task = idx / per, e = idx % per;           // e: double2 index within the set
+      const unsigned int k = task / 3, which = task % 3;
       const OpRec & q = cops[k];
       if (q.ctl & OP_EVAL) continue;
+      unsigned int pm; double * dst;
       if (which == 0)
       {
-        if (q.ctl & OP_PUSH) Pup[((size_t)k * RL + r) * PM_STRIDE + x] = L.pmat[((size_t)q.up_pm * RL + r) * 16 + x];
+        if (!(q.ctl & OP_PUSH)) continue;
+        pm = q.up_pm; dst = Pup + (size_t)k * RL * PM_STRIDE;
       }
       else
       {
         const unsigned int kind = (q.ctl >> (which == 1 ? OP_AKIND_SHIFT : OP_BKIND_SHIFT)) & 15u;
-        if (kind == SRC_TIP_PACKED)
-        {
-          const unsigned int s = (which == 1 ? q.a_off : q.b_off) / lut_unit;
-          const unsigned int pm = which == 1 ? q.a_pm : q.b_pm;
-          tipP[((size_t)s * RL + r) * PM_STRIDE + x] = L.pmat[((size_t)pm * RL + r) * 16 + x];
-        }
+        if (kind != SRC_TIP_PACKED) continue;
+        pm = which == 1 ? q.a_pm : q.b_pm;
+        dst = tipP + (size_t)((which == 1 ? q.a_off : q.b_off) / lut_unit) * RL * PM_STRIDE;
       }
+      const unsigned int r = e >> 3, x = (e & 7u) * 2;
+      const double2 v = *reinterpret_cast<const double2 *>(L.pmat + ((size_t)pm * RL + r) * 16 + x);
+      *reinterpret_cast<double2 *>(dst + (size_t)r * PM_STRIDE + x) = v;
     }
   }
 }

@@ -58,6 +58,52 @@ __device__ __forceinline__ void pmatrix_row(const LocusDev & L, unsigned int pm_
   }
 }
 
+// whole 4x4 matrix of one (branch, category): the expm1 / exp values are shared by the four rows
+__device__ __forceinline__ void pmatrix_full4(const LocusDev & L, unsigned int pm_idx, double t, unsigned int n)
+{
+  const unsigned int R = L.rate_cats;
+  const double bt = t * L.rates[n];
+  double2 * P = reinterpret_cast<double2 *>(L.pmat + ((size_t)pm_idx * R + n) * 16);
+  if (bt < 1e-100)
+  {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { P[2 * j] = make_double2(j == 0 ? 1.0 : 0.0, j == 1 ? 1.0 : 0.0); P[2 * j + 1] = make_double2(j == 2 ? 1.0 : 0.0, j == 3 ? 1.0 : 0.0); }
+  }
+  else if (L.model_kind == 0)
+  {
+    const double a = (1 + 3 * exp(-4 * bt / 3)) / 4;
+    const double b = (1 - a) / 3;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { P[2 * j] = make_double2(j == 0 ? a : b, j == 1 ? a : b); P[2 * j + 1] = make_double2(j == 2 ? a : b, j == 3 ? a : b); }
+  }
+  else
+  {
+    const double * __restrict__ V = L.eigenvecs;
+    const double * __restrict__ Vi = L.inv_eigenvecs;
+    double ex[4], v[16];
+#pragma unroll
+    for (int mm = 0; mm < 4; ++mm) ex[mm] = expm1(L.eigenvals[mm] * bt);
+#pragma unroll
+    for (int e = 0; e < 16; ++e) v[e] = V[e];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+    {
+      double temp[4], row[4];
+#pragma unroll
+      for (int mm = 0; mm < 4; ++mm) temp[mm] = __dmul_rn(Vi[j * 4 + mm], ex[mm]);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+      {
+        double acc = (j == k) ? 1.0 : 0.0;
+#pragma unroll
+        for (int mm = 0; mm < 4; ++mm) acc = __dadd_rn(acc, __dmul_rn(temp[mm], v[mm * 4 + k]));
+        row[k] = acc;
+      }
+      P[2 * j] = make_double2(row[0], row[1]); P[2 * j + 1] = make_double2(row[2], row[3]);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(128)
 pmatrix_kernel(const LocusDev * __restrict__ loci, const unsigned int * __restrict__ batch_locus,
                const unsigned int * __restrict__ mat_off, const unsigned int * __restrict__ mat_idx,
