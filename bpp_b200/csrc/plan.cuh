@@ -154,9 +154,11 @@ plan_small_parallel(const LocusDev & L, const RawOp * o, unsigned int n, unsigne
   s_push[lane] = 0;
   __syncwarp();
   // slots and chunks, position by position (uniform control flow)
+  // children that need a staged P-matrix slot: packed tips (lookup table) and CLVs that this list does
+  // not produce (HBM-resident children of partial updates)
   unsigned int ntip = 0;
 #pragma unroll
-  for (int c = 0; c < 2; ++c) if (tip[c] && !dense[c]) ++ntip;
+  for (int c = 0; c < 2; ++c) if (act && ((tip[c] && !dense[c]) || (!tip[c] && kid[c] < 0))) ++ntip;
   unsigned int free_slots = (max_slots >= 32) ? FULL : ((1u << max_slots) - 1u);
   unsigned int c_idx = 0, c_nops = 0, c_ntips = 0;
   int myslot = -1;
@@ -224,7 +226,13 @@ plan_small_parallel(const LocusDev & L, const RawOp * o, unsigned int n, unsigne
     else
     {
       op0[c] = child[c] - T; osc[c] = c ? r.rsc : r.lsc;
-      if (kid[c] >= 0 && kchunk == mychunk) { okind[c] = SRC_HBML; ooff[c] = kidx; s_push[kid[c]] = opm[c] + 1; }
+      if (kid[c] >= 0)
+      {
+        // produced by this list but neither in the register nor in a slot: re-read it with the producer's Pup
+        if (kchunk == mychunk) { okind[c] = SRC_HBML; ooff[c] = kidx; s_push[kid[c]] = opm[c] + 1; }
+        else op_fast = false;
+      }
+      else { ooff[c] = lutn; ++lutn; }         // HBM-resident child: its edge's P-matrix is staged in slot lutn
     }
   }
   __syncwarp();
@@ -234,7 +242,6 @@ plan_small_parallel(const LocusDev & L, const RawOp * o, unsigned int n, unsigne
     int ia = prev_child == 0 ? 1 : 0;
     if (prev_child < 0 && okind[1] == SRC_HBML && okind[0] != SRC_HBML) ia = 1;
     const int ib = 1 - ia;
-    if (okind[ia] == SRC_HBM || okind[ib] == SRC_HBM || okind[ib] == SRC_HBML) op_fast = false;
     OpRec q;
     q.ctl = (okind[ia] << OP_AKIND_SHIFT) | (okind[ib] << OP_BKIND_SHIFT);
     q.dst_cell = (r.parent - T) * cells_per_buf; q.dsc = r.psc; q.pad = 0;
@@ -636,9 +643,13 @@ plan_kernel_blocks(const LocusDev * __restrict__ loci, const unsigned int * __re
       else
       {
         const unsigned int kind = (q.ctl >> (which == 1 ? OP_AKIND_SHIFT : OP_BKIND_SHIFT)) & 15u;
-        if (kind != SRC_TIP_PACKED) continue;
+        const unsigned int off = which == 1 ? q.a_off : q.b_off;
+        unsigned int slot;
+        if (kind == SRC_TIP_PACKED) slot = off / lut_unit;
+        else if (kind == SRC_HBM && small) slot = off;
+        else continue;
         pm = which == 1 ? q.a_pm : q.b_pm;
-        dst = tipP + (size_t)((which == 1 ? q.a_off : q.b_off) / lut_unit) * RL * PM_STRIDE;
+        dst = tipP + (size_t)slot * RL * PM_STRIDE;
       }
       const unsigned int r = e >> 3, x = (e & 7u) * 2;
       const double2 v = *reinterpret_cast<const double2 *>(L.pmat + ((size_t)pm * RL + r) * 16 + x);

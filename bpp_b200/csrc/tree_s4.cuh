@@ -126,6 +126,7 @@ __device__ __forceinline__ double tile_fast(const TreeParams & prm, const TileCt
   const unsigned int lut_t = Lay::LUT + tc.cat * 49;
   const unsigned int stk_t = Lay::STACK + tid * 2;
   const unsigned int pup_t = sb + Lay::PUP + tc.cat * 9;
+  const unsigned int tipp_t = sb + Lay::TIPP + tc.cat * 9;
   const unsigned int ops = sb + Lay::OPS;
   const unsigned int cn = s1[(sb + Lay::CH) * 4];
   unsigned char * const clv0 = reinterpret_cast<unsigned char *>(H->clv);
@@ -149,22 +150,32 @@ __device__ __forceinline__ double tile_fast(const TreeParams & prm, const TileCt
       const bool aw1 = (w0.z & 16u) != 0;
       const unsigned int bmask = w1.x & 15u, bsh = (w1.x >> 8) & 31u;
       const bool bw1 = (w1.x & 16u) != 0;
-      const bool a_hbml = ((ctl >> OP_AKIND_SHIFT) & 15u) == SRC_HBML;
-      unsigned int a_cell0 = 0;
-      if (a_hbml) a_cell0 = s1[(ops + 4 * k + 2) * 4] * (sites * RL);      // a_p0 = buffer index
+      // HBM-class operands: a CLV re-read from global memory (written earlier in this pass by this very
+      // thread, or resident from an earlier call) times its edge's staged P-matrix: the producer's Pup
+      // (SRC_HBML) or a tipP slot (SRC_HBM)
+      const unsigned int akind = (ctl >> OP_AKIND_SHIFT) & 15u, bkind = (ctl >> OP_BKIND_SHIFT) & 15u;
+      const bool a_hbm = akind == SRC_HBML || akind == SRC_HBM, b_hbm = bkind == SRC_HBML || bkind == SRC_HBM;
+      unsigned int a_cell0 = 0, b_cell0 = 0, a_pi = 0, b_pi = 0;
+      if (a_hbm)
+      {
+        a_cell0 = s1[(ops + 4 * k + 2) * 4] * (sites * RL);                 // a_p0 = buffer index
+        a_pi = (akind == SRC_HBML ? pup_t : tipp_t) + w0.w * (RL * 9);
+      }
+      if (b_hbm)
+      {
+        b_cell0 = s1[(ops + 4 * k + 3) * 4] * (sites * RL);                 // b_p0
+        b_pi = (bkind == SRC_HBML ? pup_t : tipp_t) + w1.y * (RL * 9);
+      }
 #pragma unroll
       for (int j = 0; j < CPT; ++j)
       {
         double2 a0, a1;
-        if (a_hbml)
+        if (a_hbm)
         {
-          // child CLV written earlier in this pass by this very thread but no longer on chip: re-read it
-          // (an L2 hit) and apply its edge's P-matrix, the producer's Pup of this chunk
           double v0, v1, v2, v3;
           ld256(reinterpret_cast<const double *>(clv0 + (((size_t)a_cell0 + tc.cell[j]) << 5)), v0, v1, v2, v3);
-          const unsigned int pa = pup_t + w0.w * (RL * 9);
-          a0.x = dot4<EXACT>(sd2[pa + 0], sd2[pa + 1], v0, v1, v2, v3); a0.y = dot4<EXACT>(sd2[pa + 2], sd2[pa + 3], v0, v1, v2, v3);
-          a1.x = dot4<EXACT>(sd2[pa + 4], sd2[pa + 5], v0, v1, v2, v3); a1.y = dot4<EXACT>(sd2[pa + 6], sd2[pa + 7], v0, v1, v2, v3);
+          a0.x = dot4<EXACT>(sd2[a_pi + 0], sd2[a_pi + 1], v0, v1, v2, v3); a0.y = dot4<EXACT>(sd2[a_pi + 2], sd2[a_pi + 3], v0, v1, v2, v3);
+          a1.x = dot4<EXACT>(sd2[a_pi + 4], sd2[a_pi + 5], v0, v1, v2, v3); a1.y = dot4<EXACT>(sd2[a_pi + 6], sd2[a_pi + 7], v0, v1, v2, v3);
         }
         else
         {
@@ -176,10 +187,20 @@ __device__ __forceinline__ double tile_fast(const TreeParams & prm, const TileCt
         {
           // operand B is not the register X: load it INTO the X registers (they are dead: a pushed X
           // is consumed by exactly one op, and that op has OP_BPREV)
-          const unsigned int wb = bw1 ? tc.tw1[j] : tc.tw0[j];
-          const unsigned int ib = (bmask ? lut_t : stk_t + j * (2 * TREE_NT)) + w1.y + ((wb >> bsh) & bmask) * 3;
-          const double2 b0 = sd2[ib], b1 = sd2[ib + 1];
-          x[j][0] = b0.x; x[j][1] = b0.y; x[j][2] = b1.x; x[j][3] = b1.y;
+          if (b_hbm)
+          {
+            double v0, v1, v2, v3;
+            ld256(reinterpret_cast<const double *>(clv0 + (((size_t)b_cell0 + tc.cell[j]) << 5)), v0, v1, v2, v3);
+            x[j][0] = dot4<EXACT>(sd2[b_pi + 0], sd2[b_pi + 1], v0, v1, v2, v3); x[j][1] = dot4<EXACT>(sd2[b_pi + 2], sd2[b_pi + 3], v0, v1, v2, v3);
+            x[j][2] = dot4<EXACT>(sd2[b_pi + 4], sd2[b_pi + 5], v0, v1, v2, v3); x[j][3] = dot4<EXACT>(sd2[b_pi + 6], sd2[b_pi + 7], v0, v1, v2, v3);
+          }
+          else
+          {
+            const unsigned int wb = bw1 ? tc.tw1[j] : tc.tw0[j];
+            const unsigned int ib = (bmask ? lut_t : stk_t + j * (2 * TREE_NT)) + w1.y + ((wb >> bsh) & bmask) * 3;
+            const double2 b0 = sd2[ib], b1 = sd2[ib + 1];
+            x[j][0] = b0.x; x[j][1] = b0.y; x[j][2] = b1.x; x[j][3] = b1.y;
+          }
         }
         o[j][0] = __dmul_rn(x[j][0], a0.x); o[j][1] = __dmul_rn(x[j][1], a0.y);
         o[j][2] = __dmul_rn(x[j][2], a1.x); o[j][3] = __dmul_rn(x[j][3], a1.y);
@@ -196,7 +217,10 @@ __device__ __forceinline__ double tile_fast(const TreeParams & prm, const TileCt
       {
         unsigned int sc = 0;
         if (a_slot) sc += s1[tc.sst1 + w2.x * (CPT * TREE_NT) + j * TREE_NT + tid];
-        if (((ctl >> OP_AKIND_SHIFT) & 15u) == SRC_HBML && (int)w2.z >= 0) sc += H->scale[(size_t)(int)w2.z * sites + tc.cell[j] / RL];
+        const unsigned int ak = (ctl >> OP_AKIND_SHIFT) & 15u, bk = (ctl >> OP_BKIND_SHIFT) & 15u;
+        if ((ak == SRC_HBML || ak == SRC_HBM) && (int)w2.z >= 0) sc += H->scale[(size_t)(int)w2.z * sites + tc.cell[j] / RL];
+        if (!(ctl & OP_BPREV) && (bk == SRC_HBML || bk == SRC_HBM) && (int)w3.z >= 0)
+          sc += H->scale[(size_t)(int)w3.z * sites + tc.cell[j] / RL];
         if (ctl & OP_BPREV) sc += psc[j];
         else if (b_slot) sc += s1[tc.sst1 + w3.x * (CPT * TREE_NT) + j * TREE_NT + tid];
         unsigned int below = (o[j][0] < BPPGPU_SCALE_THRESHOLD) & (o[j][1] < BPPGPU_SCALE_THRESHOLD) &
