@@ -106,7 +106,8 @@ struct OpRec
 };
 static_assert(sizeof(OpRec) == 64, "OpRec must be 64 bytes");
 
-enum : unsigned { HDR_FAST = 1u };   // every op of the locus uses fast operands only
+enum : unsigned { HDR_FAST = 1u,     // every op of the locus uses fast operands only
+                  HDR_SIMPLE = 2u }; // ... and none is HBM-class or scaled: the lean instantiation of tile_fast
 
 struct LocusHdr
 {

@@ -116,7 +116,9 @@ struct TileCtx
 // ------------------------------------------------------------------------------------------------
 // fast path: every operand is a register-resident packed tip, a stack slot or the previous X
 // ------------------------------------------------------------------------------------------------
-template <int RL, bool EXACT, int CPT>
+// FULL = false is the lean instantiation for loci flagged HDR_SIMPLE (no HBM-class operand, no scaler):
+// full-tree passes without scaling, the headline workload.
+template <int RL, bool EXACT, int CPT, bool FULL>
 __device__ __forceinline__ double tile_fast(const TreeParams & prm, const TileCtx<CPT> & tc)
 {
   using Lay = S4Layout<RL, CPT>;
@@ -154,7 +156,7 @@ __device__ __forceinline__ double tile_fast(const TreeParams & prm, const TileCt
       // thread, or resident from an earlier call) times its edge's staged P-matrix: the producer's Pup
       // (SRC_HBML) or a tipP slot (SRC_HBM)
       const unsigned int akind = (ctl >> OP_AKIND_SHIFT) & 15u, bkind = (ctl >> OP_BKIND_SHIFT) & 15u;
-      const bool a_hbm = akind == SRC_HBML || akind == SRC_HBM, b_hbm = bkind == SRC_HBML || bkind == SRC_HBM;
+      const bool a_hbm = FULL && (akind == SRC_HBML || akind == SRC_HBM), b_hbm = FULL && (bkind == SRC_HBML || bkind == SRC_HBM);
       unsigned int a_cell0 = 0, b_cell0 = 0, a_pi = 0, b_pi = 0;
       if (a_hbm)
       {
@@ -208,7 +210,7 @@ __device__ __forceinline__ double tile_fast(const TreeParams & prm, const TileCt
       }
     }
     // ---- per-site scaling (core_partials.c:720,739-754)
-    if (ctl & OP_SCALE)
+    if (FULL && (ctl & OP_SCALE))
     {
       const uint4 w2 = s4[ops + 4 * k + 2], w3 = s4[ops + 4 * k + 3];
       const bool a_slot = ((ctl >> OP_AKIND_SHIFT) & 15u) == SRC_SLOT, b_slot = ((ctl >> OP_BKIND_SHIFT) & 15u) == SRC_SLOT;
@@ -263,7 +265,7 @@ __device__ __forceinline__ double tile_fast(const TreeParams & prm, const TileCt
         {
           sd2[stk_t + j * (2 * TREE_NT) + po] = make_double2(x[j][0], x[j][1]);
           sd2[stk_t + j * (2 * TREE_NT) + po + 1] = make_double2(x[j][2], x[j][3]);
-          if (ctl & OP_SCALE) s1[tc.sst1 + (po / Lay::SLOT) * (CPT * TREE_NT) + j * TREE_NT + tid] = psc[j];
+          if (FULL && (ctl & OP_SCALE)) s1[tc.sst1 + (po / Lay::SLOT) * (CPT * TREE_NT) + j * TREE_NT + tid] = psc[j];
         }
       }
     }
@@ -287,7 +289,7 @@ __device__ __forceinline__ double tile_fast(const TreeParams & prm, const TileCt
         else
         {
           s = log(term);
-          if (osc[j]) s = __dadd_rn(s, __dmul_rn((double)osc[j], prm.log_threshold));
+          if (FULL && osc[j]) s = __dadd_rn(s, __dmul_rn((double)osc[j], prm.log_threshold));
           s = __dmul_rn(s, (double)tc.wgt[j]);
         }
         if (tc.valid[j] && tc.cat == 0)
@@ -583,7 +585,8 @@ tree_kernel_s4(const TreeParams prm)
     }
 
     double site_sum;
-    if (H->flags & HDR_FAST) site_sum = tile_fast<RL, EXACT, CPT>(prm, tc);
+    if (H->flags & HDR_SIMPLE) site_sum = tile_fast<RL, EXACT, CPT, false>(prm, tc);
+    else if (H->flags & HDR_FAST) site_sum = tile_fast<RL, EXACT, CPT, true>(prm, tc);
     else
     {
       // general path: chunk by chunk (later chunks are staged in place, synchronously), cell by cell
