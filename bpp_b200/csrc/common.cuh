@@ -172,6 +172,7 @@ struct TreeParams
   double * persite;                   // optional per-site output of the (single) locus, or nullptr
   int persite_mode;                   // 1 = weighted site lnL, 2 = site likelihood (vector form)
   int n_slots;                        // shared-memory stack slots per cell
+  unsigned int lut_cap;               // tip-slot capacity of the launch (4-state kernel), <= lut_cap(RL)
   double log_threshold;               // log(PLL_SCALE_THRESHOLD) as the host libm evaluates it
 };
 
@@ -183,6 +184,14 @@ __device__ __forceinline__ void ld256_nc(const double * p, double & a, double & 
 {
   asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];"
                : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+}
+// prefetch load: volatile so that the compiler issues it where it is written (a plain __ldg whose result
+// is only used after a long loop gets sunk below the loop, which turns the prefetch into a stall)
+__device__ __forceinline__ unsigned int ld_u32_prefetch(const unsigned int * p)
+{
+  unsigned int v;
+  asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
 }
 // coherent variant: a CLV written earlier in the same kernel by the same thread may be re-read
 __device__ __forceinline__ void ld256(const double * p, double & a, double & b, double & c, double & d)

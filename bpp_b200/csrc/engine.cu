@@ -186,6 +186,7 @@ struct bppgpu_batch
   // layout of the staged blob
   size_t o_mat_off = 0, o_mat_idx = 0, o_mat_bl = 0, o_op_off = 0, o_ops = 0, o_root_clv = 0, o_root_sc = 0, o_blk_off = 0;
   unsigned int total_mats = 0, total_ops = 0;
+  unsigned int lut_cap_rt = 0;         // tip-slot capacity of the 4-state launches: the batch's largest tree
   bool staged_mats = false, staged_ops = false, staged_roots = false;
   cudaEvent_t t0 = nullptr, t1 = nullptr;
 };
@@ -710,6 +711,10 @@ static void batch_launch_cfg(bppgpu_batch * b)
   const size_t mean = cells / b->n;
   // 4-state kernel: 2 cells per thread once the loci are big enough to fill such tiles
   b->cpt = (b->kernel_kind == 0 && mean >= 2 * TREE_NT) ? 2 : 1;
+  // with rate categories the shared-memory pipe limits the kernel: 4 cells per thread halve the P-matrix loads per cell
+  if (b->kernel_kind == 0 && R >= 4 && mean >= 7 * (TREE_NT / 2)) b->cpt = 4;
+  if (const char * ev = getenv("BPPGPU_CPT"))                 // tuning knob
+    if (b->kernel_kind == 0 && (atoi(ev) == 1 || atoi(ev) == 2 || atoi(ev) == 4)) b->cpt = (unsigned)atoi(ev);
   b->tile_threads = b->kernel_kind != 1 ? TREE_NT : 128;
 }
 
@@ -939,11 +944,12 @@ static void batch_sync_loci(bppgpu_batch * b, bool need_eigen)
 // persistent launch: as many CTAs as fit on the device at once, each walks a contiguous tile range.
 // The stack-slot count is a performance knob only (a value that finds no slot is re-read from L2), so it
 // is lowered until two CTAs fit on an SM.
-template <int RL, bool EXACT, int CPT>
-static int tree_s4_slots(bppgpu_batch * b, int wanted)
+template <int RL, int CPT>
+static int tree_s4_slots(bppgpu_batch * b, int wanted, unsigned cap)
 {
   int slots = wanted;
-  while (slots > 1 && 2 * (S4Layout<RL, CPT>::bytes(slots) + 1024) > b->e->smem_per_sm) --slots;
+  const size_t ctas = CPT == 4 ? 1 : 2;
+  while (slots > 1 && ctas * (S4Layout<RL, CPT>::bytes(slots, cap) + 1024) > b->e->smem_per_sm) --slots;
   return slots;
 }
 
@@ -951,7 +957,7 @@ template <int RL, bool EXACT, int CPT>
 static void launch_tree_s4_impl(bppgpu_batch * b, const TreeParams & prm)
 {
   bppgpu_engine * e = b->e;
-  const size_t smem = S4Layout<RL, CPT>::bytes(prm.n_slots);
+  const size_t smem = S4Layout<RL, CPT>::bytes(prm.n_slots, prm.lut_cap);
   CUDA_CHECK(cudaFuncSetAttribute(tree_kernel_s4<RL, EXACT, CPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
   CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tree_kernel_s4<RL, EXACT, CPT>, TREE_NT, smem));
@@ -965,6 +971,7 @@ static void launch_tree_s4(bppgpu_batch * b, const TreeParams & prm)
 {
   const bool exact = b->e->math == BPPGPU_MATH_EXACT;
   if (b->cpt == 2) { if (exact) launch_tree_s4_impl<RL, true, 2>(b, prm); else launch_tree_s4_impl<RL, false, 2>(b, prm); }
+  else if (b->cpt == 4) { if (exact) launch_tree_s4_impl<RL, true, 4>(b, prm); else launch_tree_s4_impl<RL, false, 4>(b, prm); }
   else { if (exact) launch_tree_s4_impl<RL, true, 1>(b, prm); else launch_tree_s4_impl<RL, false, 1>(b, prm); }
 }
 
@@ -1016,6 +1023,7 @@ static int batch_run(bppgpu_batch * b, bool do_mats, bool do_tree, bool want_roo
   // shared-memory stack slots per thread: ceil(log2 T) covers balanced trees in recursive post-order;
   // beyond that the plan falls back to re-reading the child from HBM (still correct)
   int slots = 0;
+  unsigned lut_cap_rt = 0;
   if (b->kernel_kind == 2)
     for (auto * l : b->loci)
       if (l->col_overflow)
@@ -1035,17 +1043,23 @@ static int batch_run(bppgpu_batch * b, bool do_mats, bool do_tree, bool want_roo
     if (b->kernel_kind == 2) slots = 0;
     if (b->kernel_kind == 0)
     {
+      // tip-slot capacity: any op list over a T-tip tree has at most T tip or HBM-resident children
+      lut_cap_rt = std::min<unsigned>((unsigned)lut_cap((int)b->RL), std::max(4u, (maxT + 3u) & ~3u));
       const int w = slots;
       switch (b->RL * 10 + b->cpt)
       {
-        case 11: slots = tree_s4_slots<1, true, 1>(b, w); break;
-        case 12: slots = tree_s4_slots<1, true, 2>(b, w); break;
-        case 21: slots = tree_s4_slots<2, true, 1>(b, w); break;
-        case 22: slots = tree_s4_slots<2, true, 2>(b, w); break;
-        case 41: slots = tree_s4_slots<4, true, 1>(b, w); break;
-        case 42: slots = tree_s4_slots<4, true, 2>(b, w); break;
-        case 81: slots = tree_s4_slots<8, true, 1>(b, w); break;
-        case 82: slots = tree_s4_slots<8, true, 2>(b, w); break;
+        case 11: slots = tree_s4_slots<1, 1>(b, w, lut_cap_rt); break;
+        case 12: slots = tree_s4_slots<1, 2>(b, w, lut_cap_rt); break;
+        case 14: slots = tree_s4_slots<1, 4>(b, w, lut_cap_rt); break;
+        case 24: slots = tree_s4_slots<2, 4>(b, w, lut_cap_rt); break;
+        case 44: slots = tree_s4_slots<4, 4>(b, w, lut_cap_rt); break;
+        case 84: slots = tree_s4_slots<8, 4>(b, w, lut_cap_rt); break;
+        case 21: slots = tree_s4_slots<2, 1>(b, w, lut_cap_rt); break;
+        case 22: slots = tree_s4_slots<2, 2>(b, w, lut_cap_rt); break;
+        case 41: slots = tree_s4_slots<4, 1>(b, w, lut_cap_rt); break;
+        case 42: slots = tree_s4_slots<4, 2>(b, w, lut_cap_rt); break;
+        case 81: slots = tree_s4_slots<8, 1>(b, w, lut_cap_rt); break;
+        case 82: slots = tree_s4_slots<8, 2>(b, w, lut_cap_rt); break;
         default: break;
       }
     }
@@ -1057,7 +1071,7 @@ static int batch_run(bppgpu_batch * b, bool do_mats, bool do_tree, bool want_roo
       plan_kernel_blocks<<<(n * 32 + 127) / 128, 128, 0, b->stream>>>(
           e->d_loci, b->d_batch_locus, n, d_op_off, d_ops, d_root_clv, d_root_sc, want_root ? 1 : 0,
           b->d_blocks, d_blk_off, b->d_tile_first, b->d_tile_blk, b->d_plan_count, b->d_scratch, b->d_scratch_off,
-          slots, b->RL, b->cpt, fuse_mats ? d_mat_off : nullptr, d_mat_idx, d_mat_bl);
+          slots, b->RL, b->cpt, lut_cap_rt, fuse_mats ? d_mat_off : nullptr, d_mat_idx, d_mat_bl);
     else if (b->kernel_kind == 2)
       plan_kernel_blocks20<<<(n * 32 + 127) / 128, 128, 0, b->stream>>>(
           e->d_loci, b->d_batch_locus, n, d_op_off, d_ops, d_root_clv, d_root_sc, want_root ? 1 : 0,
@@ -1075,7 +1089,7 @@ static int batch_run(bppgpu_batch * b, bool do_mats, bool do_tree, bool want_roo
   prm.tile_cell0 = b->d_tile_cell0; prm.op_off = d_op_off; prm.plan = b->d_plan; prm.plan_count = b->d_plan_count;
   prm.tiles = b->d_tiles; prm.blocks = b->d_blocks; prm.tile_blk = b->d_tile_blk; prm.n_tiles = b->n_tiles;
   prm.tile_partial = want_root ? b->d_tile_partial : nullptr;
-  prm.persite = persite; prm.persite_mode = persite_mode; prm.n_slots = slots;
+  prm.persite = persite; prm.persite_mode = persite_mode; prm.n_slots = slots; prm.lut_cap = lut_cap_rt;
   prm.log_threshold = e->log_threshold;
   {
     ProfScope ps(e, b->stream, BPPGPU_KERNEL_TREE);

@@ -321,7 +321,7 @@ plan_kernel_blocks(const LocusDev * __restrict__ loci, const unsigned int * __re
                    const unsigned int * __restrict__ tile_first, unsigned long long * __restrict__ tile_blk,
                    unsigned int * __restrict__ plan_count,
                    unsigned char * __restrict__ scratch, const unsigned long long * __restrict__ scratch_off,
-                   int max_slots, unsigned int RL, unsigned int cpt,
+                   int max_slots, unsigned int RL, unsigned int cpt, unsigned int cap,
                    const unsigned int * __restrict__ mat_off, const unsigned int * __restrict__ mat_idx,
                    const double * __restrict__ mat_bl)
 {
@@ -346,7 +346,6 @@ plan_kernel_blocks(const LocusDev * __restrict__ loci, const unsigned int * __re
   unsigned char * blk = blocks + blk_off[bl];
   const size_t cb = chunk_bytes(RL);
   const unsigned int chunks0 = (unsigned int)(sizeof(LocusHdr) + rw_bytes(RL));
-  const unsigned int cap = (unsigned int)lut_cap((int)RL);
   const unsigned int lut_unit = RL * (LUT_CAT / 2);      // uint4 units per tip table set
   const unsigned int slot_unit = 2 * cpt * TREE_NT;      // uint4 units per stack slot
   const unsigned int T = L.tips;

@@ -90,14 +90,20 @@ struct S4Layout               // everything in uint4 (16-byte) units
   static constexpr unsigned STAGE = TIPP + CAP * RL * 9;          // one stage buffer
   static constexpr unsigned CHUNK = STAGE - CH;                   // chunk size
   static constexpr unsigned NSTAGE = RL >= 4 ? 1 : 2;             // double-buffered staging only where shared memory allows
-  static constexpr unsigned LUT = NSTAGE * STAGE;                 // [CAP][RL] x 49
-  static constexpr unsigned RING = LUT + CAP * RL * 49;           // 4 x (TileDesc 2 + blk 1)
-  static constexpr unsigned RED = RING + 12;                      // 32 doubles
-  static constexpr unsigned STACK = RED + 16;                     // [slots][CPT*TREE_NT][2] uint4, then [slots][CPT*TREE_NT] u32
+  // shared memory of the kernel: [RING 4 x (TileDesc 2 + blk 1)][RED 32 doubles][NSTAGE stage buffers]
+  // [LUT [cap][RL] x 49][STACK [slots][CPT*TREE_NT][2] uint4, then [slots][CPT*TREE_NT] u32].  cap is the
+  // launch's tip-slot capacity (<= CAP, sized to the batch's largest tree): a stage buffer holds only
+  // the first cap slots of the block's tipP area, which is why tipP comes last in the block.
+  static constexpr unsigned RING = 0;
+  static constexpr unsigned RED = 12;
+  static constexpr unsigned STAGE0 = 28;
   static constexpr unsigned SLOT = 2 * CPT * TREE_NT;             // uint4 per slot
-  __host__ __device__ static constexpr size_t bytes(int slots)
+  __host__ __device__ static constexpr unsigned stage_sz(unsigned cap) { return TIPP + cap * RL * 9; }
+  __host__ __device__ static constexpr unsigned lut0(unsigned cap) { return STAGE0 + NSTAGE * stage_sz(cap); }
+  __host__ __device__ static constexpr unsigned stack0(unsigned cap) { return lut0(cap) + cap * RL * 49; }
+  __host__ __device__ static constexpr size_t bytes(int slots, unsigned cap)
   {
-    return (size_t)STACK * 16 + (size_t)slots * ((size_t)SLOT * 16 + CPT * TREE_NT * 4);
+    return (size_t)stack0(cap) * 16 + (size_t)slots * ((size_t)SLOT * 16 + CPT * TREE_NT * 4);
   }
 };
 
@@ -106,6 +112,7 @@ template <int CPT>
 struct TileCtx
 {
   unsigned int sb;               // stage buffer base (uint4 units)
+  unsigned int lut0, stack0;     // lookup tables and stack (uint4 units)
   unsigned int sst1;             // u32 index of the scaler stack
   unsigned int cat;
   unsigned int cell[CPT];        // clamped cell index
@@ -125,8 +132,8 @@ __device__ __forceinline__ double tile_fast(const TreeParams & prm, const TileCt
   const unsigned int tid = threadIdx.x, lane = tid & 31u;
   const unsigned int sb = tc.sb;
   const LocusHdr * H = reinterpret_cast<const LocusHdr *>(&s4[sb]);
-  const unsigned int lut_t = Lay::LUT + tc.cat * 49;
-  const unsigned int stk_t = Lay::STACK + tid * 2;
+  const unsigned int lut_t = tc.lut0 + tc.cat * 49;
+  const unsigned int stk_t = tc.stack0 + tid * 2;
   const unsigned int pup_t = sb + Lay::PUP + tc.cat * 9;
   const unsigned int tipp_t = sb + Lay::TIPP + tc.cat * 9;
   const unsigned int ops = sb + Lay::OPS;
@@ -325,7 +332,7 @@ __device__ __forceinline__ Vec4 load_global_x(const LocusHdr * H, unsigned int k
 
 // One chunk of ops for cell slot j of the thread.  X / psc persist across chunks in xs / pscs.
 template <int RL, bool EXACT, int CPT>
-__device__ __noinline__ double chunk_general(const TreeParams prm, unsigned int sb, unsigned int sst1, unsigned int j,
+__device__ __noinline__ double chunk_general(const TreeParams prm, unsigned int sb, unsigned int lay, unsigned int sst1, unsigned int j,
                                              unsigned int cell, bool valid, unsigned int cat, unsigned int tw0,
                                              unsigned int tw1, unsigned int wgt, double * xs, unsigned int * pscs)
 {
@@ -333,8 +340,8 @@ __device__ __noinline__ double chunk_general(const TreeParams prm, unsigned int 
   const unsigned int tid = threadIdx.x, lane = tid & 31u;
   const LocusHdr * H = reinterpret_cast<const LocusHdr *>(&s4[sb]);
   const unsigned int pattern = cell / RL;
-  const unsigned int lut_t = Lay::LUT + cat * 49;
-  const unsigned int stk_t = Lay::STACK + tid * 2 + j * (2 * TREE_NT);
+  const unsigned int lut_t = (lay & 0xFFFFu) + cat * 49;               // lay = lut0 | stack0 << 16
+  const unsigned int stk_t = (lay >> 16) + tid * 2 + j * (2 * TREE_NT);
   const unsigned int ops = sb + Lay::OPS;
   const unsigned int cn = s1[(sb + Lay::CH) * 4];
   double x0 = xs[0], x1 = xs[1], x2 = xs[2], x3 = xs[3];
@@ -466,7 +473,7 @@ __device__ __noinline__ double chunk_general(const TreeParams prm, unsigned int 
 
 // LUT[s][cat][mask] = P_tip-edge . bits(mask), same operation order as the mat-vec
 template <int RL, bool EXACT, int CPT>
-__device__ __forceinline__ void build_lut(unsigned int sb)
+__device__ __forceinline__ void build_lut(unsigned int sb, unsigned int lut0)
 {
   using Lay = S4Layout<RL, CPT>;
   const unsigned int entries = s1[(sb + Lay::CH) * 4 + 1] * RL * 16;       // ChunkHdr.ntips
@@ -475,17 +482,21 @@ __device__ __forceinline__ void build_lut(unsigned int sb)
     const unsigned int mask = e & 15u, sc = e >> 4;      // sc = slot*RL + cat
     const Vec4 v = matvec_s4<EXACT>(sb + Lay::TIPP + sc * 9, (double)(mask & 1u), (double)((mask >> 1) & 1u),
                                     (double)((mask >> 2) & 1u), (double)((mask >> 3) & 1u));
-    s4[Lay::LUT + sc * 49 + mask * 3] = as_u4(v.a, v.b);
-    s4[Lay::LUT + sc * 49 + mask * 3 + 1] = as_u4(v.c, v.d);
+    s4[lut0 + sc * 49 + mask * 3] = as_u4(v.a, v.b);
+    s4[lut0 + sc * 49 + mask * 3 + 1] = as_u4(v.c, v.d);
   }
 }
 
+// CTAs per SM: 3 / 2 / 1 for 1 / 2 / 4 cells per thread (85 / 128 / 255 registers).  Measured on B200:
+// 2 cells at 2 CTAs beats 3 CTAs at 80 registers (spills) for R = 1; 4 cells win for R >= 4, where the
+// shared-memory pipe is the limit and the P-matrix loads are amortised over twice the cells.
 template <int RL, bool EXACT, int CPT>
-__global__ void __launch_bounds__(TREE_NT, CPT == 1 ? 3 : 2)
+__global__ void __launch_bounds__(TREE_NT, CPT == 1 ? 3 : (CPT == 2 ? 2 : 1))
 tree_kernel_s4(const TreeParams prm)
 {
   using Lay = S4Layout<RL, CPT>;
   const unsigned int tid = threadIdx.x, lane = tid & 31u;
+  const unsigned int stage_sz = Lay::stage_sz(prm.lut_cap), lut0 = Lay::lut0(prm.lut_cap), stack0 = Lay::stack0(prm.lut_cap);
 
   const unsigned int t_begin = (unsigned int)(((unsigned long long)prm.n_tiles * blockIdx.x) / gridDim.x);
   const unsigned int t_end = (unsigned int)(((unsigned long long)prm.n_tiles * (blockIdx.x + 1)) / gridDim.x);
@@ -503,7 +514,7 @@ tree_kernel_s4(const TreeParams prm)
   auto stage_fetch = [&](unsigned int buf, unsigned long long blk)   // header + rate weights + chunk 0
   {
     const uint4 * src = reinterpret_cast<const uint4 *>(prm.blocks + blk);
-    for (unsigned int w = tid; w < Lay::STAGE; w += TREE_NT) cp_async16(&s4[buf * Lay::STAGE + w], src + w);
+    for (unsigned int w = tid; w < stage_sz; w += TREE_NT) cp_async16(&s4[Lay::STAGE0 + buf * stage_sz + w], src + w);
   };
   auto load_tips = [&](const TileDesc & d, unsigned int * tw0, unsigned int * tw1, unsigned int * wgt)
   {
@@ -512,9 +523,9 @@ tree_kernel_s4(const TreeParams prm)
     {
       const unsigned int craw = d.cell0 + tid + j * TREE_NT;
       const unsigned int pat = (craw < d.ncell ? craw : d.ncell - 1) / RL;
-      tw0[j] = __ldg(d.tipwords + (size_t)pat * d.tip_words);
-      tw1[j] = (d.tip_words > 1) ? __ldg(d.tipwords + (size_t)pat * d.tip_words + 1) : 0u;
-      wgt[j] = __ldg(d.weights + pat);
+      tw0[j] = ld_u32_prefetch(d.tipwords + (size_t)pat * d.tip_words);
+      tw1[j] = (d.tip_words > 1) ? ld_u32_prefetch(d.tipwords + (size_t)pat * d.tip_words + 1) : 0u;
+      wgt[j] = ld_u32_prefetch(d.weights + pat);
     }
   };
 
@@ -525,7 +536,8 @@ tree_kernel_s4(const TreeParams prm)
   __syncthreads();
 
   TileCtx<CPT> tc;
-  tc.sst1 = (Lay::STACK + (unsigned)prm.n_slots * Lay::SLOT) * 4;
+  tc.lut0 = lut0; tc.stack0 = stack0;
+  tc.sst1 = (stack0 + (unsigned)prm.n_slots * Lay::SLOT) * 4;
   load_tips(*reinterpret_cast<const TileDesc *>(&s4[Lay::RING + (t_begin & 3u) * 3]), tc.tw0, tc.tw1, tc.wgt);
 
   unsigned int buf = 0;
@@ -549,7 +561,7 @@ tree_kernel_s4(const TreeParams prm)
         __syncthreads();
       }
       prefetched_locus = 0xFFFFFFFFu;
-      build_lut<RL, EXACT, CPT>(buf * Lay::STAGE);
+      build_lut<RL, EXACT, CPT>(Lay::STAGE0 + buf * stage_sz, lut0);
       __syncthreads();
       staged_locus = d.locus;
     }
@@ -572,7 +584,7 @@ tree_kernel_s4(const TreeParams prm)
     ring_fetch(t + 2);
     cp_async_commit();
 
-    const unsigned int sb = buf * Lay::STAGE;
+    const unsigned int sb = Lay::STAGE0 + buf * stage_sz;
     const LocusHdr * H = reinterpret_cast<const LocusHdr *>(&s4[sb]);
     tc.sb = sb;
     tc.cat = (d.cell0 + tid) % RL;
@@ -602,15 +614,15 @@ tree_kernel_s4(const TreeParams prm)
         {
           __syncthreads();
           const uint4 * src = reinterpret_cast<const uint4 *>(prm.blocks + blk) + Lay::CH + (size_t)c * Lay::CHUNK;
-          for (unsigned int w = tid; w < Lay::CHUNK; w += TREE_NT) s4[sb + Lay::CH + w] = __ldg(src + w);
+          for (unsigned int w = tid; w < stage_sz - Lay::CH; w += TREE_NT) s4[sb + Lay::CH + w] = __ldg(src + w);
           __syncthreads();
-          build_lut<RL, EXACT, CPT>(sb);
+          build_lut<RL, EXACT, CPT>(sb, lut0);
           __syncthreads();
           staged_locus = 0xFFFFFFFFu;          // chunk 0 is gone
         }
 #pragma unroll
         for (int j = 0; j < CPT; ++j)
-          site_sum += chunk_general<RL, EXACT, CPT>(prm, sb, tc.sst1, j, tc.cell[j], tc.valid[j], tc.cat, tc.tw0[j],
+          site_sum += chunk_general<RL, EXACT, CPT>(prm, sb, lut0 | (stack0 << 16), tc.sst1, j, tc.cell[j], tc.valid[j], tc.cat, tc.tw0[j],
                                                     tc.tw1[j], tc.wgt[j], xs[j], &pscs[j]);
       }
     }
