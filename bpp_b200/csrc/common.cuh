@@ -172,7 +172,11 @@ struct TreeParams
   double * persite;                   // optional per-site output of the (single) locus, or nullptr
   int persite_mode;                   // 1 = weighted site lnL, 2 = site likelihood (vector form)
   int n_slots;                        // shared-memory stack slots per cell
-  unsigned int lut_cap;               // tip-slot capacity of the launch (4-state kernel), <= lut_cap(RL)
+  unsigned int lut_cap;               // tip-slot capacity of the launch (4-state kernel), <= lut_cap(RL);
+                                      // 20-state category-major kernel: staged P-matrix capacity
+  double * rootdot;                   // 20-state category-major kernel: pi . clv_root per (locus, category, site)
+  const unsigned long long * site_off; // ... and the first site of each batch locus in it (prefix sums)
+  unsigned int max_tips;              // ... and the largest tip count of the batch (tip-column staging)
   double log_threshold;               // log(PLL_SCALE_THRESHOLD) as the host libm evaluates it
 };
 

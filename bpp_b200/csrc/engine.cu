@@ -11,6 +11,7 @@
 #include "plan.cuh"
 #include "tree_s4.cuh"
 #include "tree_s20.cuh"
+#include "tree_s20c.cuh"
 #include "tree_generic.cuh"
 #include "reduce.cuh"
 
@@ -187,6 +188,9 @@ struct bppgpu_batch
   size_t o_mat_off = 0, o_mat_idx = 0, o_mat_bl = 0, o_op_off = 0, o_ops = 0, o_root_clv = 0, o_root_sc = 0, o_blk_off = 0;
   unsigned int total_mats = 0, total_ops = 0;
   unsigned int lut_cap_rt = 0;         // tip-slot capacity of the 4-state launches: the batch's largest tree
+  bool s20_cat = false;                // 20 states: category-major tiles (tree_kernel_s20c)
+  double * d_rootdot = nullptr;        // ... its per (category, site) root dot products
+  unsigned long long * d_site_off = nullptr;
   bool staged_mats = false, staged_ops = false, staged_roots = false;
   cudaEvent_t t0 = nullptr, t1 = nullptr;
 };
@@ -735,6 +739,16 @@ extern "C" bppgpu_batch * bppgpu_batch_create(bppgpu_engine * e, unsigned int n,
   batch_launch_cfg(b);
   std::vector<unsigned int> ids(n), tile_locus, tile_cell0, tile_first(n + 1, 0);
   std::vector<TileDesc> tiles;
+  std::vector<unsigned long long> site_off(n + 1, 0);
+  if (b->kernel_kind == 2)
+  {
+    // category-major tiles with staged P-matrices unless a locus scales per site (needs all categories of a
+    // site in one CTA) or the tree is too big for the matrices of one (locus, category) to fit in shared memory
+    unsigned maxT = 0; bool scaled = false;
+    for (unsigned i = 0; i < n; ++i) { maxT = std::max(maxT, loci[i]->tips); scaled = scaled || loci[i]->scale_buffers > 0; }
+    b->s20_cat = !scaled && s20c_smem_bytes(2 * maxT - 1, maxT, 0) + 1024 <= e->smem_optin;
+    if (const char * ev = getenv("BPPGPU_S20C")) b->s20_cat = b->s20_cat && atoi(ev) != 0;      // tuning knob
+  }
   std::vector<unsigned long long> soff(n);
   size_t sbytes = 0;
   for (unsigned i = 0; i < n; ++i)
@@ -744,6 +758,13 @@ extern "C" bppgpu_batch * bppgpu_batch_create(bppgpu_engine * e, unsigned int n,
     const unsigned cells = l->sites * (b->kernel_kind != 1 ? b->RL : 1);
     tile_first[i] = (unsigned)tile_locus.size();
     const unsigned tile_cells = b->kernel_kind == 2 ? (unsigned)S20_TILE : b->tile_threads * b->cpt;
+    site_off[i + 1] = site_off[i] + l->sites;
+    if (b->s20_cat)
+    {
+      const unsigned nsb = (l->sites + S20C_SITES - 1) / S20C_SITES;
+      for (unsigned j = 0; j < b->RL * nsb; ++j) { tile_locus.push_back(i); tile_cell0.push_back(j); }
+    }
+    else
     for (unsigned c = 0; c < cells; c += tile_cells)
     {
       tile_locus.push_back(i); tile_cell0.push_back(c);
@@ -786,6 +807,12 @@ extern "C" bppgpu_batch * bppgpu_batch_create(bppgpu_engine * e, unsigned int n,
     CUDA_CHECK(cudaMalloc(&b->d_tile_blk, tiles.size() * 16));
   }
   if (b->kernel_kind == 2) CUDA_CHECK(cudaMalloc(&b->d_tile_blk, (size_t)b->n_tiles * 16));
+  if (b->s20_cat)
+  {
+    CUDA_CHECK(cudaMalloc(&b->d_rootdot, (size_t)site_off[n] * b->RL * 8));
+    CUDA_CHECK(cudaMalloc(&b->d_site_off, (size_t)(n + 1) * 8));
+    CUDA_CHECK(cudaMemcpy(b->d_site_off, site_off.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice));
+  }
   CUDA_CHECK(cudaMemset(b->d_plan_count, 0, n * 4));
   CUDA_CHECK(cudaMemset(b->d_tile_partial, 0, b->n_tiles * 8));
   CUDA_CHECK(cudaEventCreate(&b->t0));
@@ -802,6 +829,7 @@ extern "C" void bppgpu_batch_destroy(bppgpu_batch * b)
   cudaFree(b->d_batch_locus); cudaFree(b->d_tile_locus); cudaFree(b->d_tile_cell0); cudaFree(b->d_tile_first);
   cudaFree(b->d_scratch_off); cudaFree(b->d_scratch); cudaFree(b->d_plan_count); cudaFree(b->d_tile_partial);
   cudaFree(b->d_lnl); cudaFree(b->d_in); cudaFree(b->d_plan); cudaFree(b->d_persite);
+  cudaFree(b->d_rootdot); cudaFree(b->d_site_off);
   cudaFree(b->d_blocks); cudaFree(b->d_tiles); cudaFree(b->d_tile_blk); cudaFree(b->d_block_sums); cudaFree(b->d_counter);
   cudaFreeHost(b->h_out); cudaFreeHost(b->h_in);
   cudaEventDestroy(b->t0); cudaEventDestroy(b->t1);
@@ -1040,7 +1068,13 @@ static int batch_run(bppgpu_batch * b, bool do_mats, bool do_tree, bool want_roo
     // 20 states: a parked X costs 3.4 kB of shared memory per warp and slot, which would push the
     // P-matrices (read through L1) out of the SM; re-reading the child's CLV (an L2 hit) and redoing one
     // DMMA mat-vec is cheaper, so nothing is parked
-    if (b->kernel_kind == 2) slots = 0;
+    if (b->kernel_kind == 2 && !b->s20_cat) slots = 0;
+    if (b->s20_cat)
+    {
+      // one CTA of 16 warps per SM: the stack takes what the staged matrices leave
+      lut_cap_rt = 2 * maxT - 1;
+      while (slots > 0 && s20c_smem_bytes(lut_cap_rt, maxT, slots) + 1024 > e->smem_optin) --slots;
+    }
     if (b->kernel_kind == 0)
     {
       // tip-slot capacity: any op list over a T-tip tree has at most T tip or HBM-resident children
@@ -1106,6 +1140,27 @@ static int batch_run(bppgpu_batch * b, bool do_mats, bool do_tree, bool want_roo
     }
     else if (b->kernel_kind == 2)
     {
+      if (b->s20_cat)
+      {
+        unsigned maxT = 0;
+        for (auto * l : b->loci) maxT = std::max(maxT, l->tips);
+        prm.max_tips = maxT; prm.rootdot = b->d_rootdot; prm.site_off = b->d_site_off;
+        const size_t smem = s20c_smem_bytes(prm.lut_cap, maxT, prm.n_slots);
+        const unsigned grid = std::min<unsigned>(b->n_tiles, (unsigned)e->sm_count);
+        switch (b->RL)
+        {
+#define BPPGPU_S20C_CASE(R) case R: \
+          CUDA_CHECK(cudaFuncSetAttribute(tree_kernel_s20c<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+          tree_kernel_s20c<R><<<grid, S20C_NT, smem, b->stream>>>(prm); break;
+          BPPGPU_S20C_CASE(1) BPPGPU_S20C_CASE(2) BPPGPU_S20C_CASE(4) BPPGPU_S20C_CASE(8)
+#undef BPPGPU_S20C_CASE
+          default: fatal("internal: RL=%u", b->RL); return BPPGPU_FAILURE;
+        }
+        if (want_root)
+          root20_kernel<<<n, 128, 0, b->stream>>>(e->d_loci, b->d_batch_locus, b->d_rootdot, b->d_site_off, b->d_tile_first,
+                                                  b->d_tile_partial, persite, persite_mode);
+      }
+      else
       switch (b->RL)
       {
         case 1: launch_tree_s20<1>(b, prm); break;

@@ -39,7 +39,7 @@ struct OpRec20                      // 64 bytes
   unsigned int a_p0, a_pm; int a_sc; unsigned int a_ext;    // ext: offset (doubles) of the tip's extra columns in the block
   unsigned int b_p0, b_pm; int b_sc; unsigned int b_ext;
   unsigned int up_pm; int dsc; unsigned int park_slot;
-  unsigned int pad[3];
+  unsigned int a_st, b_st, up_st;   // staged-matrix indices of the three edges (category-major kernel)
 };
 static_assert(sizeof(OpRec20) == 64, "OpRec20 must be 64 bytes");
 
@@ -55,14 +55,16 @@ struct Hdr20                        // 384 bytes, start of the locus block
   unsigned int sites, nops, tips, n_ext_ops;
   double freqs[S20];
   double rw[8];
-  double pad[11];
+  unsigned int n_stage, stage_off;  // staged-matrix list: n entries of (pmatrix index, ext offset | 0) at byte stage_off
+  double pad[10];
 };
 static_assert(sizeof(Hdr20) == 384, "Hdr20 must be 384 bytes");
 
 __host__ __device__ inline size_t block20_bytes(unsigned RL, unsigned nops_max)
 {
-  // header + ops + extra columns for at most two tip children per op
-  return sizeof(Hdr20) + (size_t)nops_max * sizeof(OpRec20) + (size_t)nops_max * 2 * RL * S20 * S20_EXT * 8;
+  // header + ops + staged-matrix list (three edges per op) + extra columns for at most two tip children per op
+  return sizeof(Hdr20) + (size_t)nops_max * sizeof(OpRec20) + (size_t)nops_max * 3 * 8 + 16 +
+         (size_t)nops_max * 2 * RL * S20 * S20_EXT * 8;
 }
 
 // ---------------------------------------------------------------- planner (one warp per locus)
@@ -105,27 +107,32 @@ plan_kernel_blocks20(const LocusDev * __restrict__ loci, const unsigned int * __
     }
     const unsigned int rootc = want_root ? root_clv[bl] : 0xFFFFFFFFu;
     const unsigned int total = n + (want_root ? 1u : 0u);
-    const unsigned int ext0 = (unsigned int)((sizeof(Hdr20) + (size_t)total * sizeof(OpRec20)) / 8);   // doubles
+    const unsigned int stage_off = (unsigned int)(sizeof(Hdr20) + (size_t)total * sizeof(OpRec20));
+    uint2 * stage = reinterpret_cast<uint2 *>(blk + stage_off);
+    unsigned int n_stage = 0;
+    const unsigned int ext0 = (unsigned int)(((stage_off + (size_t)total * 3 * 8 + 15) & ~(size_t)15) / 8);   // doubles, 16-byte aligned
     unsigned int free_slots = (max_slots >= 32) ? 0xFFFFFFFFu : ((1u << max_slots) - 1u);
     unsigned int prev = 0xFFFFFFFFu, prev_k = 0;
     bool root_done = false;
     const unsigned int cells_per_buf = L.sites * RL;
     for (unsigned int k = 0; k < n; ++k)
     {
-      const RawOp r = o[k];
+      RawOp r = o[k];
+      if (L.scale_buffers == 0) r.psc = r.lsc = r.rsc = -1;        // a locus without scale buffers cannot scale
       const unsigned int child[2] = { r.left, r.right };
-      unsigned int kind[2], p0[2], pm[2], ext[2]; int sc[2];
+      unsigned int kind[2], p0[2], pm[2], ext[2], st[2]; int sc[2];
       int prev_child = -1;
       unsigned int consumed_slots = 0;
       for (int c = 0; c < 2; ++c)
       {
         const unsigned int idx = child[c];
-        pm[c] = c ? r.rpm : r.lpm; p0[c] = 0; ext[c] = 0; sc[c] = -1;
+        pm[c] = c ? r.rpm : r.lpm; p0[c] = 0; ext[c] = 0; sc[c] = -1; st[c] = 0;
         if (idx < T)
         {
           p0[c] = idx;
           if (L.tip_is_dense[idx]) kind[c] = SRC_TIP_DENSE;
           else { kind[c] = SRC_TIP_PACKED; ext[c] = ext0 + n_ext * RL * S20 * S20_EXT; ++n_ext; }
+          st[c] = n_stage; stage[n_stage++] = make_uint2(pm[c], ext[c]);
         }
         else
         {
@@ -134,15 +141,21 @@ plan_kernel_blocks20(const LocusDev * __restrict__ loci, const unsigned int * __
           {
             kind[c] = SRC_PREV; prev_child = c;
             recs[prev_k].ctl |= OP_PUSH; recs[prev_k].up_pm = pm[c];
+            recs[prev_k].up_st = n_stage; stage[n_stage++] = make_uint2(pm[c], 0u);
           }
           else if (where[b])
           {
             const unsigned int s = slot_of[b];
             kind[c] = SRC_SLOT; p0[c] = s; consumed_slots |= 1u << s;
             recs[where[b] - 1].ctl |= OP_PUSH; recs[where[b] - 1].up_pm = pm[c];
+            recs[where[b] - 1].up_st = n_stage; stage[n_stage++] = make_uint2(pm[c], 0u);
             where[b] = 0;
           }
-          else { kind[c] = SRC_HBM; p0[c] = b; sc[c] = c ? r.rsc : r.lsc; }
+          else
+          {
+            kind[c] = SRC_HBM; p0[c] = b; sc[c] = c ? r.rsc : r.lsc;
+            st[c] = n_stage; stage[n_stage++] = make_uint2(pm[c], 0u);
+          }
         }
       }
       if (prev != 0xFFFFFFFFu && prev_child < 0 && free_slots)
@@ -157,7 +170,7 @@ plan_kernel_blocks20(const LocusDev * __restrict__ loci, const unsigned int * __
       OpRec20 q;
       q.ctl = (kind[ia] << OP_AKIND_SHIFT) | (kind[ib] << OP_BKIND_SHIFT);
       q.dst_cell = (r.parent - T) * cells_per_buf; q.dsc = r.psc; q.park_slot = 0; q.up_pm = 0;
-      q.pad[0] = q.pad[1] = q.pad[2] = 0;
+      q.a_st = st[ia]; q.b_st = st[ib]; q.up_st = 0;
       q.a_p0 = p0[ia]; q.a_pm = pm[ia]; q.a_sc = sc[ia]; q.a_ext = ext[ia];
       q.b_p0 = p0[ib]; q.b_pm = pm[ib]; q.b_sc = sc[ib]; q.b_ext = ext[ib];
       if (r.psc >= 0) q.ctl |= OP_SCALE;
@@ -182,7 +195,7 @@ plan_kernel_blocks20(const LocusDev * __restrict__ loci, const unsigned int * __
     Hdr20 * H = reinterpret_cast<Hdr20 *>(blk);
     H->clv = L.clv; H->tip_dense = L.tip_dense; H->scale = L.scale; H->tip_cols = L.tip_cols; H->pmat = L.pmat;
     H->weights = L.weights; H->clv_stride = L.clv_stride; H->sites = L.sites; H->nops = cnt; H->tips = L.tips;
-    H->n_ext_ops = n_ext;
+    H->n_ext_ops = n_ext; H->n_stage = n_stage; H->stage_off = stage_off;
     for (int j = 0; j < S20; ++j) H->freqs[j] = L.freqs[j];
     for (unsigned int j = 0; j < 8; ++j) H->rw[j] = j < RL ? L.rate_weights[j] : 0.0;
     plan_count[bl] = cnt;
