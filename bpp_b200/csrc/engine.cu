@@ -1039,8 +1039,9 @@ static int batch_run(bppgpu_batch * b, bool do_mats, bool do_tree, bool want_roo
     const unsigned S = b->loci[0]->states;
     if (S > 8)
     {
-      const size_t sm = 3 * (size_t)S * S * 8;
-      pmatrix_kernel_wide<<<dim3(n, 8), 128, sm, b->stream>>>(e->d_loci, b->d_batch_locus, d_mat_off, d_mat_idx, d_mat_bl);
+      const size_t sm = (2 * (size_t)S * S + 4 * ((size_t)S * (S + 1) + S)) * 8;
+      if (S == 20) pmatrix_kernel_wide<20><<<dim3(n, 8), 128, sm, b->stream>>>(e->d_loci, b->d_batch_locus, d_mat_off, d_mat_idx, d_mat_bl);
+      else pmatrix_kernel_wide<0><<<dim3(n, 8), 128, sm, b->stream>>>(e->d_loci, b->d_batch_locus, d_mat_off, d_mat_idx, d_mat_bl);
     }
     else
       pmatrix_kernel<<<n, 64, 0, b->stream>>>(e->d_loci, b->d_batch_locus, d_mat_off, d_mat_idx, d_mat_bl);

@@ -70,27 +70,22 @@ __global__ void plan_kernel_flat(const LocusDev * __restrict__ loci, const unsig
 // below produces for the same evaluation order.
 struct SmallPlanOut { unsigned int n_chunks, cnt; bool fast, simple; };
 
-__device__ __forceinline__ SmallPlanOut
-plan_small_parallel(const LocusDev & L, const RawOp * o, unsigned int n, unsigned int rootc, int rootsc, bool want_root,
-                    unsigned char * blk, unsigned int chunks0, size_t cb, unsigned int cap, unsigned int lut_unit,
-                    unsigned int slot_unit, int max_slots, unsigned int RL, OpRec * rec,
-                    unsigned char * s_order, unsigned int * s_push)
+// Evaluation order of a list of <= 32 ops, lane k = op k: DFS post-order over the forest the list forms,
+// the child with the larger Sethi-Ullman need first (so that the fewest intermediate X values are alive
+// at once).  Returns the lane's op, its producer links and its position.
+struct SuLane { RawOp r; int kid[2]; int par; unsigned int pos; };
+
+__device__ __forceinline__ SuLane su_order_small(const RawOp * o, unsigned int n, unsigned int T)
 {
   const unsigned int FULL = 0xFFFFFFFFu;
   const unsigned int lane = threadIdx.x & 31u;
-  const unsigned int T = L.tips;
   const bool act = lane < n;
+  SuLane out;
   RawOp r;
   if (act) r = o[lane];
   else { r.parent = 0xFFFFFFFFu; r.left = r.right = 0; r.lpm = r.rpm = 0; r.psc = r.lsc = r.rsc = -1; }
   const unsigned int child[2] = { r.left, r.right };
-  bool tip[2], dense[2];
-#pragma unroll
-  for (int c = 0; c < 2; ++c)
-  {
-    tip[c] = act && child[c] < T;
-    dense[c] = tip[c] && L.tip_is_dense[child[c]] != 0;
-  }
+  const bool tip[2] = { act && child[0] < T, act && child[1] < T };
   // producer of each inner child: the latest earlier op that writes that buffer
   int kid[2] = { -1, -1 };
   for (unsigned int j = 0; j < n; ++j)
@@ -149,7 +144,33 @@ plan_small_parallel(const LocusDev & L, const RawOp * o, unsigned int n, unsigne
     const unsigned int szf = __shfl_sync(FULL, sz, fkk >= 0 ? fkk : 0);
     if (par == it) start = st + ((int)lane == fkk ? 0u : szf);
   }
-  const unsigned int pos = start + sz - 1;
+  out.r = r; out.kid[0] = kid[0]; out.kid[1] = kid[1]; out.par = par; out.pos = start + sz - 1;
+  return out;
+}
+
+__device__ __forceinline__ SmallPlanOut
+plan_small_parallel(const LocusDev & L, const RawOp * o, unsigned int n, unsigned int rootc, int rootsc, bool want_root,
+                    unsigned char * blk, unsigned int chunks0, size_t cb, unsigned int cap, unsigned int lut_unit,
+                    unsigned int slot_unit, int max_slots, unsigned int RL, OpRec * rec,
+                    unsigned char * s_order, unsigned int * s_push)
+{
+  const unsigned int FULL = 0xFFFFFFFFu;
+  const unsigned int lane = threadIdx.x & 31u;
+  const unsigned int T = L.tips;
+  const bool act = lane < n;
+  const SuLane su = su_order_small(o, n, T);
+  const RawOp r = su.r;
+  const unsigned int child[2] = { r.left, r.right };
+  bool tip[2], dense[2];
+#pragma unroll
+  for (int c = 0; c < 2; ++c)
+  {
+    tip[c] = act && child[c] < T;
+    dense[c] = tip[c] && L.tip_is_dense[child[c]] != 0;
+  }
+  const int kid[2] = { su.kid[0], su.kid[1] };
+  const int par = su.par;
+  const unsigned int pos = su.pos;
   if (act) s_order[pos] = (unsigned char)lane;
   s_push[lane] = 0;
   __syncwarp();

@@ -121,43 +121,81 @@ pmatrix_kernel(const LocusDev * __restrict__ loci, const unsigned int * __restri
   }
 }
 
-// 20-state variant of the eigen form: grid (locus, slice); a block handles every gridDim.y-th (branch, category)
-// pair of its locus with V and V^-1 staged in shared memory and temp = V^-1 . diag(expm1) formed once per pair
+// Wide-state variant of the eigen form (20 states): grid (locus, slice), V and V^-1 of the locus staged in
+// shared memory once per block; every WARP then takes its own (branch, category) pairs -- expm1 of the S
+// eigenvalues, temp = V^-1 . diag(expm1) in a padded (S+1)-stride private buffer (conflict-free row reads),
+// and P = I + temp . V in 1 x 4 register tiles -- with warp-level synchronisation only.
+// ST = compile-time state count (full unrolling), 0 = read it from the locus.
+template <int ST>
 __global__ void __launch_bounds__(128)
 pmatrix_kernel_wide(const LocusDev * __restrict__ loci, const unsigned int * __restrict__ batch_locus,
                     const unsigned int * __restrict__ mat_off, const unsigned int * __restrict__ mat_idx,
                     const double * __restrict__ mat_bl)
 {
-  extern __shared__ double s_pm[];        // V[S*S] | Vinv[S*S] | temp[S*S]
+  extern __shared__ double s_pm[];        // V[S*S] | Vinv[S*S] | per warp: temp[S*(S+1)] | expm1[S]
   const unsigned int bl = blockIdx.x;
   const LocusDev & L = loci[batch_locus[bl]];
   const unsigned int first = mat_off[bl], count = mat_off[bl + 1] - first;
-  const unsigned int S = L.states, R = L.rate_cats, SS = S * S;
-  double * sV = s_pm, * sVi = s_pm + SS, * sT = s_pm + 2 * SS;
-  if (blockIdx.y >= count * R) return;
+  const unsigned int S = ST ? (unsigned)ST : L.states, R = L.rate_cats, SS = S * S;
+  const unsigned int lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  double * sV = s_pm, * sVi = s_pm + SS;
+  double * sT = s_pm + 2 * SS + (size_t)warp * (S * (S + 1) + S), * sE = sT + S * (S + 1);
+  if (blockIdx.y * nw >= count * R) return;
   for (unsigned int t = threadIdx.x; t < SS; t += blockDim.x) { sV[t] = L.eigenvecs[t]; sVi[t] = L.inv_eigenvecs[t]; }
   __syncthreads();
-  for (unsigned int g = blockIdx.y; g < count * R; g += gridDim.y)
+  const bool quad = (S & 3u) == 0;         // 1 x 4 register tile per thread: one temp load feeds four columns
+  for (unsigned int g = blockIdx.y * nw + warp; g < count * R; g += gridDim.y * nw)
   {
     const unsigned int n = g % R, m = g / R;
     const double bt = mat_bl[first + m] * L.rates[n];
     double * P = L.pmat + ((size_t)mat_idx[first + m] * R + n) * SS;
     if (bt < 1e-100)
     {
-      for (unsigned int t = threadIdx.x; t < SS; t += blockDim.x) P[t] = (t / S == t % S) ? 1.0 : 0.0;
+      for (unsigned int t = lane; t < SS; t += 32) P[t] = (t / S == t % S) ? 1.0 : 0.0;
       continue;
     }
-    __syncthreads();                       // the previous pair is done with temp
-    for (unsigned int t = threadIdx.x; t < SS; t += blockDim.x)
-      sT[t] = __dmul_rn(sVi[t], expm1(L.eigenvals[t % S] * bt));          // core_pmatrix.c:753-758
-    __syncthreads();
-    for (unsigned int t = threadIdx.x; t < SS; t += blockDim.x)
+    __syncwarp();                          // the previous pair is done with temp and expm1
+    for (unsigned int t = lane; t < S; t += 32) sE[t] = expm1(L.eigenvals[t] * bt);                   // core_pmatrix.c:753-754
+    __syncwarp();
+    for (unsigned int t = lane; t < SS; t += 32) sT[(t / S) * (S + 1) + t % S] = __dmul_rn(sVi[t], sE[t % S]);   // :756-758
+    __syncwarp();
+    if (quad)
     {
-      const unsigned int j = t / S, k = t % S;
-      double acc = (j == k) ? 1.0 : 0.0;
-      for (unsigned int mm = 0; mm < S; ++mm) acc = __dadd_rn(acc, __dmul_rn(sT[j * S + mm], sV[mm * S + k]));   // :760-771
-      P[t] = acc;
+      // 4 x 4 register tiles: per inner index four temp loads and one 32-byte V load feed 16 multiply-adds
+      const unsigned int q4 = S >> 2;
+      for (unsigned int t = lane; t < q4 * q4; t += 32)
+      {
+        const unsigned int j = (t / q4) * 4, k = (t % q4) * 4;
+        double a[4][4];
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+#pragma unroll
+          for (int y = 0; y < 4; ++y) a[x][y] = (j + x == k + y) ? 1.0 : 0.0;
+#pragma unroll
+        for (unsigned int mm = 0; mm < S; ++mm)                                                      // :760-771
+        {
+          const double2 v0 = *reinterpret_cast<const double2 *>(sV + mm * S + k);
+          const double2 v1 = *reinterpret_cast<const double2 *>(sV + mm * S + k + 2);
+#pragma unroll
+          for (int x = 0; x < 4; ++x)
+          {
+            const double tv = sT[(j + x) * (S + 1) + mm];
+            a[x][0] = __dadd_rn(a[x][0], __dmul_rn(tv, v0.x)); a[x][1] = __dadd_rn(a[x][1], __dmul_rn(tv, v0.y));
+            a[x][2] = __dadd_rn(a[x][2], __dmul_rn(tv, v1.x)); a[x][3] = __dadd_rn(a[x][3], __dmul_rn(tv, v1.y));
+          }
+        }
+#pragma unroll
+        for (int x = 0; x < 4; ++x) st256(P + (j + x) * S + k, a[x][0], a[x][1], a[x][2], a[x][3]);
+      }
     }
+    else
+      for (unsigned int t = lane; t < SS; t += 32)
+      {
+        const unsigned int j = t / S, k = t % S;
+        double acc = (j == k) ? 1.0 : 0.0;
+        for (unsigned int mm = 0; mm < S; ++mm) acc = __dadd_rn(acc, __dmul_rn(sT[j * (S + 1) + mm], sV[mm * S + k]));
+        P[t] = acc;
+      }
   }
 }
 

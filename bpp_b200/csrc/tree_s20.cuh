@@ -23,6 +23,7 @@
 // from each other in rounding; parity here is the lnL bar (<= 1e-10 relative), not bit identity.
 #pragma once
 #include "common.cuh"
+#include "plan.cuh"
 
 namespace bppgpu {
 
@@ -95,6 +96,17 @@ plan_kernel_blocks20(const LocusDev * __restrict__ loci, const unsigned int * __
   const unsigned int T = L.tips;
   unsigned int cnt = 0, n_ext = 0;
 
+  // evaluation order: Sethi-Ullman DFS for lists of <= 32 ops (fewest parked values), as given otherwise
+  __shared__ unsigned char s_ord[4][32];
+  unsigned char * ord = s_ord[(threadIdx.x >> 5) & 3u];
+  const bool reorder = n <= 32;
+  if (reorder)
+  {
+    const SuLane su = su_order_small(o, n, T);
+    if (lane < n) ord[su.pos] = (unsigned char)lane;
+  }
+  __syncwarp();
+
   if (lane == 0)
   {
     unsigned int * where = reinterpret_cast<unsigned int *>(scratch + scratch_off[bl]);
@@ -115,9 +127,9 @@ plan_kernel_blocks20(const LocusDev * __restrict__ loci, const unsigned int * __
     unsigned int prev = 0xFFFFFFFFu, prev_k = 0;
     bool root_done = false;
     const unsigned int cells_per_buf = L.sites * RL;
-    for (unsigned int k = 0; k < n; ++k)
+    for (unsigned int k = 0; k < n; ++k)       // k = position in the evaluation order = index of the OpRec20
     {
-      RawOp r = o[k];
+      RawOp r = o[reorder ? ord[k] : k];
       if (L.scale_buffers == 0) r.psc = r.lsc = r.rsc = -1;        // a locus without scale buffers cannot scale
       const unsigned int child[2] = { r.left, r.right };
       unsigned int kind[2], p0[2], pm[2], ext[2], st[2]; int sc[2];
@@ -233,7 +245,7 @@ plan_kernel_blocks20(const LocusDev * __restrict__ loci, const unsigned int * __
 // ---------------------------------------------------------------- DMMA helpers
 __device__ __forceinline__ void dmma(double & d0, double & d1, const double a, const double b)
 {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
@@ -252,21 +264,23 @@ __device__ __forceinline__ void matvec20(const double * __restrict__ P, const do
       const unsigned int i = 8 * mt + r;
       a[mt][ks] = (i < S20) ? __ldg(P + i * S20 + 4 * ks + q) : 0.0;
     }
+  // k-steps outermost: the S20_NG x 3 accumulator chains are independent, so consecutive DMMAs never wait
+  // for each other (five dependent DMMAs back to back would expose the tensor pipe's latency)
+  double b[S20_NG][5];
 #pragma unroll
   for (int g = 0; g < S20_NG; ++g)
-  {
-    double b[5];
 #pragma unroll
-    for (int ks = 0; ks < 5; ++ks) b[ks] = tile[(8 * g + r) * S20 + 4 * ks + q];
+    for (int ks = 0; ks < 5; ++ks) b[g][ks] = tile[(8 * g + r) * S20 + 4 * ks + q];
 #pragma unroll
-    for (int mt = 0; mt < 3; ++mt)
-    {
-      double d0 = 0.0, d1 = 0.0;
+  for (int g = 0; g < S20_NG; ++g)
 #pragma unroll
-      for (int ks = 0; ks < 5; ++ks) dmma(d0, d1, a[mt][ks], b[ks]);
-      out.v[g][mt][0] = d0; out.v[g][mt][1] = d1;
-    }
-  }
+    for (int mt = 0; mt < 3; ++mt) out.v[g][mt][0] = out.v[g][mt][1] = 0.0;
+#pragma unroll
+  for (int ks = 0; ks < 5; ++ks)
+#pragma unroll
+    for (int g = 0; g < S20_NG; ++g)
+#pragma unroll
+      for (int mt = 0; mt < 3; ++mt) dmma(out.v[g][mt][0], out.v[g][mt][1], a[mt][ks], b[g][ks]);
 }
 
 // ---------------------------------------------------------------- the kernel

@@ -9,6 +9,9 @@
 //   stage[m] = 20 rows x 28 doubles: columns 0..19 = P, 20..23 = the tip edge's ambiguity columns.
 //   Row stride 28 doubles puts the four rows a half-warp touches on disjoint bank groups.
 // Tip column ids are staged per warp (T x 16 bytes); a parked X lives in a shared-memory stack slot.
+// The warp's CLV tile (16 sites x 20 states) rotates the states of sites 4..7 and 12..15 by 4 positions
+// (tile_idx): accumulator-layout stores, B-fragment loads and the 16-byte row copies are then all free of
+// bank conflicts (without it the stores are 2-way conflicted: sites 4 apart are 160 banks apart).
 //
 // Categories of a site are now in different CTAs, so
 //   * the root only writes pi . clv per (category, site); root20_kernel (reduce.cuh) combines the
@@ -33,6 +36,13 @@ __host__ inline size_t s20c_smem_bytes(unsigned cap, unsigned max_tips, int slot
          (size_t)slots * S20C_NW * 32 * S20_NG * 6 * 8 + 16;
 }
 
+// index (doubles) of state i of local site n in the warp's swizzled tile
+__device__ __forceinline__ unsigned int tile_idx(unsigned int n, unsigned int i)
+{
+  const unsigned int j = i + (n & 4u);
+  return n * S20 + (j >= S20 ? j - S20 : j);
+}
+
 // V = P . tile with P staged in shared memory (row stride S20C_PST)
 __device__ __forceinline__ void matvec20_staged(const double * P, const double * tile, unsigned int r, unsigned int q,
                                                 V20 & out)
@@ -46,21 +56,22 @@ __device__ __forceinline__ void matvec20_staged(const double * P, const double *
       const unsigned int i = 8 * mt + r;
       a[mt][ks] = (i < S20) ? P[i * S20C_PST + 4 * ks + q] : 0.0;
     }
+  // k-steps outermost: the S20_NG x 3 accumulator chains are independent (see matvec20)
+  double b[S20_NG][5];
 #pragma unroll
   for (int g = 0; g < S20_NG; ++g)
-  {
-    double b[5];
 #pragma unroll
-    for (int ks = 0; ks < 5; ++ks) b[ks] = tile[(8 * g + r) * S20 + 4 * ks + q];
+    for (int ks = 0; ks < 5; ++ks) b[g][ks] = tile[tile_idx(8 * g + r, 4 * ks + q)];
 #pragma unroll
-    for (int mt = 0; mt < 3; ++mt)
-    {
-      double d0 = 0.0, d1 = 0.0;
+  for (int g = 0; g < S20_NG; ++g)
 #pragma unroll
-      for (int ks = 0; ks < 5; ++ks) dmma(d0, d1, a[mt][ks], b[ks]);
-      out.v[g][mt][0] = d0; out.v[g][mt][1] = d1;
-    }
-  }
+    for (int mt = 0; mt < 3; ++mt) out.v[g][mt][0] = out.v[g][mt][1] = 0.0;
+#pragma unroll
+  for (int ks = 0; ks < 5; ++ks)
+#pragma unroll
+    for (int g = 0; g < S20_NG; ++g)
+#pragma unroll
+      for (int mt = 0; mt < 3; ++mt) dmma(out.v[g][mt][0], out.v[g][mt][1], a[mt][ks], b[g][ks]);
 }
 
 template <int RL>
@@ -147,6 +158,8 @@ tree_kernel_s20c(const TreeParams prm)
 #pragma unroll
         for (int mt = 0; mt < 3; ++mt) X.v[g][mt][e] = 0.0;
 
+    // global <-> tile, coalesced in 32-byte chunks: chunk c of the warp = site c/5, states 4*(c%5)..+3, which the
+    // rotation keeps contiguous (256-bit global accesses: 2 x 128-bit stores reach only half the bandwidth)
     auto tile_to_global = [&](double * dst_buf)
     {
 #pragma unroll
@@ -155,8 +168,9 @@ tree_kernel_s20c(const TreeParams prm)
         const unsigned int c = it * 32 + lane, n = c / 5, part = c % 5;
         if (c >= S20_WS * 5) break;
         const unsigned int s = site0 + n;
-        const double2 u = *reinterpret_cast<const double2 *>(s_tile + n * S20 + part * 4);
-        const double2 w = *reinterpret_cast<const double2 *>(s_tile + n * S20 + part * 4 + 2);
+        const double * src = s_tile + tile_idx(n, part * 4);
+        const double2 u = *reinterpret_cast<const double2 *>(src);
+        const double2 w = *reinterpret_cast<const double2 *>(src + 2);
         if (s < sites) st256(dst_buf + ((size_t)s * RL + cat) * S20 + part * 4, u.x, u.y, w.x, w.y);
       }
     };
@@ -171,8 +185,9 @@ tree_kernel_s20c(const TreeParams prm)
         double a, b, cc, d;
         if (coherent) ld256(src_buf + ((size_t)s * RL + cat) * S20 + part * 4, a, b, cc, d);
         else ld256_nc(src_buf + ((size_t)s * RL + cat) * S20 + part * 4, a, b, cc, d);
-        *reinterpret_cast<double2 *>(s_tile + n * S20 + part * 4) = make_double2(a, b);
-        *reinterpret_cast<double2 *>(s_tile + n * S20 + part * 4 + 2) = make_double2(cc, d);
+        double * dst = s_tile + tile_idx(n, part * 4);
+        *reinterpret_cast<double2 *>(dst) = make_double2(a, b);
+        *reinterpret_cast<double2 *>(dst + 2) = make_double2(cc, d);
       }
     };
     auto fetch = [&](unsigned int kind, unsigned int p0, unsigned int st, V20 & v)
@@ -214,12 +229,19 @@ tree_kernel_s20c(const TreeParams prm)
       }
     };
 
+    // op records are prefetched one op ahead (w2 = scalers / ext offsets is not used by this kernel)
+    uint4 n0 = __ldg(reinterpret_cast<const uint4 *>(recs));
+    uint4 n1 = __ldg(reinterpret_cast<const uint4 *>(recs) + 1);
+    uint4 n3 = __ldg(reinterpret_cast<const uint4 *>(recs) + 3);
     for (unsigned int k = 0; k < nops; ++k)
     {
-      const uint4 w0 = __ldg(reinterpret_cast<const uint4 *>(recs + k));
-      const uint4 w1 = __ldg(reinterpret_cast<const uint4 *>(recs + k) + 1);
-      const uint4 w2 = __ldg(reinterpret_cast<const uint4 *>(recs + k) + 2);
-      const uint4 w3 = __ldg(reinterpret_cast<const uint4 *>(recs + k) + 3);
+      const uint4 w0 = n0, w1 = n1, w3 = n3;
+      if (k + 1 < nops)
+      {
+        n0 = __ldg(reinterpret_cast<const uint4 *>(recs + k + 1));
+        n1 = __ldg(reinterpret_cast<const uint4 *>(recs + k + 1) + 1);
+        n3 = __ldg(reinterpret_cast<const uint4 *>(recs + k + 1) + 3);
+      }
       const unsigned int ctl = w0.x;
       const unsigned int akind = (ctl >> OP_AKIND_SHIFT) & 15u, bkind = (ctl >> OP_BKIND_SHIFT) & 15u;
       V20 O;
@@ -253,7 +275,7 @@ tree_kernel_s20c(const TreeParams prm)
               for (int e = 0; e < 2; ++e)
               {
                 const unsigned int i = 8 * mt + r;
-                O.v[g][mt][e] = (i < S20) ? s_tile[(8 * g + 2 * q + e) * S20 + i] : 0.0;
+                O.v[g][mt][e] = (i < S20) ? s_tile[tile_idx(8 * g + 2 * q + e, i)] : 0.0;
               }
         }
       }
@@ -278,7 +300,7 @@ tree_kernel_s20c(const TreeParams prm)
             for (int e = 0; e < 2; ++e)
             {
               const unsigned int i = 8 * mt + r;
-              if (i < S20) s_tile[(8 * g + 2 * q + e) * S20 + i] = O.v[g][mt][e];
+              if (i < S20) s_tile[tile_idx(8 * g + 2 * q + e, i)] = O.v[g][mt][e];
             }
         __syncwarp();
         tile_to_global(clv + ((size_t)w0.y) * S20);
