@@ -321,7 +321,9 @@ def main():
     b_pass, b_min = w.b_pass(), w.b_min()
     achieved = b_pass * w.n_loci / (tree_ms / 1000.0) / 1e9 if tree_ms > 0 else None
     achieved_min = b_min * w.n_loci / (tree_ms / 1000.0) / 1e9 if tree_ms > 0 else None
-    roofline = {"bound": "hbm", "kernel": "tree_kernel_s4" if w.states == 4 else "tree_kernel_generic",
+    roofline = {"bound": "hbm", "kernel": "tree_kernel_s4" if w.states == 4 else
+                ("tree_kernel_s20c" if w.states == 20 and not args.scaling else
+                 ("tree_kernel_s20" if w.states == 20 else "tree_kernel_generic")),
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if achieved else None,
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_locus": b_pass,
@@ -332,7 +334,8 @@ def main():
                 "compulsory_bytes_per_locus": b_min,
                 "kernel_ms": tree_ms, "kernel_share_of_step": tree_ms / ms_step if ms_step else None,
                 "per_kernel_ms": {k: (v["ms"] / max(1, v["launches"])) for k, v in prof.items()},
-                "traffic": NCU_TRAFFIC.get(args.config)}
+                "traffic": NCU_TRAFFIC.get(args.config) if not args.scaling and args.loci is None else None,
+                "traffic_source": NCU_TRAFFIC_SOURCE.get(args.config)}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -359,7 +362,17 @@ def main():
 
 # dram__bytes_read.sum + dram__bytes_write.sum per tree-kernel launch from the committed ncu capture
 # (profiles/), filled in after each profiling pass; None = not captured for that config yet.
-NCU_TRAFFIC = {}
+# Bytes per launch at the config's full size, scaling off.
+NCU_TRAFFIC = {
+    "config2": 2.184687e9 + 0.131348e9,      # tree_kernel_s4<1,exact,2>
+    "config3": 19.141006e9 + 0.325830e9,     # tree_kernel_s4<4,exact,4>
+    "config4": 4.476720e9 + 0.430410e9,      # tree_kernel_s20c<4>
+}
+NCU_TRAFFIC_SOURCE = {
+    "config2": "profiles/r1_tree_final_config2_ncu_summary.txt",
+    "config3": "profiles/r1_tree_final_config3_ncu_summary.txt",
+    "config4": "profiles/r1_s20c_v1_config4_ncu_summary.txt",
+}
 
 
 if __name__ == "__main__":
