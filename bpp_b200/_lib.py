@@ -24,7 +24,7 @@ SYMBOLS = [
     "bppgpu_get_clv", "bppgpu_get_pmatrix", "bppgpu_set_pmatrix", "bppgpu_get_scaler",
     "bppgpu_batch_create", "bppgpu_batch_destroy", "bppgpu_batch_size",
     "bppgpu_batch_update_matrices", "bppgpu_batch_update_partials", "bppgpu_batch_root_loglikelihood",
-    "bppgpu_batch_full_pass", "bppgpu_batch_stage", "bppgpu_batch_run", "bppgpu_batch_collect",
+    "bppgpu_batch_full_pass", "bppgpu_batch_stage", "bppgpu_batch_run", "bppgpu_batch_set_waves", "bppgpu_batch_collect",
     "bppgpu_batch_lnl_sum_dev", "bppgpu_batch_stream", "bppgpu_batch_timer_start",
     "bppgpu_batch_timer_stop_ms", "bppgpu_batch_synchronize",
 ]
@@ -106,6 +106,7 @@ def load():
         "bppgpu_batch_full_pass": (i, [vp, up, up, dp, up, opp, up, ip, dp, dp]),
         "bppgpu_batch_stage": (i, [vp, up, up, dp, up, opp, up, ip]),
         "bppgpu_batch_run": (i, [vp]),
+        "bppgpu_batch_set_waves": (None, [vp, u]),
         "bppgpu_batch_collect": (i, [vp, dp, dp]),
         "bppgpu_batch_lnl_sum_dev": (vp, [vp]),
         "bppgpu_batch_stream": (vp, [vp]),

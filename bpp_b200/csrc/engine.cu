@@ -16,6 +16,7 @@
 #include "reduce.cuh"
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -27,6 +28,8 @@
 #include <vector>
 
 using namespace bppgpu;
+
+#define BPPGPU_MAX_WAVES 8
 
 // ------------------------------------------------------------------------------------ errors
 static thread_local std::string g_last_error;
@@ -118,6 +121,7 @@ struct bppgpu_engine
   std::vector<bppgpu_locus *> loci;      // by id (nullptr = free)
   std::vector<unsigned int> free_ids;
   unsigned long long launches = 0;
+  std::atomic<unsigned long long> dirty_epoch{1};   // bumped whenever a locus' host mirrors change
   int sm_count = 148;
   size_t smem_optin = 0, smem_per_sm = 0;
   // profiling
@@ -193,6 +197,28 @@ struct bppgpu_batch
   unsigned long long * d_site_off = nullptr;
   bool staged_mats = false, staged_ops = false, staged_roots = false;
   cudaEvent_t t0 = nullptr, t1 = nullptr;
+  unsigned long long synced_epoch = 0; // engine dirty_epoch at the last batch_sync_loci
+  bool synced_eigen = false;           // ... which also brought the eigen-decompositions up to date
+  // pipelined step (4-state kernel, big batches): the step's host arrays are uploaded in waves of loci on
+  // copy_stream while the planner / tree kernels of earlier waves already run (alternating between
+  // `stream` and alt_stream so that a wave fills the tail of the previous one)
+  cudaStream_t copy_stream = nullptr, alt_stream = nullptr;
+  unsigned int n_waves = 1;            // waves of the CURRENT staged inputs
+  unsigned int wave_first[BPPGPU_MAX_WAVES + 1] = {0};
+  cudaEvent_t ev_copy[BPPGPU_MAX_WAVES] = {nullptr}, ev_fork = nullptr, ev_join = nullptr;
+  bool inputs_pending = false;         // staged with waves and not run yet: run() issues the copies
+  struct Pending { const unsigned int * midx; const double * mbl; const bppgpu_partial_op * ops;
+                   const unsigned int * rclv; const int * rsc; } pend = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_tables = nullptr;
+  bool tables_on_device = false;       // the three offset tables of the last stage are still valid in d_in
+  size_t tables_tm = 0, tables_to = 0;
+  bool have_m = false, have_o = false;
+  std::vector<unsigned int> last_mcounts, last_ocounts;
+  unsigned int max_tips = 0;
+  unsigned int wave_pref = 0;          // 0 = automatic
+  std::vector<unsigned int> h_tile_first;
+  // launch configuration of the tree kernel, resolved once per (shared-memory size)
+  size_t cfg_smem = 0; int cfg_per_sm = 0; unsigned int cfg_key = 0xFFFFFFFFu;
 };
 
 // ------------------------------------------------------------------------------------ helpers
@@ -313,7 +339,7 @@ static void host_update_eigen(bppgpu_locus * l)
       l->h_ievecs[(size_t)i * S + j] = a[(size_t)j * S + i] / std::sqrt(f[i]);
     }
   l->eigen_valid = true;
-  l->model_dirty = true;
+  l->model_dirty = true, l->e->dirty_epoch++;
 }
 
 static inline void set_code(bppgpu_locus * l, unsigned tip, size_t site, unsigned int c)
@@ -549,7 +575,7 @@ extern "C" bppgpu_locus * bppgpu_locus_create(bppgpu_engine * e, unsigned int dt
   l->h_rates.assign(R, 1.0);
   l->h_rate_weights.assign(R, 1.0 / (double)R);    // locus.c:845-848
   l->h_evecs.assign(S * S, 0.0); l->h_ievecs.assign(S * S, 0.0); l->h_evals.assign(S, 0.0);
-  l->model_dirty = true;
+  l->model_dirty = true, l->e->dirty_epoch++;
   if (!e->free_ids.empty()) { l->id = e->free_ids.back(); e->free_ids.pop_back(); e->loci[l->id] = l; }
   else { l->id = (unsigned)e->loci.size(); e->loci.push_back(l); }
   engine_publish_locus(e, l);
@@ -593,8 +619,8 @@ extern "C" int bppgpu_set_tip_states(bppgpu_locus * l, unsigned int tip, const u
     if (c == 0) { fatal("Illegal state code in tip \"%c\"", seq[i]); return BPPGPU_FAILURE; }   // locus.c:538
     set_code(l, tip, i, c);
   }
-  l->codes_dirty = true;
-  if (l->h_tip_dense_flag[tip]) { l->h_tip_dense_flag[tip] = 0; l->flags_dirty = true; }
+  l->codes_dirty = true, l->e->dirty_epoch++;
+  if (l->h_tip_dense_flag[tip]) { l->h_tip_dense_flag[tip] = 0; l->flags_dirty = true, l->e->dirty_epoch++; }
   return BPPGPU_SUCCESS;
 }
 
@@ -613,8 +639,8 @@ extern "C" int bppgpu_set_tip_clv(bppgpu_locus * l, unsigned int tip, const doub
       for (size_t j = 0; j < S; ++j) if (clv[i * S + j] == 1.0) c |= 1u << j;
       set_code(l, tip, i, c);
     }
-    l->codes_dirty = true;
-    if (l->h_tip_dense_flag[tip]) { l->h_tip_dense_flag[tip] = 0; l->flags_dirty = true; }
+    l->codes_dirty = true, l->e->dirty_epoch++;
+    if (l->h_tip_dense_flag[tip]) { l->h_tip_dense_flag[tip] = 0; l->flags_dirty = true, l->e->dirty_epoch++; }
     return BPPGPU_SUCCESS;
   }
   bppgpu_engine * e = l->e;
@@ -629,7 +655,7 @@ extern "C" int bppgpu_set_tip_clv(bppgpu_locus * l, unsigned int tip, const doub
   std::vector<double> full(P * R * S);             // replicate over categories, locus.c:609-616
   for (size_t i = 0; i < P; ++i) for (size_t r = 0; r < R; ++r) memcpy(&full[(i * R + r) * S], clv + i * S, S * 8);
   CUDA_CHECK(cudaMemcpy(l->dev.tip_dense + (size_t)tip * P * R * S, full.data(), full.size() * 8, cudaMemcpyHostToDevice));
-  l->h_tip_dense_flag[tip] = 1; l->flags_dirty = true;
+  l->h_tip_dense_flag[tip] = 1; l->flags_dirty = true, l->e->dirty_epoch++;
   return BPPGPU_SUCCESS;
 }
 
@@ -641,27 +667,27 @@ extern "C" void bppgpu_set_pattern_weights(bppgpu_locus * l, const unsigned int 
 extern "C" void bppgpu_set_frequencies(bppgpu_locus * l, unsigned int idx, const double * f)
 {
   if (idx != 0) { fatal("freqs_index must be 0"); return; }
-  l->h_freqs.assign(f, f + l->states); l->eigen_valid = false; l->model_dirty = true;   // locus.c:889-897
+  l->h_freqs.assign(f, f + l->states); l->eigen_valid = false; l->model_dirty = true, l->e->dirty_epoch++;   // locus.c:889-897
 }
 extern "C" void bppgpu_set_subst_params(bppgpu_locus * l, unsigned int idx, const double * p)
 {
   if (idx != 0) { fatal("params_index must be 0"); return; }
-  l->h_subst.assign(p, p + l->states * (l->states - 1) / 2); l->eigen_valid = false;    // locus.c:877-887
+  l->h_subst.assign(p, p + l->states * (l->states - 1) / 2); l->eigen_valid = false; l->e->dirty_epoch++;    // locus.c:877-887
 }
 extern "C" void bppgpu_set_category_rates(bppgpu_locus * l, const double * r)
 {
-  l->h_rates.assign(r, r + l->rate_cats); l->model_dirty = true;
+  l->h_rates.assign(r, r + l->rate_cats); l->model_dirty = true, l->e->dirty_epoch++;
 }
 extern "C" void bppgpu_set_category_weights(bppgpu_locus * l, const double * w)
 {
-  l->h_rate_weights.assign(w, w + l->rate_cats); l->model_dirty = true;
+  l->h_rate_weights.assign(w, w + l->rate_cats); l->model_dirty = true, l->e->dirty_epoch++;
 }
 extern "C" void bppgpu_set_eigen(bppgpu_locus * l, unsigned int idx, const double * ev, const double * iev, const double * lam)
 {
   if (idx != 0) { fatal("params_index must be 0"); return; }
   const size_t S = l->states;
   l->h_evecs.assign(ev, ev + S * S); l->h_ievecs.assign(iev, iev + S * S); l->h_evals.assign(lam, lam + S);
-  l->eigen_valid = true; l->model_dirty = true;
+  l->eigen_valid = true; l->model_dirty = true, l->e->dirty_epoch++;
 }
 extern "C" void bppgpu_get_eigen(bppgpu_locus * l, unsigned int idx, double * ev, double * iev, double * lam)
 {
@@ -817,6 +843,18 @@ extern "C" bppgpu_batch * bppgpu_batch_create(bppgpu_engine * e, unsigned int n,
   CUDA_CHECK(cudaMemset(b->d_tile_partial, 0, b->n_tiles * 8));
   CUDA_CHECK(cudaEventCreate(&b->t0));
   CUDA_CHECK(cudaEventCreate(&b->t1));
+  b->h_tile_first = tile_first;
+  for (unsigned i = 0; i < n; ++i) b->max_tips = std::max(b->max_tips, loci[i]->tips);
+  if (b->kernel_kind == 0)
+  {
+    CUDA_CHECK(cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking));
+    CUDA_CHECK(cudaStreamCreateWithFlags(&b->alt_stream, cudaStreamNonBlocking));
+    for (auto & ev : b->ev_copy) CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    CUDA_CHECK(cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming));
+    CUDA_CHECK(cudaEventCreateWithFlags(&b->ev_join, cudaEventDisableTiming));
+    CUDA_CHECK(cudaEventCreateWithFlags(&b->ev_tables, cudaEventDisableTiming));
+    if (const char * ev = getenv("BPPGPU_WAVES")) b->wave_pref = (unsigned)std::min(std::max(atoi(ev), 0), BPPGPU_MAX_WAVES);
+  }
   return b;
 }
 
@@ -833,11 +871,22 @@ extern "C" void bppgpu_batch_destroy(bppgpu_batch * b)
   cudaFree(b->d_blocks); cudaFree(b->d_tiles); cudaFree(b->d_tile_blk); cudaFree(b->d_block_sums); cudaFree(b->d_counter);
   cudaFreeHost(b->h_out); cudaFreeHost(b->h_in);
   cudaEventDestroy(b->t0); cudaEventDestroy(b->t1);
+  if (b->copy_stream)
+  {
+    cudaStreamSynchronize(b->copy_stream); cudaStreamSynchronize(b->alt_stream);
+    for (auto & ev : b->ev_copy) cudaEventDestroy(ev);
+    cudaEventDestroy(b->ev_fork); cudaEventDestroy(b->ev_join); cudaEventDestroy(b->ev_tables);
+    cudaStreamDestroy(b->copy_stream); cudaStreamDestroy(b->alt_stream);
+  }
   if (b->own_stream) cudaStreamDestroy(b->stream);
   delete b;
 }
 
 extern "C" unsigned int bppgpu_batch_size(const bppgpu_batch * b) { return b->n; }
+extern "C" void bppgpu_batch_set_waves(bppgpu_batch * b, unsigned int waves)
+{
+  b->wave_pref = waves > BPPGPU_MAX_WAVES ? BPPGPU_MAX_WAVES : waves;
+}
 extern "C" void * bppgpu_batch_lnl_sum_dev(bppgpu_batch * b) { return (void *)b->d_lnl_sum; }
 extern "C" void * bppgpu_batch_stream(bppgpu_batch * b) { return (void *)b->stream; }
 extern "C" void bppgpu_batch_synchronize(bppgpu_batch * b) { CUDA_CHECK(cudaStreamSynchronize(b->stream)); }
@@ -851,8 +900,40 @@ extern "C" double bppgpu_batch_timer_stop_ms(bppgpu_batch * b)
   return ms;
 }
 
-// Stage the inputs of one step into the pinned blob and copy it to the device in ONE transfer.
-// Any of the three groups may be absent (nullptr counts).
+// Copy the slice of the staged step that belongs to loci [i0, i1) to the device on stream cs.
+static void batch_issue_copies(bppgpu_batch * b, unsigned i0, unsigned i1, cudaStream_t cs)
+{
+  const bppgpu_batch::Pending & q = b->pend;
+  const unsigned int * moff = (const unsigned int *)(b->h_in + b->o_mat_off);
+  const unsigned int * ooff = (const unsigned int *)(b->h_in + b->o_op_off);
+  auto put = [&](size_t dst, const void * from, size_t bytes)
+  {
+    if (bytes) CUDA_CHECK(cudaMemcpyAsync(b->d_in + dst, from, bytes, cudaMemcpyHostToDevice, cs));
+  };
+  if (q.midx)
+  {
+    const size_t m0 = moff[i0], m1 = moff[i1];
+    put(b->o_mat_idx + m0 * 4, q.midx + m0, (m1 - m0) * 4);
+    put(b->o_mat_bl + m0 * 8, q.mbl + m0, (m1 - m0) * 8);
+  }
+  if (q.ops)
+  {
+    const size_t o0 = ooff[i0], o1 = ooff[i1];
+    put(b->o_ops + o0 * sizeof(bppgpu_partial_op), q.ops + o0, (o1 - o0) * sizeof(bppgpu_partial_op));
+  }
+  if (q.rclv)
+  {
+    put(b->o_root_clv + (size_t)i0 * 4, q.rclv + i0, (size_t)(i1 - i0) * 4);
+    put(b->o_root_sc + (size_t)i0 * 4, q.rsc + i0, (size_t)(i1 - i0) * 4);
+  }
+}
+
+// Stage the inputs of one step: build the per-locus offset tables and hand the caller's arrays to the copy
+// engine.  Arrays in pinned memory (bppgpu_host_alloc / cudaHostRegister) are copied from where they are,
+// anything else goes through the batch's pinned blob.  Any of the three groups may be absent (nullptr counts).
+// A step that will run in waves (see bppgpu_batch_set_waves) only records the sources here: its copies are
+// issued wave by wave in batch_run, interleaved with the launches, so that the first kernel starts after
+// 1/waves of the upload.
 static int batch_stage(bppgpu_batch * b, const unsigned int * mcounts, const unsigned int * midx, const double * mbl,
                        const unsigned int * ocounts, const bppgpu_partial_op * ops,
                        const unsigned int * rclv, const int * rsc)
@@ -860,87 +941,145 @@ static int batch_stage(bppgpu_batch * b, const unsigned int * mcounts, const uns
   bppgpu_engine * e = b->e;
   CUDA_CHECK(cudaSetDevice(e->device));
   const unsigned n = b->n;
-  size_t tm = 0, to = 0;
-  if (mcounts) for (unsigned i = 0; i < n; ++i) tm += mcounts[i];
-  if (ocounts) for (unsigned i = 0; i < n; ++i) to += ocounts[i];
-  size_t off = 0;
-  b->o_mat_off = off; off = align_up(off + (n + 1) * 4, 16);
-  b->o_mat_idx = off; off = align_up(off + tm * 4, 16);
-  b->o_mat_bl = off;  off = align_up(off + tm * 8, 16);
-  b->o_op_off = off;  off = align_up(off + (n + 1) * 4, 16);
-  b->o_ops = off;     off = align_up(off + to * sizeof(bppgpu_partial_op), 16);
-  b->o_root_clv = off; off = align_up(off + n * 4, 16);
-  b->o_root_sc = off;  off = align_up(off + n * 4, 16);
-  b->o_blk_off = off;  off = align_up(off + (size_t)(n + 1) * 8, 16);
-  if (off > b->h_in_cap)
+  // unchanged counts (the usual case: same trees, new branch lengths / flipped indices): the offset tables
+  // in the pinned blob and on the device are still right
+  bool same = b->tables_on_device && (mcounts != nullptr) == b->have_m && (ocounts != nullptr) == b->have_o &&
+              (!mcounts || memcmp(mcounts, b->last_mcounts.data(), (size_t)n * 4) == 0) &&
+              (!ocounts || memcmp(ocounts, b->last_ocounts.data(), (size_t)n * 4) == 0);
+  size_t tm = b->tables_tm, to = b->tables_to;
+  if (!same)
   {
-    CUDA_CHECK(cudaStreamSynchronize(b->stream));
-    if (b->h_in) cudaFreeHost(b->h_in);
-    if (b->d_in) cudaFree(b->d_in);
-    b->h_in_cap = b->d_in_cap = off + off / 4;
-    CUDA_CHECK(cudaHostAlloc(&b->h_in, b->h_in_cap, cudaHostAllocDefault));
-    CUDA_CHECK(cudaMalloc(&b->d_in, b->d_in_cap));
+    tm = to = 0;
+    if (mcounts) for (unsigned i = 0; i < n; ++i) tm += mcounts[i];
+    if (ocounts) for (unsigned i = 0; i < n; ++i) to += ocounts[i];
+    size_t off = 0;
+    b->o_mat_off = off; off = align_up(off + (n + 1) * 4, 16);
+    b->o_mat_idx = off; off = align_up(off + tm * 4, 16);
+    b->o_mat_bl = off;  off = align_up(off + tm * 8, 16);
+    b->o_op_off = off;  off = align_up(off + (n + 1) * 4, 16);
+    b->o_ops = off;     off = align_up(off + to * sizeof(bppgpu_partial_op), 16);
+    b->o_root_clv = off; off = align_up(off + n * 4, 16);
+    b->o_root_sc = off;  off = align_up(off + n * 4, 16);
+    b->o_blk_off = off;  off = align_up(off + (size_t)(n + 1) * 8, 16);
+    if (off > b->h_in_cap)
+    {
+      CUDA_CHECK(cudaStreamSynchronize(b->stream));
+      if (b->copy_stream) CUDA_CHECK(cudaStreamSynchronize(b->copy_stream));
+      if (b->h_in) cudaFreeHost(b->h_in);
+      if (b->d_in) cudaFree(b->d_in);
+      b->h_in_cap = b->d_in_cap = off + off / 4;
+      CUDA_CHECK(cudaHostAlloc(&b->h_in, b->h_in_cap, cudaHostAllocDefault));
+      CUDA_CHECK(cudaMalloc(&b->d_in, b->d_in_cap));
+    }
+    if (b->kernel_kind == 1 && to + n > b->plan_cap)
+    {
+      CUDA_CHECK(cudaStreamSynchronize(b->stream));
+      if (b->d_plan) cudaFree(b->d_plan);
+      b->plan_cap = (to + n) + (to + n) / 4;
+      CUDA_CHECK(cudaMalloc(&b->d_plan, b->plan_cap * sizeof(PlanOp)));
+    }
   }
-  if (b->kernel_kind == 1 && to + n > b->plan_cap)
-  {
-    CUDA_CHECK(cudaStreamSynchronize(b->stream));
-    if (b->d_plan) cudaFree(b->d_plan);
-    b->plan_cap = (to + n) + (to + n) / 4;
-    CUDA_CHECK(cudaMalloc(&b->d_plan, b->plan_cap * sizeof(PlanOp)));
-  }
-  // the previous step's blob may still be in flight on the stream
+  // the previous step's blob may still be in flight on the stream (a waved step joins alt_stream into it)
   CUDA_CHECK(cudaStreamSynchronize(b->stream));
+  if (b->copy_stream) CUDA_CHECK(cudaStreamSynchronize(b->copy_stream));      // tables of a step that never ran
+  b->inputs_pending = false;
   unsigned int * moff = (unsigned int *)(b->h_in + b->o_mat_off);
   unsigned int * ooff = (unsigned int *)(b->h_in + b->o_op_off);
-  moff[0] = 0; ooff[0] = 0;
   unsigned long long * boff = (unsigned long long *)(b->h_in + b->o_blk_off);
-  boff[0] = 0;
-  for (unsigned i = 0; i < n; ++i)
+  if (!same)
   {
-    moff[i + 1] = moff[i] + (mcounts ? mcounts[i] : 0);
-    ooff[i + 1] = ooff[i] + (ocounts ? ocounts[i] : 0);
-    // one spare op per locus for a root that the list does not produce (CTL_EVAL_ONLY)
-    const unsigned nmax = (ocounts ? ocounts[i] : 0) + 1;
-    boff[i + 1] = boff[i] + (b->kernel_kind == 2 ? align_up(block20_bytes(b->RL, nmax), 256) : block_bytes(b->RL, nmax));
+    unsigned int mo = 0, oo = 0;
+    unsigned long long bo = 0;
+    moff[0] = 0; ooff[0] = 0; boff[0] = 0;
+    for (unsigned i = 0; i < n; ++i)
+    {
+      const unsigned oc = ocounts ? ocounts[i] : 0;
+      mo += mcounts ? mcounts[i] : 0;
+      oo += oc;
+      // one spare op per locus for a root that the list does not produce (CTL_EVAL_ONLY)
+      bo += b->kernel_kind == 2 ? align_up(block20_bytes(b->RL, oc + 1), 256) : block_bytes(b->RL, oc + 1);
+      moff[i + 1] = mo; ooff[i + 1] = oo; boff[i + 1] = bo;
+    }
+    b->have_m = mcounts != nullptr; b->have_o = ocounts != nullptr;
+    if (mcounts) b->last_mcounts.assign(mcounts, mcounts + n);
+    if (ocounts) b->last_ocounts.assign(ocounts, ocounts + n);
+    b->tables_tm = tm; b->tables_to = to;
+    if (b->kernel_kind != 1 && boff[n] > b->blocks_cap)
+    {
+      if (b->d_blocks) cudaFree(b->d_blocks);
+      b->blocks_cap = boff[n] + boff[n] / 4;
+      CUDA_CHECK(cudaMalloc(&b->d_blocks, b->blocks_cap));
+    }
   }
-  if (b->kernel_kind != 1 && boff[n] > b->blocks_cap)
+  // waves: a full pass of a big 4-state batch uploads and runs in slices of loci (balanced by tiles)
+  unsigned W = 1;
+  if (b->kernel_kind == 0 && b->copy_stream && mcounts && ocounts && rclv)
   {
-    CUDA_CHECK(cudaStreamSynchronize(b->stream));
-    if (b->d_blocks) cudaFree(b->d_blocks);
-    b->blocks_cap = boff[n] + boff[n] / 4;
-    CUDA_CHECK(cudaMalloc(&b->d_blocks, b->blocks_cap));
+    if (b->wave_pref) W = b->wave_pref;
+    else if (n >= 1024 && tm * 12 + to * sizeof(bppgpu_partial_op) >= (1u << 20)) W = 4;
+    if (W > n) W = n;
   }
-  // the three offset tables are built here; the caller's arrays go to the device directly when they live in
-  // pinned memory (bppgpu_host_alloc / cudaHostRegister), otherwise through the pinned blob
+  if (W > BPPGPU_MAX_WAVES) W = BPPGPU_MAX_WAVES;
+  if (W != b->n_waves || !same)
+  {
+    b->n_waves = W;
+    b->wave_first[0] = 0;
+    // geometric wave sizes (ratio r): the first wave is small so that the kernels start early, and each
+    // later upload still hides under the compute of the wave before it (compute : upload is about 5 : 1)
+    double ratio = 3.0;
+    if (const char * ev = getenv("BPPGPU_WAVE_RATIO")) ratio = std::max(1.0, atof(ev));
+    double total_w = 0, acc = 0, cur = 1;
+    for (unsigned w = 0; w < W; ++w) { total_w += cur; cur *= ratio; }
+    cur = 1;
+    for (unsigned w = 1, i = 0; w <= W; ++w)
+    {
+      acc += cur; cur *= ratio;
+      const unsigned long long goal = (unsigned long long)((double)b->n_tiles * (acc / total_w));
+      while (i < n && b->h_tile_first[i] < goal) ++i;
+      b->wave_first[w] = (w == W) ? n : i;
+    }
+  }
+  cudaStream_t cs = W > 1 ? b->copy_stream : b->stream;
+  if (!same)
+  {
+    CUDA_CHECK(cudaMemcpyAsync(b->d_in + b->o_mat_off, b->h_in + b->o_mat_off, (n + 1) * 4, cudaMemcpyHostToDevice, cs));
+    CUDA_CHECK(cudaMemcpyAsync(b->d_in + b->o_op_off, b->h_in + b->o_op_off, (n + 1) * 4, cudaMemcpyHostToDevice, cs));
+    CUDA_CHECK(cudaMemcpyAsync(b->d_in + b->o_blk_off, b->h_in + b->o_blk_off, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, cs));
+    b->tables_on_device = true;
+  }
+  // sources: the caller's pinned arrays, or their copy in the pinned blob
   auto is_pinned = [](const void * p) -> bool
   {
     cudaPointerAttributes a;
     if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
     return a.type == cudaMemoryTypeHost;
   };
-  auto put = [&](size_t dst, const void * src, size_t bytes)
+  auto source = [&](size_t dst, const void * src, size_t bytes) -> const void *
   {
-    if (!bytes) return;
-    const void * from = src;
-    if (!is_pinned(src)) { memcpy(b->h_in + dst, src, bytes); from = b->h_in + dst; }
-    CUDA_CHECK(cudaMemcpyAsync(b->d_in + dst, from, bytes, cudaMemcpyHostToDevice, b->stream));
+    if (!src || !bytes) return nullptr;
+    if (is_pinned(src)) return src;
+    memcpy(b->h_in + dst, src, bytes);
+    return b->h_in + dst;
   };
-  CUDA_CHECK(cudaMemcpyAsync(b->d_in + b->o_mat_off, b->h_in + b->o_mat_off, (n + 1) * 4, cudaMemcpyHostToDevice, b->stream));
-  CUDA_CHECK(cudaMemcpyAsync(b->d_in + b->o_op_off, b->h_in + b->o_op_off, (n + 1) * 4, cudaMemcpyHostToDevice, b->stream));
-  CUDA_CHECK(cudaMemcpyAsync(b->d_in + b->o_blk_off, b->h_in + b->o_blk_off, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, b->stream));
-  if (tm) { put(b->o_mat_idx, midx, tm * 4); put(b->o_mat_bl, mbl, tm * 8); }
-  if (to) put(b->o_ops, ops, to * sizeof(bppgpu_partial_op));
-  if (rclv)
+  bppgpu_batch::Pending & q = b->pend;
+  q.midx = (const unsigned int *)source(b->o_mat_idx, mcounts ? midx : nullptr, tm * 4);
+  q.mbl = (const double *)source(b->o_mat_bl, mcounts ? mbl : nullptr, tm * 8);
+  q.ops = (const bppgpu_partial_op *)source(b->o_ops, ocounts ? ops : nullptr, to * sizeof(bppgpu_partial_op));
+  q.rclv = (const unsigned int *)source(b->o_root_clv, rclv, (size_t)n * 4);
+  if (rclv && !rsc)
   {
-    put(b->o_root_clv, rclv, n * 4);
-    if (rsc) put(b->o_root_sc, rsc, n * 4);
-    else
-    {
-      int * p = (int *)(b->h_in + b->o_root_sc);
-      for (unsigned i = 0; i < n; ++i) p[i] = -1;
-      CUDA_CHECK(cudaMemcpyAsync(b->d_in + b->o_root_sc, p, n * 4, cudaMemcpyHostToDevice, b->stream));
-    }
+    int * p = (int *)(b->h_in + b->o_root_sc);
+    for (unsigned i = 0; i < n; ++i) p[i] = -1;
+    q.rsc = p;
   }
+  else q.rsc = (const int *)source(b->o_root_sc, rclv ? rsc : nullptr, (size_t)n * 4);
+  if (W > 1)
+  {
+    // copies are issued by batch_run, wave by wave; the tables (if any) are already on their way
+    CUDA_CHECK(cudaEventRecord(b->ev_tables, cs));
+    b->inputs_pending = true;
+  }
+  else batch_issue_copies(b, 0, n, cs);
   b->total_mats = (unsigned)tm; b->total_ops = (unsigned)to;
   b->staged_mats = mcounts != nullptr; b->staged_ops = ocounts != nullptr; b->staged_roots = rclv != nullptr;
   return BPPGPU_SUCCESS;
@@ -962,11 +1101,15 @@ extern "C" void bppgpu_host_free(void * p) { if (p) cudaFreeHost(p); }
 
 static void batch_sync_loci(bppgpu_batch * b, bool need_eigen)
 {
+  // nothing of any locus changed since this batch last looked (and it then decomposed what it needed)
+  if (b->synced_epoch == b->e->dirty_epoch.load() && (!need_eigen || b->synced_eigen)) return;
   for (bppgpu_locus * l : b->loci)
   {
     if (need_eigen && !l->eigen_valid && !model_is_closed_form(l)) host_update_eigen(l);   // locus.c:2462-2476
     if (l->codes_dirty || l->model_dirty || l->flags_dirty) locus_sync(l, b->stream);
   }
+  b->synced_epoch = b->e->dirty_epoch.load();
+  b->synced_eigen = need_eigen;
 }
 
 // persistent launch: as many CTAs as fit on the device at once, each walks a contiguous tile range.
@@ -982,25 +1125,43 @@ static int tree_s4_slots(bppgpu_batch * b, int wanted, unsigned cap)
 }
 
 template <int RL, bool EXACT, int CPT>
-static void launch_tree_s4_impl(bppgpu_batch * b, const TreeParams & prm)
+static void launch_tree_s4_impl(bppgpu_batch * b, const TreeParams & prm, cudaStream_t st)
 {
   bppgpu_engine * e = b->e;
   const size_t smem = S4Layout<RL, CPT>::bytes(prm.n_slots, prm.lut_cap);
-  CUDA_CHECK(cudaFuncSetAttribute(tree_kernel_s4<RL, EXACT, CPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int per_sm = 0;
-  CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tree_kernel_s4<RL, EXACT, CPT>, TREE_NT, smem));
-  if (per_sm < 1) { fatal("tree kernel does not fit on an SM (smem %zu)", smem); return; }
-  const unsigned grid = std::min<unsigned>(b->n_tiles, (unsigned)(per_sm * e->sm_count));
-  tree_kernel_s4<RL, EXACT, CPT><<<grid, TREE_NT, smem, b->stream>>>(prm);
+  const unsigned key = (unsigned)(RL * 100 + CPT * 10 + (EXACT ? 1 : 0));
+  if (b->cfg_key != key || b->cfg_smem != smem)
+  {
+    CUDA_CHECK(cudaFuncSetAttribute(tree_kernel_s4<RL, EXACT, CPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tree_kernel_s4<RL, EXACT, CPT>, TREE_NT, smem));
+    if (per_sm < 1) { fatal("tree kernel does not fit on an SM (smem %zu)", smem); return; }
+    b->cfg_key = key; b->cfg_smem = smem; b->cfg_per_sm = per_sm;
+  }
+  const unsigned grid = std::min<unsigned>(prm.n_tiles, (unsigned)(b->cfg_per_sm * e->sm_count));
+  tree_kernel_s4<RL, EXACT, CPT><<<grid, TREE_NT, smem, st>>>(prm);
 }
 
 template <int RL>
-static void launch_tree_s4(bppgpu_batch * b, const TreeParams & prm)
+static void launch_tree_s4_rl(bppgpu_batch * b, const TreeParams & prm, cudaStream_t st)
 {
   const bool exact = b->e->math == BPPGPU_MATH_EXACT;
-  if (b->cpt == 2) { if (exact) launch_tree_s4_impl<RL, true, 2>(b, prm); else launch_tree_s4_impl<RL, false, 2>(b, prm); }
-  else if (b->cpt == 4) { if (exact) launch_tree_s4_impl<RL, true, 4>(b, prm); else launch_tree_s4_impl<RL, false, 4>(b, prm); }
-  else { if (exact) launch_tree_s4_impl<RL, true, 1>(b, prm); else launch_tree_s4_impl<RL, false, 1>(b, prm); }
+  if (b->cpt == 2) { if (exact) launch_tree_s4_impl<RL, true, 2>(b, prm, st); else launch_tree_s4_impl<RL, false, 2>(b, prm, st); }
+  else if (b->cpt == 4) { if (exact) launch_tree_s4_impl<RL, true, 4>(b, prm, st); else launch_tree_s4_impl<RL, false, 4>(b, prm, st); }
+  else { if (exact) launch_tree_s4_impl<RL, true, 1>(b, prm, st); else launch_tree_s4_impl<RL, false, 1>(b, prm, st); }
+}
+
+static int launch_tree_s4(bppgpu_batch * b, const TreeParams & prm, cudaStream_t st)
+{
+  switch (b->RL)
+  {
+    case 1: launch_tree_s4_rl<1>(b, prm, st); break;
+    case 2: launch_tree_s4_rl<2>(b, prm, st); break;
+    case 4: launch_tree_s4_rl<4>(b, prm, st); break;
+    case 8: launch_tree_s4_rl<8>(b, prm, st); break;
+    default: fatal("internal: RL=%u", b->RL); return BPPGPU_FAILURE;
+  }
+  return BPPGPU_SUCCESS;
 }
 
 template <int RL>
@@ -1062,8 +1223,7 @@ static int batch_run(bppgpu_batch * b, bool do_mats, bool do_tree, bool want_roo
       }
   if (b->kernel_kind != 1)
   {
-    unsigned maxT = 0;
-    for (auto * l : b->loci) maxT = std::max(maxT, l->tips);
+    const unsigned maxT = b->max_tips;
     slots = 1; while ((1u << slots) < maxT) ++slots;
     slots = std::min(std::max(slots - 1, 1), 6);
     // 20 states: a parked X costs 3.4 kB of shared memory per warp and slot, which would push the
@@ -1100,6 +1260,16 @@ static int batch_run(bppgpu_batch * b, bool do_mats, bool do_tree, bool want_roo
     }
   }
   const unsigned long long * d_blk_off = (const unsigned long long *)(b->d_in + b->o_blk_off);
+  // inputs staged in waves and not consumed yet: either run wave by wave (full pass of the 4-state kernel),
+  // or make the stream wait for the whole upload
+  const bool waved = b->inputs_pending && b->n_waves > 1 && b->kernel_kind == 0 && fuse_mats && want_root && !persite;
+  if (b->inputs_pending && !waved)
+  {
+    CUDA_CHECK(cudaStreamWaitEvent(b->stream, b->ev_tables, 0));
+    batch_issue_copies(b, 0, n, b->stream);
+  }
+  b->inputs_pending = false;
+  if (!waved)
   {
     ProfScope ps(e, b->stream, BPPGPU_KERNEL_PLAN);
     if (b->kernel_kind == 0)
@@ -1126,25 +1296,53 @@ static int batch_run(bppgpu_batch * b, bool do_mats, bool do_tree, bool want_roo
   prm.tile_partial = want_root ? b->d_tile_partial : nullptr;
   prm.persite = persite; prm.persite_mode = persite_mode; prm.n_slots = slots; prm.lut_cap = lut_cap_rt;
   prm.log_threshold = e->log_threshold;
+  if (waved)
+  {
+    // wave w: [upload on copy_stream] -> planner -> tree kernel on stream (even w) / alt_stream (odd w); the
+    // two compute streams let wave w+1 start on the SMs that wave w's tail frees
+    CUDA_CHECK(cudaEventRecord(b->ev_fork, b->stream));
+    CUDA_CHECK(cudaStreamWaitEvent(b->alt_stream, b->ev_fork, 0));
+    for (unsigned w = 0; w < b->n_waves; ++w)
+    {
+      const unsigned i0 = b->wave_first[w], i1 = b->wave_first[w + 1];
+      if (i1 <= i0) continue;
+      cudaStream_t st = (w & 1u) ? b->alt_stream : b->stream;
+      batch_issue_copies(b, i0, i1, b->copy_stream);
+      CUDA_CHECK(cudaEventRecord(b->ev_copy[w], b->copy_stream));
+      CUDA_CHECK(cudaStreamWaitEvent(st, b->ev_copy[w], 0));
+      {
+        ProfScope ps(e, st, BPPGPU_KERNEL_PLAN);
+        plan_kernel_blocks<<<((i1 - i0) * 32 + 127) / 128, 128, 0, st>>>(
+            e->d_loci, b->d_batch_locus + i0, i1 - i0, d_op_off + i0, d_ops, d_root_clv + i0, d_root_sc + i0, 1,
+            b->d_blocks, d_blk_off + i0, b->d_tile_first + i0, b->d_tile_blk, b->d_plan_count + i0, b->d_scratch,
+            b->d_scratch_off + i0, slots, b->RL, b->cpt, lut_cap_rt, d_mat_off + i0, d_mat_idx, d_mat_bl);
+        CUDA_CHECK(cudaGetLastError());
+      }
+      const unsigned t0 = b->h_tile_first[i0], t1 = b->h_tile_first[i1];
+      TreeParams pw = prm;
+      pw.tiles = b->d_tiles + t0; pw.tile_blk = b->d_tile_blk + 2 * (size_t)t0; pw.tile_partial = b->d_tile_partial + t0;
+      pw.n_tiles = t1 - t0;
+      {
+        ProfScope ps(e, st, BPPGPU_KERNEL_TREE);
+        if (!launch_tree_s4(b, pw, st)) return BPPGPU_FAILURE;
+        CUDA_CHECK(cudaGetLastError());
+      }
+    }
+    CUDA_CHECK(cudaEventRecord(b->ev_join, b->alt_stream));
+    CUDA_CHECK(cudaStreamWaitEvent(b->stream, b->ev_join, 0));
+  }
+  else
   {
     ProfScope ps(e, b->stream, BPPGPU_KERNEL_TREE);
     if (b->kernel_kind == 0)
     {
-      switch (b->RL)
-      {
-        case 1: launch_tree_s4<1>(b, prm); break;
-        case 2: launch_tree_s4<2>(b, prm); break;
-        case 4: launch_tree_s4<4>(b, prm); break;
-        case 8: launch_tree_s4<8>(b, prm); break;
-        default: fatal("internal: RL=%u", b->RL); return BPPGPU_FAILURE;
-      }
+      if (!launch_tree_s4(b, prm, b->stream)) return BPPGPU_FAILURE;
     }
     else if (b->kernel_kind == 2)
     {
       if (b->s20_cat)
       {
-        unsigned maxT = 0;
-        for (auto * l : b->loci) maxT = std::max(maxT, l->tips);
+        const unsigned maxT = b->max_tips;
         prm.max_tips = maxT; prm.rootdot = b->d_rootdot; prm.site_off = b->d_site_off;
         const size_t smem = s20c_smem_bytes(prm.lut_cap, maxT, prm.n_slots);
         const unsigned grid = std::min<unsigned>(b->n_tiles, (unsigned)e->sm_count);

@@ -339,6 +339,14 @@ class Batch:
         return (_u32(mc), _u32(mi), _f64(mb), _u32(oc), np.ascontiguousarray(ops, dtype=OP_DTYPE),
                 _u32(rc), _i32(rs))
 
+    def prepare(self, step):
+        """Resolve the ctypes pointers of a step's arrays once; the returned PreparedStep can be staged
+        repeatedly (its arrays may be modified in place between steps, like a C caller's buffers)."""
+        return PreparedStep(self._step_args(step))
+
+    def set_waves(self, waves):
+        self.L.bppgpu_batch_set_waves(self.h, int(waves))
+
     def full_pass(self, step):
         """step = (matrix_counts, pmatrix_indices, branch_lengths, op_counts, ops, root_clv, root_scaler)
         host arrays; returns (lnl[n], lnl_sum).  H2D + kernels + D2H in one call."""
@@ -351,18 +359,29 @@ class Batch:
         return out, tot.value
 
     def stage(self, step):
-        mc, mi, mb, oc, ops, rc, rs = self._step_args(step)
-        self.L.bppgpu_batch_stage(self.h, _up(mc), _up(mi), _dp(mb), _up(oc), _opp(ops), _up(rc), _ip(rs))
+        if isinstance(step, PreparedStep):
+            self.L.bppgpu_batch_stage(self.h, *step.ptrs)
+        else:
+            mc, mi, mb, oc, ops, rc, rs = self._step_args(step)
+            self.L.bppgpu_batch_stage(self.h, _up(mc), _up(mi), _dp(mb), _up(oc), _opp(ops), _up(rc), _ip(rs))
         _lib.check()
 
     def run(self):
         self.L.bppgpu_batch_run(self.h)
         _lib.check()
 
-    def collect(self):
-        out = np.zeros(self.n)
+    def collect(self, out=None):
+        """D2H of the n per-locus lnL values and their sum; `out` (float64[n]) is reused when given."""
+        if out is None:
+            out = np.zeros(self.n)
+            ptr = _dp(out)
+        else:
+            ptr = getattr(self, "_out_ptr", None)
+            if ptr is None or self._out_ref is not out:
+                ptr = _dp(out)
+                self._out_ptr, self._out_ref = ptr, out
         tot = C.c_double(0)
-        self.L.bppgpu_batch_collect(self.h, _dp(out), C.byref(tot))
+        self.L.bppgpu_batch_collect(self.h, ptr, C.byref(tot))
         _lib.check()
         return out, tot.value
 
@@ -383,6 +402,15 @@ class Batch:
     @property
     def stream(self):
         return self.L.bppgpu_batch_stream(self.h)
+
+
+class PreparedStep:
+    """The 7 arrays of a full-pass step with their ctypes pointers resolved (see Batch.prepare)."""
+
+    def __init__(self, arrays):
+        self.arrays = arrays
+        mc, mi, mb, oc, ops, rc, rs = arrays
+        self.ptrs = (_up(mc), _up(mi), _dp(mb), _up(oc), _opp(ops), _up(rc), _ip(rs))
 
 
 class GeneTrees:

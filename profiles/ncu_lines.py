@@ -9,7 +9,8 @@ import sys
 def main():
     rep = sys.argv[1]
     top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
-    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"],
+    kn = ["--kernel-name", sys.argv[3]] if len(sys.argv) > 3 else []
+    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"] + kn,
                          capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     hdr, cur = None, None
