@@ -35,14 +35,19 @@ struct LocusDev
   unsigned long long * dip_map; // diploid mapping
   unsigned long long clv_stride;
   unsigned int tips, sites, states, rate_cats;
-  unsigned int clv_buffers, prob_matrices, scale_buffers, model_kind;   // model_kind 0 = JC69, 1 = eigen
+  unsigned int clv_buffers, prob_matrices, scale_buffers, model_kind;   // MODEL_* below
   unsigned int unphased, tip_words;                                     // tip_words = ceil(tips/8) (4 states)
   // > 4 states: column ids of the tips (0..S-1 = one-hot state, S.. = ambiguity mask colmask[id-S])
   unsigned char * tip_cols;     // [tips][sites]
   unsigned int * colmask;       // [4] ambiguity masks
   unsigned int n_ext_cols, pad1;
   unsigned int * dip_weights;   // diploid loci: weights of the unphased sites [unphased]
+  double * subst;               // [S(S-1)/2] substitution parameters (closed-form DNA models read qrates here)
 };
+
+// how the P-matrices of a locus are built (locus_update_matrices dispatch, locus.c:2417-2479)
+enum : unsigned { MODEL_JC69 = 0, MODEL_EIGEN = 1, MODEL_K80 = 2, MODEL_F81 = 3, MODEL_HKY = 4, MODEL_T92 = 5,
+                  MODEL_TN93 = 6, MODEL_F84 = 7 };
 
 // operand kinds of a planned pruning step
 enum : unsigned { SRC_TIP_PACKED = 0, SRC_TIP_DENSE = 1, SRC_HBM = 2, SRC_SLOT = 3, SRC_PREV = 4,

@@ -374,7 +374,7 @@ static inline unsigned int get_code(const bppgpu_locus * l, unsigned tip, size_t
   return l->h_codes[(size_t)tip * l->sites + site];
 }
 
-static size_t model_doubles(unsigned S, unsigned R) { return (size_t)S + R + R + 2 * (size_t)S * S + S; }
+static size_t model_doubles(unsigned S, unsigned R) { return (size_t)S + R + R + 2 * (size_t)S * S + S + (size_t)S * (S - 1) / 2; }
 
 // push dirty host mirrors (tip codes, dense flags, model block) of a locus to the device
 static void locus_sync(bppgpu_locus * l, cudaStream_t s)
@@ -409,17 +409,31 @@ static void locus_sync(bppgpu_locus * l, cudaStream_t s)
     memcpy(w, l->h_rate_weights.data(), R * 8); w += R;
     memcpy(w, l->h_evecs.data(), (size_t)S * S * 8); w += (size_t)S * S;
     memcpy(w, l->h_ievecs.data(), (size_t)S * S * 8); w += (size_t)S * S;
-    memcpy(w, l->h_evals.data(), S * 8);
+    memcpy(w, l->h_evals.data(), S * 8); w += S;
+    memcpy(w, l->h_subst.data(), (size_t)S * (S - 1) / 2 * 8);
     // pageable source: the copy is staged by the runtime before the call returns
     CUDA_CHECK(cudaMemcpyAsync(l->dev.freqs, blk.data(), blk.size() * 8, cudaMemcpyHostToDevice, s));
     l->model_dirty = false;
   }
 }
 
-static bool model_is_closed_form(const bppgpu_locus * l)
+// locus_update_matrices dispatch (locus.c:2426-2455): every DNA model but GTR has a closed form
+static unsigned model_kind_of(const bppgpu_locus * l)
 {
-  return l->dtype == BPPGPU_DATA_DNA && l->model == BPPGPU_DNA_MODEL_JC69;
+  if (l->dtype != BPPGPU_DATA_DNA) return MODEL_EIGEN;
+  switch (l->model)
+  {
+    case BPPGPU_DNA_MODEL_JC69: return MODEL_JC69;
+    case BPPGPU_DNA_MODEL_K80:  return MODEL_K80;
+    case BPPGPU_DNA_MODEL_F81:  return MODEL_F81;
+    case BPPGPU_DNA_MODEL_HKY:  return MODEL_HKY;
+    case BPPGPU_DNA_MODEL_T92:  return MODEL_T92;
+    case BPPGPU_DNA_MODEL_TN93: return MODEL_TN93;
+    case BPPGPU_DNA_MODEL_F84:  return MODEL_F84;
+    default: return MODEL_EIGEN;
+  }
 }
+static bool model_is_closed_form(const bppgpu_locus * l) { return model_kind_of(l) != MODEL_EIGEN; }
 
 // ------------------------------------------------------------------------------------ engine API
 extern "C" int bppgpu_device_count(void)
@@ -551,11 +565,11 @@ extern "C" bppgpu_locus * bppgpu_locus_create(bppgpu_engine * e, unsigned int dt
   d.weights = (unsigned int *)e->arena.alloc(l->b_weights);
   double * m = (double *)e->arena.alloc(l->b_model);
   d.freqs = m; d.rates = m + S; d.rate_weights = d.rates + R; d.eigenvecs = d.rate_weights + R;
-  d.inv_eigenvecs = d.eigenvecs + S * S; d.eigenvals = d.inv_eigenvecs + S * S;
+  d.inv_eigenvecs = d.eigenvecs + S * S; d.eigenvals = d.inv_eigenvecs + S * S; d.subst = d.eigenvals + S;
   d.clv_stride = clv_doubles;
   d.tips = tips; d.sites = sites; d.states = states; d.rate_cats = rate_cats;
   d.clv_buffers = clv_buffers; d.prob_matrices = prob_matrices; d.scale_buffers = scale_buffers;
-  d.model_kind = model_is_closed_form(l) ? 0 : 1;
+  d.model_kind = model_kind_of(l);
   d.tip_words = (unsigned)TW;
   // zero what the reference zeroes (locus.c:745-755,765-771,859-867); weights default to 1 (:852)
   CUDA_CHECK(cudaMemsetAsync(d.clv, 0, l->b_clv, e->stream));
@@ -672,7 +686,7 @@ extern "C" void bppgpu_set_frequencies(bppgpu_locus * l, unsigned int idx, const
 extern "C" void bppgpu_set_subst_params(bppgpu_locus * l, unsigned int idx, const double * p)
 {
   if (idx != 0) { fatal("params_index must be 0"); return; }
-  l->h_subst.assign(p, p + l->states * (l->states - 1) / 2); l->eigen_valid = false; l->e->dirty_epoch++;    // locus.c:877-887
+  l->h_subst.assign(p, p + l->states * (l->states - 1) / 2); l->eigen_valid = false; l->model_dirty = true, l->e->dirty_epoch++;    // locus.c:877-887
 }
 extern "C" void bppgpu_set_category_rates(bppgpu_locus * l, const double * r)
 {

@@ -4,6 +4,111 @@
 
 namespace bppgpu {
 
+
+// Closed-form DNA models other than JC69, one whole matrix per call.  Expressions and their order are
+// the reference's: K80 locus.c:2300-2322, F81 :2236-2254, HKY / F84 / TN93 :2116-2162, T92 :2039-2066
+// (no zero-length special case there: expm1(-0) makes the identity by itself).
+__device__ __forceinline__ void pmatrix_closed4(const LocusDev & L, double bl, double * __restrict__ pmat)
+{
+  const double * __restrict__ freqs = L.freqs;
+  const double * __restrict__ qrates = L.subst;
+  if (L.model_kind == MODEL_K80)
+  {
+    const double kappa = qrates[1] / qrates[0];
+    const double e1 = expm1(-4 * bl / (kappa + 2));
+    if (fabs(kappa - 1) < 1e-20)
+    {
+      for (int j = 0; j < 4; ++j)
+        for (int k = 0; k < 4; ++k) pmat[j * 4 + k] = (j == k) ? 1. + 3 / 4. * e1 : -e1 / 4;
+    }
+    else
+    {
+      const double e2 = expm1(-2 * bl * (kappa + 1) / (kappa + 2));
+      const double dg = 1 + (e1 + 2 * e2) / 4, tv = -e1 / 4, ts = (e1 - 2 * e2) / 4;
+      for (int j = 0; j < 4; ++j)
+        for (int k = 0; k < 4; ++k) pmat[j * 4 + k] = (j == k) ? dg : (((j ^ k) == 2) ? ts : tv);
+    }
+  }
+  else if (L.model_kind == MODEL_F81)
+  {
+    double beta = 1;
+    for (int j = 0; j < 4; ++j) beta -= freqs[j] * freqs[j];
+    beta = 1. / beta;
+    const double e = exp(-beta * bl), em1 = expm1(-beta * bl);
+    for (int j = 0; j < 4; ++j)
+      for (int k = 0; k < 4; ++k) pmat[j * 4 + k] = (j == k) ? e - freqs[k] * em1 : -freqs[k] * em1;
+  }
+  else if (L.model_kind == MODEL_T92)
+  {
+    const double GC = freqs[3] + freqs[2];
+    const double e1 = expm1(-bl);
+    const double e2 = expm1(-(qrates[0] / qrates[1] + 1) * bl / 2);
+    pmat[0]  = -(1 - GC) / 2 * e1;
+    pmat[1]  = GC / 2 * e1 - GC * e2;
+    pmat[2]  = -GC / 2 * e1;
+    pmat[3]  = 1 + 0.5 * (1 - GC) * e1 + GC * e2;
+    pmat[4]  = -(1 - GC) / 2 * e1;
+    pmat[5]  = 1 + GC / 2 * e1 + (1 - GC) * e2;
+    pmat[6]  = -GC / 2 * e1;
+    pmat[7]  = (1 - GC) / 2 * e1 - (1 - GC) * e2;
+    pmat[8]  = 1 + 0.5 * (1 - GC) * e1 + GC * e2;
+    pmat[9]  = -GC / 2 * e1;
+    pmat[10] = GC / 2 * e1 - GC * e2;
+    pmat[11] = -(1 - GC) / 2 * e1;
+    pmat[12] = (1 - GC) / 2 * e1 - (1 - GC) * e2;
+    pmat[13] = -GC / 2 * e1;
+    pmat[14] = 1 + GC / 2 * e1 + (1 - GC) * e2;
+    pmat[15] = -(1 - GC) / 2 * e1;
+  }
+  else    // HKY, F84, TN93 share the TN93 formulas
+  {
+    const double A = freqs[0], C = freqs[1], G = freqs[2], T = freqs[3];
+    const double Y = T + C, R = A + G;
+    double bt, a1t, a2t;
+    if (L.model_kind == MODEL_HKY)
+    {
+      const double kappa = qrates[1] / qrates[0];
+      const double mr = 1 / (2 * T * C * kappa + 2 * A * G * kappa + 2 * Y * R);
+      bt = bl * mr;
+      a1t = a2t = kappa * bt;
+    }
+    else if (L.model_kind == MODEL_F84)
+    {
+      const double kappa = qrates[0] / qrates[1];
+      const double mr = 1 / (2 * T * C * kappa + 2 * A * G * kappa + 2 * Y * R);
+      bt = bl * mr;
+      a1t = (1 + kappa / Y) * bt;
+      a2t = (1 + kappa / R) * bt;
+    }
+    else
+    {
+      const double mr = 1 / (2 * T * C * qrates[0] + 2 * A * G * qrates[1] + 2 * Y * R);
+      bt = bl * mr;
+      a1t = (qrates[0] / qrates[2]) * bt;
+      a2t = (qrates[1] / qrates[2]) * bt;
+    }
+    const double e1 = expm1(-bt);
+    const double e2 = expm1(-(R * a2t + Y * bt));
+    const double e3 = expm1(-(Y * a1t + R * bt));
+    pmat[0]  = 1 + Y * A / R * e1 + G / R * e2;
+    pmat[1]  = -C * e1;
+    pmat[2]  = Y * G / R * e1 - G / R * e2;
+    pmat[3]  = -T * e1;
+    pmat[4]  = -A * e1;
+    pmat[5]  = 1 + (R * C * e1 + T * e3) / Y;
+    pmat[6]  = -G * e1;
+    pmat[7]  = (R * e1 - e3) * T / Y;
+    pmat[8]  = Y * A / R * e1 - A / R * e2;
+    pmat[9]  = -C * e1;
+    pmat[10] = 1 + Y * G / R * e1 + A / R * e2;
+    pmat[11] = -T * e1;
+    pmat[12] = -A * e1;
+    pmat[13] = (R * e1 - e3) * C / Y;
+    pmat[14] = -G * e1;
+    pmat[15] = 1 + (R * T * e1 + C * e3) / Y;
+  }
+}
+
 // ----------------------------------------------------------------------------- P-matrix kernel
 // grid.x = loci of the batch; the threads of a block stride over (op, cat, row) of their locus.
 // JC69: locus.c:2390-2391 (exp form).  Eigen: core_pmatrix.c:745-771 -- expm1, temp = Vinv*expd,
@@ -14,11 +119,17 @@ __device__ __forceinline__ void pmatrix_row(const LocusDev & L, unsigned int pm_
   const unsigned int S = L.states, R = L.rate_cats;
   const double bt = t * L.rates[n];
   double * row = L.pmat + ((size_t)pm_idx * R + n) * S * S + (size_t)j * S;
-  if (bt < 1e-100)
+  if (L.model_kind >= MODEL_K80)
+  {
+    double m[16];
+    pmatrix_closed4(L, bt, m);
+    for (unsigned int k = 0; k < 4; ++k) row[k] = m[j * 4 + k];
+  }
+  else if (bt < 1e-100)
   {
     for (unsigned int k = 0; k < S; ++k) row[k] = (j == k) ? 1.0 : 0.0;
   }
-  else if (L.model_kind == 0)
+  else if (L.model_kind == MODEL_JC69)
   {
     const double a = (1 + 3 * exp(-4 * bt / 3)) / 4;
     const double b = (1 - a) / 3;
@@ -64,12 +175,19 @@ __device__ __forceinline__ void pmatrix_full4(const LocusDev & L, unsigned int p
   const unsigned int R = L.rate_cats;
   const double bt = t * L.rates[n];
   double2 * P = reinterpret_cast<double2 *>(L.pmat + ((size_t)pm_idx * R + n) * 16);
-  if (bt < 1e-100)
+  if (L.model_kind >= MODEL_K80)
+  {
+    double m[16];
+    pmatrix_closed4(L, bt, m);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) P[j] = make_double2(m[2 * j], m[2 * j + 1]);
+  }
+  else if (bt < 1e-100)
   {
 #pragma unroll
     for (int j = 0; j < 4; ++j) { P[2 * j] = make_double2(j == 0 ? 1.0 : 0.0, j == 1 ? 1.0 : 0.0); P[2 * j + 1] = make_double2(j == 2 ? 1.0 : 0.0, j == 3 ? 1.0 : 0.0); }
   }
-  else if (L.model_kind == 0)
+  else if (L.model_kind == MODEL_JC69)
   {
     const double a = (1 + 3 * exp(-4 * bt / 3)) / 4;
     const double b = (1 - a) / 3;
@@ -113,6 +231,12 @@ pmatrix_kernel(const LocusDev * __restrict__ loci, const unsigned int * __restri
   const LocusDev & L = loci[batch_locus[bl]];
   const unsigned int first = mat_off[bl], count = mat_off[bl + 1] - first;
   const unsigned int S = L.states, R = L.rate_cats;
+  if (S == 4)
+  {
+    for (unsigned int t = threadIdx.x; t < count * R; t += blockDim.x)
+      pmatrix_full4(L, mat_idx[first + t / R], mat_bl[first + t / R], t % R);
+    return;
+  }
   const unsigned int tasks = count * R * S;
   for (unsigned int t = threadIdx.x; t < tasks; t += blockDim.x)
   {

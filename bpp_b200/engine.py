@@ -18,6 +18,8 @@ from ._lib import PartialOp, BppGpuError  # noqa: F401
 
 DATA_DNA, DATA_AA = 0, 1
 DNA_MODEL_JC69, DNA_MODEL_GTR = 0, 7
+# bpp.h:215-222
+DNA_MODELS = {"JC69": 0, "K80": 1, "F81": 2, "HKY": 3, "T92": 4, "TN93": 5, "F84": 6, "GTR": 7}
 SCALE_BUFFER_NONE = -1
 MATH_EXACT, MATH_FMA = 0, 1
 ATTRIB_ARCH_CUDA = 1 << 6
@@ -509,7 +511,7 @@ def load_workload(engine, w, charmap=None):
     from . import synth
     if charmap is None:
         charmap = synth.iupac_nt_map() if w.states == 4 else synth.aa_map()
-    model = {"JC69": DNA_MODEL_JC69, "GTR": DNA_MODEL_GTR, "LG": 1}[w.model]
+    model = 1 if w.model == "LG" else DNA_MODELS[w.model]
     loci = []
     for i in range(w.n_loci):
         l = Locus.create_like_bpp(engine, w.tips, w.sites, w.states, w.rate_cats, w.scaling, model)

@@ -170,6 +170,18 @@ def make_workload(name, n_loci, tips, sites, states=4, rate_cats=1, model="JC69"
         freqs = f / f.sum(axis=1, keepdims=True)
         subst = rng.uniform(0.5, 1.5, size=(n_loci, nsub))
         subst[:, -1] = 1.0
+    elif model in ("K80", "F81", "HKY", "T92", "TN93", "F84"):
+        # closed-form DNA models (locus.c:1981-2324): qrates[0..2] carry kappa-like parameters the way the
+        # reference reads them; K80 has equal base frequencies, T92 is parameterised by its GC content
+        if model == "K80":
+            freqs = np.full((n_loci, states), 0.25)
+        elif model == "T92":
+            gc = rng.uniform(0.35, 0.65, size=n_loci)
+            freqs = np.stack([(1 - gc) / 2, gc / 2, gc / 2, (1 - gc) / 2], axis=1)   # T C A G
+        else:
+            f = rng.uniform(0.6, 1.4, size=(n_loci, states))
+            freqs = f / f.sum(axis=1, keepdims=True)
+        subst = rng.uniform(0.5, 4.0, size=(n_loci, nsub))
     elif model == "LG":
         assert lg is not None, "pass lg=(rates190, freqs20)"
         subst = np.tile(np.asarray(lg[0], dtype=np.float64), (n_loci, 1))

@@ -37,6 +37,12 @@ extern "C" {
 #define BPPGPU_DATA_DNA        0
 #define BPPGPU_DATA_AA         1
 #define BPPGPU_DNA_MODEL_JC69  0
+#define BPPGPU_DNA_MODEL_K80   1
+#define BPPGPU_DNA_MODEL_F81   2
+#define BPPGPU_DNA_MODEL_HKY   3
+#define BPPGPU_DNA_MODEL_T92   4
+#define BPPGPU_DNA_MODEL_TN93  5
+#define BPPGPU_DNA_MODEL_F84   6
 #define BPPGPU_DNA_MODEL_GTR   7
 
 /* bpp.h:380 PLL_SCALE_BUFFER_NONE */
@@ -134,8 +140,10 @@ void bppgpu_get_eigen(bppgpu_locus * l, unsigned int params_index,
 
 /* replaces locus_update_matrices (locus.c:2417) for `count` branches: P-matrix of the edge above
    a node goes to pmatrix[pmatrix_indices[i]]; branch_lengths[i] = (parent.time-node.time)*rate_mui
-   (core_pmatrix.c:711-715) is computed by the caller.  JC69 closed form (locus.c:2325) or
-   eigen form (core_pmatrix.c:674) by the locus' model. */
+   (core_pmatrix.c:711-715) is computed by the caller.  Dispatch by the locus' model like locus.c:2426-2455:
+   closed forms for JC69 (locus.c:2325), K80 (:2256), F81 (:2190), HKY / F84 / TN93 (:2068) and T92 (:1981),
+   whose parameters are read from subst_params / frequencies exactly as there; eigen form
+   (core_pmatrix.c:674) for GTR and the amino-acid models. */
 int  bppgpu_update_matrices(bppgpu_locus * l, unsigned int count,
                             const unsigned int * pmatrix_indices, const double * branch_lengths);
 /* replaces locus_update_partials (locus.c:2530): ops must be post-ordered */

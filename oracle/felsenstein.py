@@ -62,6 +62,102 @@ def pmatrix_jc69(t, rates):
     return out
 
 
+def pmatrix_closed(model, t, rates, freqs, subst):
+    """Closed-form DNA models other than JC69: locus_update_matrices_k80 (locus.c:2256-2323), _f81
+    (:2190-2255), _tn93 for HKY / F84 / TN93 (:2068-2164), _t92 (:1981-2066).  Same expressions, same
+    order; none of them has a zero-length special case. -> [R,4,4]"""
+    R = len(rates)
+    out = np.zeros((R, 16))
+    f, q = np.asarray(freqs, dtype=np.float64), np.asarray(subst, dtype=np.float64)
+    for n in range(R):
+        bl = t * rates[n]
+        pm = out[n]
+        if model == "K80":
+            kappa = q[1] / q[0]
+            e1 = np.expm1(-4 * bl / (kappa + 2))
+            if abs(kappa - 1) < 1e-20:
+                pm[:] = -e1 / 4
+                pm[[0, 5, 10, 15]] = 1. + 3 / 4. * e1
+            else:
+                e2 = np.expm1(-2 * bl * (kappa + 1) / (kappa + 2))
+                pm[:] = -e1 / 4
+                pm[[0, 5, 10, 15]] = 1 + (e1 + 2 * e2) / 4
+                pm[[2, 7, 8, 13]] = (e1 - 2 * e2) / 4
+        elif model == "F81":
+            beta = 1.0
+            for j in range(4):
+                beta -= f[j] * f[j]
+            beta = 1. / beta
+            e, em1 = np.exp(-beta * bl), np.expm1(-beta * bl)
+            for j in range(4):
+                for k in range(4):
+                    pm[4 * j + k] = e - f[k] * em1 if j == k else -f[k] * em1
+        elif model == "T92":
+            GC = f[3] + f[2]
+            e1 = np.expm1(-bl)
+            e2 = np.expm1(-(q[0] / q[1] + 1) * bl / 2)
+            pm[0] = -(1 - GC) / 2 * e1
+            pm[1] = GC / 2 * e1 - GC * e2
+            pm[2] = -GC / 2 * e1
+            pm[3] = 1 + 0.5 * (1 - GC) * e1 + GC * e2
+            pm[4] = -(1 - GC) / 2 * e1
+            pm[5] = 1 + GC / 2 * e1 + (1 - GC) * e2
+            pm[6] = -GC / 2 * e1
+            pm[7] = (1 - GC) / 2 * e1 - (1 - GC) * e2
+            pm[8] = 1 + 0.5 * (1 - GC) * e1 + GC * e2
+            pm[9] = -GC / 2 * e1
+            pm[10] = GC / 2 * e1 - GC * e2
+            pm[11] = -(1 - GC) / 2 * e1
+            pm[12] = (1 - GC) / 2 * e1 - (1 - GC) * e2
+            pm[13] = -GC / 2 * e1
+            pm[14] = 1 + GC / 2 * e1 + (1 - GC) * e2
+            pm[15] = -(1 - GC) / 2 * e1
+        elif model in ("HKY", "F84", "TN93"):
+            A, C, G, T = f[0], f[1], f[2], f[3]
+            Y, Rr = T + C, A + G
+            if model == "HKY":
+                kappa = q[1] / q[0]
+                mr = 1 / (2 * T * C * kappa + 2 * A * G * kappa + 2 * Y * Rr)
+                bt = bl * mr
+                a1t = a2t = kappa * bt
+            elif model == "F84":
+                kappa = q[0] / q[1]
+                mr = 1 / (2 * T * C * kappa + 2 * A * G * kappa + 2 * Y * Rr)
+                bt = bl * mr
+                a1t = (1 + kappa / Y) * bt
+                a2t = (1 + kappa / Rr) * bt
+            else:
+                mr = 1 / (2 * T * C * q[0] + 2 * A * G * q[1] + 2 * Y * Rr)
+                bt = bl * mr
+                a1t = (q[0] / q[2]) * bt
+                a2t = (q[1] / q[2]) * bt
+            e1 = np.expm1(-bt)
+            e2 = np.expm1(-(Rr * a2t + Y * bt))
+            e3 = np.expm1(-(Y * a1t + Rr * bt))
+            pm[0] = 1 + Y * A / Rr * e1 + G / Rr * e2
+            pm[1] = -C * e1
+            pm[2] = Y * G / Rr * e1 - G / Rr * e2
+            pm[3] = -T * e1
+            pm[4] = -A * e1
+            pm[5] = 1 + (Rr * C * e1 + T * e3) / Y
+            pm[6] = -G * e1
+            pm[7] = (Rr * e1 - e3) * T / Y
+            pm[8] = Y * A / Rr * e1 - A / Rr * e2
+            pm[9] = -C * e1
+            pm[10] = 1 + Y * G / Rr * e1 + A / Rr * e2
+            pm[11] = -T * e1
+            pm[12] = -A * e1
+            pm[13] = (Rr * e1 - e3) * C / Y
+            pm[14] = -G * e1
+            pm[15] = 1 + (Rr * T * e1 + C * e3) / Y
+        else:
+            raise ValueError(model)
+    return out.reshape(R, 4, 4)
+
+
+CLOSED_FORM_MODELS = ("K80", "F81", "HKY", "T92", "TN93", "F84")
+
+
 def ratematrix_sym(subst, freqs):
     """create_ratematrix, core_pmatrix.c:186-237: symmetrised Q with mean rate 1."""
     S = len(freqs)
@@ -302,6 +398,8 @@ class OracleLocus:
             t = branch_length(self.times[self.parent[n]], self.times[n], self.rate_mui)
             if self.model == "JC69":
                 pm = pmatrix_jc69(t, self.rates)
+            elif self.model in CLOSED_FORM_MODELS:
+                pm = pmatrix_closed(self.model, t, self.rates, self.freqs, self.subst)
             else:
                 if self.eigen is None:
                     self.eigen = update_eigen(self.subst, self.freqs)

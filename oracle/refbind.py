@@ -18,6 +18,8 @@ ARCH_CPU, ARCH_SSE, ARCH_AVX, ARCH_AVX2 = 0, 1, 2, 4
 # bpp.h:208-222
 DATA_DNA, DATA_AA = 0, 1
 MODEL_JC69, MODEL_GTR = 0, 7
+# bpp.h:215-222
+DNA_MODELS = {"JC69": 0, "K80": 1, "F81": 2, "HKY": 3, "T92": 4, "TN93": 5, "F84": 6, "GTR": 7}
 AA_MODEL_LG = 1  # bpp.h BPP_AA_MODEL_LG; the shim overrides freqs/rates anyway
 
 _lib = None

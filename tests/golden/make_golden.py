@@ -35,6 +35,13 @@ CASES = {
                              seed=15, dt_lo=0.05, dt_hi=0.4), 1),
     "gtr_g4_deep_scale": (dict(n_loci=2, tips=260, sites=9, states=4, rate_cats=4, model="GTR", scaling=True,
                                seed=16, dt_lo=0.05, dt_hi=0.4), 1),
+    # closed-form DNA models (locus.c:1981-2324)
+    "k80_g4":        (dict(n_loci=3, tips=7, sites=29, states=4, rate_cats=4, model="K80", seed=21), 1),
+    "f81_r1_scale":  (dict(n_loci=3, tips=9, sites=31, states=4, rate_cats=1, model="F81", scaling=True, seed=22), 1),
+    "hky_g4":        (dict(n_loci=3, tips=8, sites=27, states=4, rate_cats=4, model="HKY", seed=23), 1),
+    "t92_g4":        (dict(n_loci=3, tips=6, sites=25, states=4, rate_cats=4, model="T92", seed=24), 1),
+    "tn93_g4_scale": (dict(n_loci=3, tips=10, sites=23, states=4, rate_cats=4, model="TN93", scaling=True, seed=25), 1),
+    "f84_r2":        (dict(n_loci=3, tips=5, sites=33, states=4, rate_cats=2, model="F84", seed=26, rates=[0.3, 1.7]), 1),
     "lg_g4_deep_scale": (dict(n_loci=1, tips=90, sites=6, states=20, rate_cats=4, model="LG", scaling=True,
                               seed=17, dt_lo=0.05, dt_hi=0.4), 1),
 }
@@ -57,7 +64,7 @@ def dump_locus(rs, w, i):
     out["clv"] = np.stack([rs.clv(i, rs.node_get(i, n, 0)) for n in range(T, 2 * T - 1)])
     if w.scaling:
         out["scaler"] = np.stack([rs.scaler(i, rs.node_get(i, n, 1)) for n in range(T, 2 * T - 1)])
-    if w.model != "JC69":
+    if w.model in ("GTR", "LG"):
         ev, iev, lam = rs.eigen(i)
         out["eigenvecs"], out["inv_eigenvecs"], out["eigenvals"] = ev, iev, lam
     return out
@@ -65,13 +72,17 @@ def dump_locus(rs, w, i):
 
 def main():
     rates_lg, freqs_lg = refbind.aa_lg()
-    np.savez(os.path.join(GOLDEN, "lg_model.npz"), rates=rates_lg, freqs=freqs_lg)
-    np.savez(os.path.join(GOLDEN, "gamma_rates.npz"),
-             **{"a%g_k%d" % (a, k): refbind.gamma_rates(a, k)
-                for a in (0.05, 0.2, 0.5, 1.0, 2.5, 10.0) for k in (2, 3, 4, 5, 8)})
-    nt, aa = refbind.char_maps()
-    np.savez(os.path.join(GOLDEN, "char_maps.npz"), nt=nt, aa=aa)
+    if len(sys.argv) == 1:
+        np.savez(os.path.join(GOLDEN, "lg_model.npz"), rates=rates_lg, freqs=freqs_lg)
+        np.savez(os.path.join(GOLDEN, "gamma_rates.npz"),
+                 **{"a%g_k%d" % (a, k): refbind.gamma_rates(a, k)
+                    for a in (0.05, 0.2, 0.5, 1.0, 2.5, 10.0) for k in (2, 3, 4, 5, 8)})
+        nt, aa = refbind.char_maps()
+        np.savez(os.path.join(GOLDEN, "char_maps.npz"), nt=nt, aa=aa)
+    only = set(sys.argv[1:])          # optional: regenerate only the named cases
     for name, (kw, keep) in CASES.items():
+        if only and name not in only:
+            continue
         w = synth.make_workload(name, lg=(rates_lg, freqs_lg), **kw)
         rs = ref_set_from_workload(w)
         data = workload_to_dict(w)

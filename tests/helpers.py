@@ -21,7 +21,7 @@ def char_map(states):
 
 def ref_set_from_workload(w, arch=refbind.ARCH_AVX2):
     """Load a synth.Workload into the compiled reference (oracle/_ref)."""
-    model = {"JC69": refbind.MODEL_JC69, "GTR": refbind.MODEL_GTR, "LG": refbind.AA_MODEL_LG}[w.model]
+    model = refbind.AA_MODEL_LG if w.model == "LG" else refbind.DNA_MODELS[w.model]
     rs = refbind.RefSet(w.n_loci, w.states, w.rate_cats, w.scaling, model=model, arch=arch)
     for i in range(w.n_loci):
         rs.create(i, w.tips, w.sites)
@@ -59,7 +59,7 @@ def load_case(name):
 
 
 GOLDEN_CASES = ["jc69_r1", "gtr_g4_scale", "gtr_g4", "lg_g4", "jc69_deep_scale", "gtr_g4_deep_scale",
-                "lg_g4_deep_scale"]
+                "lg_g4_deep_scale", "k80_g4", "f81_r1_scale", "hky_g4", "t92_g4", "tn93_g4_scale", "f84_r2"]
 
 
 def frogs_fixture():
