@@ -218,6 +218,11 @@ __device__ __forceinline__ void cp_async16(void * smem_dst, const void * gsrc)
   const unsigned int s = (unsigned int)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(s), "l"(gsrc) : "memory");
 }
+__device__ __forceinline__ void cp_async4(void * smem_dst, const void * gsrc)
+{
+  const unsigned int s = (unsigned int)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(s), "l"(gsrc) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 

@@ -101,9 +101,16 @@ struct S4Layout               // everything in uint4 (16-byte) units
   __host__ __device__ static constexpr unsigned stage_sz(unsigned cap) { return TIPP + cap * RL * 9; }
   __host__ __device__ static constexpr unsigned lut0(unsigned cap) { return STAGE0 + NSTAGE * stage_sz(cap); }
   __host__ __device__ static constexpr unsigned stack0(unsigned cap) { return lut0(cap) + cap * RL * 49; }
+  // after the stack: packed tip words and pattern weights of the current and the next tile,
+  // [2 buffers][3: tip word 0, tip word 1, weight][CPT][TREE_NT] u32, filled by 4-byte cp.async
+  static constexpr unsigned TIPS_BUF = 3 * CPT * TREE_NT;         // u32 per buffer
+  __host__ __device__ static constexpr unsigned tips0_u32(int slots, unsigned cap)
+  {
+    return (stack0(cap) + (unsigned)slots * SLOT) * 4 + (unsigned)slots * CPT * TREE_NT;
+  }
   __host__ __device__ static constexpr size_t bytes(int slots, unsigned cap)
   {
-    return (size_t)stack0(cap) * 16 + (size_t)slots * ((size_t)SLOT * 16 + CPT * TREE_NT * 4);
+    return (size_t)tips0_u32(slots, cap) * 4 + 2 * (size_t)TIPS_BUF * 4;
   }
 };
 
@@ -117,7 +124,9 @@ struct TileCtx
   unsigned int cat;
   unsigned int cell[CPT];        // clamped cell index
   bool valid[CPT];
-  unsigned int tw0[CPT], tw1[CPT], wgt[CPT];
+  unsigned int tw0[CPT];         // tip word 0 (tips 0..7) of the thread's cells
+  unsigned int tips_s;           // u32 index of this thread's entry in the tile's tip buffer: word 1 of cell j at
+                                 // tips_s + (CPT + j) * TREE_NT, pattern weight at tips_s + (2 * CPT + j) * TREE_NT
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -188,7 +197,7 @@ __device__ __forceinline__ double tile_fast(const TreeParams & prm, const TileCt
         }
         else
         {
-          const unsigned int wa = aw1 ? tc.tw1[j] : tc.tw0[j];
+          const unsigned int wa = aw1 ? s1[tc.tips_s + (CPT + j) * TREE_NT] : tc.tw0[j];
           const unsigned int ia = (amask ? lut_t : stk_t + j * (2 * TREE_NT)) + w0.w + ((wa >> ash) & amask) * 3;
           a0 = sd2[ia]; a1 = sd2[ia + 1];
         }
@@ -205,7 +214,7 @@ __device__ __forceinline__ double tile_fast(const TreeParams & prm, const TileCt
           }
           else
           {
-            const unsigned int wb = bw1 ? tc.tw1[j] : tc.tw0[j];
+            const unsigned int wb = bw1 ? s1[tc.tips_s + (CPT + j) * TREE_NT] : tc.tw0[j];
             const unsigned int ib = (bmask ? lut_t : stk_t + j * (2 * TREE_NT)) + w1.y + ((wb >> bsh) & bmask) * 3;
             const double2 b0 = sd2[ib], b1 = sd2[ib + 1];
             x[j][0] = b0.x; x[j][1] = b0.y; x[j][2] = b1.x; x[j][3] = b1.y;
@@ -297,7 +306,7 @@ __device__ __forceinline__ double tile_fast(const TreeParams & prm, const TileCt
         {
           s = log(term);
           if (FULL && osc[j]) s = __dadd_rn(s, __dmul_rn((double)osc[j], prm.log_threshold));
-          s = __dmul_rn(s, (double)tc.wgt[j]);
+          s = __dmul_rn(s, (double)s1[tc.tips_s + (2 * CPT + j) * TREE_NT]);
         }
         if (tc.valid[j] && tc.cat == 0)
         {
@@ -516,16 +525,20 @@ tree_kernel_s4(const TreeParams prm)
     const uint4 * src = reinterpret_cast<const uint4 *>(prm.blocks + blk);
     for (unsigned int w = tid; w < stage_sz; w += TREE_NT) cp_async16(&s4[Lay::STAGE0 + buf * stage_sz + w], src + w);
   };
-  auto load_tips = [&](const TileDesc & d, unsigned int * tw0, unsigned int * tw1, unsigned int * wgt)
+  const unsigned int tips0 = Lay::tips0_u32(prm.n_slots, prm.lut_cap);
+  // packed tip words + pattern weight of the thread's cells of tile d -> tip buffer `tb` (asynchronous; each
+  // thread copies and later reads only its own entries, so the cp.async wait alone orders them)
+  auto load_tips = [&](const TileDesc & d, unsigned int tb)
   {
 #pragma unroll
     for (int j = 0; j < CPT; ++j)
     {
       const unsigned int craw = d.cell0 + tid + j * TREE_NT;
       const unsigned int pat = (craw < d.ncell ? craw : d.ncell - 1) / RL;
-      tw0[j] = ld_u32_prefetch(d.tipwords + (size_t)pat * d.tip_words);
-      tw1[j] = (d.tip_words > 1) ? ld_u32_prefetch(d.tipwords + (size_t)pat * d.tip_words + 1) : 0u;
-      wgt[j] = ld_u32_prefetch(d.weights + pat);
+      unsigned int * dst = &s1[tips0 + tb * Lay::TIPS_BUF + j * TREE_NT + tid];
+      cp_async4(dst, d.tipwords + (size_t)pat * d.tip_words);
+      if (d.tip_words > 1) cp_async4(dst + CPT * TREE_NT, d.tipwords + (size_t)pat * d.tip_words + 1);
+      cp_async4(dst + 2 * CPT * TREE_NT, d.weights + pat);
     }
   };
 
@@ -538,7 +551,9 @@ tree_kernel_s4(const TreeParams prm)
   TileCtx<CPT> tc;
   tc.lut0 = lut0; tc.stack0 = stack0;
   tc.sst1 = (stack0 + (unsigned)prm.n_slots * Lay::SLOT) * 4;
-  load_tips(*reinterpret_cast<const TileDesc *>(&s4[Lay::RING + (t_begin & 3u) * 3]), tc.tw0, tc.tw1, tc.wgt);
+  load_tips(*reinterpret_cast<const TileDesc *>(&s4[Lay::RING + (t_begin & 3u) * 3]), 0u);
+  cp_async_commit();
+  cp_async_wait_all();
 
   unsigned int buf = 0;
   unsigned int staged_locus = 0xFFFFFFFFu;      // locus whose header + chunk 0 + LUT are valid in stage[buf]
@@ -567,14 +582,12 @@ tree_kernel_s4(const TreeParams prm)
     }
     // ---- prefetch: tips/weight of tile t+1 -> registers; block of the next locus -> other stage buffer;
     //      descriptor of tile t+2 -> ring
-    unsigned int ntw0[CPT], ntw1[CPT], nwgt[CPT];
-#pragma unroll
-    for (int j = 0; j < CPT; ++j) { ntw0[j] = ntw1[j] = nwgt[j] = 0; }
+    const unsigned int tb = (t - t_begin) & 1u;          // tip buffer of this tile
     if (t + 1 < t_end)
     {
       const unsigned int rn = Lay::RING + ((t + 1) & 3u) * 3;
       const TileDesc dn = *reinterpret_cast<const TileDesc *>(&s4[rn]);
-      load_tips(dn, ntw0, ntw1, nwgt);
+      load_tips(dn, tb ^ 1u);
       if (Lay::NSTAGE == 2 && dn.locus != d.locus && dn.locus != prefetched_locus)
       {
         stage_fetch(buf ^ 1u, *reinterpret_cast<const unsigned long long *>(&s4[rn + 2]));
@@ -588,6 +601,9 @@ tree_kernel_s4(const TreeParams prm)
     const LocusHdr * H = reinterpret_cast<const LocusHdr *>(&s4[sb]);
     tc.sb = sb;
     tc.cat = (d.cell0 + tid) % RL;
+    tc.tips_s = tips0 + tb * Lay::TIPS_BUF + tid;
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) tc.tw0[j] = s1[tc.tips_s + j * TREE_NT];
 #pragma unroll
     for (int j = 0; j < CPT; ++j)
     {
@@ -623,7 +639,8 @@ tree_kernel_s4(const TreeParams prm)
 #pragma unroll
         for (int j = 0; j < CPT; ++j)
           site_sum += chunk_general<RL, EXACT, CPT>(prm, sb, lut0 | (stack0 << 16), tc.sst1, j, tc.cell[j], tc.valid[j], tc.cat, tc.tw0[j],
-                                                    tc.tw1[j], tc.wgt[j], xs[j], &pscs[j]);
+                                                    d.tip_words > 1 ? s1[tc.tips_s + (CPT + j) * TREE_NT] : 0u,
+                                                    s1[tc.tips_s + (2 * CPT + j) * TREE_NT], xs[j], &pscs[j]);
       }
     }
 
@@ -643,8 +660,6 @@ tree_kernel_s4(const TreeParams prm)
       for (unsigned int w = 0; w < (TREE_NT >> 5); ++w) acc += s8[Lay::RED * 2 + (t & 1u) * 16 + w];
       prm.tile_partial[t] = acc;
     }
-#pragma unroll
-    for (int j = 0; j < CPT; ++j) { tc.tw0[j] = ntw0[j]; tc.tw1[j] = ntw1[j]; tc.wgt[j] = nwgt[j]; }
   }
 }
 
