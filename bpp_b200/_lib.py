@@ -50,10 +50,11 @@ def load():
     global _lib, _handler_ref
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("BPPGPU_LIB", LIB_PATH)        # tuning builds (tools/): another build of the same library
+    if not os.path.exists(path):
         raise BppGpuError("%s not found: build it with `python -m bpp_b200.build` "
-                          "(there is no CPU fallback)" % LIB_PATH)
-    L = C.CDLL(LIB_PATH)
+                          "(there is no CPU fallback)" % path)
+    L = C.CDLL(path)
     vp, u, i, d = C.c_void_p, C.c_uint, C.c_int, C.c_double
     up, ip, dp = C.POINTER(C.c_uint), C.POINTER(C.c_int), C.POINTER(C.c_double)
     opp = C.POINTER(PartialOp)

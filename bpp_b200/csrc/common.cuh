@@ -78,7 +78,18 @@ struct RawOp                    // == bppgpu_partial_op
 //         [double tipP[lut_cap(RL)][RL][PM_STRIDE]]
 // Pup[k]  = P-matrix of the edge ABOVE the node op k computes (the consumer's lpm/rpm);
 // tipP[s] = P-matrix of the edge above the packed tip child that was given LUT slot s.
-constexpr int TREE_NT    = 256;     // threads (= cells) per tile of the 4-state kernel
+#ifndef BPPGPU_TREE_NT
+#define BPPGPU_TREE_NT 256
+#endif
+#ifndef BPPGPU_S4_CTAS2
+#define BPPGPU_S4_CTAS2 (2 * (256 / BPPGPU_TREE_NT))   // CTAs per SM targeted by the 2-cells-per-thread kernel
+#endif
+constexpr int TREE_NT    = BPPGPU_TREE_NT;     // threads (= cells) per tile of the 4-state kernel
+// CTAs per SM the 4-state kernel is compiled for, by cells per thread (register budget 85 / 128 / 255)
+__host__ __device__ constexpr int s4_ctas_per_sm(int cpt)
+{
+  return cpt == 2 ? BPPGPU_S4_CTAS2 : (cpt == 1 ? 3 : 1) * (256 / TREE_NT);
+}
 constexpr int TREE_CHUNK = 16;      // ops per staged chunk
 constexpr int PM_STRIDE  = 18;      // doubles per (matrix, cat) in shared memory (16 + 2 pad: the RL
                                     // categories of a site land in different banks)

@@ -759,7 +759,7 @@ static void batch_launch_cfg(bppgpu_batch * b)
   if (b->kernel_kind == 0 && R >= 4 && mean >= 7 * (TREE_NT / 2)) b->cpt = 4;
   if (const char * ev = getenv("BPPGPU_CPT"))                 // tuning knob
     if (b->kernel_kind == 0 && (atoi(ev) == 1 || atoi(ev) == 2 || atoi(ev) == 4)) b->cpt = (unsigned)atoi(ev);
-  b->tile_threads = b->kernel_kind != 1 ? TREE_NT : 128;
+  b->tile_threads = b->kernel_kind == 0 ? TREE_NT : (b->kernel_kind == 2 ? S20_NT : 128);
 }
 
 extern "C" bppgpu_batch * bppgpu_batch_create(bppgpu_engine * e, unsigned int n, bppgpu_locus * const * loci)
@@ -1133,7 +1133,7 @@ template <int RL, int CPT>
 static int tree_s4_slots(bppgpu_batch * b, int wanted, unsigned cap)
 {
   int slots = wanted;
-  const size_t ctas = CPT == 4 ? 1 : 2;
+  const size_t ctas = s4_ctas_per_sm(CPT);
   while (slots > 1 && ctas * (S4Layout<RL, CPT>::bytes(slots, cap) + 1024) > b->e->smem_per_sm) --slots;
   return slots;
 }
@@ -1185,10 +1185,10 @@ static void launch_tree_s20(bppgpu_batch * b, const TreeParams & prm)
   const size_t smem = s20_smem_bytes<RL>(prm.n_slots);
   CUDA_CHECK(cudaFuncSetAttribute(tree_kernel_s20<RL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
-  CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tree_kernel_s20<RL>, TREE_NT, smem));
+  CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tree_kernel_s20<RL>, S20_NT, smem));
   if (per_sm < 1) { fatal("20-state tree kernel does not fit on an SM (smem %zu)", smem); return; }
   const unsigned grid = std::min<unsigned>(b->n_tiles, (unsigned)(per_sm * e->sm_count));
-  tree_kernel_s20<RL><<<grid, TREE_NT, smem, b->stream>>>(prm);
+  tree_kernel_s20<RL><<<grid, S20_NT, smem, b->stream>>>(prm);
 }
 
 // launches: [pmatrix] [plan + tree (+ finish)] on the batch stream, using the staged blob

@@ -31,7 +31,8 @@ constexpr int S20 = 20;
 constexpr int S20_EXT = 4;          // extra tip columns (ambiguity masks) per tip edge and category
 constexpr int S20_NG = 2;           // groups of 8 sites per warp (16 sites): keeps the kernel at <= 128 registers
 constexpr int S20_WS = 8 * S20_NG;  // sites per warp
-constexpr int S20_TILE = (TREE_NT / 32) * S20_WS;   // cells (site, category) per CTA tile
+constexpr int S20_NT = 256;              // threads per CTA of the site-major 20-state kernel
+constexpr int S20_TILE = (S20_NT / 32) * S20_WS;   // cells (site, category) per CTA tile
 
 struct OpRec20                      // 64 bytes
 {
@@ -284,13 +285,13 @@ __device__ __forceinline__ void matvec20(const double * __restrict__ P, const do
 }
 
 // ---------------------------------------------------------------- the kernel
-// grid: persistent; tile t = TREE_NT cells = (TREE_NT / RL) sites x RL categories of one locus
+// grid: persistent; tile t = S20_NT cells = (S20_NT / RL) sites x RL categories of one locus
 template <int RL>
-__global__ void __launch_bounds__(TREE_NT, 2)
+__global__ void __launch_bounds__(S20_NT, 2)
 tree_kernel_s20(const TreeParams prm)
 {
   extern __shared__ __align__(16) unsigned char smem20[];
-  constexpr int NW = TREE_NT / 32;                 // warps
+  constexpr int NW = S20_NT / 32;                 // warps
   constexpr int SPT = S20_TILE / RL;               // sites per tile
   const unsigned int tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
   const unsigned int r = lane >> 2, q = lane & 3u;
@@ -678,7 +679,7 @@ tree_kernel_s20(const TreeParams prm)
 template <int RL>
 __host__ inline size_t s20_smem_bytes(int slots)
 {
-  constexpr int NW = TREE_NT / 32, SPT = S20_TILE / RL;
+  constexpr int NW = S20_NT / 32, SPT = S20_TILE / RL;
   return (size_t)NW * S20_WS * S20 * 8 + (size_t)SPT * RL * 8 + (size_t)SPT * RL * 4 + 32 * 8 +
          (size_t)slots * NW * 32 * S20_NG * (6 * 8 + 2 * 4);
 }
