@@ -641,7 +641,9 @@ plan_kernel_blocks(const LocusDev * __restrict__ loci, const unsigned int * __re
   for (unsigned int j = lane; j < RL; j += 32) rw[j] = L.rate_weights[j];
   // gather: per chunk, per op: Pup (if pushed) and the tipP of its packed tip children.  A matrix set is
   // RL*8 double2; `per` lanes copy one set, so a warp moves 32/per sets per step.
-  const unsigned int per = RL * 8;                      // double2 per (op, which) matrix set
+  const unsigned int per = RL * 8;                      // double2 per (op, which) matrix set; RL is a power of two
+  const unsigned int per_sh = 31u - (unsigned)__clz((int)per);
+  const float inv_lut_unit = 1.0f / (float)lut_unit;
   for (unsigned int c = 0; c < n_chunks; ++c)
   {
     unsigned char * ch = blk + chunks0 + (size_t)c * cb;
@@ -652,7 +654,7 @@ plan_kernel_blocks(const LocusDev * __restrict__ loci, const unsigned int * __re
     const unsigned int total = hdr.nops * 3 * per;
     for (unsigned int idx = lane; idx < total; idx += 32)
     {
-      const unsigned int task = idx / per, e = idx % per;           // e: double2 index within the set
+      const unsigned int task = idx >> per_sh, e = idx & (per - 1u);   // e: double2 index within the set
       const unsigned int k = task / 3, which = task % 3;
       const OpRec & q = cops[k];
       if (q.ctl & OP_EVAL) continue;
@@ -667,7 +669,7 @@ plan_kernel_blocks(const LocusDev * __restrict__ loci, const unsigned int * __re
         const unsigned int kind = (q.ctl >> (which == 1 ? OP_AKIND_SHIFT : OP_BKIND_SHIFT)) & 15u;
         const unsigned int off = which == 1 ? q.a_off : q.b_off;
         unsigned int slot;
-        if (kind == SRC_TIP_PACKED) slot = off / lut_unit;
+        if (kind == SRC_TIP_PACKED) slot = (unsigned int)((float)off * inv_lut_unit + 0.5f);   // off = slot * lut_unit, exact
         else if (kind == SRC_HBM && small) slot = off;
         else continue;
         pm = which == 1 ? q.a_pm : q.b_pm;
