@@ -123,7 +123,8 @@ struct OpRec
 static_assert(sizeof(OpRec) == 64, "OpRec must be 64 bytes");
 
 enum : unsigned { HDR_FAST = 1u,     // every op of the locus uses fast operands only
-                  HDR_SIMPLE = 2u }; // ... and none is HBM-class or scaled: the lean instantiation of tile_fast
+                  HDR_SIMPLE = 2u,   // ... and none is HBM-class or scaled: the lean instantiation of tile_fast
+                  HDR_NOHBM = 4u };  // ... and none is HBM-class (scaling allowed): full passes with scale buffers
 
 struct LocusHdr
 {

@@ -68,7 +68,7 @@ __global__ void plan_kernel_flat(const LocusDev * __restrict__ loci, const unsig
 // positions are computed with warp shuffles; only the slot / chunk bookkeeping walks the positions
 // one by one (uniformly, ~20 instructions per op).  Produces exactly the program the serial planner
 // below produces for the same evaluation order.
-struct SmallPlanOut { unsigned int n_chunks, cnt; bool fast, simple; };
+struct SmallPlanOut { unsigned int n_chunks, cnt; bool fast, simple, nohbm; };
 
 // Evaluation order of a list of <= 32 ops, lane k = op k: DFS post-order over the forest the list forms,
 // the child with the larger Sethi-Ullman need first (so that the fewest intermediate X values are alive
@@ -277,8 +277,9 @@ plan_small_parallel(const LocusDev & L, const RawOp * o, unsigned int n, unsigne
     rec[mychunk * TREE_CHUNK + myidx] = q;
   }
   bool fast = __ballot_sync(FULL, !act || op_fast) == FULL;
-  const bool op_simple = r.psc < 0 && okind[0] != SRC_HBM && okind[0] != SRC_HBML && okind[1] != SRC_HBM && okind[1] != SRC_HBML;
-  const bool simple = __ballot_sync(FULL, !act || op_simple) == FULL;
+  const bool op_nohbm = okind[0] != SRC_HBM && okind[0] != SRC_HBML && okind[1] != SRC_HBM && okind[1] != SRC_HBML;
+  const bool nohbm = __ballot_sync(FULL, !act || op_nohbm) == FULL;
+  const bool simple = nohbm && __ballot_sync(FULL, !act || r.psc < 0) == FULL;
   unsigned int cnt = n;
   if (want_root && !root_done)
   {
@@ -320,7 +321,7 @@ plan_small_parallel(const LocusDev & L, const RawOp * o, unsigned int n, unsigne
   }
   __syncwarp();
   SmallPlanOut out;
-  out.n_chunks = c_idx; out.cnt = cnt; out.fast = fast && c_idx == 1; out.simple = out.fast && simple;
+  out.n_chunks = c_idx; out.cnt = cnt; out.fast = fast && c_idx == 1; out.simple = out.fast && simple; out.nohbm = out.fast && nohbm;
   return out;
 }
 
@@ -414,7 +415,7 @@ plan_kernel_blocks(const LocusDev * __restrict__ loci, const unsigned int * __re
       H->clv = L.clv; H->tip_dense = L.tip_dense; H->scale = L.scale;
       H->tipwords = reinterpret_cast<const unsigned int *>(L.tip_codes); H->pmat = L.pmat;
       H->clv_stride = L.clv_stride; H->sites = L.sites; H->nops = cnt; H->tip_words = L.tip_words;
-      H->n_chunks = n_chunks; H->flags = (sp.fast ? HDR_FAST : 0u) | (sp.simple ? HDR_SIMPLE : 0u); H->pad0 = 0;
+      H->n_chunks = n_chunks; H->flags = (sp.fast ? HDR_FAST : 0u) | (sp.simple ? HDR_SIMPLE : 0u) | (sp.nohbm ? HDR_NOHBM : 0u); H->pad0 = 0;
       for (int j = 0; j < 4; ++j) H->freqs[j] = L.freqs[j];
       plan_count[bl] = cnt;
     }

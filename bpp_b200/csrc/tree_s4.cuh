@@ -132,11 +132,14 @@ struct TileCtx
 // ------------------------------------------------------------------------------------------------
 // fast path: every operand is a register-resident packed tip, a stack slot or the previous X
 // ------------------------------------------------------------------------------------------------
-// FULL = false is the lean instantiation for loci flagged HDR_SIMPLE (no HBM-class operand, no scaler):
-// full-tree passes without scaling, the headline workload.
-template <int RL, bool EXACT, int CPT, bool FULL>
+// MODE 0 is the lean instantiation for loci flagged HDR_SIMPLE (no HBM-class operand, no scaler): full-tree
+// passes without scaling, the headline workload.  MODE 1 adds per-site scaling (HDR_NOHBM: full passes with
+// scale buffers), MODE 2 also HBM-class operands (partial updates).
+template <int RL, bool EXACT, int CPT, int MODE>
 __device__ __forceinline__ double tile_fast(const TreeParams & prm, const TileCtx<CPT> & tc)
 {
+  constexpr bool SCALED = MODE >= 1, FULL = MODE == 2;
+  constexpr unsigned int LOG2RL = RL == 1 ? 0 : (RL == 2 ? 1 : (RL == 4 ? 2 : 3));
   using Lay = S4Layout<RL, CPT>;
   const unsigned int tid = threadIdx.x, lane = tid & 31u;
   const unsigned int sb = tc.sb;
@@ -226,21 +229,24 @@ __device__ __forceinline__ double tile_fast(const TreeParams & prm, const TileCt
       }
     }
     // ---- per-site scaling (core_partials.c:720,739-754)
-    if (FULL && (ctl & OP_SCALE))
+    if (SCALED && (ctl & OP_SCALE))
     {
       const uint4 w2 = s4[ops + 4 * k + 2], w3 = s4[ops + 4 * k + 3];
-      const bool a_slot = ((ctl >> OP_AKIND_SHIFT) & 15u) == SRC_SLOT, b_slot = ((ctl >> OP_BKIND_SHIFT) & 15u) == SRC_SLOT;
+      const unsigned int ak = (ctl >> OP_AKIND_SHIFT) & 15u, bk = (ctl >> OP_BKIND_SHIFT) & 15u;
+      const bool a_slot = ak == SRC_SLOT, b_slot = !(ctl & OP_BPREV) && bk == SRC_SLOT;
+      const bool a_glob = FULL && (ak == SRC_HBML || ak == SRC_HBM) && (int)w2.z >= 0;
+      const bool b_glob = FULL && !(ctl & OP_BPREV) && (bk == SRC_HBML || bk == SRC_HBM) && (int)w3.z >= 0;
+      const unsigned int a_sl = tc.sst1 + w2.x * (CPT * TREE_NT) + tid, b_sl = tc.sst1 + w3.x * (CPT * TREE_NT) + tid;
+      unsigned int * const sc_out = H->scale + (size_t)(int)w1.z * sites;
 #pragma unroll
       for (int j = 0; j < CPT; ++j)
       {
-        unsigned int sc = 0;
-        if (a_slot) sc += s1[tc.sst1 + w2.x * (CPT * TREE_NT) + j * TREE_NT + tid];
-        const unsigned int ak = (ctl >> OP_AKIND_SHIFT) & 15u, bk = (ctl >> OP_BKIND_SHIFT) & 15u;
-        if ((ak == SRC_HBML || ak == SRC_HBM) && (int)w2.z >= 0) sc += H->scale[(size_t)(int)w2.z * sites + tc.cell[j] / RL];
-        if (!(ctl & OP_BPREV) && (bk == SRC_HBML || bk == SRC_HBM) && (int)w3.z >= 0)
-          sc += H->scale[(size_t)(int)w3.z * sites + tc.cell[j] / RL];
-        if (ctl & OP_BPREV) sc += psc[j];
-        else if (b_slot) sc += s1[tc.sst1 + w3.x * (CPT * TREE_NT) + j * TREE_NT + tid];
+        const unsigned int site = tc.cell[j] >> LOG2RL;
+        unsigned int sc = (ctl & OP_BPREV) ? psc[j] : 0u;
+        if (a_slot) sc += s1[a_sl + j * TREE_NT];
+        if (b_slot) sc += s1[b_sl + j * TREE_NT];
+        if (a_glob) sc += H->scale[(size_t)(int)w2.z * sites + site];
+        if (b_glob) sc += H->scale[(size_t)(int)w3.z * sites + site];
         unsigned int below = (o[j][0] < BPPGPU_SCALE_THRESHOLD) & (o[j][1] < BPPGPU_SCALE_THRESHOLD) &
                              (o[j][2] < BPPGPU_SCALE_THRESHOLD) & (o[j][3] < BPPGPU_SCALE_THRESHOLD);
 #pragma unroll
@@ -252,7 +258,7 @@ __device__ __forceinline__ double tile_fast(const TreeParams & prm, const TileCt
           sc += 1;
         }
         osc[j] = sc;
-        if (tc.valid[j] && tc.cat == 0) H->scale[(size_t)(int)w1.z * sites + tc.cell[j] / RL] = sc;
+        if (tc.valid[j] && tc.cat == 0) sc_out[site] = sc;
       }
     }
     // ---- the CLV goes to HBM exactly once
@@ -281,7 +287,7 @@ __device__ __forceinline__ double tile_fast(const TreeParams & prm, const TileCt
         {
           sd2[stk_t + j * (2 * TREE_NT) + po] = make_double2(x[j][0], x[j][1]);
           sd2[stk_t + j * (2 * TREE_NT) + po + 1] = make_double2(x[j][2], x[j][3]);
-          if (FULL && (ctl & OP_SCALE)) s1[tc.sst1 + (po / Lay::SLOT) * (CPT * TREE_NT) + j * TREE_NT + tid] = psc[j];
+          if (SCALED && (ctl & OP_SCALE)) s1[tc.sst1 + (po / Lay::SLOT) * (CPT * TREE_NT) + j * TREE_NT + tid] = psc[j];
         }
       }
     }
@@ -305,7 +311,7 @@ __device__ __forceinline__ double tile_fast(const TreeParams & prm, const TileCt
         else
         {
           s = log(term);
-          if (FULL && osc[j]) s = __dadd_rn(s, __dmul_rn((double)osc[j], prm.log_threshold));
+          if (SCALED && osc[j]) s = __dadd_rn(s, __dmul_rn((double)osc[j], prm.log_threshold));
           s = __dmul_rn(s, (double)s1[tc.tips_s + (2 * CPT + j) * TREE_NT]);
         }
         if (tc.valid[j] && tc.cat == 0)
@@ -613,8 +619,9 @@ tree_kernel_s4(const TreeParams prm)
     }
 
     double site_sum;
-    if (H->flags & HDR_SIMPLE) site_sum = tile_fast<RL, EXACT, CPT, false>(prm, tc);
-    else if (H->flags & HDR_FAST) site_sum = tile_fast<RL, EXACT, CPT, true>(prm, tc);
+    if (H->flags & HDR_SIMPLE) site_sum = tile_fast<RL, EXACT, CPT, 0>(prm, tc);
+    else if (H->flags & HDR_NOHBM) site_sum = tile_fast<RL, EXACT, CPT, 1>(prm, tc);
+    else if (H->flags & HDR_FAST) site_sum = tile_fast<RL, EXACT, CPT, 2>(prm, tc);
     else
     {
       // general path: chunk by chunk (later chunks are staged in place, synchronously), cell by cell
