@@ -1030,7 +1030,7 @@ static int batch_stage(bppgpu_batch * b, const unsigned int * mcounts, const uns
   if (b->kernel_kind == 0 && b->copy_stream && mcounts && ocounts && rclv)
   {
     if (b->wave_pref) W = b->wave_pref;
-    else if (n >= 1024 && tm * 12 + to * sizeof(bppgpu_partial_op) >= (1u << 20)) W = 4;
+    else if (n >= 1024 && tm * 12 + to * sizeof(bppgpu_partial_op) >= (1u << 20)) W = 2;
     if (W > n) W = n;
   }
   if (W > BPPGPU_MAX_WAVES) W = BPPGPU_MAX_WAVES;
@@ -1039,8 +1039,11 @@ static int batch_stage(bppgpu_batch * b, const unsigned int * mcounts, const uns
     b->n_waves = W;
     b->wave_first[0] = 0;
     // geometric wave sizes (ratio r): the first wave is small so that the kernels start early, and each
-    // later upload still hides under the compute of the wave before it (compute : upload is about 5 : 1)
-    double ratio = 3.0;
+    // later upload still hides under the compute of the wave before it (compute : upload is about 5 : 1).
+    // Measured on config 2 (tools/run_waves.sh): 2 waves of 20 % + 80 % are as good as it gets (0.556 ms per
+    // step against 0.603 ms unpipelined); every further wave costs about as much in launch gaps and kernel
+    // tails as its earlier start saves.
+    double ratio = 4.0;
     if (const char * ev = getenv("BPPGPU_WAVE_RATIO")) ratio = std::max(1.0, atof(ev));
     double total_w = 0, acc = 0, cur = 1;
     for (unsigned w = 0; w < W; ++w) { total_w += cur; cur *= ratio; }

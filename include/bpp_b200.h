@@ -200,8 +200,10 @@ int  bppgpu_batch_stage(bppgpu_batch * b,
                         const unsigned int * root_clv_indices, const int * root_scaler_indices);
 int  bppgpu_batch_run(bppgpu_batch * b);
 /* A full pass of a big 4-state batch is pipelined: the step's arrays are uploaded in `waves` slices of loci
-   on a copy stream while planner and tree kernel of earlier slices already run (0 = automatic: 4 waves once
-   the step's arrays exceed 1 MB, else 1; 1 = off; at most 8).  Results do not depend on the setting. */
+   on a copy stream while planner and tree kernel of earlier slices already run (0 = automatic: 2 waves of
+   20 % + 80 % of the loci once the step's arrays exceed 1 MB, else 1; 1 = off; at most 8).  The arrays handed
+   to bppgpu_batch_stage must stay valid and unchanged until the following bppgpu_batch_run has returned.
+   Results do not depend on the setting. */
 void bppgpu_batch_set_waves(bppgpu_batch * b, unsigned int waves);
 int  bppgpu_batch_collect(bppgpu_batch * b, double * lnl_out, double * lnl_sum_out);
 /* device address of the batch's lnL sum (one double), valid after run; lets the caller hand it to

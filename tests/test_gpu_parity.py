@@ -399,3 +399,43 @@ def test_pipelined_waves_give_identical_results(eng, waves):
     for h in holders:
         h.free()
     _free(loci, batch)
+
+
+def test_concurrent_host_threads_on_disjoint_batches(eng):
+    """threads.c:87-200 calls the locus seam from up to opt_threads pthreads on disjoint loci without locks;
+    the ABI promises the same.  Four host threads, each with its own loci and batch on the same engine, run
+    full passes concurrently; every result must equal the single-threaded one bit for bit."""
+    import threading
+    from bpp_b200 import engine
+    ws = [synth.make_workload("thr%d" % k, n_loci=40, tips=6 + k, sites=300 + 17 * k, states=4, rate_cats=4,
+                              model="GTR", scaling=bool(k & 1), seed=700 + k) for k in range(4)]
+    serial = []
+    for w in ws:
+        loci, trees, batch = _load(eng, w)
+        serial.append(batch.full_pass(trees.full_pass_step())[0])
+        _free(loci, batch)
+    out, errs = [None] * 4, []
+
+    def work(k):
+        try:
+            loci, trees = engine.load_workload(eng, ws[k])
+            batch = engine.Batch(eng, loci)
+            step = trees.full_pass_step()
+            r = None
+            for _ in range(20):
+                r = batch.full_pass(step)[0]
+            out[k] = r
+            batch.destroy()
+            for l in loci:
+                l.destroy()
+        except Exception as ex:          # noqa: BLE001
+            errs.append(ex)
+
+    ts = [threading.Thread(target=work, args=(k,)) for k in range(4)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errs, errs
+    for k in range(4):
+        assert np.array_equal(out[k], serial[k]), k

@@ -18,7 +18,7 @@ pstep, holders = engine.pin_step(step)
 prep = batch.prepare(pstep)
 out = np.zeros(w.n_loci)
 K = 200
-for waves in (1, 2, 3, 4, 5):
+for waves in (1, 2, 3):
     batch.set_waves(waves)
     for _ in range(5):
         batch.stage(prep); batch.run(); batch.collect(out)
@@ -31,8 +31,12 @@ for waves in (1, 2, 3, 4, 5):
         t3 = time.perf_counter()
         ts += t1 - t0; tr += t2 - t1; tc += t3 - t2
     tot = time.perf_counter() - t00
-    print("waves %d: step %.4f ms  (stage %.4f  run %.4f  collect %.4f)  %.2f M evals/s" %
-          (waves, 1e3 * tot / K, 1e3 * ts / K, 1e3 * tr / K, 1e3 * tc / K, w.n_loci * K / tot / 1e6), flush=True)
+    # device span: event on the idle batch stream before stage -> event after the finish kernel
+    span = 0.0
+    for _ in range(50):
+        batch.timer_start(); batch.stage(prep); batch.run(); span += batch.timer_stop_ms(); batch.collect(out)
+    print("waves %d: step %.4f ms  (stage %.4f  run %.4f  collect %.4f)  %.2f M evals/s   device span %.4f ms" %
+          (waves, 1e3 * tot / K, 1e3 * ts / K, 1e3 * tr / K, 1e3 * tc / K, w.n_loci * K / tot / 1e6, span / 50), flush=True)
 # device-only reference
 batch.set_waves(1)
 batch.stage(prep)
