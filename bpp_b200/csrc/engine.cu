@@ -14,6 +14,7 @@
 #include "tree_s20c.cuh"
 #include "tree_generic.cuh"
 #include "reduce.cuh"
+#include "model.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -154,6 +155,7 @@ struct bppgpu_locus
   std::vector<unsigned char> h_tip_dense_flag;
   std::vector<double> h_freqs, h_subst, h_rates, h_rate_weights, h_evecs, h_ievecs, h_evals;
   bool eigen_valid = false;            // locus->eigen_decomp_valid[0]
+  bool eigen_on_device = false;        // ... computed by model_update_kernel: the host mirrors h_evecs.. are stale
   bool codes_dirty = false, model_dirty = false, flags_dirty = false;
   bppgpu_batch * self_batch = nullptr; // batch of one for the synchronous per-locus API
 };
@@ -198,6 +200,9 @@ struct bppgpu_batch
   bool staged_mats = false, staged_ops = false, staged_roots = false;
   cudaEvent_t t0 = nullptr, t1 = nullptr;
   unsigned long long synced_epoch = 0; // engine dirty_epoch at the last batch_sync_loci
+  // batched model sync: pinned blob + device copy, record offsets, ids, eigen modes, Jacobi scratch
+  char * h_model = nullptr, * d_model = nullptr; size_t model_cap = 0;
+  double * d_eig_scratch = nullptr; size_t eig_scratch_cap = 0;
   bool synced_eigen = false;           // ... which also brought the eigen-decompositions up to date
   // pipelined step (4-state kernel, big batches): the step's host arrays are uploaded in waves of loci on
   // copy_stream while the planner / tree kernels of earlier waves already run (alternating between
@@ -412,7 +417,17 @@ static void locus_sync(bppgpu_locus * l, cudaStream_t s)
     memcpy(w, l->h_evals.data(), S * 8); w += S;
     memcpy(w, l->h_subst.data(), (size_t)S * (S - 1) / 2 * 8);
     // pageable source: the copy is staged by the runtime before the call returns
-    CUDA_CHECK(cudaMemcpyAsync(l->dev.freqs, blk.data(), blk.size() * 8, cudaMemcpyHostToDevice, s));
+    if (l->eigen_on_device && l->eigen_valid)
+    {
+      // the decomposition on the device is the current one (the host mirror is stale): leave it alone
+      CUDA_CHECK(cudaMemcpyAsync(l->dev.freqs, blk.data(), (size_t)(S + 2 * R) * 8, cudaMemcpyHostToDevice, s));
+      CUDA_CHECK(cudaMemcpyAsync(l->dev.subst, l->h_subst.data(), (size_t)S * (S - 1) / 2 * 8, cudaMemcpyHostToDevice, s));
+    }
+    else
+    {
+      CUDA_CHECK(cudaMemcpyAsync(l->dev.freqs, blk.data(), blk.size() * 8, cudaMemcpyHostToDevice, s));
+      l->eigen_on_device = false;
+    }
     l->model_dirty = false;
   }
 }
@@ -701,13 +716,24 @@ extern "C" void bppgpu_set_eigen(bppgpu_locus * l, unsigned int idx, const doubl
   if (idx != 0) { fatal("params_index must be 0"); return; }
   const size_t S = l->states;
   l->h_evecs.assign(ev, ev + S * S); l->h_ievecs.assign(iev, iev + S * S); l->h_evals.assign(lam, lam + S);
-  l->eigen_valid = true; l->model_dirty = true, l->e->dirty_epoch++;
+  l->eigen_valid = true; l->eigen_on_device = false; l->model_dirty = true, l->e->dirty_epoch++;
 }
 extern "C" void bppgpu_get_eigen(bppgpu_locus * l, unsigned int idx, double * ev, double * iev, double * lam)
 {
   (void)idx;
-  if (!l->eigen_valid) host_update_eigen(l);
   const size_t S = l->states;
+  if (!l->eigen_valid) { host_update_eigen(l); l->eigen_on_device = false; }
+  else if (l->eigen_on_device)
+  {
+    // decomposed by model_update_kernel: fetch it (the kernel ran on the stream of the batch that synced the locus;
+    // a device-wide synchronisation is the simple, rarely needed answer)
+    CUDA_CHECK(cudaSetDevice(l->e->device));
+    CUDA_CHECK(cudaDeviceSynchronize());
+    CUDA_CHECK(cudaMemcpy(l->h_evecs.data(), l->dev.eigenvecs, S * S * 8, cudaMemcpyDeviceToHost));
+    CUDA_CHECK(cudaMemcpy(l->h_ievecs.data(), l->dev.inv_eigenvecs, S * S * 8, cudaMemcpyDeviceToHost));
+    CUDA_CHECK(cudaMemcpy(l->h_evals.data(), l->dev.eigenvals, S * 8, cudaMemcpyDeviceToHost));
+    l->eigen_on_device = false;
+  }
   memcpy(ev, l->h_evecs.data(), S * S * 8); memcpy(iev, l->h_ievecs.data(), S * S * 8); memcpy(lam, l->h_evals.data(), S * 8);
 }
 
@@ -884,6 +910,8 @@ extern "C" void bppgpu_batch_destroy(bppgpu_batch * b)
   cudaFree(b->d_rootdot); cudaFree(b->d_site_off);
   cudaFree(b->d_blocks); cudaFree(b->d_tiles); cudaFree(b->d_tile_blk); cudaFree(b->d_block_sums); cudaFree(b->d_counter);
   cudaFreeHost(b->h_out); cudaFreeHost(b->h_in);
+  if (b->h_model) cudaFreeHost(b->h_model);
+  cudaFree(b->d_model); cudaFree(b->d_eig_scratch);
   cudaEventDestroy(b->t0); cudaEventDestroy(b->t1);
   if (b->copy_stream)
   {
@@ -1120,12 +1148,99 @@ static void batch_sync_loci(bppgpu_batch * b, bool need_eigen)
 {
   // nothing of any locus changed since this batch last looked (and it then decomposed what it needed)
   if (b->synced_epoch == b->e->dirty_epoch.load() && (!need_eigen || b->synced_eigen)) return;
+  bppgpu_engine * e = b->e;
+  // loci whose model block must travel, and those that need pll_update_eigen first (locus.c:2462-2476)
+  std::vector<bppgpu_locus *> dirty;
   for (bppgpu_locus * l : b->loci)
   {
-    if (need_eigen && !l->eigen_valid && !model_is_closed_form(l)) host_update_eigen(l);   // locus.c:2462-2476
-    if (l->codes_dirty || l->model_dirty || l->flags_dirty) locus_sync(l, b->stream);
+    if (l->codes_dirty || l->flags_dirty)
+    {
+      const bool md = l->model_dirty;
+      l->model_dirty = false;
+      locus_sync(l, b->stream);
+      l->model_dirty = md;
+    }
+    if (l->model_dirty || (need_eigen && !l->eigen_valid && !model_is_closed_form(l))) dirty.push_back(l);
   }
-  b->synced_epoch = b->e->dirty_epoch.load();
+  size_t min_dirty = 8;
+  if (const char * ev = getenv("BPPGPU_MODEL_BATCH_MIN")) min_dirty = (size_t)std::max(1, atoi(ev));   // tuning / test knob
+  if (dirty.size() < min_dirty)
+  {
+    for (bppgpu_locus * l : dirty)
+    {
+      if (need_eigen && !l->eigen_valid && !model_is_closed_form(l)) { host_update_eigen(l); l->eigen_on_device = false; }
+      if (l->model_dirty) locus_sync(l, b->stream);
+    }
+  }
+  else
+  {
+    // one pinned blob: [ids u32][eigen modes u8][record offsets u64][scratch offsets u64][records f64]
+    const size_t nd = dirty.size();
+    size_t rec_doubles = 0, scr_doubles = 0;
+    std::vector<unsigned long long> roff(nd), soff(nd);
+    std::vector<unsigned char> mode(nd);
+    for (size_t d = 0; d < nd; ++d)
+    {
+      bppgpu_locus * l = dirty[d];
+      const size_t S = l->states, R = l->rate_cats;
+      const bool compute = need_eigen && !l->eigen_valid && !model_is_closed_form(l);
+      // a valid decomposition that lives only on the device stays where it is
+      mode[d] = compute ? EIGEN_COMPUTE : ((l->eigen_valid && !l->eigen_on_device) ? EIGEN_COPY : EIGEN_KEEP);
+      roff[d] = rec_doubles; soff[d] = scr_doubles;
+      rec_doubles += S + 2 * R + S * (S - 1) / 2 + (mode[d] == EIGEN_COPY ? 2 * S * S + S : 0);
+      if (compute) scr_doubles += 2 * S * S;
+    }
+    const size_t o_ids = 0, o_mode = align_up(o_ids + nd * 4, 16), o_roff = align_up(o_mode + nd, 16),
+                 o_soff = o_roff + nd * 8, o_rec = o_soff + nd * 8, total = o_rec + rec_doubles * 8;
+    if (total > b->model_cap)
+    {
+      CUDA_CHECK(cudaStreamSynchronize(b->stream));
+      if (b->h_model) cudaFreeHost(b->h_model);
+      if (b->d_model) cudaFree(b->d_model);
+      b->model_cap = total + total / 4;
+      CUDA_CHECK(cudaHostAlloc(&b->h_model, b->model_cap, cudaHostAllocDefault));
+      CUDA_CHECK(cudaMalloc(&b->d_model, b->model_cap));
+    }
+    else CUDA_CHECK(cudaStreamSynchronize(b->stream));       // the blob of the previous sync may still be in flight
+    if (scr_doubles * 8 > b->eig_scratch_cap)
+    {
+      if (b->d_eig_scratch) cudaFree(b->d_eig_scratch);
+      b->eig_scratch_cap = scr_doubles * 8 + scr_doubles * 2;
+      CUDA_CHECK(cudaMalloc(&b->d_eig_scratch, b->eig_scratch_cap));
+    }
+    unsigned int * ids = (unsigned int *)(b->h_model + o_ids);
+    memcpy(b->h_model + o_mode, mode.data(), nd);
+    memcpy(b->h_model + o_roff, roff.data(), nd * 8);
+    memcpy(b->h_model + o_soff, soff.data(), nd * 8);
+    double * recs = (double *)(b->h_model + o_rec);
+    for (size_t d = 0; d < nd; ++d)
+    {
+      bppgpu_locus * l = dirty[d];
+      const size_t S = l->states, R = l->rate_cats, np = S * (S - 1) / 2;
+      ids[d] = l->id;
+      double * w = recs + roff[d];
+      memcpy(w, l->h_freqs.data(), S * 8); w += S;
+      memcpy(w, l->h_rates.data(), R * 8); w += R;
+      memcpy(w, l->h_rate_weights.data(), R * 8); w += R;
+      memcpy(w, l->h_subst.data(), np * 8); w += np;
+      if (mode[d] == EIGEN_COPY)
+      {
+        memcpy(w, l->h_evecs.data(), S * S * 8); w += S * S;
+        memcpy(w, l->h_ievecs.data(), S * S * 8); w += S * S;
+        memcpy(w, l->h_evals.data(), S * 8);
+      }
+      else if (mode[d] == EIGEN_COMPUTE) { l->eigen_valid = true; l->eigen_on_device = true; }
+      l->model_dirty = false;
+    }
+    CUDA_CHECK(cudaMemcpyAsync(b->d_model, b->h_model, total, cudaMemcpyHostToDevice, b->stream));
+    e->launches++;
+    model_update_kernel<<<(unsigned)nd, 64, 0, b->stream>>>(
+        e->d_loci, (const unsigned int *)(b->d_model + o_ids), (const double *)(b->d_model + o_rec),
+        (const unsigned long long *)(b->d_model + o_roff), (const unsigned char *)(b->d_model + o_mode),
+        b->d_eig_scratch, (const unsigned long long *)(b->d_model + o_soff));
+    CUDA_CHECK(cudaGetLastError());
+  }
+  b->synced_epoch = e->dirty_epoch.load();
   b->synced_eigen = need_eigen;
 }
 

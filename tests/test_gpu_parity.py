@@ -439,3 +439,50 @@ def test_concurrent_host_threads_on_disjoint_batches(eng):
     assert not errs, errs
     for k in range(4):
         assert np.array_equal(out[k], serial[k]), k
+
+
+@pytest.mark.parametrize("cfg", [dict(tips=9, sites=120, states=4, rate_cats=4, model="GTR"),
+                                 dict(tips=6, sites=40, states=20, rate_cats=4, model="LG"),
+                                 dict(tips=7, sites=90, states=4, rate_cats=4, model="TN93")])
+def test_batched_model_update_and_device_eigen(eng, cfg, monkeypatch):
+    """Model changes of many loci (propose_alpha, propose_qrates / propose_freqs) travel in one blob and
+    pll_update_eigen runs on the device (model_update_kernel); a batch below the threshold takes the per-locus
+    path with the host-side decomposition.  Both must agree with each other to rounding and with the oracle to
+    the lnL bar, also after a second round of changes (new rates, new Q) and for bppgpu_get_eigen."""
+    w = synth.make_workload("mdl", n_loci=10, seed=4711, lg=lg_tables(), **cfg)
+    cm = char_map(w.states)
+    new_rates = np.array([0.1, 0.5, 1.1, 2.3])
+    res = {}
+    for mode, thresh in (("host", "1000000"), ("device", "1")):
+        monkeypatch.setenv("BPPGPU_MODEL_BATCH_MIN", thresh)
+        loci, trees, batch = _load(eng, w)
+        step = trees.full_pass_step()
+        a, _ = batch.full_pass(step)
+        eig = loci[2].get_eigen() if w.model in ("GTR", "LG") else None
+        pm = loci[1].get_pmatrix(int(step[1][0]))
+        # second round: every locus gets new category rates, every other one new exchangeabilities / frequencies
+        for i, l in enumerate(loci):
+            l.set_category_rates(new_rates)
+            if i % 2 == 0 and w.model != "LG":
+                l.set_subst_params(w.subst[i][::-1].copy())
+                l.set_frequencies(w.freqs[(i + 1) % w.n_loci])
+        b, _ = batch.full_pass(step)
+        res[mode] = (a, b, eig, pm)
+        _free(loci, batch)
+    monkeypatch.delenv("BPPGPU_MODEL_BATCH_MIN", raising=False)
+    assert rel_err(res["device"][0], res["host"][0]) < 1e-12 and rel_err(res["device"][1], res["host"][1]) < 1e-12
+    assert np.allclose(res["device"][3], res["host"][3], rtol=1e-12, atol=1e-15)
+    if res["device"][2] is not None:
+        ev, iev, lam = res["device"][2]
+        S = w.states
+        assert np.allclose(iev.reshape(S, S) @ ev.reshape(S, S), np.eye(S), atol=1e-12)
+        assert np.allclose(np.sort(lam), np.sort(res["host"][2][2]), rtol=1e-10, atol=1e-13)
+    for i in range(0, w.n_loci, 3):
+        o = F.locus_from_workload(w, i, cm)
+        ref = o.full_pass()
+        assert abs(res["device"][0][i] - ref) <= LNL_RTOL * abs(ref)
+        o.set_model(rates=new_rates)
+        if i % 2 == 0 and w.model != "LG":
+            o.set_model(subst=w.subst[i][::-1].copy(), freqs=w.freqs[(i + 1) % w.n_loci])
+        ref2 = o.full_pass()
+        assert abs(res["device"][1][i] - ref2) <= LNL_RTOL * abs(ref2)
