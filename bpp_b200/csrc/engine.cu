@@ -25,6 +25,7 @@
 #include <cstring>
 #include <map>
 #include <mutex>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -133,7 +134,23 @@ struct bppgpu_engine
   std::vector<PendingEvent> pending;
   std::vector<cudaEvent_t> event_pool;
   double log_threshold = 0;
+  // kernels whose dynamic shared-memory limit has been raised on this device.  The limit is a property of the
+  // FUNCTION, shared by every batch and host thread: it is raised once to the device maximum, never per launch
+  // (two batches with different sizes would otherwise lower it under each other's feet).
+  std::mutex attr_mu;
+  std::set<const void *> attr_done;
 };
+
+template <typename K>
+static void ensure_max_smem(bppgpu_engine * e, K kernel)
+{
+  std::lock_guard<std::mutex> lock(e->attr_mu);
+  const void * key = reinterpret_cast<const void *>(kernel);
+  if (e->attr_done.count(key)) return;
+  cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_optin);
+  if (err != cudaSuccess) { fprintf(stderr, "bppgpu: cudaFuncSetAttribute: %s\n", cudaGetErrorString(err)); cudaGetLastError(); }
+  e->attr_done.insert(key);
+}
 
 struct bppgpu_locus
 {
@@ -1264,7 +1281,7 @@ static void launch_tree_s4_impl(bppgpu_batch * b, const TreeParams & prm, cudaSt
   const unsigned key = (unsigned)(RL * 100 + CPT * 10 + (EXACT ? 1 : 0));
   if (b->cfg_key != key || b->cfg_smem != smem)
   {
-    CUDA_CHECK(cudaFuncSetAttribute(tree_kernel_s4<RL, EXACT, CPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ensure_max_smem(e, tree_kernel_s4<RL, EXACT, CPT>);
     int per_sm = 0;
     CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tree_kernel_s4<RL, EXACT, CPT>, TREE_NT, smem));
     if (per_sm < 1) { fatal("tree kernel does not fit on an SM (smem %zu)", smem); return; }
@@ -1301,7 +1318,7 @@ static void launch_tree_s20(bppgpu_batch * b, const TreeParams & prm)
 {
   bppgpu_engine * e = b->e;
   const size_t smem = s20_smem_bytes<RL>(prm.n_slots);
-  CUDA_CHECK(cudaFuncSetAttribute(tree_kernel_s20<RL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ensure_max_smem(e, tree_kernel_s20<RL>);
   int per_sm = 0;
   CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tree_kernel_s20<RL>, S20_NT, smem));
   if (per_sm < 1) { fatal("20-state tree kernel does not fit on an SM (smem %zu)", smem); return; }
@@ -1481,7 +1498,7 @@ static int batch_run(bppgpu_batch * b, bool do_mats, bool do_tree, bool want_roo
         switch (b->RL)
         {
 #define BPPGPU_S20C_CASE(R) case R: \
-          CUDA_CHECK(cudaFuncSetAttribute(tree_kernel_s20c<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+          ensure_max_smem(e, tree_kernel_s20c<R>); \
           tree_kernel_s20c<R><<<grid, S20C_NT, smem, b->stream>>>(prm); break;
           BPPGPU_S20C_CASE(1) BPPGPU_S20C_CASE(2) BPPGPU_S20C_CASE(4) BPPGPU_S20C_CASE(8)
 #undef BPPGPU_S20C_CASE

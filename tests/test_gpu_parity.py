@@ -486,3 +486,19 @@ def test_batched_model_update_and_device_eigen(eng, cfg, monkeypatch):
             o.set_model(subst=w.subst[i][::-1].copy(), freqs=w.freqs[(i + 1) % w.n_loci])
         ref2 = o.full_pass()
         assert abs(res["device"][1][i] - ref2) <= LNL_RTOL * abs(ref2)
+
+
+def test_batches_of_different_shapes_alternate(eng):
+    """Two live batches whose tree kernels need different amounts of shared memory, used in turn: the
+    function-level shared-memory limit must not be lowered by one batch under the other."""
+    wa = synth.make_workload("alt_a", n_loci=20, tips=16, sites=600, states=4, rate_cats=4, model="GTR", seed=81)
+    wb = synth.make_workload("alt_b", n_loci=20, tips=4, sites=600, states=4, rate_cats=4, model="GTR", seed=82)
+    la, ta, ba = _load(eng, wa)
+    lb, tb, bb = _load(eng, wb)
+    sa, sb = ta.full_pass_step(), tb.full_pass_step()
+    ra0, rb0 = ba.full_pass(sa)[0], bb.full_pass(sb)[0]
+    for _ in range(3):
+        assert np.array_equal(ba.full_pass(sa)[0], ra0)
+        assert np.array_equal(bb.full_pass(sb)[0], rb0)
+    _free(la, ba)
+    _free(lb, bb)
