@@ -147,7 +147,11 @@ static void ensure_max_smem(bppgpu_engine * e, K kernel)
   std::lock_guard<std::mutex> lock(e->attr_mu);
   const void * key = reinterpret_cast<const void *>(kernel);
   if (e->attr_done.count(key)) return;
-  cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_optin);
+  // the opt-in limit covers static + dynamic shared memory
+  cudaFuncAttributes fa;
+  size_t stat = 0;
+  if (cudaFuncGetAttributes(&fa, kernel) == cudaSuccess) stat = fa.sharedSizeBytes; else cudaGetLastError();
+  cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(e->smem_optin - stat));
   if (err != cudaSuccess) { fprintf(stderr, "bppgpu: cudaFuncSetAttribute: %s\n", cudaGetErrorString(err)); cudaGetLastError(); }
   e->attr_done.insert(key);
 }
