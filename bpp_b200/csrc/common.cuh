@@ -225,6 +225,10 @@ __device__ __forceinline__ void st256(double * p, double a, double b, double c, 
   asm volatile("st.global.L1::no_allocate.v4.f64 [%0], {%1,%2,%3,%4};"
                :: "l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
 }
+__device__ __forceinline__ void st128(double * p, double a, double b)
+{
+  asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1,%2};" :: "l"(p), "d"(a), "d"(b) : "memory");
+}
 __device__ __forceinline__ void cp_async16(void * smem_dst, const void * gsrc)
 {
   const unsigned int s = (unsigned int)__cvta_generic_to_shared(smem_dst);

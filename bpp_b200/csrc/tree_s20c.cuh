@@ -158,20 +158,19 @@ tree_kernel_s20c(const TreeParams prm)
 #pragma unroll
         for (int mt = 0; mt < 3; ++mt) X.v[g][mt][e] = 0.0;
 
-    // global <-> tile, coalesced in 32-byte chunks: chunk c of the warp = site c/5, states 4*(c%5)..+3, which the
-    // rotation keeps contiguous (256-bit global accesses: 2 x 128-bit stores reach only half the bandwidth)
+    // tile -> global in 16-byte pieces, consecutive lanes on consecutive pieces: piece c of the warp = site c/10,
+    // states 2*(c%10), 2*(c%10)+1 (the rotation moves whole pieces).  Shared-memory reads are then free of bank
+    // conflicts (a lane reading 32 bytes made every LDS.128 two-way conflicted: 27 % of the kernel's wavefronts) and
+    // every warp-wide 128-bit store covers 512 contiguous bytes except where it crosses to the next site.
     auto tile_to_global = [&](double * dst_buf)
     {
 #pragma unroll
-      for (int it = 0; it < (S20_WS * 5 + 31) / 32; ++it)
+      for (int it = 0; it < (S20_WS * 10) / 32; ++it)
       {
-        const unsigned int c = it * 32 + lane, n = c / 5, part = c % 5;
-        if (c >= S20_WS * 5) break;
+        const unsigned int c = it * 32 + lane, n = c / 10, part = c % 10;
         const unsigned int s = site0 + n;
-        const double * src = s_tile + tile_idx(n, part * 4);
-        const double2 u = *reinterpret_cast<const double2 *>(src);
-        const double2 w = *reinterpret_cast<const double2 *>(src + 2);
-        if (s < sites) st256(dst_buf + ((size_t)s * RL + cat) * S20 + part * 4, u.x, u.y, w.x, w.y);
+        const double2 u = *reinterpret_cast<const double2 *>(s_tile + tile_idx(n, part * 2));
+        if (s < sites) st128(dst_buf + ((size_t)s * RL + cat) * S20 + part * 2, u.x, u.y);
       }
     };
     auto global_to_tile = [&](const double * src_buf, bool coherent)
