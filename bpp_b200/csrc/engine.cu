@@ -1354,7 +1354,10 @@ static int batch_run(bppgpu_batch * b, bool do_mats, bool do_tree, bool want_roo
     if (S > 8)
     {
       const size_t sm = (2 * (size_t)S * S + 4 * ((size_t)S * (S + 1) + S)) * 8;
-      if (S == 20) pmatrix_kernel_wide<20><<<dim3(n, 8), 128, sm, b->stream>>>(e->d_loci, b->d_batch_locus, d_mat_off, d_mat_idx, d_mat_bl);
+      // BPPGPU_PMAT_DMMA=0 keeps the reference's separate multiply / add order (pmatrix_kernel_wide)
+      static const bool use_dmma = !(getenv("BPPGPU_PMAT_DMMA") && atoi(getenv("BPPGPU_PMAT_DMMA")) == 0);
+      if (S == 20 && use_dmma) pmatrix_kernel_dmma20<<<dim3(n, 4), 128, 0, b->stream>>>(e->d_loci, b->d_batch_locus, d_mat_off, d_mat_idx, d_mat_bl);
+      else if (S == 20) pmatrix_kernel_wide<20><<<dim3(n, 8), 128, sm, b->stream>>>(e->d_loci, b->d_batch_locus, d_mat_off, d_mat_idx, d_mat_bl);
       else pmatrix_kernel_wide<0><<<dim3(n, 8), 128, sm, b->stream>>>(e->d_loci, b->d_batch_locus, d_mat_off, d_mat_idx, d_mat_bl);
     }
     else

@@ -323,4 +323,85 @@ pmatrix_kernel_wide(const LocusDev * __restrict__ loci, const unsigned int * __r
   }
 }
 
+// 20 states on the FP64 tensor instruction: P = I + (V^-1 diag(expm1(lambda t))) . V is a 20x20x20 GEMM per
+// (branch, category), 45 DMMA.8x8x4 on 24x24 padded tiles.  V (B fragments) and V^-1 (the base of the A
+// fragments) are the same for every matrix of the locus and stay in registers; per matrix a warp computes the 20
+// expm1 values (one per lane, handed round by shuffles), scales its A fragments, runs the DMMA chains from the
+// identity and stores the accumulators as 16-byte pieces.  No shared memory at all -- pmatrix_kernel_wide is
+// bound by its shared-memory loads (profiles/r1_pmatrix_wide_v2_config4_ncu_summary.txt).  The m-sum is a fused
+// chain here instead of the reference's separate multiply and add (core_pmatrix.c:760-771): the matrices agree
+// with the reference's to ~1e-16, like the CLVs of the 20-state tree kernels that consume them.
+__global__ void __launch_bounds__(128)
+pmatrix_kernel_dmma20(const LocusDev * __restrict__ loci, const unsigned int * __restrict__ batch_locus,
+                      const unsigned int * __restrict__ mat_off, const unsigned int * __restrict__ mat_idx,
+                      const double * __restrict__ mat_bl)
+{
+  constexpr unsigned int S = 20, SS = 400;
+  const unsigned int bl = blockIdx.x;
+  const LocusDev & L = loci[batch_locus[bl]];
+  const unsigned int first = mat_off[bl], count = mat_off[bl + 1] - first;
+  const unsigned int R = L.rate_cats;
+  const unsigned int lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const unsigned int r = lane >> 2, q = lane & 3u;
+  if ((blockIdx.y * nw + warp) >= count * R) return;
+  const double * __restrict__ V = L.eigenvecs;
+  const double * __restrict__ Vi = L.inv_eigenvecs;
+  double vi[3][5], vb[3][5];
+#pragma unroll
+  for (int t = 0; t < 3; ++t)
+#pragma unroll
+    for (int ks = 0; ks < 5; ++ks)
+    {
+      const unsigned int i = 8 * t + r;
+      vi[t][ks] = (i < S) ? Vi[i * S + 4 * ks + q] : 0.0;          // A: row 8t+r, k = 4ks+q
+      vb[t][ks] = (i < S) ? V[(4 * ks + q) * S + i] : 0.0;         // B: k = 4ks+q, column 8t+r
+    }
+  const double lam = lane < S ? L.eigenvals[lane] : 0.0;
+  for (unsigned int g = blockIdx.y * nw + warp; g < count * R; g += gridDim.y * nw)
+  {
+    const unsigned int n = g % R, m = g / R;
+    const double bt = mat_bl[first + m] * L.rates[n];
+    double * P = L.pmat + ((size_t)mat_idx[first + m] * R + n) * SS;
+    if (bt < 1e-100)                                               // core_pmatrix.c:738-743
+    {
+      for (unsigned int t = lane; t < SS; t += 32) P[t] = (t / S == t % S) ? 1.0 : 0.0;
+      continue;
+    }
+    const double e = expm1(lam * bt);                              // :753-754, lane = eigenvalue index
+    double a[3][5];
+#pragma unroll
+    for (int ks = 0; ks < 5; ++ks)
+    {
+      const double ex = __shfl_sync(0xFFFFFFFFu, e, 4 * ks + q);
+#pragma unroll
+      for (int t = 0; t < 3; ++t) a[t][ks] = __dmul_rn(vi[t][ks], ex);      // :756-758
+    }
+    double c[3][3][2];
+#pragma unroll
+    for (int mt = 0; mt < 3; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 3; ++nt)
+      {
+        c[mt][nt][0] = (8 * mt + r == 8 * nt + 2 * q) ? 1.0 : 0.0;
+        c[mt][nt][1] = (8 * mt + r == 8 * nt + 2 * q + 1) ? 1.0 : 0.0;
+      }
+#pragma unroll
+    for (int ks = 0; ks < 5; ++ks)
+#pragma unroll
+      for (int mt = 0; mt < 3; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 3; ++nt)
+          asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+              : "+d"(c[mt][nt][0]), "+d"(c[mt][nt][1]) : "d"(a[mt][ks]), "d"(vb[nt][ks]));
+#pragma unroll
+    for (int mt = 0; mt < 3; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 3; ++nt)
+      {
+        const unsigned int i = 8 * mt + r, k = 8 * nt + 2 * q;
+        if (i < S && k < S) *reinterpret_cast<double2 *>(P + i * S + k) = make_double2(c[mt][nt][0], c[mt][nt][1]);
+      }
+  }
+}
+
 }  // namespace bppgpu
