@@ -502,3 +502,45 @@ def test_batches_of_different_shapes_alternate(eng):
         assert np.array_equal(bb.full_pass(sb)[0], rb0)
     _free(la, ba)
     _free(lb, bb)
+
+
+@pytest.mark.parametrize("cfg", [dict(tips=8, sites=300, states=4, rate_cats=4, model="HKY", scaling=True),
+                                 dict(tips=5, sites=64, states=20, rate_cats=4, model="LG")])
+def test_batch_split_calls_equal_full_pass(eng, cfg):
+    """The reference's three calls in batch form -- update_matrices, update_partials, root_loglikelihood -- give
+    what the fused full pass gives; loci with an empty op / matrix list in a batch call are left untouched."""
+    w = synth.make_workload("split", n_loci=9, seed=77, lg=lg_tables(), **cfg)
+    loci, trees, batch = _load(eng, w)
+    mc, mi, mb, oc, ops, rc, rs = trees.full_pass_step()
+    full, tot = batch.full_pass((mc, mi, mb, oc, ops, rc, rs))
+    clv_full = loci[5].get_clv(int(rc[5]))
+    loci2, trees2, batch2 = _load(eng, w)
+    batch2.update_matrices(mc, mi, mb)
+    batch2.update_partials(oc, ops)
+    split = batch2.root_loglikelihood(rc, rs)
+    assert np.array_equal(full, split)
+    assert np.array_equal(clv_full, loci2[5].get_clv(int(rc[5])))
+    # second round on the even loci only (new branch lengths), the odd ones keep their values
+    moff = np.concatenate([[0], np.cumsum(mc)]).astype(np.int64)
+    ooff = np.concatenate([[0], np.cumsum(oc)]).astype(np.int64)
+    km, ko = np.zeros(len(mi), bool), np.zeros(len(ops), bool)
+    mc2, oc2 = mc.copy(), oc.copy()
+    for i in range(w.n_loci):
+        if i % 2 == 0:
+            km[moff[i]:moff[i + 1]] = True
+            ko[ooff[i]:ooff[i + 1]] = True
+        else:
+            mc2[i] = 0
+            oc2[i] = 0
+    batch2.update_matrices(mc2, mi[km], mb[km] * 1.3)
+    batch2.update_partials(oc2, ops[ko])
+    second = batch2.root_loglikelihood(rc, rs)
+    assert np.array_equal(second[1::2], full[1::2])
+    assert np.all(second[0::2] != full[0::2])
+    cm = char_map(w.states)
+    o = F.locus_from_workload(w, 2, cm)
+    o.rate_mui = float(w.rate_mui[2]) * 1.3
+    ref = o.full_pass()
+    assert abs(second[2] - ref) <= LNL_RTOL * abs(ref)
+    _free(loci, batch)
+    _free(loci2, batch2)
