@@ -53,3 +53,21 @@ def test_two_rank_lnl_sum_allreduce():
     assert out[0][1] == out[1][1]                                # same reduced value on every rank
     assert abs(out[0][1] - sum(ref)) <= 1e-12 * abs(sum(ref))
     assert abs(out[0][0] + out[1][0] - out[0][1]) <= 1e-12 * abs(out[0][1])
+
+
+def test_zigzag_assignment_matches_reference_deal_and_balances():
+    """load_balance_zigzag, threads.c:265-353: ascending loads dealt 0,1,2,2,1,0,0,1,2,..."""
+    from bpp_b200 import shard
+    loads = [50, 10, 40, 20, 30, 60, 70]            # ascending order of indices: 1,3,4,2,0,5,6
+    got = shard.zigzag_assignment(loads, 3)
+    assert got == [[1, 5, 6], [3, 0], [4, 2]]
+    import random
+    rng = random.Random(5)
+    loads = [rng.randint(4, 40) * rng.randint(100, 3000) for _ in range(1000)]
+    parts = shard.zigzag_assignment(loads, 8)
+    assert sorted(i for p in parts for i in p) == list(range(1000))
+    assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+    work = [sum(loads[i] for i in p) for p in parts]
+    assert max(work) / min(work) < 1.02
+    assert shard.zigzag_assignment([], 4) == [[], [], [], []]
+    assert shard.zigzag_assignment([7, 3], 1) == [[1, 0]]
