@@ -906,7 +906,7 @@ extern "C" bppgpu_batch * bppgpu_batch_create(bppgpu_engine * e, unsigned int n,
   CUDA_CHECK(cudaEventCreate(&b->t1));
   b->h_tile_first = tile_first;
   for (unsigned i = 0; i < n; ++i) b->max_tips = std::max(b->max_tips, loci[i]->tips);
-  if (n > 1)          // the per-locus API keeps a batch of one per locus: no side streams for those
+  if (b->kernel_kind == 0 && n > 1)          // the per-locus API keeps a batch of one per locus: no side streams for those
   {
     CUDA_CHECK(cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking));
     CUDA_CHECK(cudaStreamCreateWithFlags(&b->alt_stream, cudaStreamNonBlocking));
@@ -1347,35 +1347,22 @@ static int batch_run(bppgpu_batch * b, bool do_mats, bool do_tree, bool want_roo
 
   // 4-state batches doing matrices and partials in one call build the P-matrices inside the planner
   const bool fuse_mats = do_mats && do_tree && b->kernel_kind == 0 && b->total_mats;
-  // 20 states: the P-matrix kernel (needs branch lengths only) and the planner (needs the op lists only) are
-  // independent and both too small to fill the GPU: they run side by side on two streams
-  const bool mats_on_alt = do_mats && b->total_mats && !fuse_mats && do_tree && b->kernel_kind == 2 && b->alt_stream;
   if (do_mats && b->total_mats && !fuse_mats)
   {
-    cudaStream_t ms = b->stream;
-    if (mats_on_alt)
-    {
-      CUDA_CHECK(cudaEventRecord(b->ev_fork, b->stream));
-      CUDA_CHECK(cudaStreamWaitEvent(b->alt_stream, b->ev_fork, 0));
-      ms = b->alt_stream;
-    }
-    {
-    ProfScope ps(e, ms, BPPGPU_KERNEL_PMATRIX);
+    ProfScope ps(e, b->stream, BPPGPU_KERNEL_PMATRIX);
     const unsigned S = b->loci[0]->states;
     if (S > 8)
     {
       const size_t sm = (2 * (size_t)S * S + 4 * ((size_t)S * (S + 1) + S)) * 8;
       // BPPGPU_PMAT_DMMA=0 keeps the reference's separate multiply / add order (pmatrix_kernel_wide)
       static const bool use_dmma = !(getenv("BPPGPU_PMAT_DMMA") && atoi(getenv("BPPGPU_PMAT_DMMA")) == 0);
-      if (S == 20 && use_dmma) pmatrix_kernel_dmma20<<<dim3(n, 4), 128, 0, ms>>>(e->d_loci, b->d_batch_locus, d_mat_off, d_mat_idx, d_mat_bl);
-      else if (S == 20) pmatrix_kernel_wide<20><<<dim3(n, 8), 128, sm, ms>>>(e->d_loci, b->d_batch_locus, d_mat_off, d_mat_idx, d_mat_bl);
-      else pmatrix_kernel_wide<0><<<dim3(n, 8), 128, sm, ms>>>(e->d_loci, b->d_batch_locus, d_mat_off, d_mat_idx, d_mat_bl);
+      if (S == 20 && use_dmma) pmatrix_kernel_dmma20<<<dim3(n, 4), 128, 0, b->stream>>>(e->d_loci, b->d_batch_locus, d_mat_off, d_mat_idx, d_mat_bl);
+      else if (S == 20) pmatrix_kernel_wide<20><<<dim3(n, 8), 128, sm, b->stream>>>(e->d_loci, b->d_batch_locus, d_mat_off, d_mat_idx, d_mat_bl);
+      else pmatrix_kernel_wide<0><<<dim3(n, 8), 128, sm, b->stream>>>(e->d_loci, b->d_batch_locus, d_mat_off, d_mat_idx, d_mat_bl);
     }
     else
-      pmatrix_kernel<<<n, 64, 0, ms>>>(e->d_loci, b->d_batch_locus, d_mat_off, d_mat_idx, d_mat_bl);
+      pmatrix_kernel<<<n, 64, 0, b->stream>>>(e->d_loci, b->d_batch_locus, d_mat_off, d_mat_idx, d_mat_bl);
     CUDA_CHECK(cudaGetLastError());
-    }
-    if (mats_on_alt) CUDA_CHECK(cudaEventRecord(b->ev_join, b->alt_stream));
   }
   if (!do_tree) return BPPGPU_SUCCESS;
 
@@ -1457,7 +1444,6 @@ static int batch_run(bppgpu_batch * b, bool do_mats, bool do_tree, bool want_roo
           b->d_plan, b->d_plan_count);
     CUDA_CHECK(cudaGetLastError());
   }
-  if (mats_on_alt) CUDA_CHECK(cudaStreamWaitEvent(b->stream, b->ev_join, 0));      // the tree kernel needs the matrices
   TreeParams prm;
   memset(&prm, 0, sizeof(prm));
   prm.loci = e->d_loci; prm.batch_locus = b->d_batch_locus; prm.tile_locus = b->d_tile_locus;
