@@ -191,11 +191,13 @@ locus_batch_gpu_t * locus_batch_create_gpu(bppgpu_engine * e, locus_gpu_t ** loc
   b->mat_cap = mats; b->op_cap = ops; b->trav_cap = maxn;
   b->mcounts = (unsigned int *)malloc(n * sizeof(unsigned int));
   b->ocounts = (unsigned int *)malloc(n * sizeof(unsigned int));
-  b->root_clv = (unsigned int *)malloc(n * sizeof(unsigned int));
-  b->root_sc = (int *)malloc(n * sizeof(int));
-  b->midx = (unsigned int *)malloc(mats * sizeof(unsigned int));
-  b->mbl = (double *)malloc(mats * sizeof(double));
-  b->ops = (bppgpu_partial_op *)malloc(ops * sizeof(bppgpu_partial_op));
+  /* the arrays that travel every step live in pinned memory: the engine copies them from where they are and
+     pipelines the upload of a big full pass against its first wave of kernels (bppgpu_batch_set_waves) */
+  b->root_clv = (unsigned int *)bppgpu_host_alloc(n * sizeof(unsigned int));
+  b->root_sc = (int *)bppgpu_host_alloc(n * sizeof(int));
+  b->midx = (unsigned int *)bppgpu_host_alloc(mats * sizeof(unsigned int));
+  b->mbl = (double *)bppgpu_host_alloc(mats * sizeof(double));
+  b->ops = (bppgpu_partial_op *)bppgpu_host_alloc(ops * sizeof(bppgpu_partial_op));
   b->trav = (gnode_gpu_t **)malloc(maxn * sizeof(gnode_gpu_t *));
   return b;
 }
@@ -204,8 +206,9 @@ void locus_batch_destroy_gpu(locus_batch_gpu_t * b)
 {
   if (!b) return;
   bppgpu_batch_destroy(b->handle);
-  free(b->loci); free(b->mcounts); free(b->ocounts); free(b->root_clv); free(b->root_sc);
-  free(b->midx); free(b->mbl); free(b->ops); free(b->trav);
+  free(b->loci); free(b->mcounts); free(b->ocounts); free(b->trav);
+  bppgpu_host_free(b->root_clv); bppgpu_host_free(b->root_sc);
+  bppgpu_host_free(b->midx); bppgpu_host_free(b->mbl); bppgpu_host_free(b->ops);
   free(b);
 }
 
