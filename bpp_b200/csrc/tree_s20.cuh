@@ -93,9 +93,17 @@ plan_kernel_blocks20(const LocusDev * __restrict__ loci, const unsigned int * __
     tile_blk[2 * (size_t)t] = blk_off[bl];
     tile_blk[2 * (size_t)t + 1] = 0;
   }
-  OpRec20 * recs = reinterpret_cast<OpRec20 *>(blk + sizeof(Hdr20));
+  OpRec20 * const recs_g = reinterpret_cast<OpRec20 *>(blk + sizeof(Hdr20));
   const unsigned int T = L.tips;
   unsigned int cnt = 0, n_ext = 0;
+  // small loci (the common case) are planned in shared memory: the serial planner below patches earlier records
+  // (OP_PUSH, OP_PARKA) and looks buffers up in `where`, and every such access was a dependent global round trip
+  __shared__ __align__(16) OpRec20 s_rec[4][33];
+  __shared__ unsigned int s_where[4][64];
+  __shared__ unsigned char s_slot[4][64];
+  const unsigned int wib = (threadIdx.x >> 5) & 3u;
+  const bool small = (n + 1 <= 33) && (L.clv_buffers <= 64);
+  OpRec20 * const recs = small ? s_rec[wib] : recs_g;
 
   // evaluation order: Sethi-Ullman DFS for lists of <= 32 ops (fewest parked values), as given otherwise
   __shared__ unsigned char s_ord[4][32];
@@ -110,8 +118,8 @@ plan_kernel_blocks20(const LocusDev * __restrict__ loci, const unsigned int * __
 
   if (lane == 0)
   {
-    unsigned int * where = reinterpret_cast<unsigned int *>(scratch + scratch_off[bl]);
-    unsigned char * slot_of = reinterpret_cast<unsigned char *>(where + L.clv_buffers);
+    unsigned int * where = small ? s_where[wib] : reinterpret_cast<unsigned int *>(scratch + scratch_off[bl]);
+    unsigned char * slot_of = small ? s_slot[wib] : reinterpret_cast<unsigned char *>(where + L.clv_buffers);
     for (unsigned int k = 0; k < n; ++k)
     {
       where[o[k].parent - T] = 0;
@@ -215,8 +223,18 @@ plan_kernel_blocks20(const LocusDev * __restrict__ loci, const unsigned int * __
   }
   cnt = __shfl_sync(0xFFFFFFFFu, cnt, 0);
   __syncwarp();
+  if (small)
+  {
+    const uint4 * src = reinterpret_cast<const uint4 *>(s_rec[wib]);
+    uint4 * dst = reinterpret_cast<uint4 *>(recs_g);
+    for (unsigned int w = lane; w < cnt * 4; w += 32) dst[w] = src[w];
+  }
   // extra tip columns: ext[cat][i][x] = sum over the states j of ambiguity mask x of P[i][j], j ascending
   double * base = reinterpret_cast<double *>(blk);
+  const unsigned int n_ext_cols = L.n_ext_cols;
+  unsigned int cmask[S20_EXT];
+#pragma unroll
+  for (int x = 0; x < S20_EXT; ++x) cmask[x] = (unsigned)x < n_ext_cols ? L.colmask[x] : 0u;
   for (unsigned int k = 0; k < cnt; ++k)
   {
     const OpRec20 q = recs[k];
@@ -227,17 +245,27 @@ plan_kernel_blocks20(const LocusDev * __restrict__ loci, const unsigned int * __
       if (kind != SRC_TIP_PACKED) continue;
       const unsigned int pm = c ? q.b_pm : q.a_pm;
       double * ext = base + (c ? q.b_ext : q.a_ext);
-      for (unsigned int e = lane; e < RL * S20 * S20_EXT; e += 32)
+      // one lane per (category, row): the row's 20 entries are read once (five 256-bit loads) and feed all the
+      // ambiguity columns (the first version re-read them entry by entry: ~200 dependent 8-byte loads per lane and
+      // tip operand, most of this kernel's time)
+      for (unsigned int row = lane; row < RL * S20; row += 32)
       {
-        const unsigned int x = e % S20_EXT, i = (e / S20_EXT) % S20, cat = e / (S20_EXT * S20);
-        double acc = 0.0;
-        if (x < L.n_ext_cols)
+        const double * P = L.pmat + ((size_t)pm * RL + row / S20) * (S20 * S20) + (size_t)(row % S20) * S20;
+        double p[S20];
+#pragma unroll
+        for (int v = 0; v < S20 / 4; ++v) ld256(P + 4 * v, p[4 * v], p[4 * v + 1], p[4 * v + 2], p[4 * v + 3]);
+        double acc[S20_EXT];
+#pragma unroll
+        for (int x = 0; x < S20_EXT; ++x)
         {
-          const unsigned int mask = L.colmask[x];
-          const double * P = L.pmat + ((size_t)pm * RL + cat) * (S20 * S20) + (size_t)i * S20;
-          for (int j = 0; j < S20; ++j) if ((mask >> j) & 1u) acc += P[j];
+          acc[x] = 0.0;
+          const unsigned int mask = (unsigned)x < n_ext_cols ? cmask[x] : 0u;
+#pragma unroll
+          for (int j = 0; j < S20; ++j) if ((mask >> j) & 1u) acc[x] += p[j];
         }
-        ext[e] = acc;
+        double2 * dst = reinterpret_cast<double2 *>(ext + (size_t)row * S20_EXT);
+        dst[0] = make_double2(acc[0], acc[1]);
+        dst[1] = make_double2(acc[2], acc[3]);
       }
     }
   }
