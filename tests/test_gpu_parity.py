@@ -467,9 +467,17 @@ def test_batched_model_update_and_device_eigen(eng, cfg, monkeypatch):
                 l.set_subst_params(w.subst[i][::-1].copy())
                 l.set_frequencies(w.freqs[(i + 1) % w.n_loci])
         b, _ = batch.full_pass(step)
-        res[mode] = (a, b, eig, pm)
+        # third round through the OTHER path: a decomposition that lives on the device only must survive a
+        # per-locus model upload (and a host-side one a batched upload)
+        monkeypatch.setenv("BPPGPU_MODEL_BATCH_MIN", "1" if mode == "host" else "1000000")
+        for l in loci[:3]:
+            l.set_category_rates(new_rates[::-1].copy() * 0.9)
+        c, _ = batch.full_pass(step)
+        res[mode] = (a, b, eig, pm, c)
         _free(loci, batch)
     monkeypatch.delenv("BPPGPU_MODEL_BATCH_MIN", raising=False)
+    assert rel_err(res["device"][4], res["host"][4]) < 1e-12
+    assert np.all(res["device"][4][:3] != res["device"][1][:3]) and np.array_equal(res["device"][4][3:], res["device"][1][3:])
     assert rel_err(res["device"][0], res["host"][0]) < 1e-12 and rel_err(res["device"][1], res["host"][1]) < 1e-12
     assert np.allclose(res["device"][3], res["host"][3], rtol=1e-12, atol=1e-15)
     if res["device"][2] is not None:
