@@ -91,6 +91,7 @@ __host__ __device__ constexpr int s4_ctas_per_sm(int cpt)
   return cpt == 2 ? BPPGPU_S4_CTAS2 : (cpt == 1 ? 3 : 1) * (256 / TREE_NT);
 }
 constexpr int TREE_CHUNK = 16;      // ops per staged chunk
+constexpr int S4_MAX_TIP_WORDS = 4; // packed tip words (8 tips each) the 4-state fast path stages per cell: 32 tips
 constexpr int PM_STRIDE  = 18;      // doubles per (matrix, cat) in shared memory (16 + 2 pad: the RL
                                     // categories of a site land in different banks)
 constexpr int LUT_ROW    = 6;       // doubles per state-mask row of a tip lookup table (4 + 2 pad: the
@@ -122,7 +123,7 @@ struct OpRec
 };
 static_assert(sizeof(OpRec) == 64, "OpRec must be 64 bytes");
 
-enum : unsigned { HDR_FAST = 1u,     // every op of the locus uses fast operands only
+enum : unsigned { HDR_FAST = 1u,     // every op of the locus uses fast operands only (any number of chunks)
                   HDR_SIMPLE = 2u,   // ... and none is HBM-class or scaled: the lean instantiation of tile_fast
                   HDR_NOHBM = 4u };  // ... and none is HBM-class (scaling allowed): full passes with scale buffers
 
@@ -189,6 +190,7 @@ struct TreeParams
   double * persite;                   // optional per-site output of the (single) locus, or nullptr
   int persite_mode;                   // 1 = weighted site lnL, 2 = site likelihood (vector form)
   int n_slots;                        // shared-memory stack slots per cell
+  unsigned int tip_words;             // 4-state kernel: packed tip words staged per cell (<= S4_MAX_TIP_WORDS)
   unsigned int lut_cap;               // tip-slot capacity of the launch (4-state kernel), <= lut_cap(RL);
                                       // 20-state category-major kernel: staged P-matrix capacity
   double * rootdot;                   // 20-state category-major kernel: pi . clv_root per (locus, category, site)

@@ -241,6 +241,7 @@ struct bppgpu_batch
   bool have_m = false, have_o = false;
   std::vector<unsigned int> last_mcounts, last_ocounts;
   unsigned int max_tips = 0;
+  unsigned int tip_words_rt = 1;       // packed tip words the 4-state kernel stages per cell
   unsigned int wave_pref = 0;          // 0 = automatic
   std::vector<unsigned int> h_tile_first;
   // launch configuration of the tree kernel, resolved once per (shared-memory size)
@@ -906,6 +907,7 @@ extern "C" bppgpu_batch * bppgpu_batch_create(bppgpu_engine * e, unsigned int n,
   CUDA_CHECK(cudaEventCreate(&b->t1));
   b->h_tile_first = tile_first;
   for (unsigned i = 0; i < n; ++i) b->max_tips = std::max(b->max_tips, loci[i]->tips);
+  b->tip_words_rt = std::min<unsigned>((b->max_tips + 7) / 8, (unsigned)S4_MAX_TIP_WORDS);
   if (b->kernel_kind == 0 && n > 1)          // the per-locus API keeps a batch of one per locus: no side streams for those
   {
     CUDA_CHECK(cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking));
@@ -1273,7 +1275,7 @@ static int tree_s4_slots(bppgpu_batch * b, int wanted, unsigned cap)
 {
   int slots = wanted;
   const size_t ctas = s4_ctas_per_sm(CPT);
-  while (slots > 1 && ctas * (S4Layout<RL, CPT>::bytes(slots, cap) + 1024) > b->e->smem_per_sm) --slots;
+  while (slots > 1 && ctas * (S4Layout<RL, CPT>::bytes(slots, cap, b->tip_words_rt) + 1024) > b->e->smem_per_sm) --slots;
   return slots;
 }
 
@@ -1281,7 +1283,7 @@ template <int RL, bool EXACT, int CPT>
 static void launch_tree_s4_impl(bppgpu_batch * b, const TreeParams & prm, cudaStream_t st)
 {
   bppgpu_engine * e = b->e;
-  const size_t smem = S4Layout<RL, CPT>::bytes(prm.n_slots, prm.lut_cap);
+  const size_t smem = S4Layout<RL, CPT>::bytes(prm.n_slots, prm.lut_cap, prm.tip_words);
   const unsigned key = (unsigned)(RL * 100 + CPT * 10 + (EXACT ? 1 : 0));
   if (b->cfg_key != key || b->cfg_smem != smem)
   {
@@ -1451,6 +1453,7 @@ static int batch_run(bppgpu_batch * b, bool do_mats, bool do_tree, bool want_roo
   prm.tiles = b->d_tiles; prm.blocks = b->d_blocks; prm.tile_blk = b->d_tile_blk; prm.n_tiles = b->n_tiles;
   prm.tile_partial = want_root ? b->d_tile_partial : nullptr;
   prm.persite = persite; prm.persite_mode = persite_mode; prm.n_slots = slots; prm.lut_cap = lut_cap_rt;
+  prm.tip_words = b->tip_words_rt;
   prm.log_threshold = e->log_threshold;
   if (waved)
   {

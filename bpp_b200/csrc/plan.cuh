@@ -239,7 +239,7 @@ plan_small_parallel(const LocusDev & L, const RawOp * o, unsigned int n, unsigne
         okind[c] = SRC_TIP_PACKED;
         osel[c] = 15u | ((child[c] >> 3) << 4) | (((child[c] & 7u) * 4) << 8);
         ooff[c] = lutn * lut_unit; ++lutn;
-        if (child[c] >= 16) op_fast = false;
+        if (child[c] >= 8 * S4_MAX_TIP_WORDS) op_fast = false;     // its tip word is not staged
       }
     }
     else if (kid[c] >= 0 && kpos + 1 == pos && prev_child < 0) { okind[c] = SRC_PREV; prev_child = c; s_push[kid[c]] = opm[c] + 1; }
@@ -251,7 +251,7 @@ plan_small_parallel(const LocusDev & L, const RawOp * o, unsigned int n, unsigne
       {
         // produced by this list but neither in the register nor in a slot: re-read it with the producer's Pup
         if (kchunk == mychunk) { okind[c] = SRC_HBML; ooff[c] = kidx; s_push[kid[c]] = opm[c] + 1; }
-        else op_fast = false;
+        else { op_fast = false; ooff[c] = 0xFFFFFFFFu; }      // re-read across chunks: no staged matrix, general walker
       }
       else { ooff[c] = lutn; ++lutn; }         // HBM-resident child: its edge's P-matrix is staged in slot lutn
     }
@@ -321,7 +321,7 @@ plan_small_parallel(const LocusDev & L, const RawOp * o, unsigned int n, unsigne
   }
   __syncwarp();
   SmallPlanOut out;
-  out.n_chunks = c_idx; out.cnt = cnt; out.fast = fast && c_idx == 1; out.simple = out.fast && simple; out.nohbm = out.fast && nohbm;
+  out.n_chunks = c_idx; out.cnt = cnt; out.fast = fast; out.simple = out.fast && simple; out.nohbm = out.fast && nohbm;
   return out;
 }
 
@@ -375,8 +375,12 @@ plan_kernel_blocks(const LocusDev * __restrict__ loci, const unsigned int * __re
 
   // small loci (the common case) are planned entirely in shared memory: raw ops, the producer map and
   // the OpRecs under construction; the block in HBM is written once, coalesced, at the end
-  constexpr unsigned int SM_OPS = 2 * TREE_CHUNK, SM_BUF = 64;
-  __shared__ __align__(16) RawOp s_raw[4][SM_OPS];
+  // SM_OPS: records of up to 4 chunks (a chunk closes after TREE_CHUNK ops or when its lookup tables are full: a
+  // 31-op list over 16 table slots, i.e. 4 rate categories, can take 4; 8 categories have 8 slots and stay on the
+  // shared-memory path up to 15 ops only -- more would cost the planner its occupancy); the lane-parallel planner
+  // itself handles lists of up to 32 ops
+  constexpr unsigned int SM_OPS = 4 * TREE_CHUNK, SM_RAW = 32, SM_BUF = 64;
+  __shared__ __align__(16) RawOp s_raw[4][SM_RAW];
   __shared__ __align__(16) OpRec s_rec[4][SM_OPS];
   __shared__ unsigned int s_where[4][SM_BUF];
   __shared__ unsigned char s_slot[4][SM_BUF];
@@ -387,7 +391,7 @@ plan_kernel_blocks(const LocusDev * __restrict__ loci, const unsigned int * __re
   const unsigned int wib = threadIdx.x >> 5;
   // every closed chunk holds >= m ops, so a list of n (+1 eval-only) ops needs <= n/m + 1 chunks
   const unsigned int m_ops = (cap / 2 < (unsigned)TREE_CHUNK) ? (cap / 2 ? cap / 2 : 1u) : (unsigned)TREE_CHUNK;
-  const bool small = (n + 1 <= SM_OPS) && (L.clv_buffers <= SM_BUF) && (n / m_ops + 1 <= SM_OPS / TREE_CHUNK);
+  const bool small = (n <= SM_RAW) && (L.clv_buffers <= SM_BUF) && (n / m_ops + 1 <= SM_OPS / TREE_CHUNK);
   if (small)
   {
     const uint4 * src = reinterpret_cast<const uint4 *>(o);
@@ -671,7 +675,7 @@ plan_kernel_blocks(const LocusDev * __restrict__ loci, const unsigned int * __re
         const unsigned int off = which == 1 ? q.a_off : q.b_off;
         unsigned int slot;
         if (kind == SRC_TIP_PACKED) slot = (unsigned int)((float)off * inv_lut_unit + 0.5f);   // off = slot * lut_unit, exact
-        else if (kind == SRC_HBM && small) slot = off;
+        else if (kind == SRC_HBM && small && off != 0xFFFFFFFFu) slot = off;
         else continue;
         pm = which == 1 ? q.a_pm : q.b_pm;
         dst = tipP + (size_t)slot * RL * PM_STRIDE;

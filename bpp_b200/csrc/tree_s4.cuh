@@ -102,15 +102,15 @@ struct S4Layout               // everything in uint4 (16-byte) units
   __host__ __device__ static constexpr unsigned lut0(unsigned cap) { return STAGE0 + NSTAGE * stage_sz(cap); }
   __host__ __device__ static constexpr unsigned stack0(unsigned cap) { return lut0(cap) + cap * RL * 49; }
   // after the stack: packed tip words and pattern weights of the current and the next tile,
-  // [2 buffers][3: tip word 0, tip word 1, weight][CPT][TREE_NT] u32, filled by 4-byte cp.async
-  static constexpr unsigned TIPS_BUF = 3 * CPT * TREE_NT;         // u32 per buffer
+  // [2 buffers][W tip words, then the weight][CPT][TREE_NT] u32 (W = the launch's tip_words), filled by 4-byte cp.async
+  __host__ __device__ static constexpr unsigned tips_buf(unsigned words) { return (words + 1) * CPT * TREE_NT; }   // u32 per buffer
   __host__ __device__ static constexpr unsigned tips0_u32(int slots, unsigned cap)
   {
     return (stack0(cap) + (unsigned)slots * SLOT) * 4 + (unsigned)slots * CPT * TREE_NT;
   }
-  __host__ __device__ static constexpr size_t bytes(int slots, unsigned cap)
+  __host__ __device__ static constexpr size_t bytes(int slots, unsigned cap, unsigned words)
   {
-    return (size_t)tips0_u32(slots, cap) * 4 + 2 * (size_t)TIPS_BUF * 4;
+    return (size_t)tips0_u32(slots, cap) * 4 + 2 * (size_t)tips_buf(words) * 4;
   }
 };
 
@@ -125,8 +125,9 @@ struct TileCtx
   unsigned int cell[CPT];        // clamped cell index
   bool valid[CPT];
   unsigned int tw0[CPT];         // tip word 0 (tips 0..7) of the thread's cells
-  unsigned int tips_s;           // u32 index of this thread's entry in the tile's tip buffer: word 1 of cell j at
-                                 // tips_s + (CPT + j) * TREE_NT, pattern weight at tips_s + (2 * CPT + j) * TREE_NT
+  unsigned int tips_s;           // u32 index of this thread's entry in the tile's tip buffer: word w of cell j at
+                                 // tips_s + (w * CPT + j) * TREE_NT, pattern weight at tips_s + wgt_off + j * TREE_NT
+  unsigned int wgt_off;          // = tip_words * CPT * TREE_NT
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -135,8 +136,11 @@ struct TileCtx
 // MODE 0 is the lean instantiation for loci flagged HDR_SIMPLE (no HBM-class operand, no scaler): full-tree
 // passes without scaling, the headline workload.  MODE 1 adds per-site scaling (HDR_NOHBM: full passes with
 // scale buffers), MODE 2 also HBM-class operands (partial updates).
+// One call runs the ops of the chunk that is staged; x / psc (the register X and its scaler count) carry over
+// from chunk to chunk of the same tile.
 template <int RL, bool EXACT, int CPT, int MODE>
-__device__ __forceinline__ double tile_fast(const TreeParams & prm, const TileCtx<CPT> & tc)
+__device__ __forceinline__ double tile_fast(const TreeParams & prm, const TileCtx<CPT> & tc, double (&x)[CPT][4],
+                                            unsigned int (&psc)[CPT])
 {
   constexpr bool SCALED = MODE >= 1, FULL = MODE == 2;
   constexpr unsigned int LOG2RL = RL == 1 ? 0 : (RL == 2 ? 1 : (RL == 4 ? 2 : 3));
@@ -153,11 +157,7 @@ __device__ __forceinline__ double tile_fast(const TreeParams & prm, const TileCt
   unsigned char * const clv0 = reinterpret_cast<unsigned char *>(H->clv);
   const unsigned int sites = H->sites;
 
-  double x[CPT][4];
-  unsigned int psc[CPT];
   double site_sum = 0.0;
-#pragma unroll
-  for (int j = 0; j < CPT; ++j) { x[j][0] = x[j][1] = x[j][2] = x[j][3] = 0.0; psc[j] = 0; }
 
   for (unsigned int k = 0; k < cn; ++k)
   {
@@ -168,9 +168,9 @@ __device__ __forceinline__ double tile_fast(const TreeParams & prm, const TileCt
     // ---- operand A (tip lookup or stack slot), then the product with B
     {
       const unsigned int amask = w0.z & 15u, ash = (w0.z >> 8) & 31u;
-      const bool aw1 = (w0.z & 16u) != 0;
+      const unsigned int aword = (w0.z >> 4) & 15u;
       const unsigned int bmask = w1.x & 15u, bsh = (w1.x >> 8) & 31u;
-      const bool bw1 = (w1.x & 16u) != 0;
+      const unsigned int bword = (w1.x >> 4) & 15u;
       // HBM-class operands: a CLV re-read from global memory (written earlier in this pass by this very
       // thread, or resident from an earlier call) times its edge's staged P-matrix: the producer's Pup
       // (SRC_HBML) or a tipP slot (SRC_HBM)
@@ -200,7 +200,7 @@ __device__ __forceinline__ double tile_fast(const TreeParams & prm, const TileCt
         }
         else
         {
-          const unsigned int wa = aw1 ? s1[tc.tips_s + (CPT + j) * TREE_NT] : tc.tw0[j];
+          const unsigned int wa = aword ? s1[tc.tips_s + (aword * CPT + j) * TREE_NT] : tc.tw0[j];
           const unsigned int ia = (amask ? lut_t : stk_t + j * (2 * TREE_NT)) + w0.w + ((wa >> ash) & amask) * 3;
           a0 = sd2[ia]; a1 = sd2[ia + 1];
         }
@@ -217,7 +217,7 @@ __device__ __forceinline__ double tile_fast(const TreeParams & prm, const TileCt
           }
           else
           {
-            const unsigned int wb = bw1 ? s1[tc.tips_s + (CPT + j) * TREE_NT] : tc.tw0[j];
+            const unsigned int wb = bword ? s1[tc.tips_s + (bword * CPT + j) * TREE_NT] : tc.tw0[j];
             const unsigned int ib = (bmask ? lut_t : stk_t + j * (2 * TREE_NT)) + w1.y + ((wb >> bsh) & bmask) * 3;
             const double2 b0 = sd2[ib], b1 = sd2[ib + 1];
             x[j][0] = b0.x; x[j][1] = b0.y; x[j][2] = b1.x; x[j][3] = b1.y;
@@ -312,7 +312,7 @@ __device__ __forceinline__ double tile_fast(const TreeParams & prm, const TileCt
         {
           s = log(term);
           if (SCALED && osc[j]) s = __dadd_rn(s, __dmul_rn((double)osc[j], prm.log_threshold));
-          s = __dmul_rn(s, (double)s1[tc.tips_s + (2 * CPT + j) * TREE_NT]);
+          s = __dmul_rn(s, (double)s1[tc.tips_s + tc.wgt_off + j * TREE_NT]);
         }
         if (tc.valid[j] && tc.cat == 0)
         {
@@ -531,7 +531,7 @@ tree_kernel_s4(const TreeParams prm)
     const uint4 * src = reinterpret_cast<const uint4 *>(prm.blocks + blk);
     for (unsigned int w = tid; w < stage_sz; w += TREE_NT) cp_async16(&s4[Lay::STAGE0 + buf * stage_sz + w], src + w);
   };
-  const unsigned int tips0 = Lay::tips0_u32(prm.n_slots, prm.lut_cap);
+  const unsigned int tips0 = Lay::tips0_u32(prm.n_slots, prm.lut_cap), tips_buf = Lay::tips_buf(prm.tip_words);
   // packed tip words + pattern weight of the thread's cells of tile d -> tip buffer `tb` (asynchronous; each
   // thread copies and later reads only its own entries, so the cp.async wait alone orders them)
   auto load_tips = [&](const TileDesc & d, unsigned int tb)
@@ -541,10 +541,10 @@ tree_kernel_s4(const TreeParams prm)
     {
       const unsigned int craw = d.cell0 + tid + j * TREE_NT;
       const unsigned int pat = (craw < d.ncell ? craw : d.ncell - 1) / RL;
-      unsigned int * dst = &s1[tips0 + tb * Lay::TIPS_BUF + j * TREE_NT + tid];
-      cp_async4(dst, d.tipwords + (size_t)pat * d.tip_words);
-      if (d.tip_words > 1) cp_async4(dst + CPT * TREE_NT, d.tipwords + (size_t)pat * d.tip_words + 1);
-      cp_async4(dst + 2 * CPT * TREE_NT, d.weights + pat);
+      unsigned int * dst = &s1[tips0 + tb * tips_buf + j * TREE_NT + tid];
+      const unsigned int nw = d.tip_words < prm.tip_words ? d.tip_words : prm.tip_words;
+      for (unsigned int w = 0; w < nw; ++w) cp_async4(dst + w * (CPT * TREE_NT), d.tipwords + (size_t)pat * d.tip_words + w);
+      cp_async4(dst + prm.tip_words * (CPT * TREE_NT), d.weights + pat);
     }
   };
 
@@ -607,7 +607,8 @@ tree_kernel_s4(const TreeParams prm)
     const LocusHdr * H = reinterpret_cast<const LocusHdr *>(&s4[sb]);
     tc.sb = sb;
     tc.cat = (d.cell0 + tid) % RL;
-    tc.tips_s = tips0 + tb * Lay::TIPS_BUF + tid;
+    tc.tips_s = tips0 + tb * tips_buf + tid;
+    tc.wgt_off = prm.tip_words * (CPT * TREE_NT);
 #pragma unroll
     for (int j = 0; j < CPT; ++j) tc.tw0[j] = s1[tc.tips_s + j * TREE_NT];
 #pragma unroll
@@ -619,9 +620,42 @@ tree_kernel_s4(const TreeParams prm)
     }
 
     double site_sum;
-    if (H->flags & HDR_SIMPLE) site_sum = tile_fast<RL, EXACT, CPT, 0>(prm, tc);
-    else if (H->flags & HDR_NOHBM) site_sum = tile_fast<RL, EXACT, CPT, 1>(prm, tc);
-    else if (H->flags & HDR_FAST) site_sum = tile_fast<RL, EXACT, CPT, 2>(prm, tc);
+    // another chunk of the current locus -> the stage buffer (synchronously, in place of the one that is there)
+    auto restage = [&](unsigned int c)
+    {
+      __syncthreads();
+      const uint4 * src = reinterpret_cast<const uint4 *>(prm.blocks + blk) + Lay::CH + (size_t)c * Lay::CHUNK;
+      for (unsigned int w = tid; w < stage_sz - Lay::CH; w += TREE_NT) s4[sb + Lay::CH + w] = __ldg(src + w);
+      __syncthreads();
+      build_lut<RL, EXACT, CPT>(sb, lut0);
+      __syncthreads();
+      staged_locus = 0xFFFFFFFFu;          // chunk 0 is gone
+    };
+#ifdef BPPGPU_NO_MULTICHUNK_FAST
+    if ((H->flags & HDR_FAST) && H->n_chunks == 1)
+#else
+    if (H->flags & HDR_FAST)
+#endif
+    {
+      const unsigned int flags = H->flags, n_chunks = H->n_chunks;
+      double x[CPT][4];
+      unsigned int psc[CPT];
+#pragma unroll
+      for (int j = 0; j < CPT; ++j) { x[j][0] = x[j][1] = x[j][2] = x[j][3] = 0.0; psc[j] = 0; }
+      // one chunk (trees of up to 16 ops whose tips fit the lookup tables) and no HBM-class operand: the lean
+      // instantiations; anything else on the fast path runs the full one, chunk by chunk
+      if (n_chunks == 1 && (flags & HDR_SIMPLE)) site_sum = tile_fast<RL, EXACT, CPT, 0>(prm, tc, x, psc);
+      else if (n_chunks == 1 && (flags & HDR_NOHBM)) site_sum = tile_fast<RL, EXACT, CPT, 1>(prm, tc, x, psc);
+      else
+      {
+        site_sum = 0.0;
+        for (unsigned int c = 0; c < n_chunks; ++c)
+        {
+          if (c > 0) restage(c);
+          site_sum += tile_fast<RL, EXACT, CPT, 2>(prm, tc, x, psc);
+        }
+      }
+    }
     else
     {
       // general path: chunk by chunk (later chunks are staged in place, synchronously), cell by cell
@@ -633,21 +667,12 @@ tree_kernel_s4(const TreeParams prm)
       const unsigned int n_chunks = H->n_chunks;
       for (unsigned int c = 0; c < n_chunks; ++c)
       {
-        if (c > 0)
-        {
-          __syncthreads();
-          const uint4 * src = reinterpret_cast<const uint4 *>(prm.blocks + blk) + Lay::CH + (size_t)c * Lay::CHUNK;
-          for (unsigned int w = tid; w < stage_sz - Lay::CH; w += TREE_NT) s4[sb + Lay::CH + w] = __ldg(src + w);
-          __syncthreads();
-          build_lut<RL, EXACT, CPT>(sb, lut0);
-          __syncthreads();
-          staged_locus = 0xFFFFFFFFu;          // chunk 0 is gone
-        }
+        if (c > 0) restage(c);
 #pragma unroll
         for (int j = 0; j < CPT; ++j)
           site_sum += chunk_general<RL, EXACT, CPT>(prm, sb, lut0 | (stack0 << 16), tc.sst1, j, tc.cell[j], tc.valid[j], tc.cat, tc.tw0[j],
-                                                    d.tip_words > 1 ? s1[tc.tips_s + (CPT + j) * TREE_NT] : 0u,
-                                                    s1[tc.tips_s + (2 * CPT + j) * TREE_NT], xs[j], &pscs[j]);
+                                                    (d.tip_words > 1 && prm.tip_words > 1) ? s1[tc.tips_s + (CPT + j) * TREE_NT] : 0u,
+                                                    s1[tc.tips_s + tc.wgt_off + j * TREE_NT], xs[j], &pscs[j]);
       }
     }
 

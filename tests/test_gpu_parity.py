@@ -552,3 +552,31 @@ def test_batch_split_calls_equal_full_pass(eng, cfg):
     assert abs(second[2] - ref) <= LNL_RTOL * abs(ref)
     _free(loci, batch)
     _free(loci2, batch2)
+
+
+@pytest.mark.parametrize("tips,rate_cats,scaling", [(17, 4, False), (24, 4, True), (32, 1, False), (32, 4, True),
+                                                    (29, 2, False), (20, 8, True)])
+def test_multi_chunk_fast_path(eng, tips, rate_cats, scaling):
+    """Trees of 17..32 tips need more than one staged chunk (16 ops, or the lookup-table capacity) and tip words
+    beyond the first two; they run the fast path chunk by chunk, X and its scaler carried in registers.  lnL
+    against the oracle, every inner CLV against the oracle's (same arithmetic, P-matrices equal to rounding),
+    scalers exactly; then a full pass in batch form after a root-path style change of all branch lengths."""
+    rates = {1: None, 4: None, 2: [0.3, 1.7], 8: list(np.linspace(0.1, 3, 8))}[rate_cats]
+    kw = dict(dt_lo=0.02, dt_hi=0.2) if scaling else {}
+    w = synth.make_workload("mchunk", n_loci=6, tips=tips, sites=530, states=4, rate_cats=rate_cats, model="GTR",
+                            scaling=scaling, seed=1000 + tips, rates=rates, **kw)
+    loci, trees, batch = _load(eng, w)
+    lnl, tot = batch.full_pass(trees.full_pass_step())
+    cm = char_map(4)
+    for i in (0, 3, 5):
+        o = F.locus_from_workload(w, i, cm)
+        ref = o.full_pass()
+        assert abs(lnl[i] - ref) <= LNL_RTOL * abs(ref), (i, lnl[i], ref)
+        for n in range(tips, 2 * tips - 1):
+            assert rel_err(loci[i].get_clv(n), np.asarray(o.clv[o.clv_index[n]]).ravel()) < 1e-11, (i, n)
+            if scaling:
+                assert np.array_equal(loci[i].get_scaler(n - tips), o.scale[o.scaler_index[n]]), (i, n)
+    # the same staged inputs again, and a second batch built the same way: bitwise reproducible
+    again, tot2 = batch.full_pass(trees.full_pass_step())
+    assert np.array_equal(lnl, again) and tot == tot2
+    _free(loci, batch)

@@ -1,0 +1,30 @@
+"""Device-resident full-pass time vs. tips per locus (fast path <= 16 tips / one chunk, general walker beyond).
+Usage: tips_sweep.py [rate_cats] [model]"""
+import sys
+
+sys.path.insert(0, ".")
+from bpp_b200 import engine, synth  # noqa: E402
+
+R = int(sys.argv[1]) if len(sys.argv) > 1 else 4
+model = sys.argv[2] if len(sys.argv) > 2 else "GTR"
+eng = engine.Engine(0)
+for tips in (8, 16, 17, 24, 32, 48):
+    n = max(200, 32000 // tips)
+    w = synth.make_workload("sweep", n_loci=n, tips=tips, sites=1000, states=4, rate_cats=R, model=model, seed=3)
+    loci, trees = engine.load_workload(eng, w)
+    batch = engine.Batch(eng, loci)
+    batch.set_waves(1)
+    batch.stage(trees.full_pass_step())
+    for _ in range(3):
+        batch.run()
+    K = 20
+    batch.timer_start()
+    for _ in range(K):
+        batch.run()
+    ms = batch.timer_stop_ms() / K
+    node_updates = n * (tips - 1)
+    print("R=%d %s tips=%2d loci=%5d: %.3f ms/pass  %.1f M node-updates/s  (%.2f GB/s of CLV writes)" % (
+        R, model, tips, n, ms, node_updates / ms / 1e3, node_updates * 1000 * R * 32 / ms / 1e6), flush=True)
+    batch.destroy()
+    for l in loci:
+        l.destroy()
