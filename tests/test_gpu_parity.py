@@ -580,3 +580,85 @@ def test_multi_chunk_fast_path(eng, tips, rate_cats, scaling):
     again, tot2 = batch.full_pass(trees.full_pass_step())
     assert np.array_equal(lnl, again) and tot == tot2
     _free(loci, batch)
+
+
+@pytest.mark.parametrize("rate_cats,scaling", [(4, True), (1, False)])
+def test_partial_update_long_root_path_multi_chunk(eng, rate_cats, scaling):
+    """A node-age move deep in a 30-tip tree: the root path can be longer than one chunk of 16 ops, its unchanged
+    siblings are HBM-resident operands with staged matrices in every chunk (full instantiation of the fast path,
+    chunk by chunk).  Batch form over all loci, against the oracle."""
+    from bpp_b200 import engine
+    T = 30
+    w = synth.make_workload("lpath", n_loci=8, tips=T, sites=300, states=4, rate_cats=rate_cats, model="GTR",
+                            scaling=scaling, seed=555)
+    # caterpillar trees (random coalescent trees of 30 tips have root paths of ~10 ops only): inner node k joins
+    # inner node k-1 and tip k+1, so the path from the first cherry to the root has all 29 ops
+    rng = np.random.default_rng(9)
+    for i in range(w.n_loci):
+        for k in range(T - 1):
+            w.left[i, k] = T + k - 1 if k > 0 else 0
+            w.right[i, k] = k + 1
+        w.times[i, :T] = 0.0
+        w.times[i, T:] = np.cumsum(rng.uniform(0.002, 0.02, size=T - 1))
+    loci, trees, batch = _load(eng, w)
+    batch.full_pass(trees.full_pass_step())
+    cm = char_map(4)
+    mcs, mis, mbs, ocs, opss, refs = [], [], [], [], [], []
+    longest = 0
+    for i in range(w.n_loci):
+        o = F.locus_from_workload(w, i, cm)
+        o.full_pass()
+        # the inner node with the longest path to the root
+        depth = {}
+        for n in range(T, 2 * T - 1):
+            d, m = 0, n
+            while o.parent[m] >= 0:
+                m = o.parent[m]
+                d += 1
+            depth[n] = d
+        node = max(depth, key=lambda n: depth[n])
+        kids = [o.left[node - T], o.right[node - T]]
+        lo = max(o.times[kids[0]], o.times[kids[1]])
+        hi = o.times[o.parent[node]]
+        newt = lo + 0.41 * (hi - lo)
+        o.times[node] = newt
+        trees.times[i, node] = newt
+        touched = kids + [node]
+        path = []
+        n = node
+        while n >= 0:
+            path.append(n)
+            n = o.parent[n]
+        longest = max(longest, len(path))
+        for n in touched:
+            o.flip_pmatrix(n)
+        o.update_matrices(touched)
+        for n in path:
+            o.flip_clv(n)
+        o.update_partials(path)
+        refs.append(o.root_loglikelihood())
+        e2 = 2 * T - 2
+        for n in touched:
+            trees.pmatrix_index[i, n] = (e2 + trees.pmatrix_index[i, n]) % (2 * e2)
+        mcs.append(len(touched))
+        mis += [trees.pmatrix_index[i, n] for n in touched]
+        mbs += [(trees.times[i, trees.parent[i, n]] - trees.times[i, n]) * trees.rate_mui[i] for n in touched]
+        for n in path:
+            trees.clv_index[i, n] = T + (trees.clv_index[i, n] - 1) % (2 * T - 2)
+            if scaling:
+                trees.scaler_index[i, n] = (T + trees.scaler_index[i, n] - 1) % (2 * T - 2)
+        ops = np.zeros(len(path), dtype=engine.OP_DTYPE)
+        for k, n in enumerate(path):
+            a, b = trees.left[i, n - T], trees.right[i, n - T]
+            ops[k] = (trees.clv_index[i, n], trees.clv_index[i, a], trees.clv_index[i, b],
+                      trees.pmatrix_index[i, a], trees.pmatrix_index[i, b],
+                      trees.scaler_index[i, n], trees.scaler_index[i, a], trees.scaler_index[i, b])
+        ocs.append(len(path))
+        opss.append(ops)
+    rc = np.array([trees.clv_index[i, trees.root] for i in range(w.n_loci)], dtype=np.uint32)
+    rs = np.array([trees.scaler_index[i, trees.root] for i in range(w.n_loci)], dtype=np.int32)
+    got, _ = batch.full_pass((np.array(mcs, dtype=np.uint32), np.array(mis, dtype=np.uint32), np.array(mbs),
+                              np.array(ocs, dtype=np.uint32), np.concatenate(opss), rc, rs))
+    assert longest == T - 1
+    assert rel_err(got, refs) <= LNL_RTOL, (got, refs, longest)
+    _free(loci, batch)
