@@ -150,15 +150,15 @@ __host__ __device__ inline size_t chunk_bytes(unsigned RL)
 }
 // upper bound on the chunks of a list of nops ops: a chunk closes after TREE_CHUNK ops or when the
 // next op's tip children no longer fit its lookup tables
-__host__ __device__ inline unsigned int max_chunks(unsigned RL, unsigned nops)
+// cap = the launch's tip-slot capacity (<= lut_cap(RL)): every closed chunk holds at least min(cap/2, TREE_CHUNK) ops
+__host__ __device__ inline unsigned int max_chunks(unsigned cap, unsigned nops)
 {
-  const unsigned cap = (unsigned)lut_cap((int)RL);
   const unsigned m = cap / 2 < (unsigned)TREE_CHUNK ? (cap / 2 ? cap / 2 : 1) : (unsigned)TREE_CHUNK;
   return (nops + m - 1) / m + 1;
 }
-__host__ __device__ inline size_t block_bytes(unsigned RL, unsigned nops_max)
+__host__ __device__ inline size_t block_bytes(unsigned RL, unsigned nops_max, unsigned cap)
 {
-  return sizeof(LocusHdr) + rw_bytes(RL) + (size_t)max_chunks(RL, nops_max) * chunk_bytes(RL);
+  return sizeof(LocusHdr) + rw_bytes(RL) + (size_t)max_chunks(cap, nops_max) * chunk_bytes(RL);
 }
 
 // one tile of blockDim cells (cell = pattern*RL + cat) of one locus; static per batch

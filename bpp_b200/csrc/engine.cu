@@ -965,6 +965,13 @@ extern "C" double bppgpu_batch_timer_stop_ms(bppgpu_batch * b)
   return ms;
 }
 
+// tip-slot capacity of a 4-state batch's launches: any op list over a T-tip tree that visits a node at most once has
+// at most T tip or HBM-resident children; lists that need more simply take more chunks (the blocks are sized for it)
+static unsigned s4_lut_cap_rt(const bppgpu_batch * b)
+{
+  return std::min<unsigned>((unsigned)lut_cap((int)b->RL), std::max(4u, (b->max_tips + 3u) & ~3u));
+}
+
 // Copy the slice of the staged step that belongs to loci [i0, i1) to the device on stream cs.
 static void batch_issue_copies(bppgpu_batch * b, unsigned i0, unsigned i1, cudaStream_t cs)
 {
@@ -1062,7 +1069,7 @@ static int batch_stage(bppgpu_batch * b, const unsigned int * mcounts, const uns
       mo += mcounts ? mcounts[i] : 0;
       oo += oc;
       // one spare op per locus for a root that the list does not produce (CTL_EVAL_ONLY)
-      bo += b->kernel_kind == 2 ? align_up(block20_bytes(b->RL, oc + 1), 256) : block_bytes(b->RL, oc + 1);
+      bo += b->kernel_kind == 2 ? align_up(block20_bytes(b->RL, oc + 1), 256) : block_bytes(b->RL, oc + 1, s4_lut_cap_rt(b));
       moff[i + 1] = mo; ooff[i + 1] = oo; boff[i + 1] = bo;
     }
     b->have_m = mcounts != nullptr; b->have_o = ocounts != nullptr;
@@ -1397,7 +1404,7 @@ static int batch_run(bppgpu_batch * b, bool do_mats, bool do_tree, bool want_roo
     if (b->kernel_kind == 0)
     {
       // tip-slot capacity: any op list over a T-tip tree has at most T tip or HBM-resident children
-      lut_cap_rt = std::min<unsigned>((unsigned)lut_cap((int)b->RL), std::max(4u, (maxT + 3u) & ~3u));
+      lut_cap_rt = s4_lut_cap_rt(b);
       const int w = slots;
       switch (b->RL * 10 + b->cpt)
       {

@@ -38,6 +38,8 @@ __global__ void plan_kernel_flat(const LocusDev * __restrict__ loci, const unsig
     if (idx < T) return ((L.tip_is_dense[idx] ? SRC_TIP_DENSE : SRC_TIP_PACKED) << 28) | idx;
     return (SRC_HBM << 28) | (idx - T);
   };
+  int last_root = -1;                          // the last op that writes the root CLV carries CTL_ROOT
+  for (unsigned int k = 0; k < n; ++k) if (want_root && o[k].parent == rootc) last_root = (int)k;
   for (unsigned int k = 0; k < n; ++k)
   {
     const RawOp r = o[k];
@@ -45,7 +47,7 @@ __global__ void plan_kernel_flat(const LocusDev * __restrict__ loci, const unsig
     q.dst = r.parent - T; q.lpm = r.lpm; q.rpm = r.rpm; q.dsc = r.psc; q.lsc = r.lsc; q.rsc = r.rsc;
     q.ctl = 0; q.root_sc = -1; q.pad[0] = q.pad[1] = 0;
     q.lsrc = classify(r.left); q.rsrc = classify(r.right);
-    if (want_root && r.parent == rootc) { q.ctl |= CTL_ROOT; q.root_sc = r.psc; root_done = true; }
+    if ((int)k == last_root) { q.ctl |= CTL_ROOT; q.root_sc = r.psc; root_done = true; }
     p[k] = q;
   }
   unsigned int cnt = n;
@@ -257,7 +259,11 @@ plan_small_parallel(const LocusDev & L, const RawOp * o, unsigned int n, unsigne
     }
   }
   __syncwarp();
-  const bool root_done = __ballot_sync(FULL, act && want_root && r.parent == rootc) != 0;
+  // the root's site log-likelihoods are summed where the root CLV is produced: by the LAST op that writes it (a list
+  // may visit a node more than once; locus_root_loglikelihood evaluates the root once)
+  const unsigned int rootmask = __ballot_sync(FULL, act && want_root && r.parent == rootc);
+  const bool root_done = rootmask != 0;
+  const bool is_root_op = act && want_root && r.parent == rootc && (lane == 31u || (rootmask >> (lane + 1u)) == 0u);
   if (act)
   {
     int ia = prev_child == 0 ? 1 : 0;
@@ -271,7 +277,7 @@ plan_small_parallel(const LocusDev & L, const RawOp * o, unsigned int n, unsigne
     q.park_off = 0; q.up_pm = 0;
     if (r.psc >= 0) q.ctl |= OP_SCALE;
     if (prev_child >= 0) q.ctl |= OP_BPREV;
-    if (want_root && r.parent == rootc) q.ctl |= OP_ROOT;
+    if (is_root_op) q.ctl |= OP_ROOT;
     if (s_push[lane]) { q.ctl |= OP_PUSH; q.up_pm = s_push[lane] - 1; }
     if (myslot >= 0) { q.ctl |= OP_PARKA; q.park_off = (unsigned)myslot * slot_unit; }
     rec[mychunk * TREE_CHUNK + myidx] = q;
@@ -318,6 +324,12 @@ plan_small_parallel(const LocusDev & L, const RawOp * o, unsigned int n, unsigne
       h->nops = c_nops; h->ntips = c_ntips; h->pad0 = h->pad1 = 0;
     }
     ++c_idx;
+  }
+  else if (c_idx == 0 && lane == 0)
+  {
+    // an empty list: the tree kernel still stages chunk 0 of every locus it has tiles of, so its header must say "nothing"
+    ChunkHdr * h = reinterpret_cast<ChunkHdr *>(blk + chunks0);
+    h->nops = 0; h->ntips = 0; h->pad0 = h->pad1 = 0;
   }
   __syncwarp();
   SmallPlanOut out;
@@ -510,6 +522,8 @@ plan_kernel_blocks(const LocusDev * __restrict__ loci, const unsigned int * __re
       ++c_idx; c_nops = 0; c_ntips = 0;
     };
     const unsigned int cells_per_buf = L.sites * RL;
+    int last_root = -1;                        // the last op that writes the root CLV carries OP_ROOT
+    for (unsigned int kk = 0; kk < n; ++kk) if (want_root && o[small ? (unsigned int)order[kk] : kk].parent == rootc) last_root = (int)kk;
     for (unsigned int kk = 0; kk < n; ++kk)
     {
       const RawOp r = o[small ? (unsigned int)order[kk] : kk];
@@ -592,7 +606,7 @@ plan_kernel_blocks(const LocusDev * __restrict__ loci, const unsigned int * __re
       q.b_sel = B.sel; q.b_off = B.off; q.b_p0 = B.p0; q.b_pm = B.pm; q.b_sc = B.sc;
       if (r.psc >= 0) q.ctl |= OP_SCALE;
       if (prev_child >= 0) q.ctl |= OP_BPREV;
-      if (want_root && r.parent == rootc) { q.ctl |= OP_ROOT; root_done = true; }
+      if ((int)kk == last_root) { q.ctl |= OP_ROOT; root_done = true; }
       const unsigned int rix = c_idx * TREE_CHUNK + c_nops;
       *rec_at(rix) = q;
       ++c_nops;
@@ -622,6 +636,11 @@ plan_kernel_blocks(const LocusDev * __restrict__ loci, const unsigned int * __re
     }
     if (c_nops) close_chunk();
     n_chunks = c_idx;
+    if (c_idx == 0)
+    {
+      ChunkHdr * h = reinterpret_cast<ChunkHdr *>(blk + chunks0);       // empty list, see plan_small_parallel
+      h->nops = 0; h->ntips = 0; h->pad0 = h->pad1 = 0;
+    }
     LocusHdr * H = reinterpret_cast<LocusHdr *>(blk);
     H->clv = L.clv; H->tip_dense = L.tip_dense; H->scale = L.scale;
     H->tipwords = reinterpret_cast<const unsigned int *>(L.tip_codes); H->pmat = L.pmat;

@@ -136,6 +136,8 @@ plan_kernel_blocks20(const LocusDev * __restrict__ loci, const unsigned int * __
     unsigned int prev = 0xFFFFFFFFu, prev_k = 0;
     bool root_done = false;
     const unsigned int cells_per_buf = L.sites * RL;
+    int last_root = -1;                        // the last op that writes the root CLV carries OP_ROOT
+    for (unsigned int k = 0; k < n; ++k) if (want_root && o[reorder ? ord[k] : k].parent == rootc) last_root = (int)k;
     for (unsigned int k = 0; k < n; ++k)       // k = position in the evaluation order = index of the OpRec20
     {
       RawOp r = o[reorder ? ord[k] : k];
@@ -196,7 +198,7 @@ plan_kernel_blocks20(const LocusDev * __restrict__ loci, const unsigned int * __
       q.b_p0 = p0[ib]; q.b_pm = pm[ib]; q.b_sc = sc[ib]; q.b_ext = ext[ib];
       if (r.psc >= 0) q.ctl |= OP_SCALE;
       if (prev_child >= 0) q.ctl |= OP_BPREV;
-      if (want_root && r.parent == rootc) { q.ctl |= OP_ROOT; root_done = true; }
+      if ((int)k == last_root) { q.ctl |= OP_ROOT; root_done = true; }
       recs[k] = q;
       prev = r.parent - T; prev_k = k;
     }

@@ -662,3 +662,19 @@ def test_partial_update_long_root_path_multi_chunk(eng, rate_cats, scaling):
     assert longest == T - 1
     assert rel_err(got, refs) <= LNL_RTOL, (got, refs, longest)
     _free(loci, batch)
+
+
+@pytest.mark.parametrize("repeat", [2, 4, 6])
+def test_op_list_longer_than_the_tree(eng, repeat):
+    """locus_update_partials accepts any node list; one that visits every inner node several times has more tip
+    children than lookup-table slots and more ops than a chunk, so it takes many chunks (the blocks are sized
+    from the launch's slot capacity).  Recomputing a node is idempotent: same lnL as the plain pass."""
+    w = synth.make_workload("long", n_loci=7, tips=8, sites=200, states=4, rate_cats=1, model="JC69", seed=66)
+    loci, trees, batch = _load(eng, w)
+    mc, mi, mb, oc, ops, rc, rs = trees.full_pass_step()
+    plain, _ = batch.full_pass((mc, mi, mb, oc, ops, rc, rs))
+    ooff = np.concatenate([[0], np.cumsum(oc)]).astype(np.int64)
+    rep = np.concatenate([np.tile(ops[ooff[i]:ooff[i + 1]], repeat) for i in range(w.n_loci)])
+    again, _ = batch.full_pass((mc, mi, mb, oc * repeat, rep, rc, rs))
+    assert np.array_equal(plain, again)
+    _free(loci, batch)
