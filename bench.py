@@ -366,12 +366,12 @@ def main():
 # (profiles/), filled in after each profiling pass; None = not captured for that config yet.
 # Bytes per launch at the config's full size, scaling off.
 NCU_TRAFFIC = {
-    "config2": 2.180250e9 + 0.131610e9,      # tree_kernel_s4<1,exact,2>
+    "config2": 2.180698e9 + 0.131435e9,      # tree_kernel_s4<1,exact,2>
     "config3": 19.141006e9 + 0.325830e9,     # tree_kernel_s4<4,exact,4>
     "config4": 4.476720e9 + 0.430410e9,      # tree_kernel_s20c<4>
 }
 NCU_TRAFFIC_SOURCE = {
-    "config2": "profiles/r1_tree_v9_config2_ncu_summary.txt",
+    "config2": "profiles/r1_tree_v10_config2_ncu_summary.txt",
     "config3": "profiles/r1_tree_final_config3_ncu_summary.txt",
     "config4": "profiles/r1_s20c_v1_config4_ncu_summary.txt",
 }
