@@ -122,7 +122,7 @@ struct bppgpu_engine
   size_t loci_cap = 0;
   std::vector<bppgpu_locus *> loci;      // by id (nullptr = free)
   std::vector<unsigned int> free_ids;
-  unsigned long long launches = 0;
+  std::atomic<unsigned long long> launches{0};   // kernels launched (host threads on disjoint batches count concurrently)
   std::atomic<unsigned long long> dirty_epoch{1};   // bumped whenever a locus' host mirrors change
   int sm_count = 148;
   size_t smem_optin = 0, smem_per_sm = 0;
@@ -523,7 +523,7 @@ extern "C" int bppgpu_engine_device(const bppgpu_engine * e) { return e->device;
 extern "C" void bppgpu_engine_set_math(bppgpu_engine * e, unsigned int m) { e->math = m & 1u; }
 extern "C" void bppgpu_engine_synchronize(bppgpu_engine * e) { cudaSetDevice(e->device); CUDA_CHECK(cudaDeviceSynchronize()); }
 extern "C" void * bppgpu_engine_stream(bppgpu_engine * e) { return (void *)e->stream; }
-extern "C" unsigned long long bppgpu_engine_launch_count(const bppgpu_engine * e) { return e->launches; }
+extern "C" unsigned long long bppgpu_engine_launch_count(const bppgpu_engine * e) { return e->launches.load(); }
 extern "C" unsigned long long bppgpu_engine_bytes_allocated(const bppgpu_engine * e) { return e->arena.total; }
 extern "C" void bppgpu_engine_set_profiling(bppgpu_engine * e, int on) { drain_profile(e); e->profiling = on != 0; }
 extern "C" void bppgpu_engine_reset_profile(bppgpu_engine * e)
