@@ -125,14 +125,17 @@ int  bppgpu_set_tip_states(bppgpu_locus * l, unsigned int tip_index, const unsig
 /* replaces pll_set_tip_clv (locus.c:596): `states` doubles per site (padding ignored: states_padded==states) */
 int  bppgpu_set_tip_clv(bppgpu_locus * l, unsigned int tip_index, const double * clv, int padding);
 /* replaces pll_set_pattern_weights, pll_set_frequencies (:889), pll_set_subst_params (:877),
-   pll_set_category_rates */
+   pll_set_category_rates.  The model setters only record the new values; the next call that needs them ships
+   the changed model blocks of all its loci in one transfer. */
 void bppgpu_set_pattern_weights(bppgpu_locus * l, const unsigned int * pattern_weights);
 void bppgpu_set_frequencies(bppgpu_locus * l, unsigned int freqs_index, const double * frequencies);
 void bppgpu_set_subst_params(bppgpu_locus * l, unsigned int params_index, const double * params);
 void bppgpu_set_category_rates(bppgpu_locus * l, const double * rates);
 void bppgpu_set_category_weights(bppgpu_locus * l, const double * rate_weights);   /* default 1/R, locus.c:845 */
 /* optional: hand over a decomposition computed by the host's own pll_update_eigen
-   (core_pmatrix.c:239); otherwise the engine decomposes lazily like locus.c:2462-2476 */
+   (core_pmatrix.c:239); otherwise the engine decomposes lazily like locus.c:2462-2476 -- on the device, in one
+   kernel for all loci of a batch whose Q changed (create_ratematrix + cyclic Jacobi), on the host for single loci.
+   bppgpu_get_eigen returns the decomposition in use (fetched from the device if it was computed there). */
 void bppgpu_set_eigen(bppgpu_locus * l, unsigned int params_index,
                       const double * eigenvecs, const double * inv_eigenvecs, const double * eigenvals);
 void bppgpu_get_eigen(bppgpu_locus * l, unsigned int params_index,
