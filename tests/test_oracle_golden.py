@@ -177,3 +177,25 @@ def test_oracle_on_frogs_real_data():
         assert abs(lnl - float(d[p + "logl"])) <= 1e-12 * abs(lnl)
         total += lnl
     assert abs(total - (-7320.932289)) < 5e-6
+
+
+@pytest.mark.parametrize("model", ["K80", "F81", "HKY", "TN93", "F84"])
+def test_closed_form_pmatrix_properties(model):
+    """Size-independent properties of the closed-form matrices (locus.c:1981-2324) as restated in the oracle: rows
+    sum to 1, P(0) = I, Chapman-Kolmogorov P(s)P(t) = P(s+t), and detailed balance pi_i P_ij = pi_j P_ji."""
+    rng = np.random.default_rng(3)
+    f = rng.uniform(0.5, 1.5, 4)
+    f /= f.sum()
+    if model == "K80":
+        f = np.full(4, 0.25)
+    q = rng.uniform(0.5, 4.0, 6)
+    rates = np.array([0.3, 1.0, 2.2])
+    P0 = F.pmatrix_closed(model, 0.0, rates, f, q)
+    assert np.allclose(P0, np.eye(4)[None], atol=1e-15)
+    s, t = 0.037, 0.21
+    Ps, Pt, Pst = (F.pmatrix_closed(model, x, rates, f, q) for x in (s, t, s + t))
+    for r in range(len(rates)):
+        assert np.allclose(Pt[r].sum(axis=1), 1.0, atol=1e-14)
+        assert np.allclose(Ps[r] @ Pt[r], Pst[r], atol=1e-14)
+        assert np.allclose(f[:, None] * Pt[r], (f[:, None] * Pt[r]).T, atol=1e-15)
+        assert (Pt[r] > 0).all()
