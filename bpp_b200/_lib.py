@@ -22,11 +22,14 @@ SYMBOLS = [
     "bppgpu_update_matrices", "bppgpu_update_partials", "bppgpu_root_loglikelihood",
     "bppgpu_root_likelihood_vector", "bppgpu_set_diploid", "bppgpu_root_loglikelihood_diploid",
     "bppgpu_get_clv", "bppgpu_get_pmatrix", "bppgpu_set_pmatrix", "bppgpu_get_scaler",
-    "bppgpu_batch_create", "bppgpu_batch_destroy", "bppgpu_batch_size",
+    "bppgpu_batch_create", "bppgpu_batch_destroy", "bppgpu_batch_size", "bppgpu_batch_kernel_name",
     "bppgpu_batch_update_matrices", "bppgpu_batch_update_partials", "bppgpu_batch_root_loglikelihood",
     "bppgpu_batch_full_pass", "bppgpu_batch_stage", "bppgpu_batch_run", "bppgpu_batch_set_waves", "bppgpu_batch_collect",
     "bppgpu_batch_lnl_sum_dev", "bppgpu_batch_stream", "bppgpu_batch_timer_start",
     "bppgpu_batch_timer_stop_ms", "bppgpu_batch_synchronize",
+    "bppgpu_comm_nccl_version", "bppgpu_comm_get_unique_id", "bppgpu_comm_init_rank", "bppgpu_comm_init_all",
+    "bppgpu_comm_destroy", "bppgpu_comm_nranks", "bppgpu_comm_rank", "bppgpu_comm_calls",
+    "bppgpu_allreduce_sum", "bppgpu_allreduce_sum_all", "bppgpu_batch_allreduce_lnl_sum",
 ]
 
 
@@ -101,6 +104,7 @@ def load():
         "bppgpu_batch_create": (vp, [vp, u, C.POINTER(vp)]),
         "bppgpu_batch_destroy": (None, [vp]),
         "bppgpu_batch_size": (u, [vp]),
+        "bppgpu_batch_kernel_name": (C.c_char_p, [vp]),
         "bppgpu_batch_update_matrices": (i, [vp, up, up, dp]),
         "bppgpu_batch_update_partials": (i, [vp, up, opp]),
         "bppgpu_batch_root_loglikelihood": (i, [vp, up, ip, dp]),
@@ -114,6 +118,17 @@ def load():
         "bppgpu_batch_timer_start": (None, [vp]),
         "bppgpu_batch_timer_stop_ms": (d, [vp]),
         "bppgpu_batch_synchronize": (None, [vp]),
+        "bppgpu_comm_nccl_version": (i, []),
+        "bppgpu_comm_get_unique_id": (i, [vp]),
+        "bppgpu_comm_init_rank": (vp, [vp, i, i, vp]),
+        "bppgpu_comm_init_all": (i, [C.POINTER(vp), i, C.POINTER(vp)]),
+        "bppgpu_comm_destroy": (None, [vp]),
+        "bppgpu_comm_nranks": (i, [vp]),
+        "bppgpu_comm_rank": (i, [vp]),
+        "bppgpu_comm_calls": (ull, [vp]),
+        "bppgpu_allreduce_sum": (i, [vp, dp, i]),
+        "bppgpu_allreduce_sum_all": (i, [C.POINTER(vp), i, C.POINTER(dp), i]),
+        "bppgpu_batch_allreduce_lnl_sum": (i, [vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

@@ -221,6 +221,7 @@ struct bppgpu_batch
   bool staged_mats = false, staged_ops = false, staged_roots = false;
   cudaEvent_t t0 = nullptr, t1 = nullptr;
   unsigned long long synced_epoch = 0; // engine dirty_epoch at the last batch_sync_loci
+  unsigned long long diploid_epoch = 0; bool any_diploid = false;   // a locus of the batch carries a diploid mapping
   // batched model sync: pinned blob + device copy, record offsets, ids, eigen modes, Jacobi scratch
   char * h_model = nullptr, * d_model = nullptr; size_t model_cap = 0;
   double * d_eig_scratch = nullptr; size_t eig_scratch_cap = 0;
@@ -781,6 +782,7 @@ extern "C" int bppgpu_set_diploid(bppgpu_locus * l, unsigned int unphased, const
   if (!mp.empty()) CUDA_CHECK(cudaMemcpy(l->dev.dip_map, mp.data(), mp.size() * 8, cudaMemcpyHostToDevice));
   l->dev.unphased = unphased;
   engine_publish_locus(e, l);
+  e->dirty_epoch++;
   return BPPGPU_SUCCESS;
 }
 
@@ -948,6 +950,17 @@ extern "C" void bppgpu_batch_destroy(bppgpu_batch * b)
 }
 
 extern "C" unsigned int bppgpu_batch_size(const bppgpu_batch * b) { return b->n; }
+// name of the tree kernel instantiation this batch launches (bench.py ties its roofline and the committed ncu
+// capture to it)
+extern "C" const char * bppgpu_batch_kernel_name(bppgpu_batch * b)
+{
+  static thread_local char buf[96];
+  const bool exact = b->e->math == BPPGPU_MATH_EXACT;
+  if (b->kernel_kind == 0) snprintf(buf, sizeof(buf), "tree_kernel_s4<%u,%s,%u>", b->RL, exact ? "true" : "false", b->cpt);
+  else if (b->kernel_kind == 2) snprintf(buf, sizeof(buf), b->s20_cat ? "tree_kernel_s20c<%u>" : "tree_kernel_s20<%u>", b->RL);
+  else snprintf(buf, sizeof(buf), "tree_kernel_generic<%s>", exact ? "true" : "false");
+  return buf;
+}
 extern "C" void bppgpu_batch_set_waves(bppgpu_batch * b, unsigned int waves)
 {
   b->wave_pref = waves > BPPGPU_MAX_WAVES ? BPPGPU_MAX_WAVES : waves;
@@ -1542,6 +1555,22 @@ static int batch_run(bppgpu_batch * b, bool do_mats, bool do_tree, bool want_roo
     }
     CUDA_CHECK(cudaGetLastError());
   }
+  if (want_root && !persite)
+  {
+    // loci with a diploid mapping: their root is the phase-resolution mean (locus.c:2586-2615)
+    if (b->diploid_epoch != e->dirty_epoch.load())
+    {
+      b->any_diploid = false;
+      for (auto * l : b->loci) b->any_diploid = b->any_diploid || l->dev.dip_off != nullptr;
+      b->diploid_epoch = e->dirty_epoch.load();
+    }
+    if (b->any_diploid)
+    {
+      ProfScope ps(e, b->stream, BPPGPU_KERNEL_FINISH);
+      diploid_batch_kernel<<<n, 256, 0, b->stream>>>(e->d_loci, b->d_batch_locus, d_root_clv, b->d_tile_first, b->d_tile_partial);
+      CUDA_CHECK(cudaGetLastError());
+    }
+  }
   if (want_root)
   {
     ProfScope ps(e, b->stream, BPPGPU_KERNEL_FINISH);
@@ -1750,3 +1779,6 @@ extern "C" int bppgpu_get_scaler(bppgpu_locus * l, unsigned int idx, unsigned in
   CUDA_CHECK(cudaMemcpy(out, l->dev.scale + (size_t)idx * l->sites, (size_t)l->sites * 4, cudaMemcpyDeviceToHost));
   return BPPGPU_SUCCESS;
 }
+
+// ------------------------------------------------------------------------------------ collective (NCCL)
+#include "comm.cuh"

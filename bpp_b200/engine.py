@@ -141,6 +141,69 @@ class Engine:
         return {k: {"ms": ms[i], "launches": int(cnt[i])} for i, k in enumerate(KERNELS)}
 
 
+class Comm:
+    """The path's one exchange step: an NCCL sum over ranks (threads.c:544-558, 583-590).
+
+    One process per GPU: rank 0 calls Comm.unique_id(), the host ships the 128 bytes to every rank
+    (bench.py: torch.distributed broadcast), every rank builds Comm(engine, nranks, rank, id).
+    One process with several engines: Comm.init_all(engines)."""
+
+    def __init__(self, engine, nranks, rank, uid, _handle=None):
+        self.L, self.e = engine.L, engine
+        if _handle is None:
+            buf = (C.c_char * 128).from_buffer_copy(bytes(uid))
+            _handle = self.L.bppgpu_comm_init_rank(engine.h, nranks, rank, C.cast(buf, C.c_void_p))
+            _lib.check()
+        if not _handle:
+            raise BppGpuError("comm init failed")
+        self.h, self.nranks, self.rank = _handle, nranks, rank
+
+    @staticmethod
+    def unique_id():
+        L = _lib.load()
+        buf = (C.c_char * 128)()
+        L.bppgpu_comm_get_unique_id(C.cast(buf, C.c_void_p))
+        _lib.check()
+        return bytes(buf)
+
+    @classmethod
+    def init_all(cls, engines):
+        L = _lib.load()
+        n = len(engines)
+        arr = (C.c_void_p * n)(*[e.h for e in engines])
+        out = (C.c_void_p * n)()
+        L.bppgpu_comm_init_all(arr, n, out)
+        _lib.check()
+        return [cls(e, n, i, None, _handle=out[i]) for i, e in enumerate(engines)]
+
+    def allreduce_sum(self, values):
+        a = _f64(values).copy()
+        self.L.bppgpu_allreduce_sum(self.h, _dp(a), a.size)
+        _lib.check()
+        return a
+
+    @staticmethod
+    def allreduce_sum_all(comms, values):
+        """One host thread driving all engines: values[i] belongs to comms[i]."""
+        L = comms[0].L
+        arrs = [_f64(v).copy() for v in values]
+        n = len(comms)
+        ch = (C.c_void_p * n)(*[c.h for c in comms])
+        vp = (C.POINTER(C.c_double) * n)(*[_dp(a) for a in arrs])
+        L.bppgpu_allreduce_sum_all(ch, n, vp, arrs[0].size)
+        _lib.check()
+        return arrs
+
+    @property
+    def calls(self):
+        return int(self.L.bppgpu_comm_calls(self.h))
+
+    def destroy(self):
+        if getattr(self, "h", None):
+            self.L.bppgpu_comm_destroy(self.h)
+            self.h = None
+
+
 class Locus:
     """Device mirror of locus_t.  `locus_create` arguments as in locus.c:622."""
 
@@ -391,11 +454,20 @@ class Batch:
         self.L.bppgpu_batch_synchronize(self.h)
         _lib.check()
 
+    def allreduce_lnl_sum(self, comm):
+        """NCCL sum of the batch's lnL sum over ranks, on the batch stream behind run()."""
+        self.L.bppgpu_batch_allreduce_lnl_sum(self.h, comm.h)
+        _lib.check()
+
     def timer_start(self):
         self.L.bppgpu_batch_timer_start(self.h)
 
     def timer_stop_ms(self):
         return self.L.bppgpu_batch_timer_stop_ms(self.h)
+
+    @property
+    def kernel_name(self):
+        return self.L.bppgpu_batch_kernel_name(self.h).decode()
 
     @property
     def lnl_sum_dev(self):

@@ -1,0 +1,512 @@
+/* locus_cuda.c -- bpp v4.8.7 itself on the B200 engine, with ZERO edits to the reference's sources.
+ *
+ * The reference has no plugin interface; its seam is the set of C functions of src/bpp.h:2032-2090
+ * (implemented in src/locus.c).  This file defines functions with exactly those names and signatures:
+ *
+ *     locus_update_matrices      locus.c:2417        locus_update_partials     locus.c:2530
+ *     locus_update_all_partials  locus.c:2523        locus_root_loglikelihood  locus.c:2573
+ *     locus_destroy              locus.c:872         prop_mixing_update_gtrees prop_mixing.c:52
+ *
+ * Linked into an executable in front of the reference built as a shared library (the recipe that compiles the reference, see INTEGRATION.md, builds
+ * libbppref.so from the unmodified sources with -fPIC, so every call to these functions -- including the ones made
+ * from inside locus.c -- goes through the PLT), ELF symbol interposition makes every caller of the seam
+ * (method.c:4285-4297, prop_mixing.c:117-131, gtree.c, stree.c, prop_gamma.c, prop_rj.c, locus.c's own
+ * propose_qrates / propose_freqs ...) land here.  With BPP_B200=1 in the environment the work is forwarded to the
+ * engine through the C-ABI (include/bpp_b200.h); otherwise to the reference's own functions (dlsym RTLD_NEXT), so
+ * the same binary is stock bpp.  INTEGRATION.md shows the equivalent source hooks (an arch bit next to
+ * PLL_ATTRIB_ARCH_AVX2) a maintainer would add instead of interposition.
+ *
+ * What lives where:
+ *   - locus_t stays the reference's struct, created by the reference's locus_create.  Its host CLV / scaler
+ *     buffers are simply never written on the CUDA path (the host never reads inner CLVs).
+ *   - per locus_t a bppgpu_locus handle is created lazily at the first call; tips come from the tip CLVs the
+ *     reference has already filled (pll_set_tip_states -> locus->clv[tip], 0/1 doubles: the engine packs them),
+ *     pattern weights / diploid mapping from the struct.
+ *   - model parameters (frequencies, qrates, category rates, eigen-decomposition) are compared with a cached copy
+ *     at every locus_update_matrices and re-sent when they changed: the proposals write them straight into the
+ *     struct (locus.c:2703-3354), not through setters.
+ *   - branch lengths: the reference's own locus_update_matrices is called first.  It writes node->length for every
+ *     node of the traversal (strict clock core_pmatrix.c:711-715, relaxed clocks locus.c:1105-1193) and runs
+ *     pll_update_eigen when needed; the engine then gets (pmatrix_index, length) and builds the matrices on the
+ *     device.  (The host-side P-matrices the call also fills are unused.)
+ *   - gnode_t index flips (SWAP_CLV_INDEX ...) stay host integers; every call passes them.
+ *   - prop_mixing_update_gtrees: the reference's loop body is kept (it is called as is), but while it runs the seam
+ *     only RECORDS each locus' triplet and returns lnL = 0; afterwards all loci of the call go to the device as one
+ *     batch (one upload, one planner + tree kernel + finish launch, one read-back) and gt->logl / lnacceptance get
+ *     their lnL added.  BPP_B200_BATCH=0 turns that off.
+ */
+#define _GNU_SOURCE
+#include <dlfcn.h>
+#include <pthread.h>
+#include <stdint.h>
+
+#include "bpp.h"        /* the reference's own header (compile with -I<reference>/src) */
+#include "bpp_b200.h"
+
+/* ------------------------------------------------------------------ the reference's own implementations */
+typedef void   (*fn_update_matrices)(locus_t *, gtree_t *, gnode_t **, stree_t *, long, unsigned int);
+typedef void   (*fn_update_partials)(locus_t *, gnode_t **, unsigned int);
+typedef void   (*fn_update_all_partials)(locus_t *, gtree_t *);
+typedef double (*fn_root_loglikelihood)(locus_t *, gnode_t *, const unsigned int *, double *);
+typedef void   (*fn_locus_destroy)(locus_t *);
+typedef void   (*fn_mixing)(locus_t **, gtree_t **, stree_t *, long, long, double, long, double *);
+
+static fn_update_matrices     real_update_matrices;
+static fn_update_partials     real_update_partials;
+static fn_update_all_partials real_update_all_partials;
+static fn_root_loglikelihood  real_root_loglikelihood;
+static fn_locus_destroy       real_locus_destroy;
+static fn_mixing              real_mixing;
+
+static int g_enabled = -1, g_batching = 1, g_verbose = 0;
+static bppgpu_engine * g_engine;
+static pthread_mutex_t g_mu = PTHREAD_MUTEX_INITIALIZER;
+static pthread_once_t g_once = PTHREAD_ONCE_INIT;
+
+/* statistics, printed at exit with BPP_B200_VERBOSE=1 */
+static unsigned long long n_mat_calls, n_part_calls, n_root_calls, n_batches, n_batch_loci;
+
+static void * next_sym(const char * name)
+{
+  void * p = dlsym(RTLD_NEXT, name);
+  if (!p) fatal("locus_cuda: the reference's %s was not found (link libbppref.so behind this file)", name);
+  return p;
+}
+
+static void report(void)
+{
+  if (g_verbose && g_enabled == 1)
+    fprintf(stderr, "[bpp_b200] %s: update_matrices %llu, update_partials %llu, root_loglikelihood %llu calls; "
+                    "%llu batched passes over %llu loci; %llu kernels launched\n", bppgpu_version(), n_mat_calls,
+            n_part_calls, n_root_calls, n_batches, n_batch_loci, g_engine ? bppgpu_engine_launch_count(g_engine) : 0ULL);
+}
+
+static void init_once(void)
+{
+  const char * ev = getenv("BPP_B200");
+  real_update_matrices = (fn_update_matrices)next_sym("locus_update_matrices");
+  real_update_partials = (fn_update_partials)next_sym("locus_update_partials");
+  real_update_all_partials = (fn_update_all_partials)next_sym("locus_update_all_partials");
+  real_root_loglikelihood = (fn_root_loglikelihood)next_sym("locus_root_loglikelihood");
+  real_locus_destroy = (fn_locus_destroy)next_sym("locus_destroy");
+  real_mixing = (fn_mixing)next_sym("prop_mixing_update_gtrees");
+  g_enabled = ev && atoi(ev) != 0;
+  if ((ev = getenv("BPP_B200_BATCH"))) g_batching = atoi(ev) != 0;
+  if ((ev = getenv("BPP_B200_VERBOSE"))) g_verbose = atoi(ev);
+  if (g_enabled)
+  {
+    int dev = (ev = getenv("BPP_B200_DEVICE")) ? atoi(ev) : 0;
+    unsigned int math = ((ev = getenv("BPP_B200_MATH")) && !strcmp(ev, "fma")) ? BPPGPU_MATH_FMA : BPPGPU_MATH_EXACT;
+    g_engine = bppgpu_engine_create(dev, math);      /* no device -> the engine's fatal(): there is no CPU fallback */
+    if (!g_engine) fatal("locus_cuda: cannot create the engine: %s", bppgpu_last_error());
+    atexit(report);
+  }
+}
+
+static int enabled(void)
+{
+  pthread_once(&g_once, init_once);
+  return g_enabled;
+}
+
+/* ------------------------------------------------------------------ per-locus state, keyed by the locus_t pointer */
+typedef struct
+{
+  locus_t * key;
+  bppgpu_locus * h;
+  int diploid_sent;
+  double * model;              /* cached copy: freqs S, qrates S(S-1)/2, rates R, rate weights R, V, V^-1, lambda */
+  int eigen_sent;
+  /* scratch for one call */
+  unsigned int cap;
+  bppgpu_partial_op * ops;
+  unsigned int * idx;
+  double * bl;
+  /* slot of this locus in the deferred batch that is being recorded (-1: none) */
+  long slot;
+} lstate_t;
+
+#define TABLE_BITS 16
+static lstate_t * g_table[1u << TABLE_BITS];
+static pthread_rwlock_t g_table_lock = PTHREAD_RWLOCK_INITIALIZER;
+
+static unsigned int hash_ptr(const void * p)
+{
+  uint64_t x = (uint64_t)(uintptr_t)p;
+  x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 29;
+  return (unsigned int)x & ((1u << TABLE_BITS) - 1);
+}
+
+static lstate_t * table_find(locus_t * l)
+{
+  unsigned int i = hash_ptr(l);
+  lstate_t * s;
+  pthread_rwlock_rdlock(&g_table_lock);
+  while ((s = g_table[i]) && s->key != l) i = (i + 1) & ((1u << TABLE_BITS) - 1);
+  pthread_rwlock_unlock(&g_table_lock);
+  return s;
+}
+
+static void ensure_cap(lstate_t * s, unsigned int count)
+{
+  if (count <= s->cap) return;
+  s->cap = count + 8;
+  s->ops = (bppgpu_partial_op *)xrealloc(s->ops, s->cap * sizeof(bppgpu_partial_op));
+  s->idx = (unsigned int *)xrealloc(s->idx, s->cap * sizeof(unsigned int));
+  s->bl = (double *)xrealloc(s->bl, s->cap * sizeof(double));
+}
+
+static size_t model_doubles(const locus_t * l)
+{
+  const size_t S = l->states, R = l->rate_cats;
+  return S + S * (S - 1) / 2 + 2 * R + 2 * S * S + S;
+}
+
+/* create the device mirror of a locus at its first use: same arguments as the reference's locus_create call
+   (method.c:4137-4147), tips from the tip CLVs the reference has filled, weights, diploid mapping */
+static lstate_t * state_of(locus_t * l)
+{
+  lstate_t * s = table_find(l);
+  unsigned int i, t;
+  if (s) return s;
+  if (l->states_padded != l->states)
+    fatal("locus_cuda: states_padded (%u) != states (%u) is not supported", l->states_padded, l->states);
+  if (l->rate_matrices != 1) fatal("locus_cuda: rate_matrices must be 1");
+  s = (lstate_t *)xcalloc(1, sizeof(lstate_t));
+  s->key = l; s->slot = -1;
+  s->h = bppgpu_locus_create(g_engine, l->dtype, l->model, l->tips, l->clv_buffers, l->states, l->sites,
+                             l->rate_matrices, l->prob_matrices, l->rate_cats, l->scale_buffers,
+                             l->attributes | BPPGPU_ATTRIB_ARCH_CUDA);
+  if (!s->h) fatal("locus_cuda: bppgpu_locus_create failed: %s", bppgpu_last_error());
+  {
+    /* locus->clv[tip] is [site][cat][state] with every category a copy of the first (locus.c:540-555) */
+    const size_t S = l->states, R = l->rate_cats, P = l->sites;
+    double * tip = (double *)xmalloc(P * S * sizeof(double));
+    for (t = 0; t < l->tips; ++t)
+    {
+      for (i = 0; i < P; ++i) memcpy(tip + i * S, l->clv[t] + i * R * S, S * sizeof(double));
+      if (!bppgpu_set_tip_clv(s->h, t, tip, 0)) fatal("locus_cuda: bppgpu_set_tip_clv failed: %s", bppgpu_last_error());
+    }
+    free(tip);
+  }
+  if (!l->diploid) bppgpu_set_pattern_weights(s->h, l->pattern_weights);
+  s->model = (double *)xcalloc(model_doubles(l), sizeof(double));
+  s->model[0] = -1;            /* no valid frequency vector starts with -1: forces the first sync */
+  ensure_cap(s, 2 * l->tips);
+  pthread_rwlock_wrlock(&g_table_lock);
+  i = hash_ptr(l);
+  while (g_table[i]) i = (i + 1) & ((1u << TABLE_BITS) - 1);
+  g_table[i] = s;
+  pthread_rwlock_unlock(&g_table_lock);
+  return s;
+}
+
+/* re-send what the proposals changed in the struct since the last call */
+static void sync_model(lstate_t * s, locus_t * l)
+{
+  const size_t S = l->states, R = l->rate_cats, NP = S * (S - 1) / 2;
+  double * c_freqs = s->model, * c_subst = c_freqs + S, * c_rates = c_subst + NP, * c_rw = c_rates + R,
+         * c_ev = c_rw + R, * c_iev = c_ev + S * S, * c_lam = c_iev + S * S;
+  const int eigen_model = !(l->dtype == BPP_DATA_DNA && l->model != BPP_DNA_MODEL_GTR);
+  int params_changed = 0;
+  if (memcmp(c_freqs, l->frequencies[0], S * sizeof(double)))
+  {
+    memcpy(c_freqs, l->frequencies[0], S * sizeof(double));
+    bppgpu_set_frequencies(s->h, 0, c_freqs);
+    params_changed = 1;
+  }
+  if (l->subst_params && l->subst_params[0] && memcmp(c_subst, l->subst_params[0], NP * sizeof(double)))
+  {
+    memcpy(c_subst, l->subst_params[0], NP * sizeof(double));
+    bppgpu_set_subst_params(s->h, 0, c_subst);
+    params_changed = 1;
+  }
+  if (memcmp(c_rates, l->rates, R * sizeof(double)))
+  {
+    memcpy(c_rates, l->rates, R * sizeof(double));
+    bppgpu_set_category_rates(s->h, c_rates);
+  }
+  if (memcmp(c_rw, l->rate_weights, R * sizeof(double)))
+  {
+    memcpy(c_rw, l->rate_weights, R * sizeof(double));
+    bppgpu_set_category_weights(s->h, c_rw);
+  }
+  /* the reference's own pll_update_eigen result (locus_update_matrices has just made it valid): handing it over
+     keeps the P-matrices on the reference's decomposition instead of the engine's Jacobi one */
+  if (eigen_model && l->eigen_decomp_valid[0] &&
+      (params_changed || !s->eigen_sent || memcmp(c_lam, l->eigenvals[0], S * sizeof(double)) ||
+       memcmp(c_ev, l->eigenvecs[0], S * S * sizeof(double))))
+  {
+    memcpy(c_ev, l->eigenvecs[0], S * S * sizeof(double));
+    memcpy(c_iev, l->inv_eigenvecs[0], S * S * sizeof(double));
+    memcpy(c_lam, l->eigenvals[0], S * sizeof(double));
+    bppgpu_set_eigen(s->h, 0, c_ev, c_iev, c_lam);
+    s->eigen_sent = 1;
+  }
+}
+
+static void sync_diploid(lstate_t * s, locus_t * l)
+{
+  long i;
+  unsigned long maplen = 0;
+  if (!l->diploid || s->diploid_sent) return;
+  for (i = 0; i < l->unphased_length; ++i) maplen += l->diploid_resolution_count[i];
+  /* for diploid loci pattern_weights holds the weights of the UNPHASED sites (method.c:4172-4193) */
+  if (!bppgpu_set_diploid(s->h, (unsigned int)l->unphased_length, l->diploid_resolution_count, l->diploid_mapping,
+                          maplen, l->pattern_weights))
+    fatal("locus_cuda: bppgpu_set_diploid failed: %s", bppgpu_last_error());
+  s->diploid_sent = 1;
+}
+
+static unsigned int fill_ops(gnode_t ** trav, unsigned int count, bppgpu_partial_op * ops)
+{
+  unsigned int i;
+  for (i = 0; i < count; ++i)        /* locus.c:2541-2570 */
+  {
+    gnode_t * node = trav[i], * lnode = node->left, * rnode = node->right;
+    ops[i].parent_clv_index = node->clv_index;
+    ops[i].left_clv_index = lnode->clv_index;
+    ops[i].right_clv_index = rnode->clv_index;
+    ops[i].left_pmatrix_index = lnode->pmatrix_index;
+    ops[i].right_pmatrix_index = rnode->pmatrix_index;
+    ops[i].parent_scaler_index = node->scaler_index;
+    ops[i].left_scaler_index = lnode->scaler_index;
+    ops[i].right_scaler_index = rnode->scaler_index;
+  }
+  return count;
+}
+
+/* ------------------------------------------------------------------ deferred batch (one per host thread) */
+typedef struct
+{
+  int active;
+  long first, count;                     /* loci [first, first+count) of the caller's array */
+  locus_t ** loci;
+  bppgpu_batch * batch;                  /* cached: same loci as last time */
+  locus_t ** batch_key; long batch_n;
+  /* step arrays, pinned */
+  unsigned int * mcounts, * ocounts, * midx, * rclv; int * rsc; double * mbl; bppgpu_partial_op * ops;
+  double * lnl;
+  size_t cap_loci, cap_mats, cap_ops, n_mats, n_ops;
+  long next_slot;
+  int overflow;                          /* a locus was touched out of order / twice: finish this call unbatched */
+} defer_t;
+
+static __thread defer_t tl_defer;
+
+static void defer_reserve(defer_t * d, size_t loci, size_t mats, size_t ops)
+{
+  if (loci > d->cap_loci)
+  {
+    bppgpu_host_free(d->mcounts); bppgpu_host_free(d->ocounts); bppgpu_host_free(d->rclv); bppgpu_host_free(d->rsc);
+    free(d->lnl);
+    d->cap_loci = loci;
+    d->mcounts = (unsigned int *)bppgpu_host_alloc(loci * sizeof(unsigned int));
+    d->ocounts = (unsigned int *)bppgpu_host_alloc(loci * sizeof(unsigned int));
+    d->rclv = (unsigned int *)bppgpu_host_alloc(loci * sizeof(unsigned int));
+    d->rsc = (int *)bppgpu_host_alloc(loci * sizeof(int));
+    d->lnl = (double *)xmalloc(loci * sizeof(double));
+  }
+  if (mats > d->cap_mats)
+  {
+    unsigned int * ni = (unsigned int *)bppgpu_host_alloc(2 * mats * sizeof(unsigned int));
+    double * nb = (double *)bppgpu_host_alloc(2 * mats * sizeof(double));
+    if (d->n_mats) { memcpy(ni, d->midx, d->n_mats * sizeof(unsigned int)); memcpy(nb, d->mbl, d->n_mats * sizeof(double)); }
+    bppgpu_host_free(d->midx); bppgpu_host_free(d->mbl);
+    d->midx = ni; d->mbl = nb; d->cap_mats = 2 * mats;
+  }
+  if (ops > d->cap_ops)
+  {
+    bppgpu_partial_op * no = (bppgpu_partial_op *)bppgpu_host_alloc(2 * ops * sizeof(bppgpu_partial_op));
+    if (d->n_ops) memcpy(no, d->ops, d->n_ops * sizeof(bppgpu_partial_op));
+    bppgpu_host_free(d->ops);
+    d->ops = no; d->cap_ops = 2 * ops;
+  }
+}
+
+/* ------------------------------------------------------------------ the seam */
+void locus_update_matrices(locus_t * locus, gtree_t * gtree, gnode_t ** traversal, stree_t * stree, long msa_index,
+                           unsigned int count)
+{
+  unsigned int i;
+  lstate_t * s;
+  defer_t * d = &tl_defer;
+  if (!enabled()) { real_update_matrices(locus, gtree, traversal, stree, msa_index, count); return; }
+  if (!opt_usedata) return;
+  /* the reference: node->length for every node (any clock), pll_update_eigen if Q changed */
+  real_update_matrices(locus, gtree, traversal, stree, msa_index, count);
+  s = state_of(locus);
+  sync_model(s, locus);
+  __atomic_add_fetch(&n_mat_calls, 1, __ATOMIC_RELAXED);
+  if (d->active && !d->overflow && s->slot == d->next_slot && d->mcounts[s->slot] == 0)
+  {
+    defer_reserve(d, 0, d->n_mats + count, 0);
+    for (i = 0; i < count; ++i) { d->midx[d->n_mats + i] = traversal[i]->pmatrix_index; d->mbl[d->n_mats + i] = traversal[i]->length; }
+    d->mcounts[s->slot] = count; d->n_mats += count;
+    return;
+  }
+  if (d->active) d->overflow = 1;
+  ensure_cap(s, count);
+  for (i = 0; i < count; ++i) { s->idx[i] = traversal[i]->pmatrix_index; s->bl[i] = traversal[i]->length; }
+  if (!bppgpu_update_matrices(s->h, count, s->idx, s->bl)) fatal("bppgpu_update_matrices: %s", bppgpu_last_error());
+}
+
+void locus_update_partials(locus_t * locus, gnode_t ** traversal, unsigned int count)
+{
+  lstate_t * s;
+  defer_t * d = &tl_defer;
+  if (!enabled()) { real_update_partials(locus, traversal, count); return; }
+  if (!opt_usedata) return;
+  s = state_of(locus);
+  __atomic_add_fetch(&n_part_calls, 1, __ATOMIC_RELAXED);
+  if (d->active && !d->overflow && s->slot == d->next_slot && d->ocounts[s->slot] == 0)
+  {
+    defer_reserve(d, 0, 0, d->n_ops + count);
+    fill_ops(traversal, count, d->ops + d->n_ops);
+    d->ocounts[s->slot] = count; d->n_ops += count;
+    return;
+  }
+  if (d->active) d->overflow = 1;
+  ensure_cap(s, count);
+  fill_ops(traversal, count, s->ops);
+  if (!bppgpu_update_partials(s->h, count, s->ops)) fatal("bppgpu_update_partials: %s", bppgpu_last_error());
+}
+
+static void all_partials_rec(gnode_t * node, gnode_t ** out, unsigned int * n)
+{
+  if (!node->left) return;
+  all_partials_rec(node->left, out, n);
+  all_partials_rec(node->right, out, n);
+  out[(*n)++] = node;
+}
+
+void locus_update_all_partials(locus_t * locus, gtree_t * gtree)
+{
+  gnode_t ** trav;
+  unsigned int n = 0;
+  if (!enabled()) { real_update_all_partials(locus, gtree); return; }
+  if (!opt_usedata) return;
+  trav = (gnode_t **)xmalloc((gtree->tip_count + gtree->inner_count) * sizeof(gnode_t *));
+  all_partials_rec(gtree->root, trav, &n);        /* locus.c:2482-2521: left, right, node */
+  locus_update_partials(locus, trav, n);
+  free(trav);
+}
+
+double locus_root_loglikelihood(locus_t * locus, gnode_t * root, const unsigned int * freqs_indices, double * persite_lnl)
+{
+  lstate_t * s;
+  defer_t * d = &tl_defer;
+  double logl;
+  if (!enabled()) return real_root_loglikelihood(locus, root, freqs_indices, persite_lnl);
+  if (!opt_usedata) return 0;
+  s = state_of(locus);
+  sync_diploid(s, locus);
+  __atomic_add_fetch(&n_root_calls, 1, __ATOMIC_RELAXED);
+  if (d->active && !d->overflow && s->slot == d->next_slot && !persite_lnl)
+  {
+    d->rclv[s->slot] = root->clv_index; d->rsc[s->slot] = root->scaler_index;
+    d->next_slot++;
+    return 0.0;                                   /* the batch adds the real value afterwards */
+  }
+  if (d->active) d->overflow = 1;
+  if (locus->diploid) logl = bppgpu_root_loglikelihood_diploid(s->h, root->clv_index);     /* locus.c:2586-2615 */
+  else logl = bppgpu_root_loglikelihood(s->h, root->clv_index, root->scaler_index, persite_lnl);
+  return opt_bfbeta * logl;                       /* locus.c:2630 */
+}
+
+void locus_destroy(locus_t * locus)
+{
+  if (enabled())
+  {
+    lstate_t * s;
+    unsigned int i = hash_ptr(locus);
+    pthread_rwlock_wrlock(&g_table_lock);
+    while ((s = g_table[i]) && s->key != locus) i = (i + 1) & ((1u << TABLE_BITS) - 1);
+    if (s) s->key = (locus_t *)(uintptr_t)1;      /* tombstone: keeps the probe chains intact */
+    pthread_rwlock_unlock(&g_table_lock);
+    if (s)
+    {
+      pthread_mutex_lock(&g_mu);
+      if (tl_defer.batch) { bppgpu_batch_destroy(tl_defer.batch); tl_defer.batch = NULL; tl_defer.batch_n = 0; }
+      pthread_mutex_unlock(&g_mu);
+      bppgpu_locus_destroy(s->h);
+      free(s->model); free(s->ops); free(s->idx); free(s->bl);
+      s->h = NULL;
+    }
+  }
+  else pthread_once(&g_once, init_once);
+  real_locus_destroy(locus);
+}
+
+/* ------------------------------------------------------------------ batched mixing move (prop_mixing.c:52-220) */
+void prop_mixing_update_gtrees(locus_t ** locus, gtree_t ** gtree, stree_t * stree, long locus_start, long locus_count,
+                               double c, long thread_index, double * ret_lnacceptance)
+{
+  defer_t * d = &tl_defer;
+  long i;
+  int same;
+  double sum = 0;
+  if (!enabled() || !g_batching || !opt_usedata || locus_count < 2 || d->active)
+  {
+    pthread_once(&g_once, init_once);
+    real_mixing(locus, gtree, stree, locus_start, locus_count, c, thread_index, ret_lnacceptance);
+    return;
+  }
+  /* the batch of these loci (cached while the caller keeps asking for the same range) */
+  same = d->batch && d->batch_n == locus_count;
+  for (i = 0; same && i < locus_count; ++i) same = d->batch_key[i] == locus[locus_start + i];
+  if (!same)
+  {
+    bppgpu_locus ** hs = (bppgpu_locus **)xmalloc(locus_count * sizeof(bppgpu_locus *));
+    int uniform = 1;
+    if (d->batch) bppgpu_batch_destroy(d->batch);
+    d->batch = NULL;
+    free(d->batch_key);
+    d->batch_key = (locus_t **)xmalloc(locus_count * sizeof(locus_t *));
+    for (i = 0; i < locus_count; ++i)
+    {
+      locus_t * l = locus[locus_start + i];
+      d->batch_key[i] = l;
+      hs[i] = state_of(l)->h;
+      uniform = uniform && l->states == locus[locus_start]->states && l->rate_cats == locus[locus_start]->rate_cats;
+    }
+    d->batch_n = locus_count;
+    if (uniform) d->batch = bppgpu_batch_create(g_engine, (unsigned int)locus_count, hs);
+    free(hs);
+    if (!d->batch)       /* mixed data types: a batch needs one (states, rate_cats) shape */
+    {
+      d->batch_n = 0;
+      real_mixing(locus, gtree, stree, locus_start, locus_count, c, thread_index, ret_lnacceptance);
+      return;
+    }
+  }
+  defer_reserve(d, (size_t)locus_count, 0, 0);
+  for (i = 0; i < locus_count; ++i)
+  {
+    lstate_t * s = state_of(locus[locus_start + i]);
+    s->slot = i;
+    d->mcounts[i] = d->ocounts[i] = 0;
+  }
+  d->n_mats = d->n_ops = 0; d->next_slot = 0; d->overflow = 0;
+  d->first = locus_start; d->count = locus_count;
+  d->active = 1;
+  /* the reference's own loop: times, index flips, priors; the seam calls above only record */
+  real_mixing(locus, gtree, stree, locus_start, locus_count, c, thread_index, ret_lnacceptance);
+  d->active = 0;
+  for (i = 0; i < locus_count; ++i) state_of(locus[locus_start + i])->slot = -1;
+  if (d->overflow || d->next_slot != locus_count)
+    fatal("locus_cuda: prop_mixing_update_gtrees did not issue one update_matrices / update_partials / "
+          "root_loglikelihood triplet per locus in order (run with BPP_B200_BATCH=0)");
+  if (!bppgpu_batch_full_pass(d->batch, d->mcounts, d->midx, d->mbl, d->ocounts, d->ops, d->rclv, d->rsc, d->lnl, NULL))
+    fatal("bppgpu_batch_full_pass: %s", bppgpu_last_error());
+  __atomic_add_fetch(&n_batches, 1, __ATOMIC_RELAXED);
+  __atomic_add_fetch(&n_batch_loci, (unsigned long long)locus_count, __ATOMIC_RELAXED);
+  /* the loop ran with logl = 0: gt->logl = 0 and lnacceptance lacks the sum of the new log-likelihoods */
+  for (i = 0; i < locus_count; ++i)
+  {
+    const double logl = opt_bfbeta * d->lnl[i];
+    gtree[locus_start + i]->logl = logl;
+    sum += logl;
+  }
+  *ret_lnacceptance += sum;
+}

@@ -179,6 +179,7 @@ int  bppgpu_get_scaler(bppgpu_locus * l, unsigned int scaler_index, unsigned int
 bppgpu_batch * bppgpu_batch_create(bppgpu_engine * e, unsigned int n_loci, bppgpu_locus * const * loci);
 void bppgpu_batch_destroy(bppgpu_batch * b);
 unsigned int bppgpu_batch_size(const bppgpu_batch * b);
+const char * bppgpu_batch_kernel_name(bppgpu_batch * b);      /* tree kernel instantiation the batch launches */
 
 int  bppgpu_batch_update_matrices(bppgpu_batch * b, const unsigned int * counts,
                                   const unsigned int * pmatrix_indices, const double * branch_lengths);
@@ -217,6 +218,32 @@ void * bppgpu_batch_stream(bppgpu_batch * b);
 void   bppgpu_batch_timer_start(bppgpu_batch * b);
 double bppgpu_batch_timer_stop_ms(bppgpu_batch * b);          /* synchronizes the stream */
 void   bppgpu_batch_synchronize(bppgpu_batch * b);
+
+/* ------------------------------------------------------------------ multi-GPU: the path's one exchange step
+ * Loci are sharded over GPUs; after a batched move the reference adds per-thread partial results on the main
+ * thread (threads.c:583-590 mixing: lnacceptance; threads.c:544-558 tau: logl_diff, logpr_diff, count_above,
+ * count_below).  Over GPUs that is one NCCL all-reduce(sum) of <= 4 doubles.  libnccl.so.2 is loaded with
+ * dlopen at the first call (override with $BPPGPU_NCCL_LIB); without it these calls fail through the fatal
+ * handler. */
+typedef struct bppgpu_comm bppgpu_comm;       /* one per (engine, communicator) */
+#define BPPGPU_COMM_ID_BYTES 128
+int  bppgpu_comm_nccl_version(void);
+/* one process per GPU: rank 0 makes the id, the host ships its 128 bytes to every rank, all call init_rank */
+int  bppgpu_comm_get_unique_id(void * id128);
+bppgpu_comm * bppgpu_comm_init_rank(bppgpu_engine * e, int nranks, int rank, const void * id128);
+/* one process, n engines on n devices (BPP's pthreads over loci ranges, threads.c:234-263) */
+int  bppgpu_comm_init_all(bppgpu_engine * const * engines, int n, bppgpu_comm ** comms_out);
+void bppgpu_comm_destroy(bppgpu_comm * c);
+int  bppgpu_comm_nranks(const bppgpu_comm * c);
+int  bppgpu_comm_rank(const bppgpu_comm * c);
+unsigned long long bppgpu_comm_calls(const bppgpu_comm * c);       /* all-reduces issued so far */
+/* v[0..n) <- sum over ranks (host doubles, in place, n <= 256); every rank / every engine's thread calls it */
+int  bppgpu_allreduce_sum(bppgpu_comm * c, double * v, int n);
+/* the same when ONE host thread drives all engines of the process: v[i] belongs to comms[i] */
+int  bppgpu_allreduce_sum_all(bppgpu_comm * const * comms, int ncomms, double * const * v, int n);
+/* device-side: all-reduce the batch's lnL sum in place on the batch stream behind bppgpu_batch_run (no host
+   round trip); bppgpu_batch_collect then returns the global sum in lnl_sum_out */
+int  bppgpu_batch_allreduce_lnl_sum(bppgpu_batch * b, bppgpu_comm * c);
 
 #ifdef __cplusplus
 }

@@ -27,11 +27,19 @@ def test_reference_arm_line():
     assert line["impl"] == "reference" and line["higher_is_better"] is True and line["vs_baseline"] is None
     assert line["metric"] == "locus_lnL_evals_per_sec_full_tree" and line["unit"] == "locus-lnL evals/s"
     assert line["value"] > 0 and line["dtype"] == "f64" and line["data"] == "synthetic"
-    assert line["config"]["workload"].startswith("config2") and line["config"]["reference_sample_loci"] == 48
+    assert line["config"]["workload"].startswith("config3") and line["config"]["reference_sample_loci"] == 48
     cb = line["cpu_baseline"]
     assert cb["kind"] == "reference" and cb["cores"] >= 1 and cb["value"] == line["value"] and "sample" in cb
     e2e = line["e2e"]
     assert e2e["value"] == line["value"] and e2e["h2d_bytes_per_step"] == 0 and e2e["d2h_bytes_per_step"] == 0
+
+
+def test_reference_arm_uses_the_config5_shard_shape_on_several_gpus():
+    r = _run({"RANK": "0", "WORLD_SIZE": "8", "LOCAL_RANK": "0"})
+    assert r.returncode == 0, r.stderr
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["config"]["workload"].startswith("config5") and line["config"]["patterns"] == 2000
+    assert line["n_gpus"] == 8
 
 
 def test_reference_arm_other_ranks_are_silent():

@@ -337,6 +337,51 @@ def test_frogs_real_data_diploid(eng):
     assert abs(total - (-7320.932289)) < 5e-6
 
 
+def test_frogs_diploid_loci_in_one_batch(eng):
+    """The same 5 diploid loci as ONE batch (the callers' `for each locus` loop as a single launch): the batch's
+    root evaluation must apply the phase-resolution mean (locus.c:2586-2615) to every locus that carries a diploid
+    mapping -- diploid_batch_kernel between the tree kernel and finish_kernel."""
+    from bpp_b200 import engine
+    from helpers import frogs_fixture
+    d = frogs_fixture()
+    loci, mc, mi, mb, oc, opl, rc, want = [], [], [], [], [], [], [], []
+    for k in range(int(d["n_loci"])):
+        p = "l%d_" % k
+        T, P, S, R = [int(x) for x in d[p + "dims"][:4]]
+        l = engine.Locus.create_like_bpp(eng, T, P, S, R, False, engine.DNA_MODEL_JC69)
+        for t in range(T):
+            l.set_tip_clv(t, ((d[p + "tip_masks"][t][:, None] >> np.arange(4)) & 1).astype(np.float64))
+        l.set_frequencies(d[p + "freqs"])
+        l.set_category_rates(d[p + "rates"])
+        l.set_diploid(d[p + "resolution_count"], d[p + "mapping"], d[p + "weights"])
+        nodes, tl = d[p + "nodes"], d[p + "time_length"]
+        by_idx = {int(r[0]): (r, t) for r, t in zip(nodes, tl)}
+        edges = [i for i in by_idx if by_idx[i][0][3] >= 0]
+        mc.append(len(edges))
+        mi += [int(by_idx[i][0][6]) for i in edges]
+        mb += [by_idx[i][1][1] for i in edges]
+        inner = [int(r[0]) for r in nodes if r[1] >= 0][::-1]
+        ops = np.zeros(len(inner), dtype=engine.OP_DTYPE)
+        for j, i in enumerate(inner):
+            r = by_idx[i][0]
+            a, b = by_idx[int(r[1])][0], by_idx[int(r[2])][0]
+            ops[j] = (r[4], a[4], b[4], a[6], b[6], -1, -1, -1)
+        oc.append(len(inner))
+        opl.append(ops)
+        rc.append(int(nodes[0][4]))
+        want.append(float(d[p + "logl"]))
+        loci.append(l)
+    batch = engine.Batch(eng, loci)
+    step = (np.array(mc), np.array(mi), np.array(mb), np.array(oc), np.concatenate(opl), np.array(rc),
+            np.full(len(loci), -1))
+    lnl, total = batch.full_pass(step)
+    assert rel_err(lnl, np.array(want)) <= LNL_RTOL
+    assert abs(total - (-7320.932289)) < 5e-6
+    # and the split form: root-only evaluation of resident CLVs
+    assert np.array_equal(batch.root_loglikelihood(np.array(rc)), lnl)
+    _free(loci, batch)
+
+
 def test_pinned_step_inputs_give_identical_results(eng):
     """Step arrays kept in pinned memory (bppgpu_host_alloc) go to the device without the staging
     copy; the result must be bit-identical to the pageable path."""
