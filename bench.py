@@ -322,29 +322,50 @@ def measure(name, n_loci, args, rank, world, local_rank, D, steps, warmup, cpu_s
     ms_step = D.reduce(ms_total, "max") / steps
     value = world * w.n_loci / (ms_step / 1000.0)
 
-    # ---- e2e: public C-ABI calls with host buffers, H2D + kernels + D2H per step, wall clock.  The step's host
-    #      inputs live in pinned host memory, as a caller that wants throughput keeps them
+    # ---- e2e: public C-ABI calls with host buffers, H2D + kernels + D2H per step, wall clock.
+    #      A step is a whole-tree proposal (the mixing move): the lists are resident, the host flips the indices on
+    #      the device (bppgpu_batch_flip_indices) and sends what changed -- the branch lengths, from pinned memory
     pstep, holders = engine.pin_step(step)
-    for _ in range(3):
+    n = w.n_loci
+    n_mat, n_op = int(step[0].sum()), int(step[3].sum())
+    out_buf = np.zeros(w.n_loci)
+    out_sum = 0.0
+    batch.stage(pstep)
+    batch.run()
+    for _ in range(4):                      # both index parities planned and cached
+        batch.flip_indices()
+        batch.set_branch_lengths(pstep[2])
+        batch.run()
+    batch.collect(out_buf)
+    D.barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        batch.flip_indices()
+        batch.set_branch_lengths(pstep[2])
+        batch.run()
+        allreduce()
+        out_lnl, out_sum = batch.collect(out_buf)
+    D.barrier()
+    e2e_s = D.reduce(time.perf_counter() - t0, "max")
+    e2e_value = world * w.n_loci * steps / e2e_s
+    h2d = n_mat * 8
+    d2h = (n + 1) * 8
+    if steps % 2 == 1:
+        batch.flip_indices()
+    # ---- the same with every array of the step staged again (new traversals every step: nothing cached)
+    for _ in range(2):
         batch.full_pass(pstep)
     D.barrier()
     t0 = time.perf_counter()
     prep = batch.prepare(pstep)
-    out_buf = np.zeros(w.n_loci)
-    out_sum = 0.0
     for _ in range(steps):
         batch.stage(prep)
         batch.run()
         allreduce()
         out_lnl, out_sum = batch.collect(out_buf)
     D.barrier()
-    e2e_s = D.reduce(time.perf_counter() - t0, "max")
+    e2e_restage_s = D.reduce(time.perf_counter() - t0, "max")
     t_region1 = time.perf_counter()
-    e2e_value = world * w.n_loci * steps / e2e_s
-    n = w.n_loci
-    n_mat, n_op = int(step[0].sum()), int(step[3].sum())
-    h2d = n_mat * 12 + n_op * 32 + n * 8          # tables travel only when the counts change
-    d2h = (n + 1) * 8
     for h in holders:
         h.free()
 
@@ -377,10 +398,15 @@ def measure(name, n_loci, args, rank, world, local_rank, D, steps, warmup, cpu_s
            "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                    "ms_per_step": 1000.0 * e2e_s / steps,
-                   "what": "bppgpu_batch_stage+run+collect with host arrays in pinned memory: branch lengths, "
-                           "P-matrix indices, pruning ops and root indices go H2D every step, n+1 doubles come "
-                           "back; tip states are device-resident like the reference's tip CLVs (set once at "
-                           "locus creation)"},
+                   "what": "one mixing-move step through the public calls: bppgpu_batch_flip_indices (device-side "
+                           "SWAP_* of every node) + bppgpu_batch_set_branch_lengths (pinned host array, H2D) + "
+                           "bppgpu_batch_run + all-reduce + bppgpu_batch_collect (n+1 doubles D2H); op lists and "
+                           "tip states are device-resident",
+                   "restage": {"value": world * w.n_loci * steps / e2e_restage_s,
+                               "ms_per_step": 1000.0 * e2e_restage_s / steps,
+                               "h2d_bytes_per_step": n_mat * 12 + n_op * 32 + n * 8,
+                               "what": "bppgpu_batch_stage+run+collect: every array of the step (branch lengths, "
+                                       "P-matrix indices, pruning ops, roots) uploaded and planned again each step"}},
            "gpu_launches": int(launches), "dataset_passes_per_sec": 1000.0 / ms_step, "setup_seconds": t_setup,
            "lnl_sum_check": float(out_sum), "hbm_bytes_allocated": eng.bytes_allocated,
            "clocks": sampler.summary(t_region0, t_region1)}

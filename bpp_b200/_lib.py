@@ -25,6 +25,7 @@ SYMBOLS = [
     "bppgpu_batch_create", "bppgpu_batch_destroy", "bppgpu_batch_size", "bppgpu_batch_kernel_name",
     "bppgpu_batch_update_matrices", "bppgpu_batch_update_partials", "bppgpu_batch_root_loglikelihood",
     "bppgpu_batch_full_pass", "bppgpu_batch_stage", "bppgpu_batch_run", "bppgpu_batch_set_waves", "bppgpu_batch_collect",
+    "bppgpu_batch_wait_inputs", "bppgpu_batch_flip_indices", "bppgpu_batch_set_branch_lengths",
     "bppgpu_batch_lnl_sum_dev", "bppgpu_batch_stream", "bppgpu_batch_timer_start",
     "bppgpu_batch_timer_stop_ms", "bppgpu_batch_synchronize",
     "bppgpu_comm_nccl_version", "bppgpu_comm_get_unique_id", "bppgpu_comm_init_rank", "bppgpu_comm_init_all",
@@ -113,6 +114,9 @@ def load():
         "bppgpu_batch_run": (i, [vp]),
         "bppgpu_batch_set_waves": (None, [vp, u]),
         "bppgpu_batch_collect": (i, [vp, dp, dp]),
+        "bppgpu_batch_wait_inputs": (i, [vp]),
+        "bppgpu_batch_flip_indices": (i, [vp]),
+        "bppgpu_batch_set_branch_lengths": (i, [vp, dp]),
         "bppgpu_batch_lnl_sum_dev": (vp, [vp]),
         "bppgpu_batch_stream": (vp, [vp]),
         "bppgpu_batch_timer_start": (None, [vp]),

@@ -125,7 +125,8 @@ static_assert(sizeof(OpRec) == 64, "OpRec must be 64 bytes");
 
 enum : unsigned { HDR_FAST = 1u,     // every op of the locus uses fast operands only (any number of chunks)
                   HDR_SIMPLE = 2u,   // ... and none is HBM-class or scaled: the lean instantiation of tile_fast
-                  HDR_NOHBM = 4u };  // ... and none is HBM-class (scaling allowed): full passes with scale buffers
+                  HDR_NOHBM = 4u,    // ... and none is HBM-class (scaling allowed): full passes with scale buffers
+                  HDR_LANEPLAN = 8u };  // planned lane-parallel: HBM-resident children own a staged P-matrix slot
 
 struct LocusHdr
 {
@@ -170,7 +171,7 @@ struct TileDesc
   unsigned int cell0;              // first cell of the tile
   unsigned int tip_words;
   unsigned int ncell;              // sites * RL
-};                                 // a tile covers TREE_NT * CPT cells: thread tid owns cells cell0 + tid + j*TREE_NT
+};                                 // a tile covers TREE_NT * CPT cells: thread tid owns cells cell0 + perm(tid) + j*TREE_NT
 static_assert(sizeof(TileDesc) == 32, "TileDesc must be 32 bytes");
 
 struct TreeParams

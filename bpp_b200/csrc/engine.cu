@@ -202,7 +202,14 @@ struct bppgpu_batch
   char * d_in = nullptr; size_t d_in_cap = 0;
   char * h_in = nullptr; size_t h_in_cap = 0;       // pinned
   PlanOp * d_plan = nullptr; size_t plan_cap = 0;   // generic kernel: flat plan
-  unsigned char * d_blocks = nullptr; size_t blocks_cap = 0;   // 4-state kernel: staged per-locus blocks
+  unsigned char * d_blocks = nullptr; size_t blocks_cap = 0;   // 4-state kernel: staged per-locus blocks (current parity)
+  // plan cache: the planned blocks of the staged op lists are kept for BOTH index parities (the lists as staged
+  // and after bppgpu_batch_flip_indices); a run whose blocks are still valid only refreshes the P-matrices
+  unsigned char * d_blocks_par[2] = {nullptr, nullptr};
+  int parity = 0;
+  bool plan_valid[2] = {false, false};
+  unsigned int plan_key[2] = {0, 0};     // want_root / slots / tip-slot capacity the cached plan was made for
+  cudaEvent_t ev_inputs = nullptr;       // recorded behind the last H2D copy of the step's host arrays
   TileDesc * d_tiles = nullptr;
   unsigned long long * d_tile_blk = nullptr;        // per tile: {block offset, 0}, written by the planner
   unsigned int * d_plan_count = nullptr;
@@ -219,6 +226,7 @@ struct bppgpu_batch
   double * d_rootdot = nullptr;        // ... its per (category, site) root dot products
   unsigned long long * d_site_off = nullptr;
   bool staged_mats = false, staged_ops = false, staged_roots = false;
+  bool all_in_blob = false; size_t blob_bytes = 0;   // the staged step lives entirely in h_in (device layout): one H2D copy
   cudaEvent_t t0 = nullptr, t1 = nullptr;
   unsigned long long synced_epoch = 0; // engine dirty_epoch at the last batch_sync_loci
   unsigned long long diploid_epoch = 0; bool any_diploid = false;   // a locus of the batch carries a diploid mapping
@@ -907,6 +915,7 @@ extern "C" bppgpu_batch * bppgpu_batch_create(bppgpu_engine * e, unsigned int n,
   CUDA_CHECK(cudaMemset(b->d_tile_partial, 0, b->n_tiles * 8));
   CUDA_CHECK(cudaEventCreate(&b->t0));
   CUDA_CHECK(cudaEventCreate(&b->t1));
+  CUDA_CHECK(cudaEventCreateWithFlags(&b->ev_inputs, cudaEventDisableTiming));
   b->h_tile_first = tile_first;
   for (unsigned i = 0; i < n; ++i) b->max_tips = std::max(b->max_tips, loci[i]->tips);
   b->tip_words_rt = std::min<unsigned>((b->max_tips + 7) / 8, (unsigned)S4_MAX_TIP_WORDS);
@@ -933,11 +942,11 @@ extern "C" void bppgpu_batch_destroy(bppgpu_batch * b)
   cudaFree(b->d_scratch_off); cudaFree(b->d_scratch); cudaFree(b->d_plan_count); cudaFree(b->d_tile_partial);
   cudaFree(b->d_lnl); cudaFree(b->d_in); cudaFree(b->d_plan); cudaFree(b->d_persite);
   cudaFree(b->d_rootdot); cudaFree(b->d_site_off);
-  cudaFree(b->d_blocks); cudaFree(b->d_tiles); cudaFree(b->d_tile_blk); cudaFree(b->d_block_sums); cudaFree(b->d_counter);
+  cudaFree(b->d_blocks_par[0]); cudaFree(b->d_blocks_par[1]); cudaFree(b->d_tiles); cudaFree(b->d_tile_blk); cudaFree(b->d_block_sums); cudaFree(b->d_counter);
   cudaFreeHost(b->h_out); cudaFreeHost(b->h_in);
   if (b->h_model) cudaFreeHost(b->h_model);
   cudaFree(b->d_model); cudaFree(b->d_eig_scratch);
-  cudaEventDestroy(b->t0); cudaEventDestroy(b->t1);
+  cudaEventDestroy(b->t0); cudaEventDestroy(b->t1); cudaEventDestroy(b->ev_inputs);
   if (b->copy_stream)
   {
     cudaStreamSynchronize(b->copy_stream); cudaStreamSynchronize(b->alt_stream);
@@ -995,6 +1004,13 @@ static void batch_issue_copies(bppgpu_batch * b, unsigned i0, unsigned i1, cudaS
   {
     if (bytes) CUDA_CHECK(cudaMemcpyAsync(b->d_in + dst, from, bytes, cudaMemcpyHostToDevice, cs));
   };
+  if (b->all_in_blob && i0 == 0 && i1 == b->n)
+  {
+    // every array of the step was staged through the batch's own pinned blob, which has the device blob's layout:
+    // one copy instead of five (what small per-locus steps are made of is launch and copy overhead)
+    put(0, b->h_in, b->blob_bytes);
+    return;
+  }
   if (q.midx)
   {
     const size_t m0 = moff[i0], m1 = moff[i1];
@@ -1046,6 +1062,7 @@ static int batch_stage(bppgpu_batch * b, const unsigned int * mcounts, const uns
     b->o_root_clv = off; off = align_up(off + n * 4, 16);
     b->o_root_sc = off;  off = align_up(off + n * 4, 16);
     b->o_blk_off = off;  off = align_up(off + (size_t)(n + 1) * 8, 16);
+    b->blob_bytes = off;
     if (off > b->h_in_cap)
     {
       CUDA_CHECK(cudaStreamSynchronize(b->stream));
@@ -1091,11 +1108,15 @@ static int batch_stage(bppgpu_batch * b, const unsigned int * mcounts, const uns
     b->tables_tm = tm; b->tables_to = to;
     if (b->kernel_kind != 1 && boff[n] > b->blocks_cap)
     {
-      if (b->d_blocks) cudaFree(b->d_blocks);
+      cudaFree(b->d_blocks_par[0]); cudaFree(b->d_blocks_par[1]);
+      b->d_blocks_par[0] = b->d_blocks_par[1] = nullptr;
       b->blocks_cap = boff[n] + boff[n] / 4;
-      CUDA_CHECK(cudaMalloc(&b->d_blocks, b->blocks_cap));
+      CUDA_CHECK(cudaMalloc(&b->d_blocks_par[0], b->blocks_cap));
     }
   }
+  // new op lists or roots: whatever was planned is void (a matrices-only stage keeps the plan)
+  if (ocounts || rclv || !same) { b->plan_valid[0] = b->plan_valid[1] = false; b->parity = 0; }
+  b->d_blocks = b->d_blocks_par[b->parity];
   // waves: a full pass of a big 4-state batch uploads and runs in slices of loci (balanced by tiles)
   unsigned W = 1;
   if (b->kernel_kind == 0 && b->copy_stream && mcounts && ocounts && rclv)
@@ -1128,13 +1149,6 @@ static int batch_stage(bppgpu_batch * b, const unsigned int * mcounts, const uns
     }
   }
   cudaStream_t cs = W > 1 ? b->copy_stream : b->stream;
-  if (!same)
-  {
-    CUDA_CHECK(cudaMemcpyAsync(b->d_in + b->o_mat_off, b->h_in + b->o_mat_off, (n + 1) * 4, cudaMemcpyHostToDevice, cs));
-    CUDA_CHECK(cudaMemcpyAsync(b->d_in + b->o_op_off, b->h_in + b->o_op_off, (n + 1) * 4, cudaMemcpyHostToDevice, cs));
-    CUDA_CHECK(cudaMemcpyAsync(b->d_in + b->o_blk_off, b->h_in + b->o_blk_off, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, cs));
-    b->tables_on_device = true;
-  }
   // sources: the caller's pinned arrays, or their copy in the pinned blob
   auto is_pinned = [](const void * p) -> bool
   {
@@ -1142,10 +1156,12 @@ static int batch_stage(bppgpu_batch * b, const unsigned int * mcounts, const uns
     if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
     return a.type == cudaMemoryTypeHost;
   };
+  b->all_in_blob = true;
   auto source = [&](size_t dst, const void * src, size_t bytes) -> const void *
   {
     if (!src || !bytes) return nullptr;
-    if (is_pinned(src)) return src;
+    // small arrays are cheaper to memcpy into the blob than to ask the driver what kind of memory they are
+    if (bytes > 4096 && is_pinned(src)) { b->all_in_blob = false; return src; }
     memcpy(b->h_in + dst, src, bytes);
     return b->h_in + dst;
   };
@@ -1161,13 +1177,20 @@ static int batch_stage(bppgpu_batch * b, const unsigned int * mcounts, const uns
     q.rsc = p;
   }
   else q.rsc = (const int *)source(b->o_root_sc, rclv ? rsc : nullptr, (size_t)n * 4);
+  if (!same && !(b->all_in_blob && W == 1))       // (a step that lives entirely in the blob travels as one copy, tables included)
+  {
+    CUDA_CHECK(cudaMemcpyAsync(b->d_in + b->o_mat_off, b->h_in + b->o_mat_off, (n + 1) * 4, cudaMemcpyHostToDevice, cs));
+    CUDA_CHECK(cudaMemcpyAsync(b->d_in + b->o_op_off, b->h_in + b->o_op_off, (n + 1) * 4, cudaMemcpyHostToDevice, cs));
+    CUDA_CHECK(cudaMemcpyAsync(b->d_in + b->o_blk_off, b->h_in + b->o_blk_off, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, cs));
+  }
+  b->tables_on_device = true;
   if (W > 1)
   {
     // copies are issued by batch_run, wave by wave; the tables (if any) are already on their way
     CUDA_CHECK(cudaEventRecord(b->ev_tables, cs));
     b->inputs_pending = true;
   }
-  else batch_issue_copies(b, 0, n, cs);
+  else { batch_issue_copies(b, 0, n, cs); CUDA_CHECK(cudaEventRecord(b->ev_inputs, cs)); }
   b->total_mats = (unsigned)tm; b->total_ops = (unsigned)to;
   b->staged_mats = mcounts != nullptr; b->staged_ops = ocounts != nullptr; b->staged_roots = rclv != nullptr;
   return BPPGPU_SUCCESS;
@@ -1283,6 +1306,8 @@ static void batch_sync_loci(bppgpu_batch * b, bool need_eigen)
         b->d_eig_scratch, (const unsigned long long *)(b->d_model + o_soff));
     CUDA_CHECK(cudaGetLastError());
   }
+  // LocusHdr carries frequencies and flags of the loci, the blocks their rate weights: replan
+  if (b->synced_epoch != e->dirty_epoch.load()) b->plan_valid[0] = b->plan_valid[1] = false;
   b->synced_epoch = e->dirty_epoch.load();
   b->synced_eigen = need_eigen;
 }
@@ -1445,9 +1470,23 @@ static int batch_run(bppgpu_batch * b, bool do_mats, bool do_tree, bool want_roo
   {
     CUDA_CHECK(cudaStreamWaitEvent(b->stream, b->ev_tables, 0));
     batch_issue_copies(b, 0, n, b->stream);
+    CUDA_CHECK(cudaEventRecord(b->ev_inputs, b->stream));
   }
   b->inputs_pending = false;
-  if (!waved)
+  // the planned program depends on the op lists (and on want_root / slots / table capacity) only: if the blocks of
+  // this index parity are still those of the staged lists, rebuild the matrices and copy them into the blocks again
+  const unsigned int pkey = 1u | (want_root ? 2u : 0u) | ((unsigned)slots << 2) | (lut_cap_rt << 8);
+  static const bool plan_cache_on = !(getenv("BPPGPU_PLAN_CACHE") && atoi(getenv("BPPGPU_PLAN_CACHE")) == 0);
+  const bool cached = plan_cache_on && b->kernel_kind == 0 && b->plan_valid[b->parity] && b->plan_key[b->parity] == pkey && !persite;
+  if (!waved && cached)
+  {
+    ProfScope ps(e, b->stream, BPPGPU_KERNEL_PLAN);
+    plan_refresh_blocks<<<(n * 32 + 127) / 128, 128, 0, b->stream>>>(
+        e->d_loci, b->d_batch_locus, n, b->d_blocks, d_blk_off, b->RL, fuse_mats ? d_mat_off : nullptr, d_mat_idx, d_mat_bl);
+    CUDA_CHECK(cudaGetLastError());
+  }
+  if (b->kernel_kind == 0 && !cached) { b->plan_valid[b->parity] = !persite; b->plan_key[b->parity] = pkey; }
+  if (!waved && !cached)
   {
     ProfScope ps(e, b->stream, BPPGPU_KERNEL_PLAN);
     if (b->kernel_kind == 0)
@@ -1488,6 +1527,7 @@ static int batch_run(bppgpu_batch * b, bool do_mats, bool do_tree, bool want_roo
       cudaStream_t st = (w & 1u) ? b->alt_stream : b->stream;
       batch_issue_copies(b, i0, i1, b->copy_stream);
       CUDA_CHECK(cudaEventRecord(b->ev_copy[w], b->copy_stream));
+      if (w + 1 == b->n_waves) CUDA_CHECK(cudaEventRecord(b->ev_inputs, b->copy_stream));
       CUDA_CHECK(cudaStreamWaitEvent(st, b->ev_copy[w], 0));
       {
         ProfScope ps(e, st, BPPGPU_KERNEL_PLAN);
@@ -1630,6 +1670,75 @@ extern "C" int bppgpu_batch_run(bppgpu_batch * b)
 extern "C" int bppgpu_batch_collect(bppgpu_batch * b, double * lnl_out, double * sum_out)
 {
   return batch_collect(b, lnl_out, sum_out);
+}
+
+// blocks until the device has read the host arrays of the last stage / set_branch_lengths (they may be reused then)
+extern "C" int bppgpu_batch_wait_inputs(bppgpu_batch * b)
+{
+  CUDA_CHECK(cudaSetDevice(b->e->device));
+  if (b->inputs_pending) { fatal("bppgpu_batch_wait_inputs: the staged step has not been run yet (its copies are issued by run)"); return BPPGPU_FAILURE; }
+  CUDA_CHECK(cudaEventSynchronize(b->ev_inputs));
+  return BPPGPU_SUCCESS;
+}
+
+// Device-side SWAP_CLV_INDEX / SWAP_SCALER_INDEX / SWAP_PMAT_INDEX of every inner node and edge of the staged step
+// (flip_indices_kernel).  The planned blocks of both parities are kept, so from the third step on a whole-tree
+// proposal costs no planning at all.
+extern "C" int bppgpu_batch_flip_indices(bppgpu_batch * b)
+{
+  bppgpu_engine * e = b->e;
+  CUDA_CHECK(cudaSetDevice(e->device));
+  if (!b->tables_on_device || !(b->staged_ops || b->staged_mats || b->staged_roots))
+  { fatal("bppgpu_batch_flip_indices: no staged step to flip"); return BPPGPU_FAILURE; }
+  for (auto * l : b->loci)
+    if (l->clv_buffers != 2 * (l->tips - 1) || l->prob_matrices != 2 * (2 * l->tips - 2) ||
+        (l->scale_buffers != 0 && l->scale_buffers != 2 * (l->tips - 1)))
+    { fatal("bppgpu_batch_flip_indices: needs BPP's 2x buffer allocation (method.c:4137-4147)"); return BPPGPU_FAILURE; }
+  if (b->inputs_pending)
+  {
+    // staged in waves and never run: bring the whole step to the device first
+    CUDA_CHECK(cudaStreamWaitEvent(b->stream, b->ev_tables, 0));
+    batch_issue_copies(b, 0, b->n, b->stream);
+    CUDA_CHECK(cudaEventRecord(b->ev_inputs, b->stream));
+    b->inputs_pending = false;
+  }
+  e->launches++;
+  flip_indices_kernel<<<(b->n * 32 + 127) / 128, 128, 0, b->stream>>>(
+      e->d_loci, b->d_batch_locus, b->n,
+      b->staged_ops ? (const unsigned int *)(b->d_in + b->o_op_off) : nullptr, (RawOp *)(b->d_in + b->o_ops),
+      b->staged_mats ? (const unsigned int *)(b->d_in + b->o_mat_off) : nullptr, (unsigned int *)(b->d_in + b->o_mat_idx),
+      b->staged_roots ? (unsigned int *)(b->d_in + b->o_root_clv) : nullptr, (int *)(b->d_in + b->o_root_sc));
+  CUDA_CHECK(cudaGetLastError());
+  b->parity ^= 1;
+  if (b->kernel_kind != 1 && !b->d_blocks_par[b->parity]) CUDA_CHECK(cudaMalloc(&b->d_blocks_par[b->parity], b->blocks_cap));
+  b->d_blocks = b->d_blocks_par[b->parity];
+  return BPPGPU_SUCCESS;
+}
+
+// new branch lengths for the staged matrix list (same order and count): the only host data a whole-tree proposal
+// has to send once its lists are on the device
+extern "C" int bppgpu_batch_set_branch_lengths(bppgpu_batch * b, const double * branch_lengths)
+{
+  CUDA_CHECK(cudaSetDevice(b->e->device));
+  if (!b->staged_mats || !b->tables_on_device) { fatal("bppgpu_batch_set_branch_lengths: no staged matrix list"); return BPPGPU_FAILURE; }
+  const size_t bytes = (size_t)b->total_mats * 8;
+  const void * src = branch_lengths;
+  cudaPointerAttributes a;
+  const bool pinned = cudaPointerGetAttributes(&a, src) == cudaSuccess && a.type == cudaMemoryTypeHost;
+  if (!pinned)
+  {
+    cudaGetLastError();
+    CUDA_CHECK(cudaStreamSynchronize(b->stream));           // the blob's previous content may still be in flight
+    memcpy(b->h_in + b->o_mat_bl, branch_lengths, bytes);
+    src = b->h_in + b->o_mat_bl;
+  }
+  if (b->inputs_pending) b->pend.mbl = (const double *)src;        // not uploaded yet: run() copies from here
+  else
+  {
+    CUDA_CHECK(cudaMemcpyAsync(b->d_in + b->o_mat_bl, src, bytes, cudaMemcpyHostToDevice, b->stream));
+    CUDA_CHECK(cudaEventRecord(b->ev_inputs, b->stream));
+  }
+  return BPPGPU_SUCCESS;
 }
 
 extern "C" int bppgpu_batch_full_pass(bppgpu_batch * b, const unsigned int * mc, const unsigned int * mi, const double * mb,

@@ -337,6 +337,56 @@ plan_small_parallel(const LocusDev & L, const RawOp * o, unsigned int n, unsigne
   return out;
 }
 
+// gather: per chunk, per op: Pup (if pushed) and the tipP of its packed tip children (and of HBM-resident children
+// that were given a table slot: lists planned lane-parallel, hbm_slots).  A matrix set is RL*8 double2; `per` lanes
+// copy one set, so a warp moves 32/per sets per step.  The op records are read from shared memory right after
+// planning (srec) or from the block itself (refresh of a cached plan).
+__device__ __forceinline__ void gather_block_matrices(const LocusDev & L, unsigned char * blk, unsigned int chunks0, size_t cb,
+                                                      unsigned int n_chunks, unsigned int RL, unsigned int lut_unit,
+                                                      bool hbm_slots, const OpRec * srec)
+{
+  const unsigned int lane = threadIdx.x & 31u;
+  const unsigned int per = RL * 8;                      // double2 per (op, which) matrix set; RL is a power of two
+  const unsigned int per_sh = 31u - (unsigned)__clz((int)per);
+  const float inv_lut_unit = 1.0f / (float)lut_unit;
+  for (unsigned int c = 0; c < n_chunks; ++c)
+  {
+    unsigned char * ch = blk + chunks0 + (size_t)c * cb;
+    const ChunkHdr hdr = *reinterpret_cast<const ChunkHdr *>(ch);
+    const OpRec * cops = srec ? &srec[c * TREE_CHUNK] : reinterpret_cast<const OpRec *>(ch + sizeof(ChunkHdr));
+    double * Pup = reinterpret_cast<double *>(ch + sizeof(ChunkHdr) + TREE_CHUNK * sizeof(OpRec));
+    double * tipP = Pup + (size_t)TREE_CHUNK * RL * PM_STRIDE;
+    const unsigned int total = hdr.nops * 3 * per;
+    for (unsigned int idx = lane; idx < total; idx += 32)
+    {
+      const unsigned int task = idx >> per_sh, e = idx & (per - 1u);   // e: double2 index within the set
+      const unsigned int k = task / 3, which = task % 3;
+      const OpRec & q = cops[k];
+      if (q.ctl & OP_EVAL) continue;
+      unsigned int pm; double * dst;
+      if (which == 0)
+      {
+        if (!(q.ctl & OP_PUSH)) continue;
+        pm = q.up_pm; dst = Pup + (size_t)k * RL * PM_STRIDE;
+      }
+      else
+      {
+        const unsigned int kind = (q.ctl >> (which == 1 ? OP_AKIND_SHIFT : OP_BKIND_SHIFT)) & 15u;
+        const unsigned int off = which == 1 ? q.a_off : q.b_off;
+        unsigned int slot;
+        if (kind == SRC_TIP_PACKED) slot = (unsigned int)((float)off * inv_lut_unit + 0.5f);   // off = slot * lut_unit, exact
+        else if (kind == SRC_HBM && hbm_slots && off != 0xFFFFFFFFu) slot = off;
+        else continue;
+        pm = which == 1 ? q.a_pm : q.b_pm;
+        dst = tipP + (size_t)slot * RL * PM_STRIDE;
+      }
+      const unsigned int r = e >> 3, x = (e & 7u) * 2;
+      const double2 v = *reinterpret_cast<const double2 *>(L.pmat + ((size_t)pm * RL + r) * 16 + x);
+      *reinterpret_cast<double2 *>(dst + (size_t)r * PM_STRIDE + x) = v;
+    }
+  }
+}
+
 // ---------------------------------------------------------------- staged blocks (4-state kernel)
 // One WARP per locus: lane 0 plans sequentially, then all lanes gather the P-matrices the kernel
 // needs (Pup of every pushed op, tipP of every packed tip child) into the block, already in the
@@ -431,7 +481,7 @@ plan_kernel_blocks(const LocusDev * __restrict__ loci, const unsigned int * __re
       H->clv = L.clv; H->tip_dense = L.tip_dense; H->scale = L.scale;
       H->tipwords = reinterpret_cast<const unsigned int *>(L.tip_codes); H->pmat = L.pmat;
       H->clv_stride = L.clv_stride; H->sites = L.sites; H->nops = cnt; H->tip_words = L.tip_words;
-      H->n_chunks = n_chunks; H->flags = (sp.fast ? HDR_FAST : 0u) | (sp.simple ? HDR_SIMPLE : 0u) | (sp.nohbm ? HDR_NOHBM : 0u); H->pad0 = 0;
+      H->n_chunks = n_chunks; H->flags = (sp.fast ? HDR_FAST : 0u) | (sp.simple ? HDR_SIMPLE : 0u) | (sp.nohbm ? HDR_NOHBM : 0u) | HDR_LANEPLAN; H->pad0 = 0;
       for (int j = 0; j < 4; ++j) H->freqs[j] = L.freqs[j];
       plan_count[bl] = cnt;
     }
@@ -663,47 +713,72 @@ plan_kernel_blocks(const LocusDev * __restrict__ loci, const unsigned int * __re
   }
   double * rw = reinterpret_cast<double *>(blk + sizeof(LocusHdr));
   for (unsigned int j = lane; j < RL; j += 32) rw[j] = L.rate_weights[j];
-  // gather: per chunk, per op: Pup (if pushed) and the tipP of its packed tip children.  A matrix set is
-  // RL*8 double2; `per` lanes copy one set, so a warp moves 32/per sets per step.
-  const unsigned int per = RL * 8;                      // double2 per (op, which) matrix set; RL is a power of two
-  const unsigned int per_sh = 31u - (unsigned)__clz((int)per);
-  const float inv_lut_unit = 1.0f / (float)lut_unit;
-  for (unsigned int c = 0; c < n_chunks; ++c)
+  gather_block_matrices(L, blk, chunks0, cb, n_chunks, RL, lut_unit, small, small ? s_rec[wib] : nullptr);
+}
+
+// ---------------------------------------------------------------- refresh of a planned block set
+// The program of a batch (op records, slots, chunks) depends only on the op lists; what changes from one proposal
+// to the next with the same lists is the VALUE of the P-matrices.  When the batch still holds the planned blocks
+// of the staged lists (bppgpu_batch_run twice on the same stage, or the other index parity after
+// bppgpu_batch_flip_indices), the planner is skipped: this kernel rebuilds the matrices from the branch lengths
+// (mat_off != nullptr) and copies them into the Pup / tipP areas of the blocks again.  One warp per locus.
+__global__ void __launch_bounds__(128)
+plan_refresh_blocks(const LocusDev * __restrict__ loci, const unsigned int * __restrict__ batch_locus,
+                    unsigned int n_loci, unsigned char * __restrict__ blocks, const unsigned long long * __restrict__ blk_off,
+                    unsigned int RL, const unsigned int * __restrict__ mat_off, const unsigned int * __restrict__ mat_idx,
+                    const double * __restrict__ mat_bl)
+{
+  const unsigned int bl = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned int lane = threadIdx.x & 31u;
+  if (bl >= n_loci) return;
+  const LocusDev & L = loci[batch_locus[bl]];
+  if (mat_off)
   {
-    unsigned char * ch = blk + chunks0 + (size_t)c * cb;
-    const ChunkHdr hdr = *reinterpret_cast<const ChunkHdr *>(ch);
-    const OpRec * cops = small ? &s_rec[wib][c * TREE_CHUNK] : reinterpret_cast<const OpRec *>(ch + sizeof(ChunkHdr));
-    double * Pup = reinterpret_cast<double *>(ch + sizeof(ChunkHdr) + TREE_CHUNK * sizeof(OpRec));
-    double * tipP = Pup + (size_t)TREE_CHUNK * RL * PM_STRIDE;
-    const unsigned int total = hdr.nops * 3 * per;
-    for (unsigned int idx = lane; idx < total; idx += 32)
+    const unsigned int mfirst = mat_off[bl], mcount = mat_off[bl + 1] - mfirst;
+    for (unsigned int t = lane; t < mcount * RL; t += 32)
     {
-      const unsigned int task = idx >> per_sh, e = idx & (per - 1u);   // e: double2 index within the set
-      const unsigned int k = task / 3, which = task % 3;
-      const OpRec & q = cops[k];
-      if (q.ctl & OP_EVAL) continue;
-      unsigned int pm; double * dst;
-      if (which == 0)
-      {
-        if (!(q.ctl & OP_PUSH)) continue;
-        pm = q.up_pm; dst = Pup + (size_t)k * RL * PM_STRIDE;
-      }
-      else
-      {
-        const unsigned int kind = (q.ctl >> (which == 1 ? OP_AKIND_SHIFT : OP_BKIND_SHIFT)) & 15u;
-        const unsigned int off = which == 1 ? q.a_off : q.b_off;
-        unsigned int slot;
-        if (kind == SRC_TIP_PACKED) slot = (unsigned int)((float)off * inv_lut_unit + 0.5f);   // off = slot * lut_unit, exact
-        else if (kind == SRC_HBM && small && off != 0xFFFFFFFFu) slot = off;
-        else continue;
-        pm = which == 1 ? q.a_pm : q.b_pm;
-        dst = tipP + (size_t)slot * RL * PM_STRIDE;
-      }
-      const unsigned int r = e >> 3, x = (e & 7u) * 2;
-      const double2 v = *reinterpret_cast<const double2 *>(L.pmat + ((size_t)pm * RL + r) * 16 + x);
-      *reinterpret_cast<double2 *>(dst + (size_t)r * PM_STRIDE + x) = v;
+      const unsigned int n = t % RL, m = t / RL;
+      pmatrix_full4(L, mat_idx[mfirst + m], mat_bl[mfirst + m], n);
     }
+    __syncwarp();
   }
+  unsigned char * blk = blocks + blk_off[bl];
+  const LocusHdr * H = reinterpret_cast<const LocusHdr *>(blk);
+  const unsigned int chunks0 = (unsigned int)(sizeof(LocusHdr) + rw_bytes(RL));
+  gather_block_matrices(L, blk, chunks0, chunk_bytes(RL), H->n_chunks, RL, RL * (LUT_CAT / 2), (H->flags & HDR_LANEPLAN) != 0, nullptr);
+}
+
+// ---------------------------------------------------------------- device-side index flips
+// SWAP_CLV_INDEX / SWAP_SCALER_INDEX / SWAP_PMAT_INDEX (locus.c:24-26) applied to EVERY inner node and EVERY edge
+// of the staged step: what a whole-tree proposal does on the host before it calls the seam (prop_mixing.c:100-124).
+// BPP's allocation is assumed (checked by the caller): clv_buffers = 2(T-1), prob_matrices = 2(2T-2),
+// scale_buffers = 2(T-1) or 0.  One warp per locus.
+__global__ void __launch_bounds__(128)
+flip_indices_kernel(const LocusDev * __restrict__ loci, const unsigned int * __restrict__ batch_locus, unsigned int n_loci,
+                    const unsigned int * __restrict__ op_off, RawOp * __restrict__ ops,
+                    const unsigned int * __restrict__ mat_off, unsigned int * __restrict__ mat_idx,
+                    unsigned int * __restrict__ root_clv, int * __restrict__ root_sc)
+{
+  const unsigned int bl = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned int lane = threadIdx.x & 31u;
+  if (bl >= n_loci) return;
+  const unsigned int T = loci[batch_locus[bl]].tips, inner = T - 1, edges = 2 * T - 2;
+  auto fclv = [&](unsigned int i) -> unsigned int { return i < T ? i : T + (i - 1) % (2 * T - 2); };
+  auto fsc = [&](int i) -> int { return i < 0 ? i : (int)((T + (unsigned)i - 1) % (2 * T - 2)); };
+  auto fpm = [&](unsigned int i) -> unsigned int { return (edges + i) % (2 * edges); };
+  (void)inner;
+  if (op_off)
+    for (unsigned int k = op_off[bl] + lane; k < op_off[bl + 1]; k += 32)
+    {
+      RawOp r = ops[k];
+      r.parent = fclv(r.parent); r.left = fclv(r.left); r.right = fclv(r.right);
+      r.lpm = fpm(r.lpm); r.rpm = fpm(r.rpm);
+      r.psc = fsc(r.psc); r.lsc = fsc(r.lsc); r.rsc = fsc(r.rsc);
+      ops[k] = r;
+    }
+  if (mat_off)
+    for (unsigned int k = mat_off[bl] + lane; k < mat_off[bl + 1]; k += 32) mat_idx[k] = fpm(mat_idx[k]);
+  if (root_clv && lane == 0) { root_clv[bl] = fclv(root_clv[bl]); root_sc[bl] = fsc(root_sc[bl]); }
 }
 
 }  // namespace bppgpu

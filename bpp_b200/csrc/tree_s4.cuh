@@ -2,7 +2,13 @@
 //
 // One persistent CTA walks a contiguous range of tiles; a tile is TREE_NT*CPT cells
 // (cell = pattern*RL + cat, RL = rate categories, a power of two <= 8 so that the RL lanes of a site
-// sit in one warp) of one locus; thread tid owns the CPT cells cell0 + tid + j*TREE_NT (same category).
+// sit in one warp) of one locus; thread tid owns the CPT cells cell0 + perm(tid) + j*TREE_NT (same category).
+// perm() permutes the 32 cells of a warp so that lanes that are neighbours share the CATEGORY and walk the sites
+// (lane = cat * (32/RL) + site): a warp still reads and writes the same contiguous 1 KB of a CLV, but its
+// shared-memory traffic is conflict-free -- the P-matrix words of a push are the same address for every lane of a
+// quarter warp, and the tip lookup rows of a quarter warp differ by the state mask only, which the row padding
+// (LUT_ROW) spreads over the banks.  With cat = lane % RL (round 1) two sites of a quarter warp collided whenever
+// their masks differed: 31 % of all shared-memory wavefronts of the 4-category kernel were conflict replays.
 // For its cells a thread executes the locus' WHOLE planned op list as a stack machine over
 // TRANSFORMED vectors X = P_edge . clv:
 //   - a packed tip child (4 bits per tip and site, fetched one tile ahead, kept in registers) is one
@@ -77,6 +83,15 @@ __device__ __forceinline__ Vec4 matvec_s4(const unsigned int p, const double v0,
   return x;
 }
 
+// cell offset (within the CTA's TREE_NT cells of one j) owned by thread tid: lanes of a warp are ordered category-major
+template <int RL>
+__device__ __forceinline__ unsigned int s4_perm(const unsigned int tid)
+{
+  constexpr unsigned int SPW = 32u / RL;              // sites per warp
+  const unsigned int lane = tid & 31u;
+  return (tid & ~31u) | ((lane % SPW) * RL + lane / SPW);
+}
+
 template <int RL, int CPT>
 struct S4Layout               // everything in uint4 (16-byte) units
 {
@@ -89,7 +104,8 @@ struct S4Layout               // everything in uint4 (16-byte) units
   static constexpr unsigned TIPP = PUP + TREE_CHUNK * RL * 9;     // [CAP][RL] x 9
   static constexpr unsigned STAGE = TIPP + CAP * RL * 9;          // one stage buffer
   static constexpr unsigned CHUNK = STAGE - CH;                   // chunk size
-  static constexpr unsigned NSTAGE = RL >= 4 ? 1 : 2;             // double-buffered staging only where shared memory allows
+  static constexpr unsigned NSTAGE = RL >= 8 ? 1 : 2;             // double-buffered staging (the next locus' block is copied while
+                                                                  // the current one computes) where shared memory allows
   // shared memory of the kernel: [RING 4 x (TileDesc 2 + blk 1)][RED 32 doubles][NSTAGE stage buffers]
   // [LUT [cap][RL] x 49][STACK [slots][CPT*TREE_NT][2] uint4, then [slots][CPT*TREE_NT] u32].  cap is the
   // launch's tip-slot capacity (<= CAP, sized to the batch's largest tree): a stage buffer holds only
@@ -250,7 +266,7 @@ __device__ __forceinline__ double tile_fast(const TreeParams & prm, const TileCt
         unsigned int below = (o[j][0] < BPPGPU_SCALE_THRESHOLD) & (o[j][1] < BPPGPU_SCALE_THRESHOLD) &
                              (o[j][2] < BPPGPU_SCALE_THRESHOLD) & (o[j][3] < BPPGPU_SCALE_THRESHOLD);
 #pragma unroll
-        for (int dd = 1; dd < RL; dd <<= 1) below &= __shfl_xor_sync(0xFFFFFFFFu, below, dd);
+        for (int dd = 1; dd < RL; dd <<= 1) below &= __shfl_xor_sync(0xFFFFFFFFu, below, dd * (32 / RL));
         if (below)
         {
           o[j][0] = __dmul_rn(o[j][0], BPPGPU_SCALE_FACTOR); o[j][1] = __dmul_rn(o[j][1], BPPGPU_SCALE_FACTOR);
@@ -294,30 +310,46 @@ __device__ __forceinline__ double tile_fast(const TreeParams & prm, const TileCt
     if (ctl & OP_ROOT)
     {
       const double f0 = H->freqs[0], f1 = H->freqs[1], f2 = H->freqs[2], f3 = H->freqs[3];
+      double term[CPT];
 #pragma unroll
       for (int j = 0; j < CPT; ++j)
       {
         const double tr = __dadd_rn(__dadd_rn(__dmul_rn(f0, o[j][0]), __dmul_rn(f1, o[j][1])),
                                     __dadd_rn(__dmul_rn(f2, o[j][2]), __dmul_rn(f3, o[j][3])));
-        double term = 0.0;
+        term[j] = 0.0;
 #pragma unroll
         for (int r = 0; r < RL; ++r)
         {
-          const double v = __shfl_sync(0xFFFFFFFFu, tr, (lane & ~(unsigned)(RL - 1)) + r);
-          term = __dadd_rn(term, __dmul_rn(v, s8[(sb + Lay::RW) * 2 + r]));
+          const double v = __shfl_sync(0xFFFFFFFFu, tr, (lane % (32 / RL)) + r * (32 / RL));
+          term[j] = __dadd_rn(term[j], __dmul_rn(v, s8[(sb + Lay::RW) * 2 + r]));
         }
-        double s;
-        if (prm.persite_mode == 2) s = term;
+      }
+      // every lane of a site now holds the site's likelihood: the RL lanes share the CPT sites among them (lane of
+      // category c finishes the sites j = c, c + RL, ...), so log() runs once per site instead of RL times
+#pragma unroll
+      for (int g = 0; g < (CPT + RL - 1) / RL; ++g)
+      {
+        double t = 1.0;
+        unsigned int sc = 0, jj = 0;
+        bool mine = false;
+#pragma unroll
+        for (int r = 0; r < RL; ++r)
+        {
+          const int j = g * RL + r;
+          if (j < CPT && (unsigned int)r == tc.cat) { t = term[j]; sc = osc[j]; jj = (unsigned int)j; mine = tc.valid[j]; }
+        }
+        double sv;
+        if (prm.persite_mode == 2) sv = t;
         else
         {
-          s = log(term);
-          if (SCALED && osc[j]) s = __dadd_rn(s, __dmul_rn((double)osc[j], prm.log_threshold));
-          s = __dmul_rn(s, (double)s1[tc.tips_s + tc.wgt_off + j * TREE_NT]);
+          sv = log(t);
+          if (SCALED && sc) sv = __dadd_rn(sv, __dmul_rn((double)sc, prm.log_threshold));
+          sv = __dmul_rn(sv, (double)s1[tc.tips_s + tc.wgt_off + jj * TREE_NT]);
         }
-        if (tc.valid[j] && tc.cat == 0)
+        if (mine)
         {
-          site_sum += s;
-          if (prm.persite) prm.persite[tc.cell[j] / RL] = s;
+          site_sum += sv;
+          if (prm.persite) prm.persite[tc.cell[jj] / RL] = sv;
         }
       }
     }
@@ -432,7 +464,7 @@ __device__ __noinline__ double chunk_general(const TreeParams prm, unsigned int 
         unsigned int below = (o0 < BPPGPU_SCALE_THRESHOLD) & (o1 < BPPGPU_SCALE_THRESHOLD) &
                              (o2 < BPPGPU_SCALE_THRESHOLD) & (o3 < BPPGPU_SCALE_THRESHOLD);
 #pragma unroll
-        for (int dd = 1; dd < RL; dd <<= 1) below &= __shfl_xor_sync(0xFFFFFFFFu, below, dd);
+        for (int dd = 1; dd < RL; dd <<= 1) below &= __shfl_xor_sync(0xFFFFFFFFu, below, dd * (32 / RL));
         if (below)
         {
           o0 = __dmul_rn(o0, BPPGPU_SCALE_FACTOR); o1 = __dmul_rn(o1, BPPGPU_SCALE_FACTOR);
@@ -462,7 +494,7 @@ __device__ __noinline__ double chunk_general(const TreeParams prm, unsigned int 
 #pragma unroll
       for (int r = 0; r < RL; ++r)
       {
-        const double v = __shfl_sync(0xFFFFFFFFu, tr, (lane & ~(unsigned)(RL - 1)) + r);
+        const double v = __shfl_sync(0xFFFFFFFFu, tr, (lane % (32 / RL)) + r * (32 / RL));
         term = __dadd_rn(term, __dmul_rn(v, s8[(sb + Lay::RW) * 2 + r]));
       }
       unsigned int rsc = osc;
@@ -511,6 +543,7 @@ tree_kernel_s4(const TreeParams prm)
 {
   using Lay = S4Layout<RL, CPT>;
   const unsigned int tid = threadIdx.x, lane = tid & 31u;
+  const unsigned int ptid = s4_perm<RL>(tid);          // which of the warp's 32 cells this lane owns
   const unsigned int stage_sz = Lay::stage_sz(prm.lut_cap), lut0 = Lay::lut0(prm.lut_cap), stack0 = Lay::stack0(prm.lut_cap);
 
   const unsigned int t_begin = (unsigned int)(((unsigned long long)prm.n_tiles * blockIdx.x) / gridDim.x);
@@ -539,7 +572,7 @@ tree_kernel_s4(const TreeParams prm)
 #pragma unroll
     for (int j = 0; j < CPT; ++j)
     {
-      const unsigned int craw = d.cell0 + tid + j * TREE_NT;
+      const unsigned int craw = d.cell0 + ptid + j * TREE_NT;
       const unsigned int pat = (craw < d.ncell ? craw : d.ncell - 1) / RL;
       unsigned int * dst = &s1[tips0 + tb * tips_buf + j * TREE_NT + tid];
       const unsigned int nw = d.tip_words < prm.tip_words ? d.tip_words : prm.tip_words;
@@ -606,7 +639,7 @@ tree_kernel_s4(const TreeParams prm)
     const unsigned int sb = Lay::STAGE0 + buf * stage_sz;
     const LocusHdr * H = reinterpret_cast<const LocusHdr *>(&s4[sb]);
     tc.sb = sb;
-    tc.cat = (d.cell0 + tid) % RL;
+    tc.cat = (d.cell0 + ptid) % RL;
     tc.tips_s = tips0 + tb * tips_buf + tid;
     tc.wgt_off = prm.tip_words * (CPT * TREE_NT);
 #pragma unroll
@@ -614,7 +647,7 @@ tree_kernel_s4(const TreeParams prm)
 #pragma unroll
     for (int j = 0; j < CPT; ++j)
     {
-      const unsigned int craw = d.cell0 + tid + j * TREE_NT;
+      const unsigned int craw = d.cell0 + ptid + j * TREE_NT;
       tc.valid[j] = craw < d.ncell;
       tc.cell[j] = tc.valid[j] ? craw : d.ncell - 1;
     }

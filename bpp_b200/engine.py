@@ -454,6 +454,24 @@ class Batch:
         self.L.bppgpu_batch_synchronize(self.h)
         _lib.check()
 
+    def wait_inputs(self):
+        self.L.bppgpu_batch_wait_inputs(self.h)
+        _lib.check()
+
+    def flip_indices(self):
+        """SWAP_CLV_INDEX / SWAP_SCALER_INDEX / SWAP_PMAT_INDEX of every inner node and edge of the staged step,
+        on the device (a whole-tree proposal, prop_mixing.c:100-124)."""
+        self.L.bppgpu_batch_flip_indices(self.h)
+        _lib.check()
+
+    def set_branch_lengths(self, bl):
+        """New branch lengths for the staged matrix list (float64, same order; keep `bl` alive and unchanged
+        until collect / wait_inputs when it is pinned)."""
+        a = bl if (isinstance(bl, np.ndarray) and bl.dtype == np.float64 and bl.flags.c_contiguous) else _f64(bl)
+        self._bl_keep = a
+        self.L.bppgpu_batch_set_branch_lengths(self.h, _dp(a))
+        _lib.check()
+
     def allreduce_lnl_sum(self, comm):
         """NCCL sum of the batch's lnL sum over ranks, on the batch stream behind run()."""
         self.L.bppgpu_batch_allreduce_lnl_sum(self.h, comm.h)

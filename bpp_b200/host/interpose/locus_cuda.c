@@ -34,6 +34,8 @@
  *     only RECORDS each locus' triplet and returns lnL = 0; afterwards all loci of the call go to the device as one
  *     batch (one upload, one planner + tree kernel + finish launch, one read-back) and gt->logl / lnacceptance get
  *     their lnL added.  BPP_B200_BATCH=0 turns that off.
+ *   - everywhere else a locus' update_matrices / update_partials are queued and leave together with its next
+ *     root_loglikelihood as one call (BPP_B200_FUSE=0: three synchronous calls, as the reference issues them).
  */
 #define _GNU_SOURCE
 #include <dlfcn.h>
@@ -58,7 +60,7 @@ static fn_root_loglikelihood  real_root_loglikelihood;
 static fn_locus_destroy       real_locus_destroy;
 static fn_mixing              real_mixing;
 
-static int g_enabled = -1, g_batching = 1, g_verbose = 0;
+static int g_enabled = -1, g_batching = 1, g_verbose = 0, g_fuse = 1;
 static bppgpu_engine * g_engine;
 static pthread_mutex_t g_mu = PTHREAD_MUTEX_INITIALIZER;
 static pthread_once_t g_once = PTHREAD_ONCE_INIT;
@@ -93,6 +95,7 @@ static void init_once(void)
   g_enabled = ev && atoi(ev) != 0;
   if ((ev = getenv("BPP_B200_BATCH"))) g_batching = atoi(ev) != 0;
   if ((ev = getenv("BPP_B200_VERBOSE"))) g_verbose = atoi(ev);
+  if ((ev = getenv("BPP_B200_FUSE"))) g_fuse = atoi(ev) != 0;
   if (g_enabled)
   {
     int dev = (ev = getenv("BPP_B200_DEVICE")) ? atoi(ev) : 0;
@@ -124,6 +127,11 @@ typedef struct
   double * bl;
   /* slot of this locus in the deferred batch that is being recorded (-1: none) */
   long slot;
+  /* work recorded but not yet sent: the host never looks at P-matrices or CLVs, only at the next log-likelihood,
+     so update_matrices / update_partials are queued and leave together with the root evaluation as ONE call
+     (one upload, planner + tree kernel + finish, one read-back) */
+  bppgpu_batch * one;          /* batch of this locus alone */
+  unsigned int p_mats, p_ops;
 } lstate_t;
 
 #define TABLE_BITS 16
@@ -150,10 +158,18 @@ static lstate_t * table_find(locus_t * l)
 static void ensure_cap(lstate_t * s, unsigned int count)
 {
   if (count <= s->cap) return;
-  s->cap = count + 8;
+  s->cap = 2 * count + 8;
   s->ops = (bppgpu_partial_op *)xrealloc(s->ops, s->cap * sizeof(bppgpu_partial_op));
   s->idx = (unsigned int *)xrealloc(s->idx, s->cap * sizeof(unsigned int));
   s->bl = (double *)xrealloc(s->bl, s->cap * sizeof(double));
+}
+
+/* send what is queued for a locus without evaluating a root (another consumer needs the buffers up to date) */
+static void flush_pending(lstate_t * s)
+{
+  if (s->p_mats && !bppgpu_update_matrices(s->h, s->p_mats, s->idx, s->bl)) fatal("bppgpu_update_matrices: %s", bppgpu_last_error());
+  if (s->p_ops && !bppgpu_update_partials(s->h, s->p_ops, s->ops)) fatal("bppgpu_update_partials: %s", bppgpu_last_error());
+  s->p_mats = s->p_ops = 0;
 }
 
 static size_t model_doubles(const locus_t * l)
@@ -346,9 +362,12 @@ void locus_update_matrices(locus_t * locus, gtree_t * gtree, gnode_t ** traversa
     return;
   }
   if (d->active) d->overflow = 1;
-  ensure_cap(s, count);
-  for (i = 0; i < count; ++i) { s->idx[i] = traversal[i]->pmatrix_index; s->bl[i] = traversal[i]->length; }
-  if (!bppgpu_update_matrices(s->h, count, s->idx, s->bl)) fatal("bppgpu_update_matrices: %s", bppgpu_last_error());
+  /* partials queued behind earlier matrices must see those, not these: keep the order by flushing */
+  if (s->p_ops) flush_pending(s);
+  ensure_cap(s, s->p_mats + count);
+  for (i = 0; i < count; ++i) { s->idx[s->p_mats + i] = traversal[i]->pmatrix_index; s->bl[s->p_mats + i] = traversal[i]->length; }
+  s->p_mats += count;
+  if (!g_fuse) flush_pending(s);
 }
 
 void locus_update_partials(locus_t * locus, gnode_t ** traversal, unsigned int count)
@@ -367,9 +386,10 @@ void locus_update_partials(locus_t * locus, gnode_t ** traversal, unsigned int c
     return;
   }
   if (d->active) d->overflow = 1;
-  ensure_cap(s, count);
-  fill_ops(traversal, count, s->ops);
-  if (!bppgpu_update_partials(s->h, count, s->ops)) fatal("bppgpu_update_partials: %s", bppgpu_last_error());
+  ensure_cap(s, s->p_ops + count);
+  fill_ops(traversal, count, s->ops + s->p_ops);
+  s->p_ops += count;
+  if (!g_fuse) flush_pending(s);
 }
 
 static void all_partials_rec(gnode_t * node, gnode_t ** out, unsigned int * n)
@@ -409,6 +429,23 @@ double locus_root_loglikelihood(locus_t * locus, gnode_t * root, const unsigned 
     return 0.0;                                   /* the batch adds the real value afterwards */
   }
   if (d->active) d->overflow = 1;
+  if (g_fuse && !persite_lnl)
+  {
+    /* matrices + partials + root of this locus in one call; a batch applies the diploid phase mean itself */
+    const unsigned int rclv = root->clv_index;
+    const int rsc = root->scaler_index;
+    if (!s->one)
+    {
+      s->one = bppgpu_batch_create(g_engine, 1, &s->h);
+      if (!s->one) fatal("bppgpu_batch_create: %s", bppgpu_last_error());
+    }
+    if (!bppgpu_batch_full_pass(s->one, s->p_mats ? &s->p_mats : NULL, s->idx, s->bl, s->p_ops ? &s->p_ops : NULL, s->ops,
+                                &rclv, &rsc, &logl, NULL))
+      fatal("bppgpu_batch_full_pass: %s", bppgpu_last_error());
+    s->p_mats = s->p_ops = 0;
+    return opt_bfbeta * logl;
+  }
+  flush_pending(s);
   if (locus->diploid) logl = bppgpu_root_loglikelihood_diploid(s->h, root->clv_index);     /* locus.c:2586-2615 */
   else logl = bppgpu_root_loglikelihood(s->h, root->clv_index, root->scaler_index, persite_lnl);
   return opt_bfbeta * logl;                       /* locus.c:2630 */
@@ -429,6 +466,7 @@ void locus_destroy(locus_t * locus)
       pthread_mutex_lock(&g_mu);
       if (tl_defer.batch) { bppgpu_batch_destroy(tl_defer.batch); tl_defer.batch = NULL; tl_defer.batch_n = 0; }
       pthread_mutex_unlock(&g_mu);
+      if (s->one) bppgpu_batch_destroy(s->one);
       bppgpu_locus_destroy(s->h);
       free(s->model); free(s->ops); free(s->idx); free(s->bl);
       s->h = NULL;
@@ -484,6 +522,7 @@ void prop_mixing_update_gtrees(locus_t ** locus, gtree_t ** gtree, stree_t * str
   for (i = 0; i < locus_count; ++i)
   {
     lstate_t * s = state_of(locus[locus_start + i]);
+    if (s->p_mats || s->p_ops) flush_pending(s);
     s->slot = i;
     d->mcounts[i] = d->ocounts[i] = 0;
   }

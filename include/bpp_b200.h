@@ -205,11 +205,26 @@ int  bppgpu_batch_stage(bppgpu_batch * b,
 int  bppgpu_batch_run(bppgpu_batch * b);
 /* A full pass of a big 4-state batch is pipelined: the step's arrays are uploaded in `waves` slices of loci
    on a copy stream while planner and tree kernel of earlier slices already run (0 = automatic: 2 waves of
-   20 % + 80 % of the loci once the step's arrays exceed 1 MB, else 1; 1 = off; at most 8).  The arrays handed
-   to bppgpu_batch_stage must stay valid and unchanged until the following bppgpu_batch_run has returned.
-   Results do not depend on the setting. */
+   20 % + 80 % of the loci once the step's arrays exceed 1 MB, else 1; 1 = off; at most 8).  Results do not depend
+   on the setting.
+   LIFETIME OF THE STEP ARRAYS: arrays that live in pinned memory (bppgpu_host_alloc) are read by the copy engine
+   straight from the caller's buffers, asynchronously: they must stay valid and unchanged until
+   bppgpu_batch_wait_inputs, bppgpu_batch_collect or bppgpu_batch_synchronize has returned after the
+   bppgpu_batch_run that consumes them (run itself never blocks).  Pageable arrays are copied into the batch's own
+   pinned blob before stage returns and may be reused at once. */
 void bppgpu_batch_set_waves(bppgpu_batch * b, unsigned int waves);
 int  bppgpu_batch_collect(bppgpu_batch * b, double * lnl_out, double * lnl_sum_out);
+int  bppgpu_batch_wait_inputs(bppgpu_batch * b);   /* returns when the device has read the step's host arrays */
+/* Whole-tree proposals (the mixing move, prop_mixing.c:52-220; debug_full_lh, method.c:4660-4696) keep their
+   traversals and flip EVERY index: SWAP_PMAT_INDEX of all edges, SWAP_CLV_INDEX / SWAP_SCALER_INDEX of all inner
+   nodes (locus.c:24-26).  bppgpu_batch_flip_indices applies exactly those flips to the staged step ON THE DEVICE
+   (ops, matrix list, roots), and the batch keeps the planned program of both index parities; with
+   bppgpu_batch_set_branch_lengths (same order and count as the staged matrix list) such a step uploads branch
+   lengths only and runs without planning.  A rejected proposal is flip_indices again (nothing is recomputed: the
+   other half of the double buffers still holds the accepted state).  Requires BPP's 2x allocation
+   (clv_buffers = 2(T-1), prob_matrices = 2(2T-2), scale_buffers = 2(T-1) or 0). */
+int  bppgpu_batch_flip_indices(bppgpu_batch * b);
+int  bppgpu_batch_set_branch_lengths(bppgpu_batch * b, const double * branch_lengths);
 /* device address of the batch's lnL sum (one double), valid after run; lets the caller hand it to
    an all-reduce (torch.distributed / NCCL) without a host round trip */
 void * bppgpu_batch_lnl_sum_dev(bppgpu_batch * b);

@@ -108,6 +108,66 @@ def test_mixing_step_with_index_flips(eng, name):
     _free(loci, batch)
 
 
+@pytest.mark.parametrize("name", ["jc69_r1", "gtr_g4_scale", "gtr_g4_deep_scale", "lg_g4"])
+def test_device_side_flip_and_cached_plan(eng, name):
+    """The same mixing move with the lists resident on the device: bppgpu_batch_flip_indices applies the SWAP_*
+    flips of every node (locus.c:24-26) to the staged step, bppgpu_batch_set_branch_lengths sends the only thing
+    that changed, and from the third step on the planned program of either index parity is reused (refresh of the
+    P-matrices only).  Every variant must give bit-identical numbers to staging the host-flipped arrays."""
+    w, d = load_case(name)
+    loci, trees, batch = _load(eng, w)
+    step0 = trees.full_pass_step()
+    batch.stage(step0)
+    batch.run()
+    lnl0, _ = batch.collect()
+    batch.run()                                   # same stage again: cached plan, matrices refreshed
+    again, _ = batch.collect()
+    assert np.array_equal(again, lnl0)
+    # proposal 1: scale the ages, flip on the device, send branch lengths
+    trees.times = trees.times * float(d["mix_c"])
+    trees.flip_pmatrix()
+    trees.flip_clv()
+    step1 = trees.full_pass_step()
+    batch.flip_indices()
+    batch.set_branch_lengths(step1[2])
+    batch.run()
+    lnl1, tot1 = batch.collect()
+    assert rel_err(lnl1, d["lnl_mix"]) <= LNL_RTOL
+    # rejected: flip back; proposal 2 with other ages lands in the same spare buffers, plan of parity 1 is cached now
+    batch.flip_indices()
+    c2 = 0.5 * (1.0 + float(d["mix_c"]))
+    trees.times = trees.times * c2
+    step2 = trees.full_pass_step()
+    batch.flip_indices()
+    bl2 = engine_pinned(step2[2])
+    batch.set_branch_lengths(bl2.array)
+    batch.run()
+    batch.wait_inputs()
+    bl2.array[:] = -1.0                           # the device has read them: the host may scribble (ADVICE r1)
+    lnl2, tot2 = batch.collect()
+    bl2.free()
+    # accepted this time; proposal 3 flips to parity 0 (cached) with new ages
+    trees.times = trees.times * 1.01
+    trees.flip_pmatrix()
+    trees.flip_clv()
+    step3 = trees.full_pass_step()
+    batch.flip_indices()
+    batch.set_branch_lengths(step3[2])
+    batch.run()
+    lnl3, _ = batch.collect()
+    # the same three states through fresh stages of host-flipped arrays
+    for step, got in ((step1, lnl1), (step2, lnl2), (step3, lnl3)):
+        want, _ = batch.full_pass(step)
+        assert np.array_equal(got, want)
+    assert abs(tot2 - lnl2.sum()) <= 1e-9 * abs(tot2)
+    _free(loci, batch)
+
+
+def engine_pinned(a):
+    from bpp_b200 import engine
+    return engine.PinnedArray(np.ascontiguousarray(a, dtype=np.float64))
+
+
 @pytest.mark.parametrize("cfg", [
     dict(tips=8, sites=1000, states=4, rate_cats=1, model="JC69"),                  # config-2 shape
     dict(tips=16, sites=1000, states=4, rate_cats=4, model="GTR", scaling=True),     # config-3 shape
