@@ -596,6 +596,72 @@ class GeneTrees:
         return mc, mi, mb, oc, ops.ravel(), rc, rs
 
 
+def age_move_step(trees, nodes, new_ages):
+    """Host arrays of one gene-tree age move per locus (gtree.c:5437-5467): node `nodes[i]` of locus i gets the age
+    `new_ages[i]`; the P-matrix indices of the 2-3 edges around it and the CLV / scaler indices of its root path
+    are flipped (in `trees`, like the reference does before it calls the seam), and the step recomputes exactly
+    those: 2-3 matrices, the root path's partials, the root lnL.  Ragged per locus."""
+    N, T = trees.N, trees.T
+    rows = np.arange(N)
+    nodes = np.asarray(nodes, dtype=np.int64)
+    trees.times[rows, nodes] = new_ages
+    e = 2 * T - 2
+    l, r = trees.left[rows, nodes - T], trees.right[rows, nodes - T]
+    not_root = trees.parent[rows, nodes] >= 0
+    for sel, who in ((np.ones(N, bool), l), (np.ones(N, bool), r), (not_root, nodes)):
+        trees.pmatrix_index[rows[sel], who[sel]] = (e + trees.pmatrix_index[rows[sel], who[sel]]) % (2 * e)
+    # root paths
+    paths, cur, alive = [], nodes.copy(), np.ones(N, bool)
+    while alive.any():
+        paths.append(np.where(alive, cur, -1))
+        ci = rows[alive], cur[alive]
+        trees.clv_index[ci] = T + (trees.clv_index[ci] - 1) % (2 * T - 2)
+        if trees.scaling:
+            trees.scaler_index[ci] = (T + trees.scaler_index[ci] - 1) % (2 * T - 2)
+        nxt = np.where(alive, trees.parent[rows, np.maximum(cur, 0)], -1)
+        alive = nxt >= 0
+        cur = nxt
+    path = np.stack(paths, axis=1)                                  # [N, depth], -1 padded
+    oc = (path >= 0).sum(axis=1).astype(np.uint32)
+    bl = trees.branch_lengths()
+    mc = (2 + not_root).astype(np.uint32)
+    mnodes = np.stack([l, r, np.where(not_root, nodes, -1)], axis=1)
+    msel = mnodes >= 0
+    mrows = np.repeat(rows, 3).reshape(N, 3)[msel]
+    mi = trees.pmatrix_index[mrows, mnodes[msel]].astype(np.uint32)
+    mb = bl[mrows, mnodes[msel]]
+    osel = path >= 0
+    orow = np.repeat(rows, path.shape[1]).reshape(path.shape)[osel]
+    on = path[osel]
+    ol, orr = trees.left[orow, on - T], trees.right[orow, on - T]
+    ops = np.zeros(on.size, dtype=OP_DTYPE)
+    ops["parent_clv_index"] = trees.clv_index[orow, on]
+    ops["left_clv_index"] = trees.clv_index[orow, ol]
+    ops["right_clv_index"] = trees.clv_index[orow, orr]
+    ops["left_pmatrix_index"] = trees.pmatrix_index[orow, ol]
+    ops["right_pmatrix_index"] = trees.pmatrix_index[orow, orr]
+    ops["parent_scaler_index"] = trees.scaler_index[orow, on]
+    ops["left_scaler_index"] = trees.scaler_index[orow, ol]
+    ops["right_scaler_index"] = trees.scaler_index[orow, orr]
+    rc = trees.clv_index[:, trees.root].astype(np.uint32)
+    rs = trees.scaler_index[:, trees.root].astype(np.int32)
+    return mc, mi, mb, oc, ops, rc, rs
+
+
+def propose_ages(trees, rng):
+    """A random inner node per locus and a new age strictly between its older child and its parent (the root: up to
+    10 % older), the way the age move samples inside its bounds (gtree.c:4585-5436)."""
+    N, T = trees.N, trees.T
+    rows = np.arange(N)
+    nodes = rng.integers(T, 2 * T - 1, size=N)
+    l, r = trees.left[rows, nodes - T], trees.right[rows, nodes - T]
+    lo = np.maximum(trees.times[rows, l], trees.times[rows, r])
+    par = trees.parent[rows, nodes]
+    hi = np.where(par >= 0, trees.times[rows, np.maximum(par, 0)], trees.times[rows, nodes] * 1.1)
+    u = rng.uniform(0.05, 0.95, size=N)
+    return nodes, lo + u * (hi - lo)
+
+
 def load_workload(engine, w, charmap=None):
     """Create the loci of a synth.Workload on `engine`; returns (loci, GeneTrees)."""
     from . import synth

@@ -305,6 +305,72 @@ double ref_full_pass_all(ref_set_t * s, int first, int count, int nthreads,
   return (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
 }
 
+/* The likelihood part of a gene-tree age move (gtree.c:5437-5467) for node `node` of locus i with its new age:
+   flip and rebuild the P-matrices of the 2-3 edges around the node, flip the CLV / scaler indices of the root
+   path, update those partials, evaluate the root.  The move is kept ("accepted"). */
+#define SHIM_SWAP_CLV(n,i)    ((n)+((i)-1)%(2*(n)-2))
+#define SHIM_SWAP_SCALER(n,i) (((n)+((i)-1))%(2*(n)-2))
+#define SHIM_SWAP_PMAT(e,i)   (((e)+(i))%((e)<<1))
+double ref_age_move(ref_set_t * s, int i, int node_id, double new_age)
+{
+  ref_locus_t * rl = s->l + i;
+  gnode_t * node = rl->nodes + node_id, * temp;
+  unsigned int k = 0, j, T = rl->tips;
+  node->time = new_age;
+  rl->trav[k++] = node->left;
+  rl->trav[k++] = node->right;
+  if (node->parent) rl->trav[k++] = node;
+  for (j = 0; j < k; ++j) rl->trav[j]->pmatrix_index = SHIM_SWAP_PMAT(rl->gtree->edge_count, rl->trav[j]->pmatrix_index);
+  locus_update_matrices(rl->locus, rl->gtree, rl->trav, NULL, i, k);
+  for (k = 0, temp = node; temp; temp = temp->parent)
+  {
+    rl->trav[k++] = temp;
+    temp->clv_index = SHIM_SWAP_CLV(T, temp->clv_index);
+    if (s->scaling) temp->scaler_index = SHIM_SWAP_SCALER(T, temp->scaler_index);
+  }
+  locus_update_partials(rl->locus, rl->trav, k);
+  return locus_root_loglikelihood(rl->locus, rl->gtree->root, rl->locus->param_indices, NULL);
+}
+
+typedef struct { ref_set_t * s; int first, count; const int * nodes; const double * ages; double * out; } agework_t;
+
+static void * age_worker(void * arg)
+{
+  agework_t * w = (agework_t *)arg;
+  int i;
+  for (i = w->first; i < w->first + w->count; ++i) w->out[i] = ref_age_move(w->s, i, w->nodes[i], w->ages[i]);
+  return NULL;
+}
+
+/* one age move per locus for loci [first, first+count), static partition over pthreads; returns wall seconds */
+double ref_age_move_all(ref_set_t * s, int first, int count, int nthreads, const int * node_ids,
+                        const double * new_ages, double * lnl_out)
+{
+  struct timespec t0, t1;
+  int t, per, rem, start;
+  if (nthreads < 1) nthreads = 1;
+  if (nthreads > count) nthreads = count;
+  pthread_t * th = (pthread_t *)calloc(nthreads, sizeof(pthread_t));
+  agework_t * w = (agework_t *)calloc(nthreads, sizeof(agework_t));
+  per = count / nthreads; rem = count % nthreads; start = first;
+  for (t = 0; t < nthreads; ++t)
+  {
+    w[t].s = s; w[t].first = start; w[t].count = per + (t < rem ? 1 : 0);
+    w[t].nodes = node_ids; w[t].ages = new_ages; w[t].out = lnl_out;
+    start += w[t].count;
+  }
+  clock_gettime(CLOCK_MONOTONIC, &t0);
+  if (nthreads == 1) age_worker(w);
+  else
+  {
+    for (t = 0; t < nthreads; ++t) pthread_create(th + t, NULL, age_worker, w + t);
+    for (t = 0; t < nthreads; ++t) pthread_join(th[t], NULL);
+  }
+  clock_gettime(CLOCK_MONOTONIC, &t1);
+  free(th); free(w);
+  return (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
+}
+
 /* raw buffer access for parity checks */
 const double * ref_clv(ref_set_t * s, int i, int clv_index)
 { return s->l[i].locus->clv[clv_index]; }

@@ -60,6 +60,10 @@ def lib():
         L.ref_full_pass.argtypes = [vp, C.c_int]
         L.ref_full_pass_all.restype = C.c_double
         L.ref_full_pass_all.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, dp]
+        L.ref_age_move.restype = C.c_double
+        L.ref_age_move.argtypes = [vp, C.c_int, C.c_int, C.c_double]
+        L.ref_age_move_all.restype = C.c_double
+        L.ref_age_move_all.argtypes = [vp, C.c_int, C.c_int, C.c_int, ip, dp, dp]
         for name in ("ref_clv", "ref_pmatrix"):
             getattr(L, name).restype = dp
             getattr(L, name).argtypes = [vp, C.c_int, C.c_int]
@@ -197,6 +201,14 @@ class RefSet:
     def full_pass_all(self, first, count, nthreads=1, passes=1):
         out = np.zeros(self.n)
         secs = self.L.ref_full_pass_all(self.h, first, count, nthreads, passes, _d(out))
+        return secs, out
+
+    def age_move_all(self, first, count, node_ids, new_ages, nthreads=1):
+        """One gene-tree age move per locus (gtree.c:5437-5467, likelihood part); returns (seconds, lnl[n])."""
+        nodes = np.ascontiguousarray(node_ids, dtype=np.int32)
+        ages = np.ascontiguousarray(new_ages, dtype=np.float64)
+        out = np.zeros(self.n)
+        secs = self.L.ref_age_move_all(self.h, first, count, nthreads, _i(nodes), _d(ages), _d(out))
         return secs, out
 
     def clv(self, i, clv_index):

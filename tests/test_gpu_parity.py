@@ -163,6 +163,37 @@ def test_device_side_flip_and_cached_plan(eng, name):
     _free(loci, batch)
 
 
+@pytest.mark.parametrize("cfg", [dict(tips=8, rate_cats=1, model="JC69", scaling=False),
+                                 dict(tips=16, rate_cats=4, model="GTR", scaling=True),
+                                 dict(tips=48, rate_cats=4, model="GTR", scaling=False)])
+def test_age_moves_across_all_loci_match_the_reference(eng, cfg):
+    """The schedule for the most frequent proposal (gene-tree age move, gtree.c:4585, 5437-5467): the SAME move in
+    every locus as one batch -- 2-3 P-matrices and the root path's partials per locus, ragged, children outside
+    the path read from HBM.  Three rounds of moves on top of each other against the compiled reference, which does
+    them locus by locus; indices are flipped exactly as the reference flips them."""
+    from bpp_b200 import engine
+    from helpers import ref_set_from_workload
+    from oracle import refbind
+    if not refbind.available():
+        pytest.skip("oracle/_ref not built")
+    w = synth.make_workload("age", n_loci=40, sites=333, states=4, seed=77, **cfg)
+    loci, trees, batch = _load(eng, w)
+    rs = ref_set_from_workload(w)
+    lnl, _ = batch.full_pass(trees.full_pass_step())
+    _, ref = rs.full_pass_all(0, w.n_loci, 1, 1)
+    assert rel_err(lnl, ref) <= LNL_RTOL
+    rng = np.random.default_rng(5)
+    for _ in range(3):
+        nodes, ages = engine.propose_ages(trees, rng)
+        step = engine.age_move_step(trees, nodes, ages)
+        lnl, total = batch.full_pass(step)
+        _, ref = rs.age_move_all(0, w.n_loci, nodes, ages, 2)
+        assert rel_err(lnl, ref) <= LNL_RTOL
+        assert abs(total - lnl.sum()) <= 1e-9 * abs(total)
+    rs.close()
+    _free(loci, batch)
+
+
 def engine_pinned(a):
     from bpp_b200 import engine
     return engine.PinnedArray(np.ascontiguousarray(a, dtype=np.float64))
