@@ -91,7 +91,7 @@ __host__ __device__ constexpr int s4_ctas_per_sm(int cpt)
   return cpt == 2 ? BPPGPU_S4_CTAS2 : (cpt == 1 ? 3 : 1) * (256 / TREE_NT);
 }
 constexpr int TREE_CHUNK = 16;      // ops per staged chunk
-constexpr int S4_MAX_TIP_WORDS = 4; // packed tip words (8 tips each) the 4-state fast path stages per cell: 32 tips
+constexpr int S4_MAX_TIP_WORDS = 16; // packed tip words (8 tips each) the 4-state fast path stages per cell: 128 tips
 constexpr int PM_STRIDE  = 18;      // doubles per (matrix, cat) in shared memory (16 + 2 pad: the RL
                                     // categories of a site land in different banks)
 constexpr int LUT_ROW    = 6;       // doubles per state-mask row of a tip lookup table (4 + 2 pad: the

@@ -817,6 +817,15 @@ static void batch_launch_cfg(bppgpu_batch * b)
   if (b->kernel_kind == 0 && R >= 4 && mean >= 7 * (TREE_NT / 2)) b->cpt = 4;
   if (const char * ev = getenv("BPPGPU_CPT"))                 // tuning knob
     if (b->kernel_kind == 0 && (atoi(ev) == 1 || atoi(ev) == 2 || atoi(ev) == 4)) b->cpt = (unsigned)atoi(ev);
+  // big trees: the packed tip words of every cell are staged in shared memory (two buffers of (words + 1) x 4 bytes per
+  // cell); fewer cells per thread keep that under 40 kB so that lookup tables and stack still fit
+  if (b->kernel_kind == 0)
+  {
+    unsigned maxT = 0;
+    for (auto * l : b->loci) maxT = std::max(maxT, l->tips);
+    const unsigned words = std::min<unsigned>((maxT + 7) / 8, (unsigned)S4_MAX_TIP_WORDS);
+    while (b->cpt > 1 && 2u * (words + 1u) * b->cpt * TREE_NT * 4u > 40u * 1024u) b->cpt /= 2;
+  }
   b->tile_threads = b->kernel_kind == 0 ? TREE_NT : (b->kernel_kind == 2 ? S20_NT : 128);
 }
 
@@ -1493,7 +1502,7 @@ static int batch_run(bppgpu_batch * b, bool do_mats, bool do_tree, bool want_roo
       plan_kernel_blocks<<<(n * 32 + 127) / 128, 128, 0, b->stream>>>(
           e->d_loci, b->d_batch_locus, n, d_op_off, d_ops, d_root_clv, d_root_sc, want_root ? 1 : 0,
           b->d_blocks, d_blk_off, b->d_tile_first, b->d_tile_blk, b->d_plan_count, b->d_scratch, b->d_scratch_off,
-          slots, b->RL, b->cpt, lut_cap_rt, fuse_mats ? d_mat_off : nullptr, d_mat_idx, d_mat_bl);
+          slots, b->RL, b->cpt, lut_cap_rt, fuse_mats ? d_mat_off : nullptr, d_mat_idx, d_mat_bl, 8u * b->tip_words_rt);
     else if (b->kernel_kind == 2)
       plan_kernel_blocks20<<<(n * 32 + 127) / 128, 128, 0, b->stream>>>(
           e->d_loci, b->d_batch_locus, n, d_op_off, d_ops, d_root_clv, d_root_sc, want_root ? 1 : 0,
@@ -1534,7 +1543,7 @@ static int batch_run(bppgpu_batch * b, bool do_mats, bool do_tree, bool want_roo
         plan_kernel_blocks<<<((i1 - i0) * 32 + 127) / 128, 128, 0, st>>>(
             e->d_loci, b->d_batch_locus + i0, i1 - i0, d_op_off + i0, d_ops, d_root_clv + i0, d_root_sc + i0, 1,
             b->d_blocks, d_blk_off + i0, b->d_tile_first + i0, b->d_tile_blk, b->d_plan_count + i0, b->d_scratch,
-            b->d_scratch_off + i0, slots, b->RL, b->cpt, lut_cap_rt, d_mat_off + i0, d_mat_idx, d_mat_bl);
+            b->d_scratch_off + i0, slots, b->RL, b->cpt, lut_cap_rt, d_mat_off + i0, d_mat_idx, d_mat_bl, 8u * b->tip_words_rt);
         CUDA_CHECK(cudaGetLastError());
       }
       const unsigned t0 = b->h_tile_first[i0], t1 = b->h_tile_first[i1];

@@ -153,7 +153,7 @@ __device__ __forceinline__ SuLane su_order_small(const RawOp * o, unsigned int n
 __device__ __forceinline__ SmallPlanOut
 plan_small_parallel(const LocusDev & L, const RawOp * o, unsigned int n, unsigned int rootc, int rootsc, bool want_root,
                     unsigned char * blk, unsigned int chunks0, size_t cb, unsigned int cap, unsigned int lut_unit,
-                    unsigned int slot_unit, int max_slots, unsigned int RL, OpRec * rec,
+                    unsigned int slot_unit, int max_slots, unsigned int RL, unsigned int max_fast_tip, OpRec * rec,
                     unsigned char * s_order, unsigned int * s_push)
 {
   const unsigned int FULL = 0xFFFFFFFFu;
@@ -241,7 +241,7 @@ plan_small_parallel(const LocusDev & L, const RawOp * o, unsigned int n, unsigne
         okind[c] = SRC_TIP_PACKED;
         osel[c] = 15u | ((child[c] >> 3) << 4) | (((child[c] & 7u) * 4) << 8);
         ooff[c] = lutn * lut_unit; ++lutn;
-        if (child[c] >= 8 * S4_MAX_TIP_WORDS) op_fast = false;     // its tip word is not staged
+        if (child[c] >= max_fast_tip) op_fast = false;             // its tip word is not staged
       }
     }
     else if (kid[c] >= 0 && kpos + 1 == pos && prev_child < 0) { okind[c] = SRC_PREV; prev_child = c; s_push[kid[c]] = opm[c] + 1; }
@@ -407,7 +407,7 @@ plan_kernel_blocks(const LocusDev * __restrict__ loci, const unsigned int * __re
                    unsigned char * __restrict__ scratch, const unsigned long long * __restrict__ scratch_off,
                    int max_slots, unsigned int RL, unsigned int cpt, unsigned int cap,
                    const unsigned int * __restrict__ mat_off, const unsigned int * __restrict__ mat_idx,
-                   const double * __restrict__ mat_bl)
+                   const double * __restrict__ mat_bl, unsigned int max_fast_tip)
 {
   const unsigned int bl = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const unsigned int lane = threadIdx.x & 31u;
@@ -446,10 +446,7 @@ plan_kernel_blocks(const LocusDev * __restrict__ loci, const unsigned int * __re
   __shared__ __align__(16) OpRec s_rec[4][SM_OPS];
   __shared__ unsigned int s_where[4][SM_BUF];
   __shared__ unsigned char s_slot[4][SM_BUF];
-  __shared__ unsigned char s_prod[4][SM_BUF];       // 1 + op slot that produced the buffer in this list
   __shared__ unsigned char s_order[4][SM_OPS];      // evaluation order (Sethi-Ullman)
-  __shared__ signed char s_kid[4][SM_OPS][2];       // producing op of the left / right child, or -1
-  __shared__ unsigned char s_need[4][SM_OPS];
   const unsigned int wib = threadIdx.x >> 5;
   // every closed chunk holds >= m ops, so a list of n (+1 eval-only) ops needs <= n/m + 1 chunks
   const unsigned int m_ops = (cap / 2 < (unsigned)TREE_CHUNK) ? (cap / 2 ? cap / 2 : 1u) : (unsigned)TREE_CHUNK;
@@ -473,7 +470,7 @@ plan_kernel_blocks(const LocusDev * __restrict__ loci, const unsigned int * __re
   {
     const SmallPlanOut sp = plan_small_parallel(L, o, n, want_root ? root_clv[bl] : 0xFFFFFFFFu, want_root ? root_sc[bl] : -1,
                                                 want_root != 0, blk, chunks0, cb, cap, lut_unit, slot_unit, max_slots, RL,
-                                                s_rec[wib], s_order[wib], s_where[wib]);
+                                                max_fast_tip, s_rec[wib], s_order[wib], s_where[wib]);
     n_chunks = sp.n_chunks; cnt = sp.cnt;
     if (lane == 0)
     {
@@ -506,47 +503,51 @@ plan_kernel_blocks(const LocusDev * __restrict__ loci, const unsigned int * __re
     // lists are re-ordered Sethi-Ullman style (the child subtree that needs more parked values first):
     // a balanced tree of T tips then needs log2(T)-1 stack slots instead of up to T/3 in the caller's
     // left-first post-order.
-    unsigned char * order = s_order[wib];
-    unsigned char * prodmap = s_prod[wib];
-    if (small)
+    // Lists of 33..PLAN_MED_OPS ops (trees of up to 129 tips: real data, the reference's frogs example has 42-60
+    // sequences per locus) are ordered the same way here, serially, with the bookkeeping in thread-local arrays.
+    constexpr unsigned int PLAN_MED_OPS = 128, PLAN_MED_BUF = 256;
+    unsigned char order[PLAN_MED_OPS];
+    unsigned char prodmap[PLAN_MED_BUF];       // 1 + op that produced the buffer in this list; later: 1 + op slot
+    const bool ordered = n <= PLAN_MED_OPS && L.clv_buffers <= PLAN_MED_BUF;
+    if (ordered)
     {
-      signed char (*kid)[2] = s_kid[wib];
-      unsigned char * need = s_need[wib];
-      unsigned int consumed = 0;
+      signed char kid[PLAN_MED_OPS][2];
+      unsigned char need[PLAN_MED_OPS];
+      unsigned char consumed[PLAN_MED_OPS], done[PLAN_MED_OPS];
       for (unsigned int k = 0; k < n; ++k)
       {
         prodmap[o[k].parent - T] = 0;
         if (o[k].left >= T) prodmap[o[k].left - T] = 0;
         if (o[k].right >= T) prodmap[o[k].right - T] = 0;
+        consumed[k] = done[k] = 0;
       }
       for (unsigned int k = 0; k < n; ++k)
       {
         int c0 = -1, c1 = -1;
         if (o[k].left >= T && prodmap[o[k].left - T]) c0 = prodmap[o[k].left - T] - 1;
         if (o[k].right >= T && prodmap[o[k].right - T]) c1 = prodmap[o[k].right - T] - 1;
-        if (c0 >= 0 && (consumed >> c0) & 1u) c0 = -1;      // a value is pushed to one consumer only
-        if (c1 >= 0 && ((consumed >> c1) & 1u || c1 == c0)) c1 = -1;
+        if (c0 >= 0 && consumed[c0]) c0 = -1;               // a value is pushed to one consumer only
+        if (c1 >= 0 && (consumed[c1] || c1 == c0)) c1 = -1;
         kid[k][0] = (signed char)c0; kid[k][1] = (signed char)c1;
-        if (c0 >= 0) consumed |= 1u << c0;
-        if (c1 >= 0) consumed |= 1u << c1;
+        if (c0 >= 0) consumed[c0] = 1;
+        if (c1 >= 0) consumed[c1] = 1;
         const unsigned int n0 = c0 >= 0 ? need[c0] : 0u, n1 = c1 >= 0 ? need[c1] : 0u;
         need[k] = (unsigned char)((c0 >= 0 && c1 >= 0) ? max(max(n0, n1), 1u + min(n0, n1)) : max(n0, n1));
         prodmap[o[k].parent - T] = (unsigned char)(k + 1);
       }
       // post-order DFS from every list root (ops nobody in the list consumes), bigger need first
       unsigned int emitted = 0;
-      unsigned char stack[SM_OPS];
-      unsigned int done = 0;
+      unsigned char stack[PLAN_MED_OPS];
       for (unsigned int root = 0; root < n; ++root)
       {
-        if ((consumed >> root) & 1u) continue;
+        if (consumed[root]) continue;
         int sp = 0;
         stack[sp++] = (unsigned char)root;
         while (sp > 0)
         {
           const unsigned int k = stack[sp - 1];
           const int c0 = kid[k][0], c1 = kid[k][1];
-          const bool p0 = c0 >= 0 && !((done >> c0) & 1u), p1 = c1 >= 0 && !((done >> c1) & 1u);
+          const bool p0 = c0 >= 0 && !done[c0], p1 = c1 >= 0 && !done[c1];
           if (p0 || p1)
           {
             int nxt;
@@ -554,7 +555,7 @@ plan_kernel_blocks(const LocusDev * __restrict__ loci, const unsigned int * __re
             else nxt = p0 ? c0 : c1;
             stack[sp++] = (unsigned char)nxt;
           }
-          else { order[emitted++] = (unsigned char)k; done |= 1u << k; --sp; }
+          else { order[emitted++] = (unsigned char)k; done[k] = 1; --sp; }
         }
       }
       for (unsigned int k = 0; k < n; ++k) prodmap[o[k].parent - T] = 0;      // reused below: op slot of the producer
@@ -573,10 +574,10 @@ plan_kernel_blocks(const LocusDev * __restrict__ loci, const unsigned int * __re
     };
     const unsigned int cells_per_buf = L.sites * RL;
     int last_root = -1;                        // the last op that writes the root CLV carries OP_ROOT
-    for (unsigned int kk = 0; kk < n; ++kk) if (want_root && o[small ? (unsigned int)order[kk] : kk].parent == rootc) last_root = (int)kk;
+    for (unsigned int kk = 0; kk < n; ++kk) if (want_root && o[ordered ? (unsigned int)order[kk] : kk].parent == rootc) last_root = (int)kk;
     for (unsigned int kk = 0; kk < n; ++kk)
     {
-      const RawOp r = o[small ? (unsigned int)order[kk] : kk];
+      const RawOp r = o[ordered ? (unsigned int)order[kk] : kk];
       const unsigned int child[2] = { r.left, r.right };
       unsigned int ntip = 0;
       for (int c = 0; c < 2; ++c) if (child[c] < T && !L.tip_is_dense[child[c]]) ++ntip;
@@ -598,7 +599,7 @@ plan_kernel_blocks(const LocusDev * __restrict__ loci, const unsigned int * __re
             q.kind = SRC_TIP_PACKED;
             q.sel = 15u | ((idx >> 3) << 4) | (((idx & 7u) * 4) << 8);
             q.off = c_ntips * lut_unit; ++c_ntips;
-            if (idx >= 16) fast = false;
+            if (idx >= max_fast_tip) fast = false;              // its tip word is not staged
           }
         }
         else
@@ -623,7 +624,7 @@ plan_kernel_blocks(const LocusDev * __restrict__ loci, const unsigned int * __re
             q.kind = SRC_HBM; q.p0 = b; q.sc = c ? r.rsc : r.lsc;
             // produced by an op of the chunk being filled: the fast path re-reads the CLV (an L2 hit)
             // and applies the producer's Pup, which is staged with this chunk
-            if (small && prodmap[b] && (unsigned)(prodmap[b] - 1) / TREE_CHUNK == c_idx)
+            if (ordered && prodmap[b] && (unsigned)(prodmap[b] - 1) / TREE_CHUNK == c_idx)
             {
               q.kind = SRC_HBML; q.off = (unsigned)(prodmap[b] - 1) % TREE_CHUNK;
               OpRec * prod = rec_at(prodmap[b] - 1);
@@ -661,7 +662,7 @@ plan_kernel_blocks(const LocusDev * __restrict__ loci, const unsigned int * __re
       *rec_at(rix) = q;
       ++c_nops;
       prev = r.parent - T; prev_off = rix;
-      if (small) prodmap[r.parent - T] = (unsigned char)(rix + 1);
+      if (ordered && rix < 255u) prodmap[r.parent - T] = (unsigned char)(rix + 1);
     }
     cnt = n;
     if (want_root && !root_done)
@@ -695,7 +696,8 @@ plan_kernel_blocks(const LocusDev * __restrict__ loci, const unsigned int * __re
     H->clv = L.clv; H->tip_dense = L.tip_dense; H->scale = L.scale;
     H->tipwords = reinterpret_cast<const unsigned int *>(L.tip_codes); H->pmat = L.pmat;
     H->clv_stride = L.clv_stride; H->sites = L.sites; H->nops = cnt; H->tip_words = L.tip_words;
-    H->n_chunks = n_chunks; H->flags = (fast && n_chunks == 1) ? HDR_FAST : 0u; H->pad0 = 0;
+    // chunk by chunk on the fast path as long as every operand is a staged tip, the register or a stack slot
+    H->n_chunks = n_chunks; H->flags = fast ? HDR_FAST : 0u; H->pad0 = 0;
     for (int j = 0; j < 4; ++j) H->freqs[j] = L.freqs[j];
     plan_count[bl] = cnt;
   }

@@ -207,6 +207,11 @@ def engine_pinned(a):
     dict(tips=3, sites=257, states=4, rate_cats=2, model="GTR", rates=[0.4, 1.6]),   # ragged last tile
     dict(tips=7, sites=300, states=4, rate_cats=3, model="GTR", rates=[0.2, 0.9, 1.9]),   # R not a power of 2
     dict(tips=33, sites=129, states=4, rate_cats=8, model="GTR", scaling=True, rates=list(np.linspace(0.1, 3, 8))),
+    # big trees: serially planned with Sethi-Ullman ordering, several chunks, up to 16 packed tip words per cell
+    dict(tips=60, sites=301, states=4, rate_cats=1, model="JC69"),                   # frogs-sized loci
+    dict(tips=100, sites=140, states=4, rate_cats=4, model="GTR", scaling=True),
+    dict(tips=129, sites=77, states=4, rate_cats=2, model="GTR", rates=[0.4, 1.6]),  # the last tip word has one tip
+    dict(tips=200, sites=40, states=4, rate_cats=1, model="JC69", scaling=True),     # beyond every fast-path limit
 ])
 def test_against_oracle_seeded(eng, cfg):
     w = synth.make_workload("seeded", n_loci=12, seed=4242, lg=lg_tables(), **cfg)

@@ -1,4 +1,5 @@
-"""Device-resident full-pass time vs. tips per locus (fast path <= 16 tips / one chunk, general walker beyond).
+"""Device-resident full-pass time vs. tips per locus (one-chunk fast path up to 16 tips, chunk-by-chunk fast path up to
+128 tips, general walker beyond).
 Usage: tips_sweep.py [rate_cats] [model]"""
 import sys
 
@@ -8,7 +9,7 @@ from bpp_b200 import engine, synth  # noqa: E402
 R = int(sys.argv[1]) if len(sys.argv) > 1 else 4
 model = sys.argv[2] if len(sys.argv) > 2 else "GTR"
 eng = engine.Engine(0)
-for tips in (8, 16, 17, 24, 32, 48):
+for tips in (8, 16, 17, 24, 32, 48, 64, 96, 128):
     n = max(200, 32000 // tips)
     w = synth.make_workload("sweep", n_loci=n, tips=tips, sites=1000, states=4, rate_cats=R, model=model, seed=3)
     loci, trees = engine.load_workload(eng, w)
