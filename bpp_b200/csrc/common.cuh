@@ -242,6 +242,49 @@ __device__ __forceinline__ void cp_async4(void * smem_dst, const void * gsrc)
   const unsigned int s = (unsigned int)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(s), "l"(gsrc) : "memory");
 }
+// ---- TMA bulk copies (1-D, no tensor map): one elected thread moves a contiguous block between global and shared
+// memory; completion of a load is signalled on an mbarrier (complete_tx), of a store through the bulk async-group
+__device__ __forceinline__ void mbar_init(unsigned long long * bar, unsigned int count)
+{
+  const unsigned int a = (unsigned int)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(a), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long * bar, unsigned int bytes)
+{
+  const unsigned int a = (unsigned int)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(a), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long * bar, unsigned int parity)
+{
+  const unsigned int a = (unsigned int)__cvta_generic_to_shared(bar);
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" :: "r"(a), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void * smem_dst, const void * gsrc, unsigned int bytes, unsigned long long * bar)
+{
+  const unsigned int d = (unsigned int)__cvta_generic_to_shared(smem_dst);
+  const unsigned int b = (unsigned int)__cvta_generic_to_shared(bar);
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(d), "l"(gsrc), "r"(bytes), "r"(b) : "memory");
+}
+__device__ __forceinline__ void bulk_store(void * gdst, const void * smem_src, unsigned int bytes)
+{
+  const unsigned int s = (unsigned int)__cvta_generic_to_shared(smem_src);
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(gdst), "r"(s), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(N) : "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait() { asm volatile("cp.async.bulk.wait_group %0;" :: "n"(N) : "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 

@@ -2,13 +2,7 @@
 //
 // One persistent CTA walks a contiguous range of tiles; a tile is TREE_NT*CPT cells
 // (cell = pattern*RL + cat, RL = rate categories, a power of two <= 8 so that the RL lanes of a site
-// sit in one warp) of one locus; thread tid owns the CPT cells cell0 + perm(tid) + j*TREE_NT (same category).
-// perm() permutes the 32 cells of a warp so that lanes that are neighbours share the CATEGORY and walk the sites
-// (lane = cat * (32/RL) + site): a warp still reads and writes the same contiguous 1 KB of a CLV, but its
-// shared-memory traffic is conflict-free -- the P-matrix words of a push are the same address for every lane of a
-// quarter warp, and the tip lookup rows of a quarter warp differ by the state mask only, which the row padding
-// (LUT_ROW) spreads over the banks.  With cat = lane % RL (round 1) two sites of a quarter warp collided whenever
-// their masks differed: 31 % of all shared-memory wavefronts of the 4-category kernel were conflict replays.
+// sit in one warp) of one locus; thread tid owns the CPT cells cell0 + tid + j*TREE_NT (same category).
 // For its cells a thread executes the locus' WHOLE planned op list as a stack machine over
 // TRANSFORMED vectors X = P_edge . clv:
 //   - a packed tip child (4 bits per tip and site, fetched one tile ahead, kept in registers) is one
@@ -84,13 +78,45 @@ __device__ __forceinline__ Vec4 matvec_s4(const unsigned int p, const double v0,
 }
 
 // cell offset (within the CTA's TREE_NT cells of one j) owned by thread tid: lanes of a warp are ordered category-major
-template <int RL>
-__device__ __forceinline__ unsigned int s4_perm(const unsigned int tid)
+#ifndef BPPGPU_S4_PERM
+#define BPPGPU_S4_PERM 0
+#endif
+// lanes of a site: with the identity mapping (cell = cell0 + tid) the RL lanes of a site are neighbours; the
+// category-major permutation (BPPGPU_S4_PERM=1, measured and rejected: every quarter warp then writes eight
+// 32-byte pieces of eight different 128-byte lines per store instead of 256 contiguous bytes, and the store path
+// is transaction-bound: config 3 went from 3.84 to 4.82 ms) puts them 32/RL lanes apart
+template <int RL> struct S4Lanes
 {
-  constexpr unsigned int SPW = 32u / RL;              // sites per warp
-  const unsigned int lane = tid & 31u;
-  return (tid & ~31u) | ((lane % SPW) * RL + lane / SPW);
-}
+  static constexpr unsigned int SPW = 32u / RL;       // sites per warp
+  __device__ static __forceinline__ unsigned int perm(const unsigned int tid)
+  {
+#if BPPGPU_S4_PERM
+    const unsigned int lane = tid & 31u;
+    return (tid & ~31u) | ((lane % SPW) * RL + lane / SPW);
+#else
+    return tid;
+#endif
+  }
+  // lane of category r of this lane's site; xor distance between the lanes of a site for step dd = 1, 2, 4
+  __device__ static __forceinline__ unsigned int cat_lane(const unsigned int lane, const unsigned int r)
+  {
+#if BPPGPU_S4_PERM
+    return (lane % SPW) + r * SPW;
+#else
+    return (lane & ~(unsigned int)(RL - 1)) + r;
+#endif
+  }
+  __device__ static __forceinline__ unsigned int xor_step(const unsigned int dd)
+  {
+#if BPPGPU_S4_PERM
+    return dd * SPW;
+#else
+    return dd;
+#endif
+  }
+};
+template <int RL>
+__device__ __forceinline__ unsigned int s4_perm(const unsigned int tid) { return S4Lanes<RL>::perm(tid); }
 
 template <int RL, int CPT>
 struct S4Layout               // everything in uint4 (16-byte) units
@@ -104,8 +130,11 @@ struct S4Layout               // everything in uint4 (16-byte) units
   static constexpr unsigned TIPP = PUP + TREE_CHUNK * RL * 9;     // [CAP][RL] x 9
   static constexpr unsigned STAGE = TIPP + CAP * RL * 9;          // one stage buffer
   static constexpr unsigned CHUNK = STAGE - CH;                   // chunk size
-  static constexpr unsigned NSTAGE = RL >= 8 ? 1 : 2;             // double-buffered staging (the next locus' block is copied while
-                                                                  // the current one computes) where shared memory allows
+#ifndef BPPGPU_S4_NSTAGE4
+#define BPPGPU_S4_NSTAGE4 2
+#endif
+  static constexpr unsigned NSTAGE = RL >= 8 ? 1 : (RL == 4 ? BPPGPU_S4_NSTAGE4 : 2);   // double-buffered staging (the next locus' block
+                                                                  // is copied while the current one computes) where shared memory allows
   // shared memory of the kernel: [RING 4 x (TileDesc 2 + blk 1)][RED 32 doubles][NSTAGE stage buffers]
   // [LUT [cap][RL] x 49][STACK [slots][CPT*TREE_NT][2] uint4, then [slots][CPT*TREE_NT] u32].  cap is the
   // launch's tip-slot capacity (<= CAP, sized to the batch's largest tree): a stage buffer holds only
@@ -266,7 +295,7 @@ __device__ __forceinline__ double tile_fast(const TreeParams & prm, const TileCt
         unsigned int below = (o[j][0] < BPPGPU_SCALE_THRESHOLD) & (o[j][1] < BPPGPU_SCALE_THRESHOLD) &
                              (o[j][2] < BPPGPU_SCALE_THRESHOLD) & (o[j][3] < BPPGPU_SCALE_THRESHOLD);
 #pragma unroll
-        for (int dd = 1; dd < RL; dd <<= 1) below &= __shfl_xor_sync(0xFFFFFFFFu, below, dd * (32 / RL));
+        for (int dd = 1; dd < RL; dd <<= 1) below &= __shfl_xor_sync(0xFFFFFFFFu, below, S4Lanes<RL>::xor_step(dd));
         if (below)
         {
           o[j][0] = __dmul_rn(o[j][0], BPPGPU_SCALE_FACTOR); o[j][1] = __dmul_rn(o[j][1], BPPGPU_SCALE_FACTOR);
@@ -320,7 +349,7 @@ __device__ __forceinline__ double tile_fast(const TreeParams & prm, const TileCt
 #pragma unroll
         for (int r = 0; r < RL; ++r)
         {
-          const double v = __shfl_sync(0xFFFFFFFFu, tr, (lane % (32 / RL)) + r * (32 / RL));
+          const double v = __shfl_sync(0xFFFFFFFFu, tr, S4Lanes<RL>::cat_lane(lane, r));
           term[j] = __dadd_rn(term[j], __dmul_rn(v, s8[(sb + Lay::RW) * 2 + r]));
         }
       }
@@ -464,7 +493,7 @@ __device__ __noinline__ double chunk_general(const TreeParams prm, unsigned int 
         unsigned int below = (o0 < BPPGPU_SCALE_THRESHOLD) & (o1 < BPPGPU_SCALE_THRESHOLD) &
                              (o2 < BPPGPU_SCALE_THRESHOLD) & (o3 < BPPGPU_SCALE_THRESHOLD);
 #pragma unroll
-        for (int dd = 1; dd < RL; dd <<= 1) below &= __shfl_xor_sync(0xFFFFFFFFu, below, dd * (32 / RL));
+        for (int dd = 1; dd < RL; dd <<= 1) below &= __shfl_xor_sync(0xFFFFFFFFu, below, S4Lanes<RL>::xor_step(dd));
         if (below)
         {
           o0 = __dmul_rn(o0, BPPGPU_SCALE_FACTOR); o1 = __dmul_rn(o1, BPPGPU_SCALE_FACTOR);
@@ -494,7 +523,7 @@ __device__ __noinline__ double chunk_general(const TreeParams prm, unsigned int 
 #pragma unroll
       for (int r = 0; r < RL; ++r)
       {
-        const double v = __shfl_sync(0xFFFFFFFFu, tr, (lane % (32 / RL)) + r * (32 / RL));
+        const double v = __shfl_sync(0xFFFFFFFFu, tr, S4Lanes<RL>::cat_lane(lane, r));
         term = __dadd_rn(term, __dmul_rn(v, s8[(sb + Lay::RW) * 2 + r]));
       }
       unsigned int rsc = osc;
@@ -507,7 +536,9 @@ __device__ __noinline__ double chunk_general(const TreeParams prm, unsigned int 
         if (rsc) s = __dadd_rn(s, __dmul_rn((double)rsc, prm.log_threshold));
         s = __dmul_rn(s, (double)wgt);
       }
-      if (valid && cat == 0)
+      // the lane that owns this site's sum is the one tile_fast picks (category j mod RL), so that a root evaluated
+      // here and one evaluated there add the same numbers in the same order
+      if (valid && cat == (j % RL))
       {
         site_sum += s;
         if (prm.persite) prm.persite[pattern] = s;
@@ -559,11 +590,20 @@ tree_kernel_s4(const TreeParams prm)
       cp_async16(&s4[Lay::RING + (t & 3u) * 3 + tid], src);
     }
   };
+  // The locus block (header + rate weights + chunk 0: op records and the P-matrices of its edges, contiguous, built
+  // by the planner) comes in as ONE TMA bulk copy issued by thread 0; every thread waits for it on the stage
+  // buffer's mbarrier when the block is first used.  (Round 1 copied it with 16-byte cp.async by all threads.)
+  unsigned long long * const mbar = reinterpret_cast<unsigned long long *>(&s8[Lay::RED * 2 + 8]);
+  unsigned int mphase[2] = {0u, 0u};
   auto stage_fetch = [&](unsigned int buf, unsigned long long blk)   // header + rate weights + chunk 0
   {
-    const uint4 * src = reinterpret_cast<const uint4 *>(prm.blocks + blk);
-    for (unsigned int w = tid; w < stage_sz; w += TREE_NT) cp_async16(&s4[Lay::STAGE0 + buf * stage_sz + w], src + w);
+    if (tid == 0)
+    {
+      mbar_expect_tx(mbar + buf, stage_sz * 16u);
+      bulk_load(&s4[Lay::STAGE0 + buf * stage_sz], prm.blocks + blk, stage_sz * 16u, mbar + buf);
+    }
   };
+  auto stage_wait = [&](unsigned int buf) { mbar_wait(mbar + buf, mphase[buf]); mphase[buf] ^= 1u; };
   const unsigned int tips0 = Lay::tips0_u32(prm.n_slots, prm.lut_cap), tips_buf = Lay::tips_buf(prm.tip_words);
   // packed tip words + pattern weight of the thread's cells of tile d -> tip buffer `tb` (asynchronous; each
   // thread copies and later reads only its own entries, so the cp.async wait alone orders them)
@@ -581,6 +621,7 @@ tree_kernel_s4(const TreeParams prm)
     }
   };
 
+  if (tid == 0) { mbar_init(mbar, 1); mbar_init(mbar + 1, 1); mbar_init_fence(); }
   ring_fetch(t_begin);
   ring_fetch(t_begin + 1);
   cp_async_commit();
@@ -606,14 +647,9 @@ tree_kernel_s4(const TreeParams prm)
     // ---- make the locus block current: either it was prefetched into the other buffer, or load it now
     if (d.locus != staged_locus)
     {
-      if (d.locus == prefetched_locus) buf ^= 1u;          // landed: wait_all + barrier at the end of the last tile
-      else
-      {
-        stage_fetch(buf, blk);
-        cp_async_commit();
-        cp_async_wait_all();
-        __syncthreads();
-      }
+      if (d.locus == prefetched_locus) buf ^= 1u;          // on its way (or landed) since the previous tile
+      else stage_fetch(buf, blk);                          // (every reader of this buffer passed the last tile's barrier)
+      stage_wait(buf);
       prefetched_locus = 0xFFFFFFFFu;
       build_lut<RL, EXACT, CPT>(Lay::STAGE0 + buf * stage_sz, lut0);
       __syncthreads();

@@ -6,6 +6,7 @@
  *     locus_update_matrices      locus.c:2417        locus_update_partials     locus.c:2530
  *     locus_update_all_partials  locus.c:2523        locus_root_loglikelihood  locus.c:2573
  *     locus_destroy              locus.c:872         prop_mixing_update_gtrees prop_mixing.c:52
+ *     propose_tau_update_gtrees  stree.c:4338
  *
  * Linked into an executable in front of the reference built as a shared library (the recipe that compiles the reference, see INTEGRATION.md, builds
  * libbppref.so from the unmodified sources with -fPIC, so every call to these functions -- including the ones made
@@ -30,10 +31,10 @@
  *     pll_update_eigen when needed; the engine then gets (pmatrix_index, length) and builds the matrices on the
  *     device.  (The host-side P-matrices the call also fills are unused.)
  *   - gnode_t index flips (SWAP_CLV_INDEX ...) stay host integers; every call passes them.
- *   - prop_mixing_update_gtrees: the reference's loop body is kept (it is called as is), but while it runs the seam
- *     only RECORDS each locus' triplet and returns lnL = 0; afterwards all loci of the call go to the device as one
- *     batch (one upload, one planner + tree kernel + finish launch, one read-back) and gt->logl / lnacceptance get
- *     their lnL added.  BPP_B200_BATCH=0 turns that off.
+ *   - prop_mixing_update_gtrees and propose_tau_update_gtrees: the reference's loop body is kept (it is called as
+ *     is), but while it runs the seam only RECORDS each locus' triplet and returns lnL = 0; afterwards all loci of
+ *     the call go to the device as one batch (one upload, one planner + tree kernel + finish launch, one
+ *     read-back) and gt->logl / lnacceptance / logl_diff get their lnL added.  BPP_B200_BATCH=0 turns that off.
  *   - everywhere else a locus' update_matrices / update_partials are queued and leave together with its next
  *     root_loglikelihood as one call (BPP_B200_FUSE=0: three synchronous calls, as the reference issues them).
  */
@@ -52,6 +53,8 @@ typedef void   (*fn_update_all_partials)(locus_t *, gtree_t *);
 typedef double (*fn_root_loglikelihood)(locus_t *, gnode_t *, const unsigned int *, double *);
 typedef void   (*fn_locus_destroy)(locus_t *);
 typedef void   (*fn_mixing)(locus_t **, gtree_t **, stree_t *, long, long, double, long, double *);
+typedef void   (*fn_tau)(locus_t **, gtree_t **, stree_t *, snode_t *, double, double, double, double, double, long, long,
+                         snode_t **, unsigned int, unsigned int *, unsigned int *, double *, double *, long);
 
 static fn_update_matrices     real_update_matrices;
 static fn_update_partials     real_update_partials;
@@ -59,6 +62,7 @@ static fn_update_all_partials real_update_all_partials;
 static fn_root_loglikelihood  real_root_loglikelihood;
 static fn_locus_destroy       real_locus_destroy;
 static fn_mixing              real_mixing;
+static fn_tau                 real_tau;
 
 static int g_enabled = -1, g_batching = 1, g_verbose = 0, g_fuse = 1;
 static bppgpu_engine * g_engine;
@@ -92,6 +96,7 @@ static void init_once(void)
   real_root_loglikelihood = (fn_root_loglikelihood)next_sym("locus_root_loglikelihood");
   real_locus_destroy = (fn_locus_destroy)next_sym("locus_destroy");
   real_mixing = (fn_mixing)next_sym("prop_mixing_update_gtrees");
+  real_tau = (fn_tau)next_sym("propose_tau_update_gtrees");
   g_enabled = ev && atoi(ev) != 0;
   if ((ev = getenv("BPP_B200_BATCH"))) g_batching = atoi(ev) != 0;
   if ((ev = getenv("BPP_B200_VERBOSE"))) g_verbose = atoi(ev);
@@ -304,8 +309,9 @@ typedef struct
   unsigned int * mcounts, * ocounts, * midx, * rclv; int * rsc; double * mbl; bppgpu_partial_op * ops;
   double * lnl;
   size_t cap_loci, cap_mats, cap_ops, n_mats, n_ops;
-  long next_slot;
-  int overflow;                          /* a locus was touched out of order / twice: finish this call unbatched */
+  long last_slot;                        /* slot of the locus whose calls are being recorded; slots only go up */
+  unsigned char * touched;               /* the locus asked for its root log-likelihood */
+  int overflow;                          /* a locus was visited out of order: the recording cannot be replayed */
 } defer_t;
 
 static __thread defer_t tl_defer;
@@ -315,7 +321,8 @@ static void defer_reserve(defer_t * d, size_t loci, size_t mats, size_t ops)
   if (loci > d->cap_loci)
   {
     bppgpu_host_free(d->mcounts); bppgpu_host_free(d->ocounts); bppgpu_host_free(d->rclv); bppgpu_host_free(d->rsc);
-    free(d->lnl);
+    free(d->lnl); free(d->touched);
+    d->touched = (unsigned char *)xmalloc(loci);
     d->cap_loci = loci;
     d->mcounts = (unsigned int *)bppgpu_host_alloc(loci * sizeof(unsigned int));
     d->ocounts = (unsigned int *)bppgpu_host_alloc(loci * sizeof(unsigned int));
@@ -354,14 +361,17 @@ void locus_update_matrices(locus_t * locus, gtree_t * gtree, gnode_t ** traversa
   s = state_of(locus);
   sync_model(s, locus);
   __atomic_add_fetch(&n_mat_calls, 1, __ATOMIC_RELAXED);
-  if (d->active && !d->overflow && s->slot == d->next_slot && d->mcounts[s->slot] == 0)
+  if (d->active && s->slot >= 0)
   {
+    /* the arrays are concatenated in slot order: a locus may be visited once, later loci only afterwards; matrices
+       behind this locus' partials would have to be replayed in between, which one fused pass cannot do */
+    if (s->slot < d->last_slot || d->ocounts[s->slot]) { d->overflow = 1; return; }
+    d->last_slot = s->slot;
     defer_reserve(d, 0, d->n_mats + count, 0);
     for (i = 0; i < count; ++i) { d->midx[d->n_mats + i] = traversal[i]->pmatrix_index; d->mbl[d->n_mats + i] = traversal[i]->length; }
-    d->mcounts[s->slot] = count; d->n_mats += count;
+    d->mcounts[s->slot] += count; d->n_mats += count;
     return;
   }
-  if (d->active) d->overflow = 1;
   /* partials queued behind earlier matrices must see those, not these: keep the order by flushing */
   if (s->p_ops) flush_pending(s);
   ensure_cap(s, s->p_mats + count);
@@ -378,14 +388,15 @@ void locus_update_partials(locus_t * locus, gnode_t ** traversal, unsigned int c
   if (!opt_usedata) return;
   s = state_of(locus);
   __atomic_add_fetch(&n_part_calls, 1, __ATOMIC_RELAXED);
-  if (d->active && !d->overflow && s->slot == d->next_slot && d->ocounts[s->slot] == 0)
+  if (d->active && s->slot >= 0)
   {
+    if (s->slot < d->last_slot) { d->overflow = 1; return; }
+    d->last_slot = s->slot;
     defer_reserve(d, 0, 0, d->n_ops + count);
     fill_ops(traversal, count, d->ops + d->n_ops);
-    d->ocounts[s->slot] = count; d->n_ops += count;
+    d->ocounts[s->slot] += count; d->n_ops += count;
     return;
   }
-  if (d->active) d->overflow = 1;
   ensure_cap(s, s->p_ops + count);
   fill_ops(traversal, count, s->ops + s->p_ops);
   s->p_ops += count;
@@ -422,13 +433,14 @@ double locus_root_loglikelihood(locus_t * locus, gnode_t * root, const unsigned 
   s = state_of(locus);
   sync_diploid(s, locus);
   __atomic_add_fetch(&n_root_calls, 1, __ATOMIC_RELAXED);
-  if (d->active && !d->overflow && s->slot == d->next_slot && !persite_lnl)
+  if (d->active && s->slot >= 0)
   {
+    if (s->slot < d->last_slot || persite_lnl) { d->overflow = 1; return 0.0; }
+    d->last_slot = s->slot;
     d->rclv[s->slot] = root->clv_index; d->rsc[s->slot] = root->scaler_index;
-    d->next_slot++;
+    d->touched[s->slot] = 1;
     return 0.0;                                   /* the batch adds the real value afterwards */
   }
-  if (d->active) d->overflow = 1;
   if (g_fuse && !persite_lnl)
   {
     /* matrices + partials + root of this locus in one call; a batch applies the diploid phase mean itself */
@@ -476,22 +488,16 @@ void locus_destroy(locus_t * locus)
   real_locus_destroy(locus);
 }
 
-/* ------------------------------------------------------------------ batched mixing move (prop_mixing.c:52-220) */
-void prop_mixing_update_gtrees(locus_t ** locus, gtree_t ** gtree, stree_t * stree, long locus_start, long locus_count,
-                               double c, long thread_index, double * ret_lnacceptance)
+/* ------------------------------------------------------------------ batched caller loops
+ * Both whole-data proposals walk `for each locus`, call the seam triplet for the loci they changed, add
+ * logl - gtree->logl to a running sum and store gtree->logl = logl; the accept / reject decision is taken
+ * afterwards for all loci together (prop_mixing.c:52-220 lnacceptance, stree.c:4338-4775 logl_diff).  The
+ * reference's own loop is run as it is, with the seam recording instead of computing and returning logl = 0; then
+ * ONE batch evaluates every recorded locus and the sums and gtree->logl get the real values added. */
+static int defer_begin(defer_t * d, locus_t ** locus, long locus_start, long locus_count)
 {
-  defer_t * d = &tl_defer;
   long i;
-  int same;
-  double sum = 0;
-  if (!enabled() || !g_batching || !opt_usedata || locus_count < 2 || d->active)
-  {
-    pthread_once(&g_once, init_once);
-    real_mixing(locus, gtree, stree, locus_start, locus_count, c, thread_index, ret_lnacceptance);
-    return;
-  }
-  /* the batch of these loci (cached while the caller keeps asking for the same range) */
-  same = d->batch && d->batch_n == locus_count;
+  int same = d->batch && d->batch_n == locus_count;
   for (i = 0; same && i < locus_count; ++i) same = d->batch_key[i] == locus[locus_start + i];
   if (!same)
   {
@@ -511,12 +517,7 @@ void prop_mixing_update_gtrees(locus_t ** locus, gtree_t ** gtree, stree_t * str
     d->batch_n = locus_count;
     if (uniform) d->batch = bppgpu_batch_create(g_engine, (unsigned int)locus_count, hs);
     free(hs);
-    if (!d->batch)       /* mixed data types: a batch needs one (states, rate_cats) shape */
-    {
-      d->batch_n = 0;
-      real_mixing(locus, gtree, stree, locus_start, locus_count, c, thread_index, ret_lnacceptance);
-      return;
-    }
+    if (!d->batch) { d->batch_n = 0; return 0; }        /* mixed data types: a batch needs one (states, rate_cats) shape */
   }
   defer_reserve(d, (size_t)locus_count, 0, 0);
   for (i = 0; i < locus_count; ++i)
@@ -525,27 +526,78 @@ void prop_mixing_update_gtrees(locus_t ** locus, gtree_t ** gtree, stree_t * str
     if (s->p_mats || s->p_ops) flush_pending(s);
     s->slot = i;
     d->mcounts[i] = d->ocounts[i] = 0;
+    d->touched[i] = 0;
   }
-  d->n_mats = d->n_ops = 0; d->next_slot = 0; d->overflow = 0;
+  d->n_mats = d->n_ops = 0; d->last_slot = 0; d->overflow = 0;
   d->first = locus_start; d->count = locus_count;
   d->active = 1;
-  /* the reference's own loop: times, index flips, priors; the seam calls above only record */
-  real_mixing(locus, gtree, stree, locus_start, locus_count, c, thread_index, ret_lnacceptance);
+  return 1;
+}
+
+/* returns the sum of the new log-likelihoods of the recorded loci, after storing them in gtree->logl */
+static double defer_end(defer_t * d, locus_t ** locus, gtree_t ** gtree, const char * who)
+{
+  long i, touched = 0;
+  double sum = 0;
   d->active = 0;
-  for (i = 0; i < locus_count; ++i) state_of(locus[locus_start + i])->slot = -1;
-  if (d->overflow || d->next_slot != locus_count)
-    fatal("locus_cuda: prop_mixing_update_gtrees did not issue one update_matrices / update_partials / "
-          "root_loglikelihood triplet per locus in order (run with BPP_B200_BATCH=0)");
+  for (i = 0; i < d->count; ++i) state_of(locus[d->first + i])->slot = -1;
+  if (d->overflow)
+    fatal("locus_cuda: %s visited its loci out of order or asked for per-site values; run with BPP_B200_BATCH=0", who);
+  for (i = 0; i < d->count; ++i)
+  {
+    if (d->touched[i]) { ++touched; continue; }
+    if (d->mcounts[i] || d->ocounts[i])
+      fatal("locus_cuda: %s updated locus %ld without evaluating it; run with BPP_B200_BATCH=0", who, d->first + i);
+    /* untouched: its root is evaluated along (and ignored) */
+    d->rclv[i] = gtree[d->first + i]->root->clv_index; d->rsc[i] = gtree[d->first + i]->root->scaler_index;
+  }
+  if (!touched) return 0;
   if (!bppgpu_batch_full_pass(d->batch, d->mcounts, d->midx, d->mbl, d->ocounts, d->ops, d->rclv, d->rsc, d->lnl, NULL))
     fatal("bppgpu_batch_full_pass: %s", bppgpu_last_error());
   __atomic_add_fetch(&n_batches, 1, __ATOMIC_RELAXED);
-  __atomic_add_fetch(&n_batch_loci, (unsigned long long)locus_count, __ATOMIC_RELAXED);
-  /* the loop ran with logl = 0: gt->logl = 0 and lnacceptance lacks the sum of the new log-likelihoods */
-  for (i = 0; i < locus_count; ++i)
+  __atomic_add_fetch(&n_batch_loci, (unsigned long long)touched, __ATOMIC_RELAXED);
+  for (i = 0; i < d->count; ++i)
+    if (d->touched[i])
+    {
+      const double logl = opt_bfbeta * d->lnl[i];
+      gtree[d->first + i]->logl = logl;       /* the loop stored 0 */
+      sum += logl;
+    }
+  return sum;
+}
+
+/* mixing move, prop_mixing.c:52-220 */
+void prop_mixing_update_gtrees(locus_t ** locus, gtree_t ** gtree, stree_t * stree, long locus_start, long locus_count,
+                               double c, long thread_index, double * ret_lnacceptance)
+{
+  defer_t * d = &tl_defer;
+  if (!enabled() || !g_batching || !opt_usedata || locus_count < 2 || d->active || !defer_begin(d, locus, locus_start, locus_count))
   {
-    const double logl = opt_bfbeta * d->lnl[i];
-    gtree[locus_start + i]->logl = logl;
-    sum += logl;
+    pthread_once(&g_once, init_once);
+    real_mixing(locus, gtree, stree, locus_start, locus_count, c, thread_index, ret_lnacceptance);
+    return;
   }
-  *ret_lnacceptance += sum;
+  real_mixing(locus, gtree, stree, locus_start, locus_count, c, thread_index, ret_lnacceptance);
+  *ret_lnacceptance += defer_end(d, locus, gtree, "prop_mixing_update_gtrees");
+}
+
+/* species-tree node age move, stree.c:4338-4775: only the loci with gene-tree nodes in the affected populations'
+   age window issue a triplet (a partial update along the marked nodes) */
+void propose_tau_update_gtrees(locus_t ** loci, gtree_t ** gtree, stree_t * stree, snode_t * snode, double oldage,
+                               double minage, double maxage, double minfactor, double maxfactor, long locus_start,
+                               long locus_count, snode_t ** affected, unsigned int paffected_count,
+                               unsigned int * ret_count_above, unsigned int * ret_count_below, double * ret_logl_diff,
+                               double * ret_logpr_diff, long thread_index)
+{
+  defer_t * d = &tl_defer;
+  if (!enabled() || !g_batching || !opt_usedata || locus_count < 2 || d->active || !defer_begin(d, loci, locus_start, locus_count))
+  {
+    pthread_once(&g_once, init_once);
+    real_tau(loci, gtree, stree, snode, oldage, minage, maxage, minfactor, maxfactor, locus_start, locus_count, affected,
+             paffected_count, ret_count_above, ret_count_below, ret_logl_diff, ret_logpr_diff, thread_index);
+    return;
+  }
+  real_tau(loci, gtree, stree, snode, oldage, minage, maxage, minfactor, maxfactor, locus_start, locus_count, affected,
+           paffected_count, ret_count_above, ret_count_below, ret_logl_diff, ret_logpr_diff, thread_index);
+  *ret_logl_diff += defer_end(d, loci, gtree, "propose_tau_update_gtrees");
 }

@@ -118,7 +118,7 @@ def test_frogs_a00_mcmc_on_the_engine(batch, fuse):
     m = re.search(r"update_partials (\d+), root_loglikelihood (\d+) calls; (\d+) batched passes over (\d+) loci; (\d+) kernels", stats[0])
     assert m and int(m.group(1)) > 1000 and int(m.group(5)) > 3000
     if batch == "1":
-        assert int(m.group(3)) > 50 and int(m.group(4)) == 5 * int(m.group(3))
+        assert int(m.group(3)) > 50 and int(m.group(3)) <= int(m.group(4)) <= 5 * int(m.group(3))
     else:
         assert int(m.group(3)) == 0
     stats[0] += " | %d iterations in %.1f s wall (whole process), stock avx2 %.1f s" % (BURNIN + 2 * NSAMPLE, secs, ref_secs)
