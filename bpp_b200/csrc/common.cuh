@@ -82,13 +82,13 @@ struct RawOp                    // == bppgpu_partial_op
 #define BPPGPU_TREE_NT 256
 #endif
 #ifndef BPPGPU_S4_CTAS2
-#define BPPGPU_S4_CTAS2 (2 * (256 / BPPGPU_TREE_NT))   // CTAs per SM targeted by the 2-cells-per-thread kernel
+#define BPPGPU_S4_CTAS2 (BPPGPU_TREE_NT > 256 ? 1 : 2 * (256 / BPPGPU_TREE_NT))   // CTAs per SM targeted by the 2-cells-per-thread kernel
 #endif
 constexpr int TREE_NT    = BPPGPU_TREE_NT;     // threads (= cells) per tile of the 4-state kernel
 // CTAs per SM the 4-state kernel is compiled for, by cells per thread (register budget 85 / 128 / 255)
 __host__ __device__ constexpr int s4_ctas_per_sm(int cpt)
 {
-  return cpt == 2 ? BPPGPU_S4_CTAS2 : (cpt == 1 ? 3 : 1) * (256 / TREE_NT);
+  return cpt == 2 ? BPPGPU_S4_CTAS2 : (TREE_NT > 256 ? 1 : (cpt == 1 ? 3 : 1) * (256 / TREE_NT));
 }
 constexpr int TREE_CHUNK = 16;      // ops per staged chunk
 constexpr int S4_MAX_TIP_WORDS = 16; // packed tip words (8 tips each) the 4-state fast path stages per cell: 128 tips
@@ -98,6 +98,20 @@ constexpr int LUT_ROW    = 6;       // doubles per state-mask row of a tip looku
                                     // one-hot masks 1,2,4,8 and 15 fall into different bank groups)
 constexpr int LUT_CAT    = 16 * LUT_ROW + 2;   // doubles per (tip child, cat) table
 __host__ __device__ constexpr int lut_cap(int RL) { return RL <= 2 ? 32 : (64 / RL); }   // tip children per chunk
+// Layout of the tip lookup tables in shared memory (uint4 = 16-byte units; an entry X = P_edge . bits(mask) is two
+// uint4: states 0,1 and states 2,3).
+//   RL <= 2: [slot][cat][mask] with padded rows (LUT_ROW) -- a quarter warp holds 8 or 4 different sites of the same
+//            one or two categories, the padding spreads their masks over the banks.
+//   RL >= 4: [slot][replica][mask][cat], no padding.  A quarter warp holds TWO sites x 4 categories (or one site x 8):
+//            with one table the two sites hit the same banks whenever their masks differ (31 % of all shared-memory
+//            wavefronts of the round-1 kernel were such replays).  Replica B holds the same entries with the two
+//            halves exchanged; the odd site of a quarter warp (lane bit 2) reads B and issues its loads in the
+//            opposite order, so every load instruction of a quarter warp covers eight different 16-byte bank groups,
+//            whatever the masks are.
+__host__ __device__ constexpr unsigned int lut_row_u4(int RL)  { return RL >= 4 ? 2u * (unsigned)RL : (unsigned)(LUT_ROW / 2); }
+__host__ __device__ constexpr unsigned int lut_cat_u4(int RL)  { return RL >= 4 ? 2u : (unsigned)(LUT_CAT / 2); }
+__host__ __device__ constexpr unsigned int lut_rep_u4(int RL)  { return RL >= 4 ? 32u * (unsigned)RL : 0u; }
+__host__ __device__ constexpr unsigned int lut_slot_u4(int RL) { return RL >= 4 ? 64u * (unsigned)RL : (unsigned)RL * (LUT_CAT / 2); }
 
 struct ChunkHdr { unsigned int nops, ntips, pad0, pad1; };
 

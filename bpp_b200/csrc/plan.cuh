@@ -430,7 +430,7 @@ plan_kernel_blocks(const LocusDev * __restrict__ loci, const unsigned int * __re
   unsigned char * blk = blocks + blk_off[bl];
   const size_t cb = chunk_bytes(RL);
   const unsigned int chunks0 = (unsigned int)(sizeof(LocusHdr) + rw_bytes(RL));
-  const unsigned int lut_unit = RL * (LUT_CAT / 2);      // uint4 units per tip table set
+  const unsigned int lut_unit = lut_slot_u4((int)RL);      // uint4 units per tip table set
   const unsigned int slot_unit = 2 * cpt * TREE_NT;      // uint4 units per stack slot
   const unsigned int T = L.tips;
   unsigned int n_chunks = 0, cnt = 0;
@@ -747,7 +747,7 @@ plan_refresh_blocks(const LocusDev * __restrict__ loci, const unsigned int * __r
   unsigned char * blk = blocks + blk_off[bl];
   const LocusHdr * H = reinterpret_cast<const LocusHdr *>(blk);
   const unsigned int chunks0 = (unsigned int)(sizeof(LocusHdr) + rw_bytes(RL));
-  gather_block_matrices(L, blk, chunks0, chunk_bytes(RL), H->n_chunks, RL, RL * (LUT_CAT / 2), (H->flags & HDR_LANEPLAN) != 0, nullptr);
+  gather_block_matrices(L, blk, chunks0, chunk_bytes(RL), H->n_chunks, RL, lut_slot_u4((int)RL), (H->flags & HDR_LANEPLAN) != 0, nullptr);
 }
 
 // ---------------------------------------------------------------- device-side index flips

@@ -81,6 +81,9 @@ __device__ __forceinline__ Vec4 matvec_s4(const unsigned int p, const double v0,
 #ifndef BPPGPU_S4_PERM
 #define BPPGPU_S4_PERM 0
 #endif
+#ifndef BPPGPU_S4_TMA_STAGE
+#define BPPGPU_S4_TMA_STAGE 1        // locus blocks arrive by one TMA bulk copy (0: 16-byte cp.async by all threads)
+#endif
 // lanes of a site: with the identity mapping (cell = cell0 + tid) the RL lanes of a site are neighbours; the
 // category-major permutation (BPPGPU_S4_PERM=1, measured and rejected: every quarter warp then writes eight
 // 32-byte pieces of eight different 128-byte lines per store instead of 256 contiguous bytes, and the store path
@@ -136,16 +139,17 @@ struct S4Layout               // everything in uint4 (16-byte) units
   static constexpr unsigned NSTAGE = RL >= 8 ? 1 : (RL == 4 ? BPPGPU_S4_NSTAGE4 : 2);   // double-buffered staging (the next locus' block
                                                                   // is copied while the current one computes) where shared memory allows
   // shared memory of the kernel: [RING 4 x (TileDesc 2 + blk 1)][RED 32 doubles][NSTAGE stage buffers]
-  // [LUT [cap][RL] x 49][STACK [slots][CPT*TREE_NT][2] uint4, then [slots][CPT*TREE_NT] u32].  cap is the
+  // [LUT cap x lut_slot_u4][STACK [slots][CPT*TREE_NT][2] uint4, then [slots][CPT*TREE_NT] u32].  cap is the
   // launch's tip-slot capacity (<= CAP, sized to the batch's largest tree): a stage buffer holds only
   // the first cap slots of the block's tipP area, which is why tipP comes last in the block.
   static constexpr unsigned RING = 0;
   static constexpr unsigned RED = 12;
-  static constexpr unsigned STAGE0 = 28;
+  static constexpr unsigned MBAR = 28;                            // two mbarriers (one per stage buffer)
+  static constexpr unsigned STAGE0 = 29;
   static constexpr unsigned SLOT = 2 * CPT * TREE_NT;             // uint4 per slot
   __host__ __device__ static constexpr unsigned stage_sz(unsigned cap) { return TIPP + cap * RL * 9; }
   __host__ __device__ static constexpr unsigned lut0(unsigned cap) { return STAGE0 + NSTAGE * stage_sz(cap); }
-  __host__ __device__ static constexpr unsigned stack0(unsigned cap) { return lut0(cap) + cap * RL * 49; }
+  __host__ __device__ static constexpr unsigned stack0(unsigned cap) { return lut0(cap) + cap * lut_slot_u4(RL); }
   // after the stack: packed tip words and pattern weights of the current and the next tile,
   // [2 buffers][W tip words, then the weight][CPT][TREE_NT] u32 (W = the launch's tip_words), filled by 4-byte cp.async
   __host__ __device__ static constexpr unsigned tips_buf(unsigned words) { return (words + 1) * CPT * TREE_NT; }   // u32 per buffer
@@ -193,14 +197,26 @@ __device__ __forceinline__ double tile_fast(const TreeParams & prm, const TileCt
   const unsigned int tid = threadIdx.x, lane = tid & 31u;
   const unsigned int sb = tc.sb;
   const LocusHdr * H = reinterpret_cast<const LocusHdr *>(&s4[sb]);
-  const unsigned int lut_t = tc.lut0 + tc.cat * 49;
-  const unsigned int stk_t = tc.stack0 + tid * 2;
+  // the two halves of an entry (states 0,1 / states 2,3) are loaded in the order that keeps a quarter warp's accesses
+  // on disjoint banks: lanes with bit 2 set fetch the upper half first -- from replica B of the lookup tables (RL >= 4,
+  // see lut_slot_u4) and from their own stack slots, which they fill in the same exchanged order
+  // Shared-memory operands are addressed by BYTE offsets from the start of the dynamic shared memory, built from
+  // per-thread invariants and per-op (warp-uniform) terms, so that a lookup costs shift / and / multiply-add per cell.
+  constexpr unsigned int ROWB = lut_row_u4(RL) * 16u, SLOTJ = 2u * TREE_NT * 16u;
+  const unsigned char * const sm = reinterpret_cast<const unsigned char *>(s4);
+  const unsigned int hs = (lane >> 2) & 1u, hl = RL >= 4 ? hs : 0u;
+  const unsigned int lut_lo = (tc.lut0 + tc.cat * lut_cat_u4(RL) + hl * lut_rep_u4(RL) + hl) * 16u;   // first-fetched half
+  const unsigned int stk_lo = (tc.stack0 + tid * 2 + hs) * 16u;
+  const int lut_d = hl ? -16 : 16, stk_d = hs ? -16 : 16;                                        // ... to the other half
   const unsigned int pup_t = sb + Lay::PUP + tc.cat * 9;
   const unsigned int tipp_t = sb + Lay::TIPP + tc.cat * 9;
   const unsigned int ops = sb + Lay::OPS;
   const unsigned int cn = s1[(sb + Lay::CH) * 4];
   unsigned char * const clv0 = reinterpret_cast<unsigned char *>(H->clv);
   const unsigned int sites = H->sites;
+  unsigned char * pc[CPT];                       // this thread's cells in CLV buffer 0
+#pragma unroll
+  for (int j = 0; j < CPT; ++j) pc[j] = clv0 + ((size_t)tc.cell[j] << 5);
 
   double site_sum = 0.0;
 
@@ -221,55 +237,71 @@ __device__ __forceinline__ double tile_fast(const TreeParams & prm, const TileCt
       // (SRC_HBML) or a tipP slot (SRC_HBM)
       const unsigned int akind = (ctl >> OP_AKIND_SHIFT) & 15u, bkind = (ctl >> OP_BKIND_SHIFT) & 15u;
       const bool a_hbm = FULL && (akind == SRC_HBML || akind == SRC_HBM), b_hbm = FULL && (bkind == SRC_HBML || bkind == SRC_HBM);
-      unsigned int a_cell0 = 0, b_cell0 = 0, a_pi = 0, b_pi = 0;
+      double2 a0[CPT], a1[CPT];
       if (a_hbm)
       {
-        a_cell0 = s1[(ops + 4 * k + 2) * 4] * (sites * RL);                 // a_p0 = buffer index
-        a_pi = (akind == SRC_HBML ? pup_t : tipp_t) + w0.w * (RL * 9);
+        const size_t a_off = (size_t)(s1[(ops + 4 * k + 2) * 4] * (sites * RL)) << 5;       // a_p0 = buffer index
+        const unsigned int a_pi = (akind == SRC_HBML ? pup_t : tipp_t) + w0.w * (RL * 9);
+#pragma unroll
+        for (int j = 0; j < CPT; ++j)
+        {
+          double v0, v1, v2, v3;
+          ld256(reinterpret_cast<const double *>(pc[j] + a_off), v0, v1, v2, v3);
+          a0[j].x = dot4<EXACT>(sd2[a_pi + 0], sd2[a_pi + 1], v0, v1, v2, v3); a0[j].y = dot4<EXACT>(sd2[a_pi + 2], sd2[a_pi + 3], v0, v1, v2, v3);
+          a1[j].x = dot4<EXACT>(sd2[a_pi + 4], sd2[a_pi + 5], v0, v1, v2, v3); a1[j].y = dot4<EXACT>(sd2[a_pi + 6], sd2[a_pi + 7], v0, v1, v2, v3);
+        }
       }
-      if (b_hbm)
+      else
       {
-        b_cell0 = s1[(ops + 4 * k + 3) * 4] * (sites * RL);                 // b_p0
-        b_pi = (bkind == SRC_HBML ? pup_t : tipp_t) + w1.y * (RL * 9);
+        // warp-uniform per op: table or stack, where the other half lies, how far apart the thread's cells are
+        const unsigned int base = (amask ? lut_lo : stk_lo) + w0.w * 16u, jst = amask ? 0u : SLOTJ;
+        const int dh = amask ? lut_d : stk_d;
+#pragma unroll
+        for (int j = 0; j < CPT; ++j)
+        {
+          const unsigned int wa = aword ? s1[tc.tips_s + (aword * CPT + j) * TREE_NT] : tc.tw0[j];
+          const unsigned int at = base + ((wa >> ash) & amask) * ROWB + j * jst;
+          a0[j] = *reinterpret_cast<const double2 *>(sm + at);
+          a1[j] = *reinterpret_cast<const double2 *>(sm + at + dh);
+        }
+      }
+      if (!(ctl & OP_BPREV))
+      {
+        // operand B is not the register X: load it INTO the X registers (they are dead: a pushed X
+        // is consumed by exactly one op, and that op has OP_BPREV)
+        if (b_hbm)
+        {
+          const size_t b_off = (size_t)(s1[(ops + 4 * k + 3) * 4] * (sites * RL)) << 5;     // b_p0
+          const unsigned int b_pi = (bkind == SRC_HBML ? pup_t : tipp_t) + w1.y * (RL * 9);
+#pragma unroll
+          for (int j = 0; j < CPT; ++j)
+          {
+            double v0, v1, v2, v3;
+            ld256(reinterpret_cast<const double *>(pc[j] + b_off), v0, v1, v2, v3);
+            x[j][0] = dot4<EXACT>(sd2[b_pi + 0], sd2[b_pi + 1], v0, v1, v2, v3); x[j][1] = dot4<EXACT>(sd2[b_pi + 2], sd2[b_pi + 3], v0, v1, v2, v3);
+            x[j][2] = dot4<EXACT>(sd2[b_pi + 4], sd2[b_pi + 5], v0, v1, v2, v3); x[j][3] = dot4<EXACT>(sd2[b_pi + 6], sd2[b_pi + 7], v0, v1, v2, v3);
+          }
+        }
+        else
+        {
+          const unsigned int base = (bmask ? lut_lo : stk_lo) + w1.y * 16u, jst = bmask ? 0u : SLOTJ;
+          const int dh = bmask ? lut_d : stk_d;
+#pragma unroll
+          for (int j = 0; j < CPT; ++j)
+          {
+            const unsigned int wb = bword ? s1[tc.tips_s + (bword * CPT + j) * TREE_NT] : tc.tw0[j];
+            const unsigned int at = base + ((wb >> bsh) & bmask) * ROWB + j * jst;
+            const double2 b0 = *reinterpret_cast<const double2 *>(sm + at);
+            const double2 b1 = *reinterpret_cast<const double2 *>(sm + at + dh);
+            x[j][0] = b0.x; x[j][1] = b0.y; x[j][2] = b1.x; x[j][3] = b1.y;
+          }
+        }
       }
 #pragma unroll
       for (int j = 0; j < CPT; ++j)
       {
-        double2 a0, a1;
-        if (a_hbm)
-        {
-          double v0, v1, v2, v3;
-          ld256(reinterpret_cast<const double *>(clv0 + (((size_t)a_cell0 + tc.cell[j]) << 5)), v0, v1, v2, v3);
-          a0.x = dot4<EXACT>(sd2[a_pi + 0], sd2[a_pi + 1], v0, v1, v2, v3); a0.y = dot4<EXACT>(sd2[a_pi + 2], sd2[a_pi + 3], v0, v1, v2, v3);
-          a1.x = dot4<EXACT>(sd2[a_pi + 4], sd2[a_pi + 5], v0, v1, v2, v3); a1.y = dot4<EXACT>(sd2[a_pi + 6], sd2[a_pi + 7], v0, v1, v2, v3);
-        }
-        else
-        {
-          const unsigned int wa = aword ? s1[tc.tips_s + (aword * CPT + j) * TREE_NT] : tc.tw0[j];
-          const unsigned int ia = (amask ? lut_t : stk_t + j * (2 * TREE_NT)) + w0.w + ((wa >> ash) & amask) * 3;
-          a0 = sd2[ia]; a1 = sd2[ia + 1];
-        }
-        if (!(ctl & OP_BPREV))
-        {
-          // operand B is not the register X: load it INTO the X registers (they are dead: a pushed X
-          // is consumed by exactly one op, and that op has OP_BPREV)
-          if (b_hbm)
-          {
-            double v0, v1, v2, v3;
-            ld256(reinterpret_cast<const double *>(clv0 + (((size_t)b_cell0 + tc.cell[j]) << 5)), v0, v1, v2, v3);
-            x[j][0] = dot4<EXACT>(sd2[b_pi + 0], sd2[b_pi + 1], v0, v1, v2, v3); x[j][1] = dot4<EXACT>(sd2[b_pi + 2], sd2[b_pi + 3], v0, v1, v2, v3);
-            x[j][2] = dot4<EXACT>(sd2[b_pi + 4], sd2[b_pi + 5], v0, v1, v2, v3); x[j][3] = dot4<EXACT>(sd2[b_pi + 6], sd2[b_pi + 7], v0, v1, v2, v3);
-          }
-          else
-          {
-            const unsigned int wb = bword ? s1[tc.tips_s + (bword * CPT + j) * TREE_NT] : tc.tw0[j];
-            const unsigned int ib = (bmask ? lut_t : stk_t + j * (2 * TREE_NT)) + w1.y + ((wb >> bsh) & bmask) * 3;
-            const double2 b0 = sd2[ib], b1 = sd2[ib + 1];
-            x[j][0] = b0.x; x[j][1] = b0.y; x[j][2] = b1.x; x[j][3] = b1.y;
-          }
-        }
-        o[j][0] = __dmul_rn(x[j][0], a0.x); o[j][1] = __dmul_rn(x[j][1], a0.y);
-        o[j][2] = __dmul_rn(x[j][2], a1.x); o[j][3] = __dmul_rn(x[j][3], a1.y);
+        o[j][0] = __dmul_rn(x[j][0], a0[j].x); o[j][1] = __dmul_rn(x[j][1], a0[j].y);
+        o[j][2] = __dmul_rn(x[j][2], a1[j].x); o[j][3] = __dmul_rn(x[j][3], a1[j].y);
         osc[j] = 0;
       }
     }
@@ -307,10 +339,12 @@ __device__ __forceinline__ double tile_fast(const TreeParams & prm, const TileCt
       }
     }
     // ---- the CLV goes to HBM exactly once
+    {
+      const size_t d_off = (size_t)w0.y << 5;        // the parent's buffer
 #pragma unroll
-    for (int j = 0; j < CPT; ++j)
-      if (tc.valid[j])
-        st256(reinterpret_cast<double *>(clv0 + (((size_t)w0.y + tc.cell[j]) << 5)), o[j][0], o[j][1], o[j][2], o[j][3]);
+      for (int j = 0; j < CPT; ++j)
+        if (tc.valid[j]) st256(reinterpret_cast<double *>(pc[j] + d_off), o[j][0], o[j][1], o[j][2], o[j][3]);
+    }
     // ---- push through the edge above: this X is what the parent's op consumes
     if (ctl & OP_PUSH)
     {
@@ -330,8 +364,9 @@ __device__ __forceinline__ double tile_fast(const TreeParams & prm, const TileCt
 #pragma unroll
         for (int j = 0; j < CPT; ++j)
         {
-          sd2[stk_t + j * (2 * TREE_NT) + po] = make_double2(x[j][0], x[j][1]);
-          sd2[stk_t + j * (2 * TREE_NT) + po + 1] = make_double2(x[j][2], x[j][3]);
+          unsigned char * const dst = const_cast<unsigned char *>(sm) + stk_lo + j * SLOTJ + po * 16u;
+          *reinterpret_cast<double2 *>(dst) = make_double2(x[j][0], x[j][1]);
+          *reinterpret_cast<double2 *>(dst + stk_d) = make_double2(x[j][2], x[j][3]);
           if (SCALED && (ctl & OP_SCALE)) s1[tc.sst1 + (po / Lay::SLOT) * (CPT * TREE_NT) + j * TREE_NT + tid] = psc[j];
         }
       }
@@ -353,32 +388,21 @@ __device__ __forceinline__ double tile_fast(const TreeParams & prm, const TileCt
           term[j] = __dadd_rn(term[j], __dmul_rn(v, s8[(sb + Lay::RW) * 2 + r]));
         }
       }
-      // every lane of a site now holds the site's likelihood: the RL lanes share the CPT sites among them (lane of
-      // category c finishes the sites j = c, c + RL, ...), so log() runs once per site instead of RL times
 #pragma unroll
-      for (int g = 0; g < (CPT + RL - 1) / RL; ++g)
+      for (int j = 0; j < CPT; ++j)
       {
-        double t = 1.0;
-        unsigned int sc = 0, jj = 0;
-        bool mine = false;
-#pragma unroll
-        for (int r = 0; r < RL; ++r)
-        {
-          const int j = g * RL + r;
-          if (j < CPT && (unsigned int)r == tc.cat) { t = term[j]; sc = osc[j]; jj = (unsigned int)j; mine = tc.valid[j]; }
-        }
         double sv;
-        if (prm.persite_mode == 2) sv = t;
+        if (prm.persite_mode == 2) sv = term[j];
         else
         {
-          sv = log(t);
-          if (SCALED && sc) sv = __dadd_rn(sv, __dmul_rn((double)sc, prm.log_threshold));
-          sv = __dmul_rn(sv, (double)s1[tc.tips_s + tc.wgt_off + jj * TREE_NT]);
+          sv = log(term[j]);
+          if (SCALED && osc[j]) sv = __dadd_rn(sv, __dmul_rn((double)osc[j], prm.log_threshold));
+          sv = __dmul_rn(sv, (double)s1[tc.tips_s + tc.wgt_off + j * TREE_NT]);
         }
-        if (mine)
+        if (tc.valid[j] && tc.cat == 0)
         {
           site_sum += sv;
-          if (prm.persite) prm.persite[tc.cell[jj] / RL] = sv;
+          if (prm.persite) prm.persite[tc.cell[j] / RL] = sv;
         }
       }
     }
@@ -416,7 +440,8 @@ __device__ __noinline__ double chunk_general(const TreeParams prm, unsigned int 
   const unsigned int tid = threadIdx.x, lane = tid & 31u;
   const LocusHdr * H = reinterpret_cast<const LocusHdr *>(&s4[sb]);
   const unsigned int pattern = cell / RL;
-  const unsigned int lut_t = (lay & 0xFFFFu) + cat * 49;               // lay = lut0 | stack0 << 16
+  const unsigned int lut_t = (lay & 0xFFFFu) + cat * lut_cat_u4(RL);   // lay = lut0 | stack0 << 16; replica A of the tables
+  const unsigned int hs = (lane >> 2) & 1u;                            // stack slots hold their halves exchanged for these lanes
   const unsigned int stk_t = (lay >> 16) + tid * 2 + j * (2 * TREE_NT);
   const unsigned int ops = sb + Lay::OPS;
   const unsigned int cn = s1[(sb + Lay::CH) * 4];
@@ -440,13 +465,13 @@ __device__ __noinline__ double chunk_general(const TreeParams prm, unsigned int 
       Vec4 r;
       if (kind == SRC_TIP_PACKED)
       {
-        const unsigned int li = lut_t + off + tipmask(sel, p0) * 3;
+        const unsigned int li = lut_t + off + tipmask(sel, p0) * lut_row_u4(RL);
         const double2 u = as_d2(s4[li]), w = as_d2(s4[li + 1]);
         r.a = u.x; r.b = u.y; r.c = w.x; r.d = w.y; sc = 0;
       }
       else if (kind == SRC_SLOT)
       {
-        const double2 u = as_d2(s4[stk_t + off]), w = as_d2(s4[stk_t + off + 1]);
+        const double2 u = as_d2(s4[stk_t + off + hs]), w = as_d2(s4[stk_t + off + (hs ^ 1u)]);
         r.a = u.x; r.b = u.y; r.c = w.x; r.d = w.y;
         sc = s1[sst1 + p0 * (CPT * TREE_NT) + j * TREE_NT + tid];
       }
@@ -509,8 +534,8 @@ __device__ __noinline__ double chunk_general(const TreeParams prm, unsigned int 
         x0 = x.a; x1 = x.b; x2 = x.c; x3 = x.d; psc = osc;
         if (ctl & OP_PARKA)
         {
-          s4[stk_t + w1.w] = as_u4(x0, x1);
-          s4[stk_t + w1.w + 1] = as_u4(x2, x3);
+          s4[stk_t + w1.w + hs] = as_u4(x0, x1);
+          s4[stk_t + w1.w + (hs ^ 1u)] = as_u4(x2, x3);
           s1[sst1 + (w1.w / Lay::SLOT) * (CPT * TREE_NT) + j * TREE_NT + tid] = psc;
         }
       }
@@ -536,9 +561,7 @@ __device__ __noinline__ double chunk_general(const TreeParams prm, unsigned int 
         if (rsc) s = __dadd_rn(s, __dmul_rn((double)rsc, prm.log_threshold));
         s = __dmul_rn(s, (double)wgt);
       }
-      // the lane that owns this site's sum is the one tile_fast picks (category j mod RL), so that a root evaluated
-      // here and one evaluated there add the same numbers in the same order
-      if (valid && cat == (j % RL))
+      if (valid && cat == 0)
       {
         site_sum += s;
         if (prm.persite) prm.persite[pattern] = s;
@@ -560,8 +583,14 @@ __device__ __forceinline__ void build_lut(unsigned int sb, unsigned int lut0)
     const unsigned int mask = e & 15u, sc = e >> 4;      // sc = slot*RL + cat
     const Vec4 v = matvec_s4<EXACT>(sb + Lay::TIPP + sc * 9, (double)(mask & 1u), (double)((mask >> 1) & 1u),
                                     (double)((mask >> 2) & 1u), (double)((mask >> 3) & 1u));
-    s4[lut0 + sc * 49 + mask * 3] = as_u4(v.a, v.b);
-    s4[lut0 + sc * 49 + mask * 3 + 1] = as_u4(v.c, v.d);
+    const unsigned int at = lut0 + (sc / RL) * lut_slot_u4(RL) + (sc % RL) * lut_cat_u4(RL) + mask * lut_row_u4(RL);
+    s4[at] = as_u4(v.a, v.b);
+    s4[at + 1] = as_u4(v.c, v.d);
+    if (RL >= 4)                                         // replica B: halves exchanged
+    {
+      s4[at + lut_rep_u4(RL)] = as_u4(v.c, v.d);
+      s4[at + lut_rep_u4(RL) + 1] = as_u4(v.a, v.b);
+    }
   }
 }
 
@@ -569,7 +598,7 @@ __device__ __forceinline__ void build_lut(unsigned int sb, unsigned int lut0)
 // 2 cells at 2 CTAs beats 3 CTAs at 80 registers (spills) for R = 1; 4 cells win for R >= 4, where the
 // shared-memory pipe is the limit and the P-matrix loads are amortised over twice the cells.
 template <int RL, bool EXACT, int CPT>
-__global__ void __launch_bounds__(TREE_NT, CPT == 1 ? 3 : (CPT == 2 ? 2 : 1))
+__global__ void __launch_bounds__(TREE_NT, s4_ctas_per_sm(CPT))
 tree_kernel_s4(const TreeParams prm)
 {
   using Lay = S4Layout<RL, CPT>;
@@ -593,8 +622,9 @@ tree_kernel_s4(const TreeParams prm)
   // The locus block (header + rate weights + chunk 0: op records and the P-matrices of its edges, contiguous, built
   // by the planner) comes in as ONE TMA bulk copy issued by thread 0; every thread waits for it on the stage
   // buffer's mbarrier when the block is first used.  (Round 1 copied it with 16-byte cp.async by all threads.)
-  unsigned long long * const mbar = reinterpret_cast<unsigned long long *>(&s8[Lay::RED * 2 + 8]);
+  unsigned long long * const mbar = reinterpret_cast<unsigned long long *>(&s4[Lay::MBAR]);
   unsigned int mphase[2] = {0u, 0u};
+#if BPPGPU_S4_TMA_STAGE
   auto stage_fetch = [&](unsigned int buf, unsigned long long blk)   // header + rate weights + chunk 0
   {
     if (tid == 0)
@@ -603,7 +633,16 @@ tree_kernel_s4(const TreeParams prm)
       bulk_load(&s4[Lay::STAGE0 + buf * stage_sz], prm.blocks + blk, stage_sz * 16u, mbar + buf);
     }
   };
-  auto stage_wait = [&](unsigned int buf) { mbar_wait(mbar + buf, mphase[buf]); mphase[buf] ^= 1u; };
+  auto stage_wait = [&](unsigned int buf, bool) { mbar_wait(mbar + buf, mphase[buf]); mphase[buf] ^= 1u; };
+#else
+  auto stage_fetch = [&](unsigned int buf, unsigned long long blk)
+  {
+    const uint4 * src = reinterpret_cast<const uint4 *>(prm.blocks + blk);
+    for (unsigned int w = tid; w < stage_sz; w += TREE_NT) cp_async16(&s4[Lay::STAGE0 + buf * stage_sz + w], src + w);
+  };
+  // a prefetched block landed with the wait + barrier at the end of the previous tile; a fresh one is waited for here
+  auto stage_wait = [&](unsigned int, bool fresh) { (void)mphase; if (fresh) { cp_async_commit(); cp_async_wait_all(); __syncthreads(); } };
+#endif
   const unsigned int tips0 = Lay::tips0_u32(prm.n_slots, prm.lut_cap), tips_buf = Lay::tips_buf(prm.tip_words);
   // packed tip words + pattern weight of the thread's cells of tile d -> tip buffer `tb` (asynchronous; each
   // thread copies and later reads only its own entries, so the cp.async wait alone orders them)
@@ -647,9 +686,10 @@ tree_kernel_s4(const TreeParams prm)
     // ---- make the locus block current: either it was prefetched into the other buffer, or load it now
     if (d.locus != staged_locus)
     {
-      if (d.locus == prefetched_locus) buf ^= 1u;          // on its way (or landed) since the previous tile
+      const bool fresh = d.locus != prefetched_locus;
+      if (!fresh) buf ^= 1u;                               // on its way (or landed) since the previous tile
       else stage_fetch(buf, blk);                          // (every reader of this buffer passed the last tile's barrier)
-      stage_wait(buf);
+      stage_wait(buf, fresh);
       prefetched_locus = 0xFFFFFFFFu;
       build_lut<RL, EXACT, CPT>(Lay::STAGE0 + buf * stage_sz, lut0);
       __syncthreads();
