@@ -1,4 +1,5 @@
 """Device-resident step time per kernel for one config.  Usage: device_time.py config [n_loci] [scaling]"""
+import os
 import sys
 
 sys.path.insert(0, ".")
@@ -12,7 +13,7 @@ if synth.CONFIGS[cfg].get("states", 4) == 20:
     import bench
     lg = bench.lg_tables()
 w = synth.make_config(cfg, n_loci=n, scaling=scaling, lg=lg)
-eng = engine.Engine(0)
+eng = engine.Engine(0, math=os.environ.get("BPPGPU_MATH", "exact"))
 loci, trees = engine.load_workload(eng, w)
 batch = engine.Batch(eng, loci)
 batch.set_waves(1)
