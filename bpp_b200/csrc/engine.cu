@@ -133,6 +133,7 @@ struct bppgpu_engine
   struct PendingEvent { cudaEvent_t a, b; int kind; };
   std::vector<PendingEvent> pending;
   std::vector<cudaEvent_t> event_pool;
+  std::mutex prof_mu;                    // host threads on disjoint batches profile concurrently
   double log_threshold = 0;
   // kernels whose dynamic shared-memory limit has been raised on this device.  The limit is a property of the
   // FUNCTION, shared by every batch and host thread: it is raised once to the device maximum, never per launch
@@ -260,6 +261,7 @@ struct bppgpu_batch
 // ------------------------------------------------------------------------------------ helpers
 static cudaEvent_t get_event(bppgpu_engine * e)
 {
+  std::lock_guard<std::mutex> lock(e->prof_mu);
   if (!e->event_pool.empty()) { cudaEvent_t ev = e->event_pool.back(); e->event_pool.pop_back(); return ev; }
   cudaEvent_t ev;
   CUDA_CHECK(cudaEventCreate(&ev));
@@ -276,12 +278,13 @@ struct ProfScope
   }
   ~ProfScope()
   {
-    if (e->profiling) { cudaEventRecord(b, s); e->pending.push_back({a, b, kind}); }
+    if (e->profiling && a) { cudaEventRecord(b, s); std::lock_guard<std::mutex> lock(e->prof_mu); e->pending.push_back({a, b, kind}); }
   }
 };
 
 static void drain_profile(bppgpu_engine * e)
 {
+  std::lock_guard<std::mutex> lock(e->prof_mu);
   for (auto & p : e->pending)
   {
     cudaEventSynchronize(p.b);
@@ -551,7 +554,7 @@ static void engine_publish_locus(bppgpu_engine * e, bppgpu_locus * l)
 {
   if (l->id >= e->loci_cap)
   {
-    size_t ncap = std::max<size_t>(1024, e->loci_cap * 2);
+    size_t ncap = std::max<size_t>(65536, e->loci_cap * 2);       // 9 MB of descriptors: growing (sync + free) stays rare
     while (ncap <= l->id) ncap *= 2;
     LocusDev * nd = nullptr;
     CUDA_CHECK(cudaDeviceSynchronize());
@@ -612,6 +615,18 @@ extern "C" bppgpu_locus * bppgpu_locus_create(bppgpu_engine * e, unsigned int dt
   double * m = (double *)e->arena.alloc(l->b_model);
   d.freqs = m; d.rates = m + S; d.rate_weights = d.rates + R; d.eigenvecs = d.rate_weights + R;
   d.inv_eigenvecs = d.eigenvecs + S * S; d.eigenvals = d.inv_eigenvecs + S * S; d.subst = d.eigenvals + S;
+  if (!d.clv || !d.tip_codes || !d.tip_is_dense || !d.pmat || (scale_buffers && !d.scale) || !d.weights || !m ||
+      (S != 4 && (!d.tip_cols || !d.colmask)))
+  {
+    // the arena's fatal() has reported the failed allocation; with a handler that returns, hand back nothing rather
+    // than a half-built locus
+    Arena & a = e->arena;
+    a.release(d.clv, l->b_clv); a.release(d.tip_codes, l->b_codes); a.release(d.tip_cols, l->b_cols);
+    a.release(d.colmask, l->b_colmask); a.release(d.tip_is_dense, l->b_flags); a.release(d.pmat, l->b_pmat);
+    a.release(d.scale, l->b_scale); a.release(d.weights, l->b_weights); a.release(m, l->b_model);
+    delete l;
+    return nullptr;
+  }
   d.clv_stride = clv_doubles;
   d.tips = tips; d.sites = sites; d.states = states; d.rate_cats = rate_cats;
   d.clv_buffers = clv_buffers; d.prob_matrices = prob_matrices; d.scale_buffers = scale_buffers;
@@ -722,6 +737,7 @@ extern "C" int bppgpu_set_tip_clv(bppgpu_locus * l, unsigned int tip, const doub
 extern "C" void bppgpu_set_pattern_weights(bppgpu_locus * l, const unsigned int * w)
 {
   CUDA_CHECK(cudaSetDevice(l->e->device));
+  CUDA_CHECK(cudaDeviceSynchronize());           // a running batch may still be reading the old weights
   CUDA_CHECK(cudaMemcpy(l->dev.weights, w, (size_t)l->sites * 4, cudaMemcpyHostToDevice));
 }
 extern "C" void bppgpu_set_frequencies(bppgpu_locus * l, unsigned int idx, const double * f)
@@ -1038,6 +1054,51 @@ static void batch_issue_copies(bppgpu_batch * b, unsigned i0, unsigned i1, cudaS
   }
 }
 
+// every index of a step against the dimensions of its locus (what the per-locus wrappers check for one locus)
+static bool locus_ops_valid(const bppgpu_locus * l, unsigned count, const bppgpu_partial_op * ops, unsigned * bad)
+{
+  const unsigned nb = l->tips + l->clv_buffers;
+  for (unsigned i = 0; i < count; ++i)
+  {
+    const bppgpu_partial_op & o = ops[i];
+    if (o.parent_clv_index < l->tips || o.parent_clv_index >= nb || o.left_clv_index >= nb || o.right_clv_index >= nb ||
+        o.left_pmatrix_index >= l->prob_matrices || o.right_pmatrix_index >= l->prob_matrices ||
+        o.parent_scaler_index >= (int)l->scale_buffers || o.left_scaler_index >= (int)l->scale_buffers ||
+        o.right_scaler_index >= (int)l->scale_buffers || o.parent_scaler_index < -1 || o.left_scaler_index < -1 ||
+        o.right_scaler_index < -1)
+    { *bad = i; return false; }
+  }
+  return true;
+}
+
+static bool batch_validate(const bppgpu_batch * b, const unsigned int * mcounts, const unsigned int * midx,
+                           const unsigned int * ocounts, const bppgpu_partial_op * ops, const unsigned int * rclv, const int * rsc)
+{
+  size_t m = 0, o = 0;
+  for (unsigned i = 0; i < b->n; ++i)
+  {
+    const bppgpu_locus * l = b->loci[i];
+    if (mcounts)
+    {
+      for (unsigned k = 0; k < mcounts[i]; ++k)
+        if (midx[m + k] >= l->prob_matrices) { fatal("batch locus %u: pmatrix index %u out of range", i, midx[m + k]); return false; }
+      m += mcounts[i];
+    }
+    if (ocounts)
+    {
+      unsigned bad = 0;
+      if (!locus_ops_valid(l, ocounts[i], ops + o, &bad)) { fatal("batch locus %u: op %u has an index out of range", i, bad); return false; }
+      o += ocounts[i];
+    }
+    if (rclv)
+    {
+      if (rclv[i] >= l->tips + l->clv_buffers) { fatal("batch locus %u: root clv index %u out of range", i, rclv[i]); return false; }
+      if (rsc && (rsc[i] >= (int)l->scale_buffers || rsc[i] < -1)) { fatal("batch locus %u: root scaler index %d out of range", i, rsc[i]); return false; }
+    }
+  }
+  return true;
+}
+
 // Stage the inputs of one step: build the per-locus offset tables and hand the caller's arrays to the copy
 // engine.  Arrays in pinned memory (bppgpu_host_alloc / cudaHostRegister) are copied from where they are,
 // anything else goes through the batch's pinned blob.  Any of the three groups may be absent (nullptr counts).
@@ -1090,6 +1151,11 @@ static int batch_stage(bppgpu_batch * b, const unsigned int * mcounts, const uns
       CUDA_CHECK(cudaMalloc(&b->d_plan, b->plan_cap * sizeof(PlanOp)));
     }
   }
+  // Indices address a shared arena: one that is out of range would silently overwrite another locus' buffers.
+  // Checked whenever the shape of the step changed (and on every stage with BPPGPU_CHECK_INDICES=1).
+  static const bool check_always = getenv("BPPGPU_CHECK_INDICES") && atoi(getenv("BPPGPU_CHECK_INDICES")) != 0;
+  if (!same || check_always)
+    if (!batch_validate(b, mcounts, midx, ocounts, ops, rclv, rsc)) return BPPGPU_FAILURE;
   // the previous step's blob may still be in flight on the stream (a waved step joins alt_stream into it)
   CUDA_CHECK(cudaStreamSynchronize(b->stream));
   if (b->copy_stream) CUDA_CHECK(cudaStreamSynchronize(b->copy_stream));      // tables of a step that never ran
@@ -1779,16 +1845,8 @@ extern "C" int bppgpu_update_matrices(bppgpu_locus * l, unsigned int count, cons
 
 extern "C" int bppgpu_update_partials(bppgpu_locus * l, unsigned int count, const bppgpu_partial_op * ops)
 {
-  const unsigned nb = l->tips + l->clv_buffers;
-  for (unsigned i = 0; i < count; ++i)
-  {
-    const bppgpu_partial_op & o = ops[i];
-    if (o.parent_clv_index < l->tips || o.parent_clv_index >= nb || o.left_clv_index >= nb || o.right_clv_index >= nb ||
-        o.left_pmatrix_index >= l->prob_matrices || o.right_pmatrix_index >= l->prob_matrices ||
-        o.parent_scaler_index >= (int)l->scale_buffers || o.left_scaler_index >= (int)l->scale_buffers ||
-        o.right_scaler_index >= (int)l->scale_buffers)
-    { fatal("update_partials: op %u has an index out of range", i); return BPPGPU_FAILURE; }
-  }
+  unsigned bad = 0;
+  if (!locus_ops_valid(l, count, ops, &bad)) { fatal("update_partials: op %u has an index out of range", bad); return BPPGPU_FAILURE; }
   return bppgpu_batch_update_partials(self_batch(l), &count, ops);
 }
 
@@ -1853,7 +1911,7 @@ extern "C" int bppgpu_get_clv(bppgpu_locus * l, unsigned int clv_index, double *
   CUDA_CHECK(cudaSetDevice(l->e->device));
   const size_t P = l->sites, R = l->rate_cats, S = l->states, nd = P * R * S;
   if (clv_index >= l->tips + l->clv_buffers) { fatal("clv index out of range"); return BPPGPU_FAILURE; }
-  if (l->self_batch) CUDA_CHECK(cudaStreamSynchronize(l->self_batch->stream));
+  CUDA_CHECK(cudaDeviceSynchronize());
   if (clv_index >= l->tips)
   {
     CUDA_CHECK(cudaMemcpy(out, l->dev.clv + (size_t)(clv_index - l->tips) * nd, nd * 8, cudaMemcpyDeviceToHost));
@@ -1872,9 +1930,12 @@ extern "C" int bppgpu_get_clv(bppgpu_locus * l, unsigned int clv_index, double *
   return BPPGPU_SUCCESS;
 }
 
+// The raw accessors are debug / test paths: they wait for everything in flight on the device (the engine's and the
+// batches' streams are non-blocking, a plain cudaMemcpy would not order against them).
 extern "C" int bppgpu_get_pmatrix(bppgpu_locus * l, unsigned int idx, double * out)
 {
   CUDA_CHECK(cudaSetDevice(l->e->device));
+  CUDA_CHECK(cudaDeviceSynchronize());
   if (idx >= l->prob_matrices) { fatal("pmatrix index out of range"); return BPPGPU_FAILURE; }
   const size_t nd = (size_t)l->rate_cats * l->states * l->states;
   CUDA_CHECK(cudaMemcpy(out, l->dev.pmat + idx * nd, nd * 8, cudaMemcpyDeviceToHost));
@@ -1884,6 +1945,7 @@ extern "C" int bppgpu_get_pmatrix(bppgpu_locus * l, unsigned int idx, double * o
 extern "C" int bppgpu_set_pmatrix(bppgpu_locus * l, unsigned int idx, const double * in)
 {
   CUDA_CHECK(cudaSetDevice(l->e->device));
+  CUDA_CHECK(cudaDeviceSynchronize());
   if (idx >= l->prob_matrices) { fatal("pmatrix index out of range"); return BPPGPU_FAILURE; }
   const size_t nd = (size_t)l->rate_cats * l->states * l->states;
   CUDA_CHECK(cudaMemcpy(l->dev.pmat + idx * nd, in, nd * 8, cudaMemcpyHostToDevice));
@@ -1893,6 +1955,7 @@ extern "C" int bppgpu_set_pmatrix(bppgpu_locus * l, unsigned int idx, const doub
 extern "C" int bppgpu_get_scaler(bppgpu_locus * l, unsigned int idx, unsigned int * out)
 {
   CUDA_CHECK(cudaSetDevice(l->e->device));
+  CUDA_CHECK(cudaDeviceSynchronize());
   if (idx >= l->scale_buffers) { fatal("scaler index out of range"); return BPPGPU_FAILURE; }
   CUDA_CHECK(cudaMemcpy(out, l->dev.scale + (size_t)idx * l->sites, (size_t)l->sites * 4, cudaMemcpyDeviceToHost));
   return BPPGPU_SUCCESS;

@@ -19,7 +19,13 @@
  *   - no silent CPU fallback: if no sm_100 device / no CUDA driver is present every
  *     compute entry point fails through the fatal handler.
  *   - thread safety: concurrent calls on DISJOINT loci/batches are safe
- *     (threads.c:87-200 calls the seam that way).
+ *     (threads.c:87-200 calls the seam that way).  Creating or destroying loci, batches and communicators is
+ *     set-up work and must not overlap compute calls on the same engine.
+ *   - a fatal handler installed with bppgpu_set_fatal_handler should not return (longjmp / exit / throw across a C++
+ *     host); if it does return, the failing call reports BPPGPU_FAILURE / NULL where it can, but the objects it
+ *     touched must not be used further.
+ *   - the raw accessors (bppgpu_get_clv / get_pmatrix / get_scaler / set_pmatrix, bppgpu_set_pattern_weights) wait
+ *     for all work in flight on the device before they copy.
  */
 #ifndef BPP_B200_H
 #define BPP_B200_H

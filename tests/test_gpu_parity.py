@@ -194,6 +194,30 @@ def test_age_moves_across_all_loci_match_the_reference(eng, cfg):
     _free(loci, batch)
 
 
+def test_batch_calls_reject_out_of_range_indices(eng):
+    """Indices address a shared arena, so one that is out of range would overwrite another locus' buffers without any
+    fault; the batch entry points check every index of a step whose shape changed."""
+    from bpp_b200 import engine
+    w = synth.make_workload("rng", n_loci=6, tips=5, sites=40, states=4, rate_cats=1, model="JC69", seed=9)
+    loci, trees, batch = _load(eng, w)
+    good = trees.full_pass_step()
+    lnl, _ = batch.full_pass(good)
+    for field, value in (("parent_clv_index", 5 + 8), ("left_clv_index", 99), ("right_pmatrix_index", 16), ("parent_scaler_index", 0)):
+        mc, mi, mb, oc, ops, rc, rs = [np.array(a, copy=True) for a in good]
+        ops[7][field] = value
+        oc[0], oc[1] = oc[0] - 1, oc[1] + 1                  # another shape: the check runs
+        with pytest.raises(engine.BppGpuError):
+            batch.full_pass((mc, mi, mb, oc, ops, rc, rs))
+    mc, mi, mb, oc, ops, rc, rs = [np.array(a, copy=True) for a in good]
+    mi[3] = 16                                               # prob_matrices = 2 * (2T - 2) = 16
+    mc[0], mc[1] = mc[0] - 1, mc[1] + 1
+    with pytest.raises(engine.BppGpuError):
+        batch.full_pass((mc, mi, mb, oc, ops, rc, rs))
+    again, _ = batch.full_pass(good)                         # the batch is still usable
+    assert np.array_equal(again, lnl)
+    _free(loci, batch)
+
+
 def engine_pinned(a):
     from bpp_b200 import engine
     return engine.PinnedArray(np.ascontiguousarray(a, dtype=np.float64))
