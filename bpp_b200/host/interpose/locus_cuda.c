@@ -6,7 +6,7 @@
  *     locus_update_matrices      locus.c:2417        locus_update_partials     locus.c:2530
  *     locus_update_all_partials  locus.c:2523        locus_root_loglikelihood  locus.c:2573
  *     locus_destroy              locus.c:872         prop_mixing_update_gtrees prop_mixing.c:52
- *     propose_tau_update_gtrees  stree.c:4338
+ *     propose_tau_update_gtrees  stree.c:4338        locus_propose_alpha_serial / _parallel  prop_gamma.c:175,197
  *
  * Linked into an executable in front of the reference built as a shared library (the recipe that compiles the reference, see INTEGRATION.md, builds
  * libbppref.so from the unmodified sources with -fPIC, so every call to these functions -- including the ones made
@@ -63,8 +63,12 @@ static fn_root_loglikelihood  real_root_loglikelihood;
 static fn_locus_destroy       real_locus_destroy;
 static fn_mixing              real_mixing;
 static fn_tau                 real_tau;
+typedef double (*fn_alpha_serial)(stree_t *, locus_t **, gtree_t **);
+typedef void   (*fn_alpha_parallel)(stree_t *, locus_t **, gtree_t **, long, long, long, long *, long *);
+static fn_alpha_serial        real_alpha_serial;
+static fn_alpha_parallel      real_alpha_parallel;
 
-static int g_enabled = -1, g_batching = 1, g_verbose = 0, g_fuse = 1;
+static int g_enabled = -1, g_batching = 1, g_verbose = 0, g_fuse = 1, g_batch_alpha = 0;
 static bppgpu_engine * g_engine;
 static pthread_mutex_t g_mu = PTHREAD_MUTEX_INITIALIZER;
 static pthread_once_t g_once = PTHREAD_ONCE_INIT;
@@ -97,10 +101,13 @@ static void init_once(void)
   real_locus_destroy = (fn_locus_destroy)next_sym("locus_destroy");
   real_mixing = (fn_mixing)next_sym("prop_mixing_update_gtrees");
   real_tau = (fn_tau)next_sym("propose_tau_update_gtrees");
+  real_alpha_serial = (fn_alpha_serial)next_sym("locus_propose_alpha_serial");
+  real_alpha_parallel = (fn_alpha_parallel)next_sym("locus_propose_alpha_parallel");
   g_enabled = ev && atoi(ev) != 0;
   if ((ev = getenv("BPP_B200_BATCH"))) g_batching = atoi(ev) != 0;
   if ((ev = getenv("BPP_B200_VERBOSE"))) g_verbose = atoi(ev);
   if ((ev = getenv("BPP_B200_FUSE"))) g_fuse = atoi(ev) != 0;
+  if ((ev = getenv("BPP_B200_BATCH_ALPHA"))) g_batch_alpha = atoi(ev) != 0;
   if (g_enabled)
   {
     int dev = (ev = getenv("BPP_B200_DEVICE")) ? atoi(ev) : 0;
@@ -600,4 +607,122 @@ void propose_tau_update_gtrees(locus_t ** loci, gtree_t ** gtree, stree_t * stre
   real_tau(loci, gtree, stree, snode, oldage, minage, maxage, minfactor, maxfactor, locus_start, locus_count, affected,
            paffected_count, ret_count_above, ret_count_below, ret_logl_diff, ret_logpr_diff, thread_index);
   *ret_logl_diff += defer_end(d, loci, gtree, "propose_tau_update_gtrees");
+}
+
+/* ------------------------------------------------------------------ batched alpha move (prop_gamma.c:53-226)
+ * The reference proposes, evaluates and accepts locus by locus.  Loci are independent, so the move is the same
+ * Markov chain when all loci propose first, ONE batch evaluates them (full-tree passes: new category rates change
+ * every P-matrix), and every locus then takes its own accept / reject decision.  Only the order in which the
+ * random numbers are consumed changes (all proposal draws, then the acceptance draws), so mcmc.txt is a different,
+ * equally valid realisation -- which is why this is opt-in (BPP_B200_BATCH_ALPHA=1); the default keeps the
+ * reference's draw order and evaluates locus by locus.  Index flips and roll-back are the reference's
+ * (prop_gamma.c:100-158).
+ */
+#define IP_SWAP_CLV_INDEX(n,i)    ((n)+((i)-1)%(2*(n)-2))
+#define IP_SWAP_SCALER_INDEX(n,i) (((n)+((i)-1))%(2*(n)-2))
+#define IP_SWAP_PMAT_INDEX(e,i)   (((e)+(i))%((e)<<1))
+
+static int batched_alpha(stree_t * stree, locus_t ** locus, gtree_t ** gtree, long start, long count, long thread_index,
+                         long * p_candidates, long * p_accepted)
+{
+  defer_t * d = &tl_defer;
+  long i, accepted = 0, candidates = 0;
+  unsigned int m, n, maxn = 0;
+  double * alpha_old, * lnacc, * old_logl, * old_rates;
+  gnode_t ** gt_nodes;
+  const double minv = -99, maxv = 99;
+  if (d->active || !defer_begin(d, locus, start, count)) return 0;
+  for (i = start; i < start + count; ++i)
+    if (gtree[i]->tip_count + gtree[i]->inner_count > maxn) maxn = gtree[i]->tip_count + gtree[i]->inner_count;
+  alpha_old = (double *)xmalloc(count * sizeof(double));
+  lnacc = (double *)xmalloc(count * sizeof(double));
+  old_logl = (double *)xmalloc(count * sizeof(double));
+  old_rates = (double *)xmalloc(count * 64 * sizeof(double));
+  gt_nodes = (gnode_t **)xmalloc(maxn * sizeof(gnode_t *));
+  /* phase 1: every candidate proposes, flips its indices and records its full-tree pass */
+  for (i = start; i < start + count; ++i)
+  {
+    locus_t * l = locus[i];
+    gtree_t * gt = gtree[i];
+    double loga_old, loga_new;
+    if (!(l->dtype == BPP_DATA_DNA && l->rate_cats > 1 && l->rate_cats <= 64)) continue;
+    ++candidates;
+    alpha_old[i - start] = l->rates_alpha;
+    old_logl[i - start] = gt->logl;
+    loga_old = log(l->rates_alpha);
+    loga_new = loga_old + opt_finetune_alpha * legacy_rnd_symmetrical(thread_index);
+    loga_new = reflect(loga_new, minv, maxv, thread_index);
+    lnacc[i - start] = loga_new - loga_old;
+    l->rates_alpha = exp(loga_new);
+    memcpy(old_rates + (i - start) * 64, l->rates, l->rate_cats * sizeof(double));
+    pll_compute_gamma_cats(l->rates_alpha, l->rates_alpha, l->rate_cats, l->rates, PLL_GAMMA_RATES_MEAN);
+    for (m = 0, n = 0; m < gt->tip_count + gt->inner_count; ++m)
+    {
+      gnode_t * p = gt->nodes[m];
+      if (p->parent) { p->pmatrix_index = IP_SWAP_PMAT_INDEX(gt->edge_count, p->pmatrix_index); gt_nodes[n++] = p; }
+    }
+    locus_update_matrices(l, gt, gt_nodes, stree, i, n);
+    n = 0;
+    all_partials_rec(gt->root, gt_nodes, &n);
+    for (m = 0; m < n; ++m)
+    {
+      gt_nodes[m]->clv_index = IP_SWAP_CLV_INDEX(gt->tip_count, gt_nodes[m]->clv_index);
+      if (opt_scaling) gt_nodes[m]->scaler_index = IP_SWAP_SCALER_INDEX(gt->tip_count, gt_nodes[m]->scaler_index);
+    }
+    locus_update_partials(l, gt_nodes, n);
+    (void)locus_root_loglikelihood(l, gt->root, l->param_indices, NULL);
+  }
+  /* phase 2: one batch; gtree->logl of every candidate now holds the PROPOSED log-likelihood */
+  (void)defer_end(d, locus, gtree, "locus_propose_alpha");
+  /* phase 3: per-locus decisions (prop_gamma.c:128-158) */
+  for (i = start; i < start + count; ++i)
+  {
+    locus_t * l = locus[i];
+    gtree_t * gt = gtree[i];
+    double lnacceptance, alpha_new;
+    if (!(l->dtype == BPP_DATA_DNA && l->rate_cats > 1 && l->rate_cats <= 64)) continue;
+    alpha_new = l->rates_alpha;
+    lnacceptance = lnacc[i - start] + (gt->logl - old_logl[i - start]);
+    lnacceptance += (opt_alpha_alpha - 1) * log(alpha_new / alpha_old[i - start]) - opt_alpha_beta * (alpha_new - alpha_old[i - start]);
+    if (lnacceptance >= -1e-10 || legacy_rndu(thread_index) < exp(lnacceptance)) { ++accepted; continue; }
+    /* rejected: the old halves of the double buffers still hold the old state */
+    l->rates_alpha = alpha_old[i - start];
+    gt->logl = old_logl[i - start];
+    for (m = 0; m < gt->tip_count + gt->inner_count; ++m)
+    {
+      gnode_t * p = gt->nodes[m];
+      if (p->parent) p->pmatrix_index = IP_SWAP_PMAT_INDEX(gt->edge_count, p->pmatrix_index);
+    }
+    n = 0;
+    all_partials_rec(gt->root, gt_nodes, &n);
+    for (m = 0; m < n; ++m)
+    {
+      gt_nodes[m]->clv_index = IP_SWAP_CLV_INDEX(gt->tip_count, gt_nodes[m]->clv_index);
+      if (opt_scaling) gt_nodes[m]->scaler_index = IP_SWAP_SCALER_INDEX(gt->tip_count, gt_nodes[m]->scaler_index);
+    }
+    pll_set_category_rates(l, old_rates + (i - start) * 64);
+  }
+  free(alpha_old); free(lnacc); free(old_logl); free(old_rates); free(gt_nodes);
+  *p_candidates = candidates; *p_accepted = accepted;
+  return 1;
+}
+
+double locus_propose_alpha_serial(stree_t * stree, locus_t ** locus, gtree_t ** gtree)
+{
+  long candidates = 0, accepted = 0;
+  if (enabled() && g_batching && g_batch_alpha && opt_usedata && opt_locus_count > 1 &&
+      batched_alpha(stree, locus, gtree, 0, opt_locus_count, 0, &candidates, &accepted))
+    return accepted ? (double)accepted / candidates : 0;
+  pthread_once(&g_once, init_once);
+  return real_alpha_serial(stree, locus, gtree);
+}
+
+void locus_propose_alpha_parallel(stree_t * stree, locus_t ** locus, gtree_t ** gtree, long locus_start, long locus_count,
+                                  long thread_index, long * p_proposal_count, long * p_accepted)
+{
+  if (enabled() && g_batching && g_batch_alpha && opt_usedata && locus_count > 1 &&
+      batched_alpha(stree, locus, gtree, locus_start, locus_count, thread_index, p_proposal_count, p_accepted))
+    return;
+  pthread_once(&g_once, init_once);
+  real_alpha_parallel(stree, locus, gtree, locus_start, locus_count, thread_index, p_proposal_count, p_accepted);
 }

@@ -38,11 +38,14 @@ LONG = os.environ.get("BPP_LONG", "0") != "0"
 BURNIN, NSAMPLE = (200, 500) if LONG else (40, 100)
 
 
-def run_bpp(binary, env_extra, extra_args=(), timeout=1500, full_length=False):
+CTL_GTR = os.path.join(ROOT, "tests", "data", "frogs_gtr_g4.ctl")      # the same data read as haploid, GTR+G4, scaling on
+
+
+def run_bpp(binary, env_extra, extra_args=(), timeout=1500, full_length=False, ctl_path=None):
     d = tempfile.mkdtemp(prefix="bpp_run_")
     for f in os.listdir(DATA):
         shutil.copy(os.path.join(DATA, f), d)
-    ctl = open(CTL).read()
+    ctl = open(ctl_path or CTL).read()
     if not (LONG or full_length):
         ctl = re.sub(r"burnin = \d+", "burnin = %d" % BURNIN, ctl)
         ctl = re.sub(r"nsample = \d+", "nsample = %d" % NSAMPLE, ctl)
@@ -156,3 +159,48 @@ def test_frogs_a00_check_logl_clean(batch):
     assert log_l0(r.stdout) == (LOG_PG0, LOG_L0)
     assert len(mcmc.splitlines()) == NSAMPLE + 1
     report("frogs A00, CHECK_LOGL build, BPP_B200=1 BATCH=%s: %d iterations clean" % (batch, BURNIN + 2 * NSAMPLE))
+
+
+@pytest.mark.gpu
+def test_frogs_gtr_gamma_with_scaling_on_the_engine():
+    """The same sequences read as haploid data under GTR+G4 with per-site scaling: exercises the eigen-form P-matrices
+    (the reference's own decomposition is handed over), the model moves (alpha, qrates, freqs write the struct
+    directly) and the scaler buffers through the seam.  The chain must start from the reference's log-L0 and agree
+    with the stock AVX2 chain sample by sample; CUDA's expm1 and glibc's differ by <= 1 ulp, so a byte-identical
+    file is expected but not guaranteed -- a divergence is reported with the first differing sample."""
+    ref, ref_mcmc = run_bpp(BIN, {}, ["--arch", "avx2"], ctl_path=CTL_GTR)
+    assert ref.returncode == 0, ref.stderr[-1500:]
+    r, mcmc = run_bpp(BIN, {"BPP_B200": "1", "BPP_B200_VERBOSE": "1"}, ctl_path=CTL_GTR)
+    assert r.returncode == 0, (r.stdout[-1500:], r.stderr[-1500:])
+    assert log_l0(r.stdout) == log_l0(ref.stdout) and log_l0(ref.stdout)[1] is not None
+    div = first_divergence(ref_mcmc, mcmc)
+    n = len(ref_mcmc.splitlines())
+    if div is None:
+        report("frogs haploid GTR+G4 scaling, BPP_B200=1: mcmc.txt byte-identical to --arch avx2 over %d lines, log-L0 %s"
+               % (n, log_l0(r.stdout)[1]))
+    else:
+        i, x, y = div
+        report("frogs haploid GTR+G4 scaling, BPP_B200=1: mcmc.txt diverges from --arch avx2 at line %d of %d\n  avx2: %s\n  b200: %s"
+               % (i, n, x, y))
+        assert i > 10 and len(mcmc.splitlines()) == n
+
+
+@pytest.mark.gpu
+def test_batched_alpha_move_check_logl_and_chain():
+    """BPP_B200_BATCH_ALPHA=1: the alpha move of all loci as one batch (propose all, evaluate once, decide per locus;
+    prop_gamma.c:53-226).  Draw order differs from the reference, so the chain is another realisation: it must pass
+    the reference's CHECK_LOGL validator at every move and sample the same posterior region as the stock chain."""
+    if not os.path.exists(BIN_CHECK):
+        pytest.skip("bpp_b200_check not built")
+    ref, ref_mcmc = run_bpp(BIN, {}, ["--arch", "avx2"], ctl_path=CTL_GTR)
+    r, mcmc = run_bpp(BIN_CHECK, {"BPP_B200": "1", "BPP_B200_BATCH_ALPHA": "1", "BPP_B200_VERBOSE": "1"}, ctl_path=CTL_GTR)
+    assert "FATAL" not in r.stdout and "Invalid logl" not in r.stderr, (r.stdout[-1500:], r.stderr[-1500:])
+    assert r.returncode == 0, (r.stdout[-1500:], r.stderr[-1500:])
+    assert len(mcmc.splitlines()) == len(ref_mcmc.splitlines())
+    lnl_ref = [float(l.split()[-1]) for l in ref_mcmc.splitlines()[1:]]
+    lnl = [float(l.split()[-1]) for l in mcmc.splitlines()[1:]]
+    half = len(lnl) // 2
+    m_ref, m = sum(lnl_ref[half:]) / (len(lnl_ref) - half), sum(lnl[half:]) / (len(lnl) - half)
+    report("frogs haploid GTR+G4, batched alpha move, CHECK_LOGL clean over %d iterations; mean lnL of the second half "
+           "%.2f (stock chain %.2f)" % (BURNIN + 2 * NSAMPLE, m, m_ref))
+    assert abs(m - m_ref) < 40.0
