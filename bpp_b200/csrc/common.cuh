@@ -5,7 +5,8 @@
 //   CLV update core_partials.c:585-756; association order of core_partials_avx.c:368-531
 //   root lnL   core_likelihood.c:24-212, core_likelihood_avx.c:98-157; vector form :214-408
 //
-// Data layout in HBM (per locus; CLVs in the reference's order so a CLV is P*R*S contiguous doubles):
+// Data layout in HBM (per locus; CLVs in the reference's order so a CLV is P*R*S contiguous doubles; 20-state loci
+// with several categories keep clv[buffer][cat][pattern][state], see LocusDev::site_stride):
 //   clv[buffer][pattern][cat][state]     pmat[idx][cat][row = parent state][col = child state]
 //   scale[buffer][pattern] (u32)         weights[pattern] (u32)
 //   tips, 4 states : 4-bit state masks, 8 tips per u32 word: tipwords[pattern][tip/8] >> 4*(tip%8)
@@ -38,11 +39,16 @@ struct LocusDev
   unsigned int clv_buffers, prob_matrices, scale_buffers, model_kind;   // MODEL_* below
   unsigned int unphased, tip_words;                                     // tip_words = ceil(tips/8) (4 states)
   // > 4 states: column ids of the tips (0..S-1 = one-hot state, S.. = ambiguity mask colmask[id-S])
-  unsigned char * tip_cols;     // [tips][sites]
+  unsigned char * tip_cols;     // [tips][cols_pitch], cols_pitch = sites rounded up to 16 (padding = column 0)
   unsigned int * colmask;       // [4] ambiguity masks
-  unsigned int n_ext_cols, pad1;
+  unsigned int n_ext_cols, cols_pitch;
   unsigned int * dip_weights;   // diploid loci: weights of the unphased sites [unphased]
   double * subst;               // [S(S-1)/2] substitution parameters (closed-form DNA models read qrates here)
+  // element (site, cat, state) of a CLV buffer or dense tip sits at site * site_stride + cat * cat_stride + state:
+  // site-major (the reference's order: R*S, S) everywhere except 20-state loci with 2..8 categories, which are
+  // category-major (S, sites*S) -- the 20-state tree kernel works on one category at a time and then writes whole
+  // site blocks contiguously (the host never reads inner CLVs except through bppgpu_get_clv, which transposes)
+  unsigned int site_stride, cat_stride;
 };
 
 // how the P-matrices of a locus are built (locus_update_matrices dispatch, locus.c:2417-2479)

@@ -11,7 +11,7 @@
 #include "plan.cuh"
 #include "tree_s4.cuh"
 #include "tree_s20.cuh"
-#include "tree_s20c.cuh"
+#include "tree_s20t.cuh"
 #include "tree_generic.cuh"
 #include "reduce.cuh"
 #include "model.cuh"
@@ -223,8 +223,10 @@ struct bppgpu_batch
   size_t o_mat_off = 0, o_mat_idx = 0, o_mat_bl = 0, o_op_off = 0, o_ops = 0, o_root_clv = 0, o_root_sc = 0, o_blk_off = 0;
   unsigned int total_mats = 0, total_ops = 0;
   unsigned int lut_cap_rt = 0;         // tip-slot capacity of the 4-state launches: the batch's largest tree
-  bool s20_cat = false;                // 20 states: category-major tiles (tree_kernel_s20c)
+  bool s20_cat = false;                // 20 states: category-major tiles (tree_kernel_s20t)
+  bool s20_scaled = false;             // ... a locus of the batch scales per site: clusters of RL CTAs, tile = (locus, site block)
   double * d_rootdot = nullptr;        // ... its per (category, site) root dot products
+  unsigned int * d_rootsc = nullptr;   // ... and the root's scaler count per site (scaled batches)
   unsigned long long * d_site_off = nullptr;
   bool staged_mats = false, staged_ops = false, staged_roots = false;
   bool all_in_blob = false; size_t blob_bytes = 0;   // the staged step lives entirely in h_in (device layout): one H2D copy
@@ -404,7 +406,7 @@ static inline void set_code(bppgpu_locus * l, unsigned tip, size_t site, unsigne
         else { l->col_overflow = true; col = 0; }
       }
     }
-    l->h_cols[(size_t)tip * l->sites + site] = (unsigned char)col;
+    l->h_cols[(size_t)tip * l->dev.cols_pitch + site] = (unsigned char)col;
   }
 }
 static inline unsigned int get_code(const bppgpu_locus * l, unsigned tip, size_t site)
@@ -603,7 +605,8 @@ extern "C" bppgpu_locus * bppgpu_locus_create(bppgpu_engine * e, unsigned int dt
   d.tip_codes = e->arena.alloc(l->b_codes);
   if (S != 4)
   {
-    l->b_cols = (size_t)tips * P; l->b_colmask = 16;
+    d.cols_pitch = (P + 15u) & ~15u;
+    l->b_cols = (size_t)tips * d.cols_pitch; l->b_colmask = 16;
     d.tip_cols = (unsigned char *)e->arena.alloc(l->b_cols);
     d.colmask = (unsigned int *)e->arena.alloc(l->b_colmask);
     l->h_cols.assign(l->b_cols, 0);
@@ -628,6 +631,10 @@ extern "C" bppgpu_locus * bppgpu_locus_create(bppgpu_engine * e, unsigned int dt
     return nullptr;
   }
   d.clv_stride = clv_doubles;
+  // 20-state loci with several categories keep their CLVs category-major (common.cuh, LocusDev::site_stride)
+  const bool cat_major = states == S20 && rate_cats > 1 && rate_cats <= 8 && (rate_cats & (rate_cats - 1)) == 0;
+  d.site_stride = cat_major ? (unsigned)S : (unsigned)(R * S);
+  d.cat_stride = cat_major ? (unsigned)(P * S) : (unsigned)S;
   d.tips = tips; d.sites = sites; d.states = states; d.rate_cats = rate_cats;
   d.clv_buffers = clv_buffers; d.prob_matrices = prob_matrices; d.scale_buffers = scale_buffers;
   d.model_kind = model_kind_of(l);
@@ -728,7 +735,7 @@ extern "C" int bppgpu_set_tip_clv(bppgpu_locus * l, unsigned int tip, const doub
     engine_publish_locus(e, l);
   }
   std::vector<double> full(P * R * S);             // replicate over categories, locus.c:609-616
-  for (size_t i = 0; i < P; ++i) for (size_t r = 0; r < R; ++r) memcpy(&full[(i * R + r) * S], clv + i * S, S * 8);
+  for (size_t i = 0; i < P; ++i) for (size_t r = 0; r < R; ++r) memcpy(&full[i * l->dev.site_stride + r * l->dev.cat_stride], clv + i * S, S * 8);
   CUDA_CHECK(cudaMemcpy(l->dev.tip_dense + (size_t)tip * P * R * S, full.data(), full.size() * 8, cudaMemcpyHostToDevice));
   l->h_tip_dense_flag[tip] = 1; l->flags_dirty = true, l->e->dirty_epoch++;
   return BPPGPU_SUCCESS;
@@ -865,12 +872,14 @@ extern "C" bppgpu_batch * bppgpu_batch_create(bppgpu_engine * e, unsigned int n,
   std::vector<unsigned long long> site_off(n + 1, 0);
   if (b->kernel_kind == 2)
   {
-    // category-major tiles with staged P-matrices unless a locus scales per site (needs all categories of a
-    // site in one CTA) or the tree is too big for the matrices of one (locus, category) to fit in shared memory
+    // category-major tiles with the matrices of one (locus, category) staged in shared memory, unless the tree is
+    // too big for them to fit; a batch with a locus that scales per site runs the cluster form of the same kernel
     unsigned maxT = 0; bool scaled = false;
     for (unsigned i = 0; i < n; ++i) { maxT = std::max(maxT, loci[i]->tips); scaled = scaled || loci[i]->scale_buffers > 0; }
-    b->s20_cat = !scaled && s20c_smem_bytes(2 * maxT - 1, maxT, 0) + 1024 <= e->smem_optin;
-    if (const char * ev = getenv("BPPGPU_S20C")) b->s20_cat = b->s20_cat && atoi(ev) != 0;      // tuning knob
+    b->s20_cat = s20t_smem_bytes(2 * maxT - 1, maxT, 0, scaled) + 1024 <= e->smem_optin;
+    b->s20_scaled = b->s20_cat && scaled;
+    if (const char * ev = getenv("BPPGPU_S20T")) b->s20_cat = b->s20_cat && atoi(ev) != 0;      // tuning knob
+    if (!b->s20_cat) b->s20_scaled = false;
   }
   std::vector<unsigned long long> soff(n);
   size_t sbytes = 0;
@@ -884,8 +893,11 @@ extern "C" bppgpu_batch * bppgpu_batch_create(bppgpu_engine * e, unsigned int n,
     site_off[i + 1] = site_off[i] + l->sites;
     if (b->s20_cat)
     {
-      const unsigned nsb = (l->sites + S20C_SITES - 1) / S20C_SITES;
-      for (unsigned j = 0; j < b->RL * nsb; ++j) { tile_locus.push_back(i); tile_cell0.push_back(j); }
+      // tile word: site block | site blocks of the locus << 12 | category << 24 (scaled: the cluster rank is the category)
+      const unsigned nsb = (l->sites + S20T_SITES - 1) / S20T_SITES;
+      if (nsb >= 4096) { fatal("20-state locus with %u patterns: more than the category-major kernel's tile word holds", l->sites); delete b; return nullptr; }
+      for (unsigned c = 0; c < (b->s20_scaled ? 1u : b->RL); ++c)
+        for (unsigned sb = 0; sb < nsb; ++sb) { tile_locus.push_back(i); tile_cell0.push_back(sb | (nsb << 12) | (c << 24)); }
     }
     else
     for (unsigned c = 0; c < cells; c += tile_cells)
@@ -935,6 +947,7 @@ extern "C" bppgpu_batch * bppgpu_batch_create(bppgpu_engine * e, unsigned int n,
     CUDA_CHECK(cudaMalloc(&b->d_rootdot, (size_t)site_off[n] * b->RL * 8));
     CUDA_CHECK(cudaMalloc(&b->d_site_off, (size_t)(n + 1) * 8));
     CUDA_CHECK(cudaMemcpy(b->d_site_off, site_off.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice));
+    if (b->s20_scaled) CUDA_CHECK(cudaMalloc(&b->d_rootsc, (size_t)site_off[n] * 4));
   }
   CUDA_CHECK(cudaMemset(b->d_plan_count, 0, n * 4));
   CUDA_CHECK(cudaMemset(b->d_tile_partial, 0, b->n_tiles * 8));
@@ -966,7 +979,7 @@ extern "C" void bppgpu_batch_destroy(bppgpu_batch * b)
   cudaFree(b->d_batch_locus); cudaFree(b->d_tile_locus); cudaFree(b->d_tile_cell0); cudaFree(b->d_tile_first);
   cudaFree(b->d_scratch_off); cudaFree(b->d_scratch); cudaFree(b->d_plan_count); cudaFree(b->d_tile_partial);
   cudaFree(b->d_lnl); cudaFree(b->d_in); cudaFree(b->d_plan); cudaFree(b->d_persite);
-  cudaFree(b->d_rootdot); cudaFree(b->d_site_off);
+  cudaFree(b->d_rootdot); cudaFree(b->d_rootsc); cudaFree(b->d_site_off);
   cudaFree(b->d_blocks_par[0]); cudaFree(b->d_blocks_par[1]); cudaFree(b->d_tiles); cudaFree(b->d_tile_blk); cudaFree(b->d_block_sums); cudaFree(b->d_counter);
   cudaFreeHost(b->h_out); cudaFreeHost(b->h_in);
   if (b->h_model) cudaFreeHost(b->h_model);
@@ -991,7 +1004,7 @@ extern "C" const char * bppgpu_batch_kernel_name(bppgpu_batch * b)
   static thread_local char buf[96];
   const bool exact = b->e->math == BPPGPU_MATH_EXACT;
   if (b->kernel_kind == 0) snprintf(buf, sizeof(buf), "tree_kernel_s4<%u,%s,%u>", b->RL, exact ? "true" : "false", b->cpt);
-  else if (b->kernel_kind == 2) snprintf(buf, sizeof(buf), b->s20_cat ? "tree_kernel_s20c<%u>" : "tree_kernel_s20<%u>", b->RL);
+  else if (b->kernel_kind == 2) snprintf(buf, sizeof(buf), b->s20_cat ? (b->s20_scaled ? "tree_kernel_s20t<%u,true>" : "tree_kernel_s20t<%u,false>") : "tree_kernel_s20<%u>", b->RL);
   else snprintf(buf, sizeof(buf), "tree_kernel_generic<%s>", exact ? "true" : "false");
   return buf;
 }
@@ -1105,6 +1118,12 @@ static bool batch_validate(const bppgpu_batch * b, const unsigned int * mcounts,
 // A step that will run in waves (see bppgpu_batch_set_waves) only records the sources here: its copies are
 // issued wave by wave in batch_run, interleaved with the launches, so that the first kernel starts after
 // 1/waves of the upload.
+// bytes in front of the header in a 20-state block: the category-major kernel's matrix images (RL x cap x 3840)
+static size_t s20_hdr_shift(const bppgpu_batch * b)
+{
+  return b->s20_cat ? (size_t)b->RL * s20t_img_bytes(2 * b->max_tips - 1) : 0;
+}
+
 static int batch_stage(bppgpu_batch * b, const unsigned int * mcounts, const unsigned int * midx, const double * mbl,
                        const unsigned int * ocounts, const bppgpu_partial_op * ops,
                        const unsigned int * rclv, const int * rsc)
@@ -1174,7 +1193,7 @@ static int batch_stage(bppgpu_batch * b, const unsigned int * mcounts, const uns
       mo += mcounts ? mcounts[i] : 0;
       oo += oc;
       // one spare op per locus for a root that the list does not produce (CTL_EVAL_ONLY)
-      bo += b->kernel_kind == 2 ? align_up(block20_bytes(b->RL, oc + 1), 256) : block_bytes(b->RL, oc + 1, s4_lut_cap_rt(b));
+      bo += b->kernel_kind == 2 ? align_up(s20_hdr_shift(b) + block20_bytes(b->RL, oc + 1), 256) : block_bytes(b->RL, oc + 1, s4_lut_cap_rt(b));
       moff[i + 1] = mo; ooff[i + 1] = oo; boff[i + 1] = bo;
     }
     b->have_m = mcounts != nullptr; b->have_o = ocounts != nullptr;
@@ -1185,7 +1204,7 @@ static int batch_stage(bppgpu_batch * b, const unsigned int * mcounts, const uns
     {
       cudaFree(b->d_blocks_par[0]); cudaFree(b->d_blocks_par[1]);
       b->d_blocks_par[0] = b->d_blocks_par[1] = nullptr;
-      b->blocks_cap = boff[n] + boff[n] / 4;
+      b->blocks_cap = boff[n] + boff[n] / 4 + 8192;          // slack: the 20-state kernel fetches fixed-size meta blocks
       CUDA_CHECK(cudaMalloc(&b->d_blocks_par[0], b->blocks_cap));
     }
   }
@@ -1452,6 +1471,50 @@ static void launch_tree_s20(bppgpu_batch * b, const TreeParams & prm)
   tree_kernel_s20<RL><<<grid, S20_NT, smem, b->stream>>>(prm);
 }
 
+// category-major 20-state kernel: persistent CTAs, one per SM; scaled batches as clusters of RL CTAs (rank = category)
+template <int RL, bool SCALED>
+static int launch_tree_s20t_inst(bppgpu_batch * b, const TreeParams & prm)
+{
+  bppgpu_engine * e = b->e;
+  const size_t smem = s20t_smem_bytes(prm.lut_cap, prm.max_tips, prm.n_slots, SCALED);
+  ensure_max_smem(e, tree_kernel_s20t<RL, SCALED>);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.blockDim = dim3(S20T_NT); cfg.dynamicSmemBytes = smem; cfg.stream = b->stream;
+  cudaLaunchAttribute attr[1];
+  unsigned grid = std::min<unsigned>(b->n_tiles, (unsigned)e->sm_count);
+  if (SCALED && RL > 1)
+  {
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = RL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cfg.gridDim = dim3(RL * (unsigned)(e->sm_count / RL));
+    int max_clusters = 0;
+    CUDA_CHECK(cudaOccupancyMaxActiveClusters(&max_clusters, tree_kernel_s20t<RL, SCALED>, &cfg));
+    if (max_clusters < 1) { fatal("20-state scaled tree kernel: no cluster of %d CTAs fits (smem %zu)", RL, smem); return BPPGPU_FAILURE; }
+    grid = RL * std::min<unsigned>(b->n_tiles, (unsigned)max_clusters);
+  }
+  cfg.gridDim = dim3(grid);
+  CUDA_CHECK(cudaLaunchKernelEx(&cfg, tree_kernel_s20t<RL, SCALED>, prm, b->d_rootsc));
+  return BPPGPU_SUCCESS;
+}
+
+static int launch_tree_s20t(bppgpu_batch * b, const TreeParams & prm)
+{
+  switch (b->RL * 2 + (b->s20_scaled ? 1 : 0))
+  {
+    case 2: return launch_tree_s20t_inst<1, false>(b, prm);
+    case 3: return launch_tree_s20t_inst<1, true>(b, prm);
+    case 4: return launch_tree_s20t_inst<2, false>(b, prm);
+    case 5: return launch_tree_s20t_inst<2, true>(b, prm);
+    case 8: return launch_tree_s20t_inst<4, false>(b, prm);
+    case 9: return launch_tree_s20t_inst<4, true>(b, prm);
+    case 16: return launch_tree_s20t_inst<8, false>(b, prm);
+    case 17: return launch_tree_s20t_inst<8, true>(b, prm);
+    default: fatal("internal: RL=%u", b->RL); return BPPGPU_FAILURE;
+  }
+}
+
 // launches: [pmatrix] [plan + tree (+ finish)] on the batch stream, using the staged blob
 static int batch_run(bppgpu_batch * b, bool do_mats, bool do_tree, bool want_root, double * persite, int persite_mode)
 {
@@ -1510,9 +1573,9 @@ static int batch_run(bppgpu_batch * b, bool do_mats, bool do_tree, bool want_roo
     if (b->kernel_kind == 2 && !b->s20_cat) slots = 0;
     if (b->s20_cat)
     {
-      // one CTA of 16 warps per SM: the stack takes what the staged matrices leave
+      // one CTA of 16 warps per SM, two stage buffers (matrix images + meta block); the stack takes what is left
       lut_cap_rt = 2 * maxT - 1;
-      while (slots > 0 && s20c_smem_bytes(lut_cap_rt, maxT, slots) + 1024 > e->smem_optin) --slots;
+      while (slots > 0 && s20t_smem_bytes(lut_cap_rt, maxT, slots, b->s20_scaled) + 1024 > e->smem_optin) --slots;
     }
     if (b->kernel_kind == 0)
     {
@@ -1573,11 +1636,20 @@ static int batch_run(bppgpu_batch * b, bool do_mats, bool do_tree, bool want_roo
       plan_kernel_blocks20<<<(n * 32 + 127) / 128, 128, 0, b->stream>>>(
           e->d_loci, b->d_batch_locus, n, d_op_off, d_ops, d_root_clv, d_root_sc, want_root ? 1 : 0,
           b->d_blocks, d_blk_off, b->d_tile_first, b->d_tile_blk, b->d_plan_count, b->d_scratch, b->d_scratch_off,
-          slots, b->RL);
+          slots, b->RL, (unsigned long long)s20_hdr_shift(b), b->s20_cat ? 0 : 1);
     else
       plan_kernel_flat<<<(n + 127) / 128, 128, 0, b->stream>>>(
           e->d_loci, b->d_batch_locus, n, d_op_off, d_ops, d_root_clv, d_root_sc, want_root ? 1 : 0,
           b->d_plan, b->d_plan_count);
+    CUDA_CHECK(cudaGetLastError());
+  }
+  if (b->kernel_kind == 2 && b->s20_cat)
+  {
+    // matrix images of every (locus, category, list entry) in front of the locus' block: what the tree kernel's
+    // TMA fetches bring into shared memory
+    ProfScope ps(e, b->stream, BPPGPU_KERNEL_PLAN);
+    image20_kernel<<<dim3(n, 4), 256, 0, b->stream>>>(e->d_loci, b->d_batch_locus, b->d_blocks, d_blk_off,
+                                                       (unsigned long long)s20_hdr_shift(b), b->RL, lut_cap_rt);
     CUDA_CHECK(cudaGetLastError());
   }
   TreeParams prm;
@@ -1638,20 +1710,10 @@ static int batch_run(bppgpu_batch * b, bool do_mats, bool do_tree, bool want_roo
       {
         const unsigned maxT = b->max_tips;
         prm.max_tips = maxT; prm.rootdot = b->d_rootdot; prm.site_off = b->d_site_off;
-        const size_t smem = s20c_smem_bytes(prm.lut_cap, maxT, prm.n_slots);
-        const unsigned grid = std::min<unsigned>(b->n_tiles, (unsigned)e->sm_count);
-        switch (b->RL)
-        {
-#define BPPGPU_S20C_CASE(R) case R: \
-          ensure_max_smem(e, tree_kernel_s20c<R>); \
-          tree_kernel_s20c<R><<<grid, S20C_NT, smem, b->stream>>>(prm); break;
-          BPPGPU_S20C_CASE(1) BPPGPU_S20C_CASE(2) BPPGPU_S20C_CASE(4) BPPGPU_S20C_CASE(8)
-#undef BPPGPU_S20C_CASE
-          default: fatal("internal: RL=%u", b->RL); return BPPGPU_FAILURE;
-        }
+        if (!launch_tree_s20t(b, prm)) return BPPGPU_FAILURE;
         if (want_root)
-          root20_kernel<<<n, 128, 0, b->stream>>>(e->d_loci, b->d_batch_locus, b->d_rootdot, b->d_site_off, b->d_tile_first,
-                                                  b->d_tile_partial, persite, persite_mode);
+          root20_kernel<<<n, 128, 0, b->stream>>>(e->d_loci, b->d_batch_locus, b->d_rootdot, b->d_site_off, b->d_rootsc,
+                                                  e->log_threshold, b->d_tile_first, b->d_tile_partial, persite, persite_mode);
       }
       else
       switch (b->RL)
@@ -1912,14 +1974,15 @@ extern "C" int bppgpu_get_clv(bppgpu_locus * l, unsigned int clv_index, double *
   const size_t P = l->sites, R = l->rate_cats, S = l->states, nd = P * R * S;
   if (clv_index >= l->tips + l->clv_buffers) { fatal("clv index out of range"); return BPPGPU_FAILURE; }
   CUDA_CHECK(cudaDeviceSynchronize());
-  if (clv_index >= l->tips)
+  if (clv_index >= l->tips || l->h_tip_dense_flag[clv_index])
   {
-    CUDA_CHECK(cudaMemcpy(out, l->dev.clv + (size_t)(clv_index - l->tips) * nd, nd * 8, cudaMemcpyDeviceToHost));
-    return BPPGPU_SUCCESS;
-  }
-  if (l->h_tip_dense_flag[clv_index])
-  {
-    CUDA_CHECK(cudaMemcpy(out, l->dev.tip_dense + (size_t)clv_index * nd, nd * 8, cudaMemcpyDeviceToHost));
+    const double * src = clv_index >= l->tips ? l->dev.clv + (size_t)(clv_index - l->tips) * nd : l->dev.tip_dense + (size_t)clv_index * nd;
+    if (l->dev.site_stride == R * S) { CUDA_CHECK(cudaMemcpy(out, src, nd * 8, cudaMemcpyDeviceToHost)); return BPPGPU_SUCCESS; }
+    // category-major on the device: hand it out in the reference's [site][cat][state] order
+    std::vector<double> raw(nd);
+    CUDA_CHECK(cudaMemcpy(raw.data(), src, nd * 8, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < P; ++i) for (size_t r = 0; r < R; ++r)
+      memcpy(out + (i * R + r) * S, &raw[i * l->dev.site_stride + r * l->dev.cat_stride], S * 8);
     return BPPGPU_SUCCESS;
   }
   for (size_t i = 0; i < P; ++i)          // expand the packed tip like set_tipclv, locus.c:540-555

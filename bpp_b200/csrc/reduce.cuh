@@ -109,9 +109,9 @@ diploid_batch_kernel(const LocusDev * __restrict__ loci, const unsigned int * __
     double mean = 0.0;
     for (unsigned long long k = a0; k < a1; ++k)
     {
-      const double * c = clv + (size_t)L.dip_map[k] * R * S;
+      const double * c = clv + (size_t)L.dip_map[k] * L.site_stride;
       double term = 0.0;
-      for (unsigned int r = 0; r < R; ++r, c += S)
+      for (unsigned int r = 0; r < R; ++r, c += L.cat_stride)
       {
         double tr;
         if (S == 4)      // core_likelihood_avx.c:121-150: (p0 + p1) + (p2 + p3)

@@ -33,7 +33,7 @@ tree_kernel_generic(const TreeParams prm)
   __syncthreads();
   const unsigned int nops = prm.plan_count[bl];
   const PlanOp * __restrict__ gplan = prm.plan + prm.op_off[bl] + bl;
-  const unsigned int S = L.states, R = L.rate_cats;
+  const unsigned int S = L.states, R = L.rate_cats, CS = L.cat_stride;
   const unsigned int praw = prm.tile_cell0[tile] + tid;       // here a "cell" is a pattern
   const bool valid = praw < L.sites;
   const unsigned int pattern = valid ? praw : L.sites - 1;
@@ -47,11 +47,11 @@ tree_kernel_generic(const TreeParams prm)
     const double * lp = nullptr, * rp = nullptr;
     unsigned int lcode = 0, rcode = 0;
     if (lk == SRC_TIP_PACKED) lcode = tip_code(L, li, pattern);
-    else lp = ((lk == SRC_TIP_DENSE) ? L.tip_dense : L.clv) + (size_t)li * L.clv_stride + (size_t)pattern * R * S;
+    else lp = ((lk == SRC_TIP_DENSE) ? L.tip_dense : L.clv) + (size_t)li * L.clv_stride + (size_t)pattern * L.site_stride;
     if (!(q.ctl & CTL_EVAL_ONLY))
     {
       if (rk == SRC_TIP_PACKED) rcode = tip_code(L, ri, pattern);
-      else rp = ((rk == SRC_TIP_DENSE) ? L.tip_dense : L.clv) + (size_t)ri * L.clv_stride + (size_t)pattern * R * S;
+      else rp = ((rk == SRC_TIP_DENSE) ? L.tip_dense : L.clv) + (size_t)ri * L.clv_stride + (size_t)pattern * L.site_stride;
     }
     unsigned int osc = 0;
     if (lk == SRC_HBM && q.lsc >= 0) osc += L.scale[(size_t)q.lsc * L.sites + pattern];
@@ -59,7 +59,7 @@ tree_kernel_generic(const TreeParams prm)
     if (!(q.ctl & CTL_EVAL_ONLY))
     {
       if (rk == SRC_HBM && q.rsc >= 0) osc += L.scale[(size_t)q.rsc * L.sites + pattern];
-      double * out = L.clv + (size_t)q.dst * L.clv_stride + (size_t)pattern * R * S;
+      double * out = L.clv + (size_t)q.dst * L.clv_stride + (size_t)pattern * L.site_stride;
       bool below = true;
       for (unsigned int n = 0; n < R; ++n)
       {
@@ -72,8 +72,8 @@ tree_kernel_generic(const TreeParams prm)
           double xa[4] = {0, 0, 0, 0}, ya[4] = {0, 0, 0, 0};
           for (unsigned int j = 0; j < S; ++j)
           {
-            const double lv = lp ? lp[n * S + j] : (((lcode >> j) & 1u) ? 1.0 : 0.0);
-            const double rv = rp ? rp[n * S + j] : (((rcode >> j) & 1u) ? 1.0 : 0.0);
+            const double lv = lp ? lp[(size_t)n * CS + j] : (((lcode >> j) & 1u) ? 1.0 : 0.0);
+            const double rv = rp ? rp[(size_t)n * CS + j] : (((rcode >> j) & 1u) ? 1.0 : 0.0);
             if (EXACT)
             {
               xa[j & 3] = __dadd_rn(xa[j & 3], __dmul_rn(Pl[i * S + j], lv));
@@ -89,14 +89,14 @@ tree_kernel_generic(const TreeParams prm)
           const double y = __dadd_rn(__dadd_rn(ya[0], ya[1]), __dadd_rn(ya[2], ya[3]));
           const double o = __dmul_rn(x, y);
           below = below && (o < BPPGPU_SCALE_THRESHOLD);
-          if (valid) out[n * S + i] = o;
+          if (valid) out[(size_t)n * CS + i] = o;
         }
       }
       if (q.dsc >= 0)
       {
         if (below)
         {
-          if (valid) for (unsigned int e = 0; e < R * S; ++e) out[e] = __dmul_rn(out[e], BPPGPU_SCALE_FACTOR);
+          if (valid) for (unsigned int n = 0; n < R; ++n) for (unsigned int e = 0; e < S; ++e) out[(size_t)n * CS + e] = __dmul_rn(out[(size_t)n * CS + e], BPPGPU_SCALE_FACTOR);
           osc += 1;
         }
         if (valid) L.scale[(size_t)q.dsc * L.sites + pattern] = osc;
@@ -106,14 +106,14 @@ tree_kernel_generic(const TreeParams prm)
 
     if (q.ctl & CTL_ROOT)
     {
-      const double * rc = (q.ctl & CTL_EVAL_ONLY) ? lp : (L.clv + (size_t)q.dst * L.clv_stride + (size_t)pattern * R * S);
+      const double * rc = (q.ctl & CTL_EVAL_ONLY) ? lp : (L.clv + (size_t)q.dst * L.clv_stride + (size_t)pattern * L.site_stride);
       double term = 0.0;
       for (unsigned int n = 0; n < R; ++n)
       {
         double la[4] = {0, 0, 0, 0};
         for (unsigned int j = 0; j < S; ++j)
         {
-          const double cv = rc ? rc[n * S + j] : (((lcode >> j) & 1u) ? 1.0 : 0.0);
+          const double cv = rc ? rc[(size_t)n * CS + j] : (((lcode >> j) & 1u) ? 1.0 : 0.0);
           la[j & 3] = __dadd_rn(la[j & 3], __dmul_rn(L.freqs[j], cv));
         }
         const double tr = __dadd_rn(__dadd_rn(la[0], la[1]), __dadd_rn(la[2], la[3]));

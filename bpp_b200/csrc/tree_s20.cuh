@@ -50,7 +50,7 @@ struct Hdr20                        // 384 bytes, start of the locus block
   double * clv;
   double * tip_dense;
   unsigned int * scale;
-  const unsigned char * tip_cols;   // [tip][site] column ids: 0..19 = state, 20.. = extra column
+  const unsigned char * tip_cols;   // [tip][cols_pitch] column ids: 0..19 = state, 20.. = extra column
   const double * pmat;
   const unsigned int * weights;
   unsigned long long clv_stride;
@@ -58,14 +58,19 @@ struct Hdr20                        // 384 bytes, start of the locus block
   double freqs[S20];
   double rw[8];
   unsigned int n_stage, stage_off;  // staged-matrix list: n entries of (pmatrix index, ext offset | 0) at byte stage_off
-  double pad[10];
+  unsigned int cols_pitch, site_stride;    // row pitch of tip_cols (bytes); CLV strides (doubles), see LocusDev
+  unsigned int cat_stride, pad0;
+  double pad[8];
 };
 static_assert(sizeof(Hdr20) == 384, "Hdr20 must be 384 bytes");
 
+// block = [Hdr20][staged-matrix list, S20_LIST_CAP entries][op records][long lists: the list moves here][extra tip columns]
+constexpr unsigned int S20_LIST_CAP = 64;                                             // (pmatrix index, ext offset | 0) entries
+constexpr unsigned int S20_RECS_OFF = (unsigned int)sizeof(Hdr20) + S20_LIST_CAP * 8;  // byte offset of the op records
 __host__ __device__ inline size_t block20_bytes(unsigned RL, unsigned nops_max)
 {
-  // header + ops + staged-matrix list (three edges per op) + extra columns for at most two tip children per op
-  return sizeof(Hdr20) + (size_t)nops_max * sizeof(OpRec20) + (size_t)nops_max * 3 * 8 + 16 +
+  // header + list + ops + a long list (three edges per op) + extra columns for at most two tip children per op
+  return S20_RECS_OFF + (size_t)nops_max * sizeof(OpRec20) + (size_t)nops_max * 3 * 8 + 16 +
          (size_t)nops_max * 2 * RL * S20 * S20_EXT * 8;
 }
 
@@ -79,28 +84,31 @@ plan_kernel_blocks20(const LocusDev * __restrict__ loci, const unsigned int * __
                      const unsigned int * __restrict__ tile_first, unsigned long long * __restrict__ tile_blk,
                      unsigned int * __restrict__ plan_count,
                      unsigned char * __restrict__ scratch, const unsigned long long * __restrict__ scratch_off,
-                     int max_slots, unsigned int RL)
+                     int max_slots, unsigned int RL, unsigned long long hdr_shift, int do_ext)
 {
+  // hdr_shift: bytes in front of the header inside the block (the category-major kernel keeps its matrix images
+  // there); do_ext: sum the tips' ambiguity columns here (the category-major path does it while building images)
   const unsigned int bl = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const unsigned int lane = threadIdx.x & 31u;
   if (bl >= n_loci) return;
   const LocusDev & L = loci[batch_locus[bl]];
   const unsigned int first = op_off[bl], n = op_off[bl + 1] - first;
   const RawOp * __restrict__ o = ops + first;
-  unsigned char * blk = blocks + blk_off[bl];
+  unsigned char * blk = blocks + blk_off[bl] + hdr_shift;
   for (unsigned int t = tile_first[bl] + lane; t < tile_first[bl + 1]; t += 32)
   {
-    tile_blk[2 * (size_t)t] = blk_off[bl];
+    tile_blk[2 * (size_t)t] = blk_off[bl] + hdr_shift;
     tile_blk[2 * (size_t)t + 1] = 0;
   }
-  OpRec20 * const recs_g = reinterpret_cast<OpRec20 *>(blk + sizeof(Hdr20));
+  OpRec20 * const recs_g = reinterpret_cast<OpRec20 *>(blk + S20_RECS_OFF);
   const unsigned int T = L.tips;
-  unsigned int cnt = 0, n_ext = 0;
+  unsigned int cnt = 0, n_ext = 0, ns_out = 0, soff_out = 0;
   // small loci (the common case) are planned in shared memory: the serial planner below patches earlier records
   // (OP_PUSH, OP_PARKA) and looks buffers up in `where`, and every such access was a dependent global round trip
   __shared__ __align__(16) OpRec20 s_rec[4][33];
   __shared__ unsigned int s_where[4][64];
   __shared__ unsigned char s_slot[4][64];
+  __shared__ uint2 s_list[4][96];
   const unsigned int wib = (threadIdx.x >> 5) & 3u;
   const bool small = (n + 1 <= 33) && (L.clv_buffers <= 64);
   OpRec20 * const recs = small ? s_rec[wib] : recs_g;
@@ -128,10 +136,26 @@ plan_kernel_blocks20(const LocusDev * __restrict__ loci, const unsigned int * __
     }
     const unsigned int rootc = want_root ? root_clv[bl] : 0xFFFFFFFFu;
     const unsigned int total = n + (want_root ? 1u : 0u);
-    const unsigned int stage_off = (unsigned int)(sizeof(Hdr20) + (size_t)total * sizeof(OpRec20));
-    uint2 * stage = reinterpret_cast<uint2 *>(blk + stage_off);
+    // staged-matrix list: one entry per distinct (P-matrix, form) -- a tip edge is staged transposed with its
+    // ambiguity columns, an inner edge as tensor fragments -- so a full pass has exactly 2T - 2 entries however
+    // often a list revisits a node.  Short lists collect it in shared memory; it ends up at the fixed offset
+    // sizeof(Hdr20) when it fits S20_LIST_CAP, behind the op records otherwise.
+    const unsigned int long_off = (unsigned int)(S20_RECS_OFF + (size_t)total * sizeof(OpRec20));
+    uint2 * stage = small ? s_list[wib] : reinterpret_cast<uint2 *>(blk + long_off);
     unsigned int n_stage = 0;
-    const unsigned int ext0 = (unsigned int)(((stage_off + (size_t)total * 3 * 8 + 15) & ~(size_t)15) / 8);   // doubles, 16-byte aligned
+    const unsigned int ext0 = (unsigned int)(((long_off + (size_t)total * 3 * 8 + 15) & ~(size_t)15) / 8);   // doubles, 16-byte aligned
+    auto stage_entry = [&](unsigned int pm, bool packed) -> unsigned int
+    {
+      for (unsigned int s = 0; s < n_stage; ++s)
+      {
+        const uint2 ent = stage[s];
+        if (ent.x == pm && (ent.y != 0u) == packed) return s;
+      }
+      unsigned int ext = 0;
+      if (packed) { ext = ext0 + n_ext * RL * S20 * S20_EXT; ++n_ext; }
+      stage[n_stage] = make_uint2(pm, ext);
+      return n_stage++;
+    };
     unsigned int free_slots = (max_slots >= 32) ? 0xFFFFFFFFu : ((1u << max_slots) - 1u);
     unsigned int prev = 0xFFFFFFFFu, prev_k = 0;
     bool root_done = false;
@@ -153,9 +177,9 @@ plan_kernel_blocks20(const LocusDev * __restrict__ loci, const unsigned int * __
         if (idx < T)
         {
           p0[c] = idx;
-          if (L.tip_is_dense[idx]) kind[c] = SRC_TIP_DENSE;
-          else { kind[c] = SRC_TIP_PACKED; ext[c] = ext0 + n_ext * RL * S20 * S20_EXT; ++n_ext; }
-          st[c] = n_stage; stage[n_stage++] = make_uint2(pm[c], ext[c]);
+          kind[c] = L.tip_is_dense[idx] ? SRC_TIP_DENSE : SRC_TIP_PACKED;
+          st[c] = stage_entry(pm[c], kind[c] == SRC_TIP_PACKED);
+          ext[c] = stage[st[c]].y;
         }
         else
         {
@@ -164,20 +188,20 @@ plan_kernel_blocks20(const LocusDev * __restrict__ loci, const unsigned int * __
           {
             kind[c] = SRC_PREV; prev_child = c;
             recs[prev_k].ctl |= OP_PUSH; recs[prev_k].up_pm = pm[c];
-            recs[prev_k].up_st = n_stage; stage[n_stage++] = make_uint2(pm[c], 0u);
+            recs[prev_k].up_st = stage_entry(pm[c], false);
           }
           else if (where[b])
           {
             const unsigned int s = slot_of[b];
             kind[c] = SRC_SLOT; p0[c] = s; consumed_slots |= 1u << s;
             recs[where[b] - 1].ctl |= OP_PUSH; recs[where[b] - 1].up_pm = pm[c];
-            recs[where[b] - 1].up_st = n_stage; stage[n_stage++] = make_uint2(pm[c], 0u);
+            recs[where[b] - 1].up_st = stage_entry(pm[c], false);
             where[b] = 0;
           }
           else
           {
             kind[c] = SRC_HBM; p0[c] = b; sc[c] = c ? r.rsc : r.lsc;
-            st[c] = n_stage; stage[n_stage++] = make_uint2(pm[c], 0u);
+            st[c] = stage_entry(pm[c], false);
           }
         }
       }
@@ -218,7 +242,9 @@ plan_kernel_blocks20(const LocusDev * __restrict__ loci, const unsigned int * __
     Hdr20 * H = reinterpret_cast<Hdr20 *>(blk);
     H->clv = L.clv; H->tip_dense = L.tip_dense; H->scale = L.scale; H->tip_cols = L.tip_cols; H->pmat = L.pmat;
     H->weights = L.weights; H->clv_stride = L.clv_stride; H->sites = L.sites; H->nops = cnt; H->tips = L.tips;
-    H->n_ext_ops = n_ext; H->n_stage = n_stage; H->stage_off = stage_off;
+    H->n_ext_ops = n_ext; H->n_stage = n_stage; H->cols_pitch = L.cols_pitch; H->site_stride = L.site_stride; H->cat_stride = L.cat_stride;
+    H->stage_off = (small && n_stage <= S20_LIST_CAP) ? (unsigned int)sizeof(Hdr20) : long_off;
+    ns_out = n_stage; soff_out = H->stage_off;
     for (int j = 0; j < S20; ++j) H->freqs[j] = L.freqs[j];
     for (unsigned int j = 0; j < 8; ++j) H->rw[j] = j < RL ? L.rate_weights[j] : 0.0;
     plan_count[bl] = cnt;
@@ -230,7 +256,11 @@ plan_kernel_blocks20(const LocusDev * __restrict__ loci, const unsigned int * __
     const uint4 * src = reinterpret_cast<const uint4 *>(s_rec[wib]);
     uint4 * dst = reinterpret_cast<uint4 *>(recs_g);
     for (unsigned int w = lane; w < cnt * 4; w += 32) dst[w] = src[w];
+    const unsigned int ns = __shfl_sync(0xFFFFFFFFu, ns_out, 0);
+    uint2 * ldst = reinterpret_cast<uint2 *>(blk + __shfl_sync(0xFFFFFFFFu, soff_out, 0));
+    for (unsigned int w = lane; w < ns; w += 32) ldst[w] = s_list[wib][w];
   }
+  if (!do_ext) return;
   // extra tip columns: ext[cat][i][x] = sum over the states j of ambiguity mask x of P[i][j], j ascending
   double * base = reinterpret_cast<double *>(blk);
   const unsigned int n_ext_cols = L.n_ext_cols;
@@ -345,9 +375,10 @@ tree_kernel_s20(const TreeParams prm)
     const unsigned int site0 = prm.tile_cell0[t] / RL + pg * S20_WS;   // first site of this warp
     const unsigned char * blk = prm.blocks + prm.tile_blk[2 * (size_t)t];
     const Hdr20 * H = reinterpret_cast<const Hdr20 *>(blk);
-    const OpRec20 * recs = reinterpret_cast<const OpRec20 *>(blk + sizeof(Hdr20));
+    const OpRec20 * recs = reinterpret_cast<const OpRec20 *>(blk + S20_RECS_OFF);
     const double * base = reinterpret_cast<const double *>(blk);
-    const unsigned int sites = __ldg(&H->sites), nops = __ldg(&H->nops);
+    const unsigned int sites = __ldg(&H->sites), nops = __ldg(&H->nops), cols_pitch = __ldg(&H->cols_pitch);
+    const unsigned int sstr = __ldg(&H->site_stride), cstr = __ldg(&H->cat_stride);
     double * const clv = H->clv;
     const double * const pmat = H->pmat;
     const unsigned long long stride = __ldg(&H->clv_stride);
@@ -390,7 +421,7 @@ tree_kernel_s20(const TreeParams prm)
         const unsigned int s = site0 + n;
         const double2 u = *reinterpret_cast<const double2 *>(s_tile + n * S20 + part * 4);
         const double2 w = *reinterpret_cast<const double2 *>(s_tile + n * S20 + part * 4 + 2);
-        if (s < sites) st256(dst_buf + ((size_t)s * RL + cat) * S20 + part * 4, u.x, u.y, w.x, w.y);
+        if (s < sites) st256(dst_buf + (size_t)s * sstr + (size_t)cat * cstr + part * 4, u.x, u.y, w.x, w.y);
       }
     };
     auto global_to_tile = [&](const double * src_buf, bool coherent)
@@ -402,8 +433,8 @@ tree_kernel_s20(const TreeParams prm)
         if (c >= S20_WS * 5) break;
         const unsigned int s = min(site0 + n, sites - 1);
         double a, b, cc, d;
-        if (coherent) ld256(src_buf + ((size_t)s * RL + cat) * S20 + part * 4, a, b, cc, d);
-        else ld256_nc(src_buf + ((size_t)s * RL + cat) * S20 + part * 4, a, b, cc, d);
+        if (coherent) ld256(src_buf + (size_t)s * sstr + (size_t)cat * cstr + part * 4, a, b, cc, d);
+        else ld256_nc(src_buf + (size_t)s * sstr + (size_t)cat * cstr + part * 4, a, b, cc, d);
         *reinterpret_cast<double2 *>(s_tile + n * S20 + part * 4) = make_double2(a, b);
         *reinterpret_cast<double2 *>(s_tile + n * S20 + part * 4 + 2) = make_double2(cc, d);
       }
@@ -447,7 +478,7 @@ tree_kernel_s20(const TreeParams prm)
 #pragma unroll
           for (int e = 0; e < 2; ++e)
           {
-            const unsigned int col = __ldg(H->tip_cols + (size_t)p0 * sites + sitev[g][e]);
+            const unsigned int col = __ldg(H->tip_cols + (size_t)p0 * cols_pitch + sitev[g][e]);
             sc[g][e] = 0;
 #pragma unroll
             for (int mt = 0; mt < 3; ++mt)
@@ -509,7 +540,7 @@ tree_kernel_s20(const TreeParams prm)
 #pragma unroll
             for (int e = 0; e < 2; ++e)
             {
-              const unsigned int col = __ldg(H->tip_cols + (size_t)w0.z * sites + sitev[g][e]);
+              const unsigned int col = __ldg(H->tip_cols + (size_t)w0.z * cols_pitch + sitev[g][e]);
               const unsigned int mask = (col < S20) ? (1u << col) : prm.loci[prm.batch_locus[bl]].colmask[col - S20];
 #pragma unroll
               for (int mt = 0; mt < 3; ++mt) O.v[g][mt][e] = (double)((mask >> (8 * mt + r)) & 1u);
