@@ -46,8 +46,14 @@
 
 namespace bppgpu {
 
-constexpr int S20T_NG = 2;                           // groups of 8 sites per warp
-constexpr int S20T_NT = 512;                         // threads per CTA
+#ifndef BPPGPU_S20T_NG
+#define BPPGPU_S20T_NG 2
+#endif
+#ifndef BPPGPU_S20T_NT
+#define BPPGPU_S20T_NT 512
+#endif
+constexpr int S20T_NG = BPPGPU_S20T_NG;              // groups of 8 sites per warp
+constexpr int S20T_NT = BPPGPU_S20T_NT;              // threads per CTA
 constexpr int S20T_NW = S20T_NT / 32;                // warps
 constexpr int S20T_WS = 8 * S20T_NG;                 // sites per warp
 constexpr int S20T_SITES = S20T_NW * S20T_WS;        // sites per tile (256)
@@ -241,7 +247,11 @@ tree_kernel_s20t(const TreeParams prm, unsigned int * __restrict__ rootsc)
   auto fetch_cols = [&](unsigned char * dst, const Hdr20 * H, unsigned int site0)
   {
     const unsigned int pitch = H->cols_pitch, T = H->tips;
-    if (site0 < pitch) for (unsigned int tip = lane; tip < T; tip += 32) cp_async16_nc(dst + tip * WS, H->tip_cols + (size_t)tip * pitch + site0);
+    for (unsigned int e = lane; e < T * (WS / 16); e += 32)
+    {
+      const unsigned int tip = e / (WS / 16), off = (e % (WS / 16)) * 16;
+      if (site0 + off < pitch) cp_async16_nc(dst + tip * WS + off, H->tip_cols + (size_t)tip * pitch + site0 + off);
+    }
   };
   auto cols_buf = [&](unsigned int i) -> unsigned char * { return s_cols_all + i * cols_bytes + (size_t)warp * maxT * WS; };
 
@@ -335,9 +345,6 @@ tree_kernel_s20t(const TreeParams prm, unsigned int * __restrict__ rootsc)
     // out = (in . P^T) for the warp's NG x 8 sites; img = fragment image of the edge
     auto push = [&](const double * img, const double (&in)[NG][6], double (&out)[NG][6])
     {
-      double bf[15];
-#pragma unroll
-      for (int f = 0; f < 15; ++f) bf[f] = img[f * 32 + lane];
       double a4[NG];
 #pragma unroll
       for (int g = 0; g < NG; ++g)
@@ -347,21 +354,26 @@ tree_kernel_s20t(const TreeParams prm, unsigned int * __restrict__ rootsc)
 #pragma unroll
         for (int i = 0; i < 6; ++i) out[g][i] = 0.0;
       }
-      // k-steps outermost: NG x 3 independent accumulator chains
-#ifdef S20T_ABL_NODMMA
-#pragma unroll
-      for (int g = 0; g < NG; ++g)
-#pragma unroll
-        for (int i = 0; i < 6; ++i) out[g][i] = in[g][i] * bf[i] + a4[g] * bf[6 + i];
-      return;
-#endif
+      // k-steps outermost: NG x 3 independent accumulator chains; the three fragments of a k-step are loaded as
+      // they are needed (15 live fragment registers would not leave room for the next op's prefetched operand)
 #pragma unroll
       for (int ks = 0; ks < 5; ++ks)
+      {
+        const double b0 = img[ks * 32 + lane], b1 = img[(5 + ks) * 32 + lane], b2 = img[(10 + ks) * 32 + lane];
+#ifdef S20T_ABL_NODMMA
+#pragma unroll
+        for (int g = 0; g < NG; ++g) { out[g][0] += in[g][ks] * b0; out[g][2] += a4[g] * b1; out[g][4] += in[g][5 - ks] * b2; }
+#else
 #pragma unroll
         for (int g = 0; g < NG; ++g)
-#pragma unroll
-          for (int nt = 0; nt < 3; ++nt)
-            dmma(out[g][2 * nt], out[g][2 * nt + 1], ks < 4 ? in[g][ks] : a4[g], bf[nt * 5 + ks]);
+        {
+          const double a = ks < 4 ? in[g][ks] : a4[g];
+          dmma(out[g][0], out[g][1], a, b0);
+          dmma(out[g][2], out[g][3], a, b1);
+          dmma(out[g][4], out[g][5], a, b2);
+        }
+#endif
+      }
     };
     auto fetch = [&](unsigned int kind, unsigned int p0, unsigned int st, int scidx, double (&v)[NG][6],
                      unsigned int (&sc)[NG])
@@ -407,6 +419,11 @@ tree_kernel_s20t(const TreeParams prm, unsigned int * __restrict__ rootsc)
       }
     };
 
+    // operand A of the next op (a packed tip or a parked value, never the previous result) is fetched before the
+    // current op's push, so its shared-memory latency hides behind the DMMAs
+    double A[NG][6];
+    unsigned int asc[NG];
+    bool a_ready = false;
     for (unsigned int k = 0; k < nops; ++k)
     {
       const uint4 w0 = recs[4 * k], w1 = recs[4 * k + 1], w2 = recs[4 * k + 2], w3 = recs[4 * k + 3];
@@ -442,9 +459,8 @@ tree_kernel_s20t(const TreeParams prm, unsigned int * __restrict__ rootsc)
       }
       else
       {
-        double A[NG][6];
-        unsigned int asc[NG];
-        fetch(akind, w0.z, w3.y, (int)w1.x, A, asc);
+        if (!a_ready) fetch(akind, w0.z, w3.y, (int)w1.x, A, asc);
+        a_ready = false;
         if (!(ctl & OP_BPREV)) fetch(bkind, w1.z, w3.z, (int)w2.x, X, xsc);         // B into the (dead) X registers
 #pragma unroll
         for (int g = 0; g < NG; ++g)
@@ -522,6 +538,17 @@ tree_kernel_s20t(const TreeParams prm, unsigned int * __restrict__ rootsc)
             if (q < 2) st128(p + 16 + 2 * q, O[g][4], O[g][5]);
           }
 #endif
+        // ---- operand A of the next op
+        if (k + 1 < nops)
+        {
+          const uint4 n0 = recs[4 * k + 4], n3 = recs[4 * k + 7];
+          const unsigned int nkind = (n0.x >> OP_AKIND_SHIFT) & 15u;
+          if (!(n0.x & OP_EVAL) && (nkind == SRC_TIP_PACKED || nkind == SRC_SLOT))
+          {
+            fetch(nkind, n0.z, n3.y, -1, A, asc);
+            a_ready = true;
+          }
+        }
         // ---- push through the edge above
         if (ctl & OP_PUSH)
         {
