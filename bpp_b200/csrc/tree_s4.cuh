@@ -189,7 +189,7 @@ struct TileCtx
 // from chunk to chunk of the same tile.
 template <int RL, bool EXACT, int CPT, int MODE>
 __device__ __forceinline__ double tile_fast(const TreeParams & prm, const TileCtx<CPT> & tc, double (&x)[CPT][4],
-                                            unsigned int (&psc)[CPT])
+                                            unsigned int (&psc)[CPT], unsigned int & wnz)
 {
   constexpr bool SCALED = MODE >= 1, FULL = MODE == 2;
   constexpr unsigned int LOG2RL = RL == 1 ? 0 : (RL == 2 ? 1 : (RL == 4 ? 2 : 3));
@@ -305,38 +305,69 @@ __device__ __forceinline__ double tile_fast(const TreeParams & prm, const TileCt
         osc[j] = 0;
       }
     }
-    // ---- per-site scaling (core_partials.c:720,739-754)
+    // ---- per-site scaling (core_partials.c:720,739-754): a site is rescaled when all its 4 x RL entries are below
+    // 2^-256.  That is rare, and the bookkeeping around it was 60 % more instructions than the unscaled op, so the
+    // common case is kept to: one integer compare per cell (entries are non-negative, and 2^-256 has a zero
+    // mantissa, so "all four below" is max(high words) < 0x2FF00000 -- off the FP64 pipe), the cells' bits packed
+    // into one word and combined over the site's RL lanes once per op, and ONE warp-uniform branch.  Scaler
+    // counts of staged children are read only once some count of the warp is non-zero (wnz).
     if (SCALED && (ctl & OP_SCALE))
     {
       const uint4 w2 = s4[ops + 4 * k + 2], w3 = s4[ops + 4 * k + 3];
       const unsigned int ak = (ctl >> OP_AKIND_SHIFT) & 15u, bk = (ctl >> OP_BKIND_SHIFT) & 15u;
-      const bool a_slot = ak == SRC_SLOT, b_slot = !(ctl & OP_BPREV) && bk == SRC_SLOT;
       const bool a_glob = FULL && (ak == SRC_HBML || ak == SRC_HBM) && (int)w2.z >= 0;
       const bool b_glob = FULL && !(ctl & OP_BPREV) && (bk == SRC_HBML || bk == SRC_HBM) && (int)w3.z >= 0;
-      const unsigned int a_sl = tc.sst1 + w2.x * (CPT * TREE_NT) + tid, b_sl = tc.sst1 + w3.x * (CPT * TREE_NT) + tid;
-      unsigned int * const sc_out = H->scale + (size_t)(int)w1.z * sites;
+      unsigned int bits = 0;
 #pragma unroll
       for (int j = 0; j < CPT; ++j)
       {
-        const unsigned int site = tc.cell[j] >> LOG2RL;
-        unsigned int sc = (ctl & OP_BPREV) ? psc[j] : 0u;
-        if (a_slot) sc += s1[a_sl + j * TREE_NT];
-        if (b_slot) sc += s1[b_sl + j * TREE_NT];
-        if (a_glob) sc += H->scale[(size_t)(int)w2.z * sites + site];
-        if (b_glob) sc += H->scale[(size_t)(int)w3.z * sites + site];
-        unsigned int below = (o[j][0] < BPPGPU_SCALE_THRESHOLD) & (o[j][1] < BPPGPU_SCALE_THRESHOLD) &
-                             (o[j][2] < BPPGPU_SCALE_THRESHOLD) & (o[j][3] < BPPGPU_SCALE_THRESHOLD);
-#pragma unroll
-        for (int dd = 1; dd < RL; dd <<= 1) below &= __shfl_xor_sync(0xFFFFFFFFu, below, S4Lanes<RL>::xor_step(dd));
-        if (below)
-        {
-          o[j][0] = __dmul_rn(o[j][0], BPPGPU_SCALE_FACTOR); o[j][1] = __dmul_rn(o[j][1], BPPGPU_SCALE_FACTOR);
-          o[j][2] = __dmul_rn(o[j][2], BPPGPU_SCALE_FACTOR); o[j][3] = __dmul_rn(o[j][3], BPPGPU_SCALE_FACTOR);
-          sc += 1;
-        }
-        osc[j] = sc;
-        if (tc.valid[j] && tc.cat == 0) sc_out[site] = sc;
+        const int h0 = __double2hiint(o[j][0]), h1 = __double2hiint(o[j][1]), h2 = __double2hiint(o[j][2]), h3 = __double2hiint(o[j][3]);
+        if (max(max(h0, h1), max(h2, h3)) < 0x2FF00000) bits |= 1u << j;
       }
+#pragma unroll
+      for (int dd = 1; dd < RL; dd <<= 1) bits &= __shfl_xor_sync(0xFFFFFFFFu, bits, S4Lanes<RL>::xor_step(dd));
+#pragma unroll
+      for (int j = 0; j < CPT; ++j) osc[j] = 0;
+      if (wnz | (FULL ? (unsigned)(a_glob || b_glob) : 0u))
+      {
+        // counts of the children: the previous X, parked values, HBM-resident CLVs of earlier calls
+        const bool a_slot = ak == SRC_SLOT, b_slot = !(ctl & OP_BPREV) && bk == SRC_SLOT;
+        const unsigned int a_sl = tc.sst1 + w2.x * (CPT * TREE_NT) + tid, b_sl = tc.sst1 + w3.x * (CPT * TREE_NT) + tid;
+#pragma unroll
+        for (int j = 0; j < CPT; ++j)
+        {
+          const unsigned int site = tc.cell[j] >> LOG2RL;
+          unsigned int sc = (ctl & OP_BPREV) ? psc[j] : 0u;
+          if (a_slot) sc += s1[a_sl + j * TREE_NT];
+          if (b_slot) sc += s1[b_sl + j * TREE_NT];
+          if (a_glob) sc += H->scale[(size_t)(int)w2.z * sites + site];
+          if (b_glob) sc += H->scale[(size_t)(int)w3.z * sites + site];
+          osc[j] = sc;
+        }
+        if (FULL)
+        {
+          unsigned int any = 0;
+#pragma unroll
+          for (int j = 0; j < CPT; ++j) any |= osc[j];
+          wnz |= __any_sync(0xFFFFFFFFu, any != 0u) ? 1u : 0u;
+        }
+      }
+      if (__any_sync(0xFFFFFFFFu, bits != 0u))
+      {
+        wnz = 1u;
+#pragma unroll
+        for (int j = 0; j < CPT; ++j)
+          if ((bits >> j) & 1u)
+          {
+            o[j][0] = __dmul_rn(o[j][0], BPPGPU_SCALE_FACTOR); o[j][1] = __dmul_rn(o[j][1], BPPGPU_SCALE_FACTOR);
+            o[j][2] = __dmul_rn(o[j][2], BPPGPU_SCALE_FACTOR); o[j][3] = __dmul_rn(o[j][3], BPPGPU_SCALE_FACTOR);
+            osc[j] += 1;
+          }
+      }
+      unsigned int * const sc_out = H->scale + (size_t)(int)w1.z * sites;
+#pragma unroll
+      for (int j = 0; j < CPT; ++j)
+        if (tc.valid[j] && tc.cat == 0) sc_out[tc.cell[j] >> LOG2RL] = osc[j];
     }
     // ---- the CLV goes to HBM exactly once
     {
@@ -749,19 +780,20 @@ tree_kernel_s4(const TreeParams prm)
       const unsigned int flags = H->flags, n_chunks = H->n_chunks;
       double x[CPT][4];
       unsigned int psc[CPT];
+      unsigned int wnz = 0;                    // some scaler count of this warp's cells is non-zero (this tile)
 #pragma unroll
       for (int j = 0; j < CPT; ++j) { x[j][0] = x[j][1] = x[j][2] = x[j][3] = 0.0; psc[j] = 0; }
       // one chunk (trees of up to 16 ops whose tips fit the lookup tables) and no HBM-class operand: the lean
       // instantiations; anything else on the fast path runs the full one, chunk by chunk
-      if (n_chunks == 1 && (flags & HDR_SIMPLE)) site_sum = tile_fast<RL, EXACT, CPT, 0>(prm, tc, x, psc);
-      else if (n_chunks == 1 && (flags & HDR_NOHBM)) site_sum = tile_fast<RL, EXACT, CPT, 1>(prm, tc, x, psc);
+      if (n_chunks == 1 && (flags & HDR_SIMPLE)) site_sum = tile_fast<RL, EXACT, CPT, 0>(prm, tc, x, psc, wnz);
+      else if (n_chunks == 1 && (flags & HDR_NOHBM)) site_sum = tile_fast<RL, EXACT, CPT, 1>(prm, tc, x, psc, wnz);
       else
       {
         site_sum = 0.0;
         for (unsigned int c = 0; c < n_chunks; ++c)
         {
           if (c > 0) restage(c);
-          site_sum += tile_fast<RL, EXACT, CPT, 2>(prm, tc, x, psc);
+          site_sum += tile_fast<RL, EXACT, CPT, 2>(prm, tc, x, psc, wnz);
         }
       }
     }
