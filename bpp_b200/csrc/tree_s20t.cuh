@@ -317,6 +317,48 @@ tree_kernel_s20t(const TreeParams prm, unsigned int * __restrict__ rootsc)
       sitev[g] = validv[g] ? s : sites - 1;
     }
 
+    // scaling handshake: a warp's bits of one op in its own shared memory, read by the same warp of the other CTAs.
+    // The 64-bit word (sequence number, bits) is all that is communicated, so relaxed accesses suffice: a release
+    // store at cluster scope is a full memory barrier that waits for every CLV store the thread has in flight, an
+    // acquire load invalidates L1 -- together they cost this kernel 1.4 ms.
+    auto publish = [&](unsigned int seq, unsigned int m)
+    {
+      if (lane == 0)
+      {
+        const unsigned int la = (unsigned int)__cvta_generic_to_shared(s_hand + (seq & 1u) * NW + warp);
+        const unsigned long long v = ((unsigned long long)seq << 32) | m;
+        asm volatile("st.relaxed.cluster.shared::cta.u64 [%0], %1;" :: "r"(la), "l"(v) : "memory");
+      }
+    };
+    auto consume = [&](unsigned int seq) -> unsigned int        // AND of the other categories' bits of op `seq`
+    {
+      unsigned int theirs = 0xFFFFFFFFu;
+      if (lane < RL && lane != cat)
+      {
+        const unsigned int la = (unsigned int)__cvta_generic_to_shared(s_hand + (seq & 1u) * NW + warp);
+        unsigned int ra;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(lane));
+        unsigned long long v;
+        do
+        {
+          asm volatile("ld.relaxed.cluster.shared::cluster.u64 %0, [%1];" : "=l"(v) : "r"(ra) : "memory");
+        } while ((unsigned int)(v >> 32) != seq);
+        theirs = (unsigned int)v;
+      }
+#pragma unroll
+      for (int d = 1; d < RL; d <<= 1) theirs &= __shfl_xor_sync(0xFFFFFFFFu, theirs, d);
+      return __shfl_sync(0xFFFFFFFFu, theirs, 0);
+    };
+    // Scaled batches run a tile optimistically first: every op publishes its under-threshold bits but goes on as if
+    // no site were rescaled, and reads the other categories' bits one scaled op later (they have had a whole op to
+    // arrive, so nobody waits).  If the AND ever is non-zero (rare: all 20 x R entries of a site below 2^-256) the
+    // warp -- and with it the same warp of the R-1 other CTAs, which see the same AND at the same op -- starts the
+    // tile again in lock-step mode, where every op waits for its peers before it stores.  Stores are idempotent.
+    bool sync_mode = false;
+    for (;;)
+    {
+    bool redo = false, pending = false;
+    unsigned int pend_m = 0, pend_seq = 0;
     double X[NG][6];
     unsigned int xsc[NG];
 #pragma unroll
@@ -471,44 +513,32 @@ tree_kernel_s20t(const TreeParams prm, unsigned int * __restrict__ rootsc)
         }
         if (SCALED && (ctl & OP_SCALE))
         {
-          // all 20 x R entries of a site strictly below 2^-256 (the padding entries of lanes q >= 2 are exact zeros)
+          // all 20 x R entries of a site strictly below 2^-256: entries are non-negative and 2^-256 has a zero
+          // mantissa, so that is max(high words) < 0x2FF00000 (integer pipe; padding entries of lanes q >= 2 are zeros)
           unsigned int mine = 1u;
 #pragma unroll
           for (int g = 0; g < NG; ++g)
           {
-            unsigned int b = 1u;
+            int hm = __double2hiint(O[g][0]);
 #pragma unroll
-            for (int i = 0; i < 6; ++i) b &= (O[g][i] < BPPGPU_SCALE_THRESHOLD) ? 1u : 0u;
+            for (int i = 1; i < 6; ++i) hm = max(hm, __double2hiint(O[g][i]));
+            unsigned int b = hm < 0x2FF00000 ? 1u : 0u;
             b &= __shfl_xor_sync(0xFFFFFFFFu, b, 1);
             b &= __shfl_xor_sync(0xFFFFFFFFu, b, 2);
             if (q == (unsigned)g) mine = b;
           }
-          unsigned int m = __ballot_sync(0xFFFFFFFFu, mine != 0u);        // bit 4r + g = site r of group g
+          unsigned int m = __ballot_sync(0xFFFFFFFFu, mine != 0u) & (NG >= 4 ? 0xFFFFFFFFu : (NG == 2 ? 0x33333333u : 0x11111111u));   // bit 4r + g = site r of group g
           if (RL > 1)
           {
+            if (!sync_mode && pending)
+            {
+              pending = false;
+              if (pend_m & consume(pend_seq)) { redo = true; break; }
+            }
             ++hand_seq;
-            unsigned long long * word = s_hand + (hand_seq & 1u) * NW + warp;
-            const unsigned int la = (unsigned int)__cvta_generic_to_shared(word);
-            if (lane == 0)
-            {
-              const unsigned long long v = ((unsigned long long)hand_seq << 32) | m;
-              asm volatile("st.release.cluster.shared::cta.u64 [%0], %1;" :: "r"(la), "l"(v) : "memory");
-            }
-            unsigned int theirs = 0xFFFFFFFFu;
-            if (lane < RL && lane != cat)
-            {
-              unsigned int ra;
-              asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(lane));
-              unsigned long long v;
-              do
-              {
-                asm volatile("ld.acquire.cluster.shared::cluster.u64 %0, [%1];" : "=l"(v) : "r"(ra) : "memory");
-              } while ((unsigned int)(v >> 32) != hand_seq);
-              theirs = (unsigned int)v;
-            }
-#pragma unroll
-            for (int d = 1; d < RL; d <<= 1) theirs &= __shfl_xor_sync(0xFFFFFFFFu, theirs, d);
-            m &= __shfl_sync(0xFFFFFFFFu, theirs, 0);
+            publish(hand_seq, m);
+            if (sync_mode) m &= consume(hand_seq);
+            else { pending = true; pend_m = m; pend_seq = hand_seq; m = 0; }
           }
 #pragma unroll
           for (int g = 0; g < NG; ++g)
@@ -594,6 +624,10 @@ tree_kernel_s20t(const TreeParams prm, unsigned int * __restrict__ rootsc)
           }
         }
       }
+    }
+    if (SCALED && RL > 1 && pending && (pend_m & consume(pend_seq))) redo = true;
+    if (!redo) break;
+    sync_mode = true;                                          // a site has to be rescaled: again, in lock step
     }
     __syncwarp();                                              // the tile's reads of its column ids are over
     }
