@@ -62,6 +62,8 @@ constexpr int S20T_IMG = 480;                        // doubles per staged matri
 // block of a locus: [RL x cap images][Hdr20][list][op records]...; tile_blk points at the header
 __host__ __device__ inline size_t s20t_img_bytes(unsigned cap) { return (size_t)cap * S20T_IMG * 8; }        // per category
 __host__ __device__ inline size_t s20t_meta_bytes(unsigned max_tips) { return S20_RECS_OFF + (size_t)2 * max_tips * sizeof(OpRec20); }
+// scaling handshake ring: two tiles' worth of op words per warp (a tile publishes at most 2 * max_tips), power of two
+__host__ __device__ inline unsigned int s20t_hand_slots(unsigned max_tips) { unsigned int h = 1; while (h < 4 * max_tips) h <<= 1; return h; }
 __host__ __device__ inline size_t s20t_cols_bytes(unsigned max_tips) { return (size_t)S20T_NW * max_tips * S20T_WS; }   // one of four buffers
 
 // shared memory: [2 x (cap images + meta)][parked X][tip columns x 4][handshake words][mbarriers, counters]
@@ -71,7 +73,7 @@ __host__ inline size_t s20t_smem_bytes(unsigned cap, unsigned max_tips, int slot
   b += (size_t)slots * S20T_NW * S20T_NG * 6 * 32 * 8;                            // parked X
   if (scaled) b += (size_t)slots * S20T_NW * S20T_NG * 32 * 4;                    // ... and their scaler counts
   b += 4 * s20t_cols_bytes(max_tips);                                             // tip column ids
-  b += (size_t)2 * S20T_NW * 8 + 2 * 8 + 2 * 8;                                   // handshake words, mbarriers, counters
+  b += (scaled ? (size_t)s20t_hand_slots(max_tips) : 2) * S20T_NW * 8 + 2 * 8 + 2 * 8;   // handshake words, mbarriers, counters
   b += (size_t)S20T_NW * 4 * 32;                                                  // group records
   return b + 16;
 }
@@ -178,7 +180,8 @@ tree_kernel_s20t(const TreeParams prm, unsigned int * __restrict__ rootsc)
   unsigned int * s_sstack = reinterpret_cast<unsigned int *>(s_stack + (size_t)prm.n_slots * NW * NG * 6 * 32);
   unsigned char * s_cols_all = reinterpret_cast<unsigned char *>(s_sstack + (SCALED ? (size_t)prm.n_slots * NW * NG * 32 : 0));
   unsigned long long * s_hand = reinterpret_cast<unsigned long long *>(s_cols_all + 4 * cols_bytes);   // [parity][warp]
-  unsigned long long * s_full = s_hand + 2 * NW;                                                         // [2] stage buffer filled
+  const unsigned int HS = SCALED ? s20t_hand_slots(maxT) : 2u;
+  unsigned long long * s_full = s_hand + HS * NW;                                                        // [2] stage buffer filled
   unsigned int * s_done = reinterpret_cast<unsigned int *>(s_full + 2);                                  // [2] warps done with the buffer
   unsigned char * s_ring = reinterpret_cast<unsigned char *>(s_done + 4);                                // [warp][4] group records
 
@@ -239,7 +242,7 @@ tree_kernel_s20t(const TreeParams prm, unsigned int * __restrict__ rootsc)
     if (ring[0].t0 < t_end) fetch_group(ring[0], 0);
     if (ring[1].t0 < t_end) fetch_group(ring[1], 1);
   }
-  if (SCALED && RL > 1 && tid < 2 * NW) s_hand[tid] = 0ull;
+  if (SCALED && RL > 1) for (unsigned int i = tid; i < HS * NW; i += S20T_NT) s_hand[i] = 0ull;
   __syncthreads();
   if (SCALED && RL > 1) cluster_sync_all();                   // every CTA of the cluster runs and has cleared its words
 
@@ -325,7 +328,7 @@ tree_kernel_s20t(const TreeParams prm, unsigned int * __restrict__ rootsc)
     {
       if (lane == 0)
       {
-        const unsigned int la = (unsigned int)__cvta_generic_to_shared(s_hand + (seq & 1u) * NW + warp);
+        const unsigned int la = (unsigned int)__cvta_generic_to_shared(s_hand + (seq & (HS - 1u)) * NW + warp);
         const unsigned long long v = ((unsigned long long)seq << 32) | m;
         asm volatile("st.relaxed.cluster.shared::cta.u64 [%0], %1;" :: "r"(la), "l"(v) : "memory");
       }
@@ -335,7 +338,7 @@ tree_kernel_s20t(const TreeParams prm, unsigned int * __restrict__ rootsc)
       unsigned int theirs = 0xFFFFFFFFu;
       if (lane < RL && lane != cat)
       {
-        const unsigned int la = (unsigned int)__cvta_generic_to_shared(s_hand + (seq & 1u) * NW + warp);
+        const unsigned int la = (unsigned int)__cvta_generic_to_shared(s_hand + (seq & (HS - 1u)) * NW + warp);
         unsigned int ra;
         asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(lane));
         unsigned long long v;
@@ -349,16 +352,43 @@ tree_kernel_s20t(const TreeParams prm, unsigned int * __restrict__ rootsc)
       for (int d = 1; d < RL; d <<= 1) theirs &= __shfl_xor_sync(0xFFFFFFFFu, theirs, d);
       return __shfl_sync(0xFFFFFFFFu, theirs, 0);
     };
+    // the ops seq0 + 1 .. seq0 + n of this tile at once: lane = (op, category); true if some site's AND is non-zero
+    auto tile_check = [&](unsigned int seq0, unsigned int n) -> bool
+    {
+      bool ev = false;
+      for (unsigned int base = 0; base < n; base += 32 / RL)
+      {
+        const unsigned int i = base + lane / RL, p = lane % RL;
+        unsigned int v = 0u;
+        if (i < n)
+        {
+          const unsigned int seq = seq0 + 1 + i;
+          const unsigned int la = (unsigned int)__cvta_generic_to_shared(s_hand + (seq & (HS - 1u)) * NW + warp);
+          unsigned int ra;
+          asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(p));
+          unsigned long long w;
+          do
+          {
+            asm volatile("ld.relaxed.cluster.shared::cluster.u64 %0, [%1];" : "=l"(w) : "r"(ra) : "memory");
+          } while ((unsigned int)(w >> 32) != seq);
+          v = (unsigned int)w;
+        }
+#pragma unroll
+        for (int d = 1; d < RL; d <<= 1) v &= __shfl_xor_sync(0xFFFFFFFFu, v, d);
+        ev = ev || __any_sync(0xFFFFFFFFu, v != 0u);
+      }
+      return ev;
+    };
     // Scaled batches run a tile optimistically first: every op publishes its under-threshold bits but goes on as if
-    // no site were rescaled, and reads the other categories' bits one scaled op later (they have had a whole op to
-    // arrive, so nobody waits).  If the AND ever is non-zero (rare: all 20 x R entries of a site below 2^-256) the
+    // no site were rescaled; the other categories' bits are read once, at the end of the tile (by then they have
+    // arrived, so nobody waits).  If the AND ever is non-zero (rare: all 20 x R entries of a site below 2^-256) the
     // warp -- and with it the same warp of the R-1 other CTAs, which see the same AND at the same op -- starts the
     // tile again in lock-step mode, where every op waits for its peers before it stores.  Stores are idempotent.
     bool sync_mode = false;
     for (;;)
     {
-    bool redo = false, pending = false;
-    unsigned int pend_m = 0, pend_seq = 0;
+    bool redo = false;
+    unsigned int n_pub = 0;
     double X[NG][6];
     unsigned int xsc[NG];
 #pragma unroll
@@ -530,26 +560,27 @@ tree_kernel_s20t(const TreeParams prm, unsigned int * __restrict__ rootsc)
           unsigned int m = __ballot_sync(0xFFFFFFFFu, mine != 0u) & (NG >= 4 ? 0xFFFFFFFFu : (NG == 2 ? 0x33333333u : 0x11111111u));   // bit 4r + g = site r of group g
           if (RL > 1)
           {
-            if (!sync_mode && pending)
-            {
-              pending = false;
-              if (pend_m & consume(pend_seq)) { redo = true; break; }
-            }
             ++hand_seq;
             publish(hand_seq, m);
             if (sync_mode) m &= consume(hand_seq);
-            else { pending = true; pend_m = m; pend_seq = hand_seq; m = 0; }
+            else { ++n_pub; m = 0; }
           }
-#pragma unroll
-          for (int g = 0; g < NG; ++g)
+          if (m)                                                         // warp-uniform, rare
           {
-            if ((m >> (4 * r + g)) & 1u)
-            {
 #pragma unroll
-              for (int i = 0; i < 6; ++i) O[g][i] *= BPPGPU_SCALE_FACTOR;
-              osc[g] += 1;
-            }
-            if (cat == 0 && q == 0 && validv[g]) H->scale[(size_t)(int)w2.w * sites + sitev[g]] = osc[g];
+            for (int g = 0; g < NG; ++g)
+              if ((m >> (4 * r + g)) & 1u)
+              {
+#pragma unroll
+                for (int i = 0; i < 6; ++i) O[g][i] *= BPPGPU_SCALE_FACTOR;
+                osc[g] += 1;
+              }
+          }
+          if (cat == 0 && q == 0)
+          {
+#pragma unroll
+            for (int g = 0; g < NG; ++g)
+              if (validv[g]) H->scale[(size_t)(int)w2.w * sites + sitev[g]] = osc[g];
           }
         }
         else
@@ -625,7 +656,7 @@ tree_kernel_s20t(const TreeParams prm, unsigned int * __restrict__ rootsc)
         }
       }
     }
-    if (SCALED && RL > 1 && pending && (pend_m & consume(pend_seq))) redo = true;
+    if (SCALED && RL > 1 && n_pub && tile_check(hand_seq - n_pub, n_pub)) redo = true;
     if (!redo) break;
     sync_mode = true;                                          // a site has to be rescaled: again, in lock step
     }
