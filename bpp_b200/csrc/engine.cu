@@ -1412,9 +1412,12 @@ static void batch_sync_loci(bppgpu_batch * b, bool need_eigen)
 template <int RL, int CPT>
 static int tree_s4_slots(bppgpu_batch * b, int wanted, unsigned cap)
 {
+  // A list whose parked values do not all get a slot leaves the fast path (its loci run the cell-at-a-time walker,
+  // 3-4x slower), so the slots a tree of this size can need come first: if they fit one CTA they are kept and the
+  // occupancy gives way (48 tips with 4 categories used to end up with one slot at two CTAs per SM -- which the
+  // shared memory did not allow anyway).  Only what does not even fit one CTA is cut.
   int slots = wanted;
-  const size_t ctas = s4_ctas_per_sm(CPT);
-  while (slots > 1 && ctas * (S4Layout<RL, CPT>::bytes(slots, cap, b->tip_words_rt) + 1024) > b->e->smem_per_sm) --slots;
+  while (slots > 1 && S4Layout<RL, CPT>::bytes(slots, cap, b->tip_words_rt) + 1024 > b->e->smem_optin) --slots;
   return slots;
 }
 
