@@ -17,22 +17,44 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
               "-Xcompiler", "-fPIC", "-shared", "--cudart", "static"]
 
 
-def _newer(target, sources):
-    if not os.path.exists(target):
+def _src_hash(sources, extra=()):
+    import hashlib
+    h = hashlib.sha256()
+    for s in sorted(sources):
+        h.update(os.path.basename(s).encode())
+        with open(s, "rb") as f:
+            h.update(f.read())
+    for e in extra:
+        h.update(str(e).encode())
+    return h.hexdigest()
+
+
+def _stale(target, sources, extra=()):
+    """A built library is current only if the hash of the sources it was built from (kept next to it in
+    <target>.srchash) equals the hash of the sources present now: modification times do not survive the copy to
+    the GPU box, a hash does -- there the driver's build() compiles exactly when the tree differs from what the
+    shipped .so was built from."""
+    if not os.path.exists(target) or not os.path.exists(target + ".srchash"):
         return True
-    t = os.path.getmtime(target)
-    return any(os.path.getmtime(s) > t for s in sources)
+    with open(target + ".srchash") as f:
+        return f.read().strip() != _src_hash(sources, extra)
+
+
+def _stamp(target, sources, extra=()):
+    with open(target + ".srchash", "w") as f:
+        f.write(_src_hash(sources, extra) + "\n")
 
 
 def build_cuda(force=False, verbose=False):
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     srcs = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh"))]
     srcs.append(os.path.join(ROOT, "include", "bpp_b200.h"))
-    if not force and not _newer(LIB, srcs):
+    if not force and not _stale(LIB, srcs, NVCC_FLAGS):
         return LIB
     cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
           ["-o", LIB, os.path.join(CSRC, "engine.cu")]
     subprocess.check_call(cmd)
+    _stamp(LIB, srcs, NVCC_FLAGS)
     return LIB
 
 
@@ -45,12 +67,14 @@ def build_host(force=False):
     srcs = [os.path.join(hdir, f) for f in sorted(os.listdir(hdir)) if f.endswith(".c")]
     if not srcs:
         return None
-    deps = srcs + [os.path.join(hdir, f) for f in os.listdir(hdir) if f.endswith(".h")] + [LIB]
-    if not force and not _newer(HOST_LIB, deps):
+    deps = srcs + [os.path.join(hdir, f) for f in os.listdir(hdir) if f.endswith(".h")] + \
+        [os.path.join(ROOT, "include", "bpp_b200.h")]
+    if not force and not _stale(HOST_LIB, deps):
         return HOST_LIB
     cmd = ["gcc", "-O2", "-std=c99", "-fPIC", "-shared", "-Wall", "-I", os.path.join(ROOT, "include"),
            "-o", HOST_LIB] + srcs + ["-L", HERE, "-lbppgpu", "-Wl,-rpath,$ORIGIN", "-lm"]
     subprocess.check_call(cmd)
+    _stamp(HOST_LIB, deps)
     return HOST_LIB
 
 

@@ -34,6 +34,33 @@ gtree_gpu_t * gtree_create_gpu(unsigned int tips, const int * left, const int * 
   return t;
 }
 
+void gtree_set_relaxed_clock_gpu(gtree_gpu_t * t, const stree_gpu_t * stree, const int * pops, double rate_scale)
+{
+  unsigned int k;
+  t->stree = stree; t->rate_scale = rate_scale;
+  if (stree && pops) for (k = 0; k < t->tip_count + t->inner_count; ++k) t->nodes[k]->pop = pops[k];
+}
+
+double gtree_branch_length_gpu(const gtree_gpu_t * t, const gnode_gpu_t * node)
+{
+  const stree_gpu_t * st = t->stree;
+  double time, length = 0;
+  int start, end;
+  if (!st) return (node->parent->time - node->time) * t->rate_mui;
+  /* walk up the species tree from the node's population to its parent's: every species branch crossed contributes
+     its time span times its rate, the last span lies in the parent's population */
+  time = node->time; start = node->pop; end = node->parent->pop;
+  while (start != end)
+  {
+    const int pop = start;
+    start = st->parent[start];
+    length += (st->tau[start] - time) * st->brate[pop] * t->rate_scale;
+    time = st->tau[start];
+  }
+  length += (node->parent->time - time) * st->brate[end] * t->rate_scale;
+  return length;
+}
+
 void gtree_destroy_gpu(gtree_gpu_t * t)
 {
   if (!t) return;
@@ -103,8 +130,8 @@ static void ensure_cap(locus_gpu_t * l, unsigned int count)
   l->bl = (double *)realloc(l->bl, l->cap * sizeof(double));
 }
 
-/* strict clock only (opt_clock == BPP_CLOCK_GLOBAL, core_pmatrix.c:711-715 / locus.c:2347-2351);
-   the relaxed-clock branch lengths are host work of the caller */
+/* node->length as locus_update_matrices sets it before it builds the matrix: strict clock or relaxed clocks
+   (gtree_branch_length_gpu) */
 static unsigned int fill_matrix_ops(gtree_gpu_t * gtree, gnode_gpu_t ** trav, unsigned int count,
                                     unsigned int * idx, double * bl)
 {
@@ -112,7 +139,7 @@ static unsigned int fill_matrix_ops(gtree_gpu_t * gtree, gnode_gpu_t ** trav, un
   for (i = 0; i < count; ++i)
   {
     gnode_gpu_t * node = trav[i];
-    node->length = (node->parent->time - node->time) * gtree->rate_mui;
+    node->length = gtree_branch_length_gpu(gtree, node);
     idx[i] = node->pmatrix_index;
     bl[i] = node->length;
   }

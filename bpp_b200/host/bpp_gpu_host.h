@@ -26,7 +26,18 @@ typedef struct gnode_gpu_s
   unsigned int clv_index;
   int scaler_index;
   unsigned int pmatrix_index;
+  int pop;                      /* species-tree node the gene node sits in (gnode_t::pop); relaxed clocks only */
 } gnode_gpu_t;
+
+/* the slice of stree_t / snode_t the relaxed-clock branch lengths read (locus.c:1105-1193): parent, tau and, for the
+   locus at hand, the branch rate of every species node (snode_t::brate[msa_index]); no hybridisation nodes */
+typedef struct stree_gpu_s
+{
+  unsigned int node_count;
+  const int * parent;           /* parent species node or -1 for the root */
+  const double * tau;
+  const double * brate;
+} stree_gpu_t;
 
 typedef struct gtree_gpu_s
 {
@@ -35,6 +46,8 @@ typedef struct gtree_gpu_s
   gnode_gpu_t * root;
   double rate_mui;
   double logl;
+  const stree_gpu_t * stree;    /* NULL = strict clock (opt_clock == BPP_CLOCK_GLOBAL) */
+  double rate_scale;            /* relaxed clocks: 1, or the locus rate for BPP_CLOCK_SIMPLE (brate[0] * locusrate) */
 } gtree_gpu_t;
 
 typedef struct locus_gpu_s
@@ -59,6 +72,12 @@ typedef struct locus_gpu_s
 gtree_gpu_t * gtree_create_gpu(unsigned int tips, const int * left, const int * right, const double * times,
                                double rate_mui, int scaling);
 void gtree_destroy_gpu(gtree_gpu_t * t);
+/* relaxed clock: pops[k] = species node of gene node k (gnode_t::pop); pass stree = NULL to go back to the strict clock */
+void gtree_set_relaxed_clock_gpu(gtree_gpu_t * t, const stree_gpu_t * stree, const int * pops, double rate_scale);
+/* length of the branch above `node` as locus_update_matrices computes it: (parent time - time) * rate_mui under the
+   strict clock (locus.c:2347-2351), the rate-weighted sum over the species-tree branches it crosses under a relaxed
+   clock (update_branchlength_relaxed_clock{,_simple}, locus.c:1105-1193) */
+double gtree_branch_length_gpu(const gtree_gpu_t * t, const gnode_gpu_t * node);
 /* recursive left,right,node traversal (prop_mixing.c:28-50) */
 void gtree_all_partials_gpu(gnode_gpu_t * root, gnode_gpu_t ** travbuffer, unsigned int * trav_size);
 

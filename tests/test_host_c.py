@@ -21,13 +21,18 @@ class GNode(C.Structure):
 
 GNode._fields_ = [("left", C.POINTER(GNode)), ("right", C.POINTER(GNode)), ("parent", C.POINTER(GNode)),
                   ("length", C.c_double), ("time", C.c_double), ("node_index", C.c_uint), ("clv_index", C.c_uint),
-                  ("scaler_index", C.c_int), ("pmatrix_index", C.c_uint)]
+                  ("scaler_index", C.c_int), ("pmatrix_index", C.c_uint), ("pop", C.c_int)]
+
+
+class STree(C.Structure):
+    _fields_ = [("node_count", C.c_uint), ("parent", C.POINTER(C.c_int)), ("tau", C.POINTER(C.c_double)),
+                ("brate", C.POINTER(C.c_double))]
 
 
 class GTree(C.Structure):
     _fields_ = [("tip_count", C.c_uint), ("inner_count", C.c_uint), ("edge_count", C.c_uint),
                 ("nodes", C.POINTER(C.POINTER(GNode))), ("root", C.POINTER(GNode)), ("rate_mui", C.c_double),
-                ("logl", C.c_double)]
+                ("logl", C.c_double), ("stree", C.POINTER(STree)), ("rate_scale", C.c_double)]
 
 
 @pytest.fixture(scope="module")
@@ -81,6 +86,48 @@ def test_gamma_rates_used_by_synth(host):
 
 def _dp(a):
     return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def test_relaxed_clock_branch_lengths(host):
+    """update_branchlength_relaxed_clock (locus.c:1146-1190): a branch that crosses species-tree nodes is the sum of
+    (time span in a population) x (that population's rate); the strict clock is (parent time - time) x locus rate."""
+    host.gtree_branch_length_gpu.restype = C.c_double
+    host.gtree_branch_length_gpu.argtypes = [C.POINTER(GTree), C.POINTER(GNode)]
+    host.gtree_set_relaxed_clock_gpu.argtypes = [C.POINTER(GTree), C.POINTER(STree), C.POINTER(C.c_int), C.c_double]
+    # species tree ((A,B)AB,C)ABC: nodes A=0 B=1 C=2 AB=3 ABC=4
+    parent = np.array([3, 3, 4, 4, -1], dtype=np.int32)
+    tau = np.array([0.0, 0.0, 0.0, 0.010, 0.025])
+    brate = np.array([0.8, 1.3, 0.9, 1.7, 0.6])
+    st = STree(5, parent.ctypes.data_as(C.POINTER(C.c_int)), _dp(tau), _dp(brate))
+    # gene tree of 4 tips (a1, a2 in A; b in B; c in C): ((a1,a2),b),c) with coalescences in A, AB and ABC
+    left = np.array([0, 4, 5], dtype=np.int32)
+    right = np.array([1, 2, 3], dtype=np.int32)
+    times = np.array([0, 0, 0, 0, 0.004, 0.018, 0.040])
+    pops = np.array([0, 0, 1, 2, 0, 3, 4], dtype=np.int32)
+    t = host.gtree_create_gpu(4, left.ctypes.data_as(C.POINTER(C.c_int)), right.ctypes.data_as(C.POINTER(C.c_int)),
+                              _dp(times), 0.7, 0)
+    gpar = {0: 4, 1: 4, 4: 5, 2: 5, 5: 6, 3: 6}
+
+    def expect(k, scale):
+        tm, pop, end, length = times[k], pops[k], pops[gpar[k]], 0.0
+        while pop != end:
+            nxt = parent[pop]
+            length += (tau[nxt] - tm) * brate[pop] * scale
+            tm, pop = tau[nxt], nxt
+        return length + (times[gpar[k]] - tm) * brate[end] * scale
+
+    for k in gpar:                                   # strict clock
+        assert host.gtree_branch_length_gpu(t, t.contents.nodes[k]) == (times[gpar[k]] - times[k]) * 0.7
+    for scale in (1.0, 2.5):                         # relaxed clocks; BPP_CLOCK_SIMPLE multiplies by the locus rate
+        host.gtree_set_relaxed_clock_gpu(t, C.byref(st), pops.ctypes.data_as(C.POINTER(C.c_int)), scale)
+        for k in gpar:
+            got = host.gtree_branch_length_gpu(t, t.contents.nodes[k])
+            assert abs(got - expect(k, scale)) <= 1e-15, (k, got, expect(k, scale))
+    # b (in B at time 0) joins at 0.018 in AB: 0.010 in B, 0.008 in AB
+    assert abs(host.gtree_branch_length_gpu(t, t.contents.nodes[2]) - 2.5 * (0.010 * 1.3 + 0.008 * 1.7)) < 1e-15
+    host.gtree_set_relaxed_clock_gpu(t, None, None, 1.0)
+    assert host.gtree_branch_length_gpu(t, t.contents.nodes[2]) == (0.018 - 0.0) * 0.7
+    host.gtree_destroy_gpu(t)
 
 
 @pytest.mark.gpu
