@@ -1618,15 +1618,18 @@ static int batch_run(bppgpu_batch * b, bool do_mats, bool do_tree, bool want_roo
   // this index parity are still those of the staged lists, rebuild the matrices and copy them into the blocks again
   const unsigned int pkey = 1u | (want_root ? 2u : 0u) | ((unsigned)slots << 2) | (lut_cap_rt << 8);
   static const bool plan_cache_on = !(getenv("BPPGPU_PLAN_CACHE") && atoi(getenv("BPPGPU_PLAN_CACHE")) == 0);
-  const bool cached = plan_cache_on && b->kernel_kind == 0 && b->plan_valid[b->parity] && b->plan_key[b->parity] == pkey && !persite;
-  if (!waved && cached)
+  // (20 states, category-major kernel: the block holds no matrices -- image20_kernel rebuilds the images from the
+  // pmatrix block every run -- so a cached plan needs no refresh at all)
+  const bool cacheable = b->kernel_kind == 0 || (b->kernel_kind == 2 && b->s20_cat);
+  const bool cached = plan_cache_on && cacheable && b->plan_valid[b->parity] && b->plan_key[b->parity] == pkey && !persite;
+  if (!waved && cached && b->kernel_kind == 0)
   {
     ProfScope ps(e, b->stream, BPPGPU_KERNEL_PLAN);
     plan_refresh_blocks<<<(n * 32 + 127) / 128, 128, 0, b->stream>>>(
         e->d_loci, b->d_batch_locus, n, b->d_blocks, d_blk_off, b->RL, fuse_mats ? d_mat_off : nullptr, d_mat_idx, d_mat_bl);
     CUDA_CHECK(cudaGetLastError());
   }
-  if (b->kernel_kind == 0 && !cached) { b->plan_valid[b->parity] = !persite; b->plan_key[b->parity] = pkey; }
+  if (cacheable && !cached) { b->plan_valid[b->parity] = !persite; b->plan_key[b->parity] = pkey; }
   if (!waved && !cached)
   {
     ProfScope ps(e, b->stream, BPPGPU_KERNEL_PLAN);

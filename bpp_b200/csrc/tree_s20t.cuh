@@ -144,8 +144,8 @@ image20_kernel(const LocusDev * __restrict__ loci, const unsigned int * __restri
         if (col < S20) v = sp[i * S20 + col];
         else
         {
-          const unsigned int mask = cmask[col - S20];
-          for (int j = 0; j < S20; ++j) if ((mask >> j) & 1u) v += sp[i * S20 + j];
+          unsigned int mask = cmask[col - S20];                // no ambiguity codes in the locus: all four are zero
+          while (mask) { const int j = __ffs(mask) - 1; mask &= mask - 1; v += sp[i * S20 + j]; }
         }
       }
       else
