@@ -22,7 +22,7 @@ SYMBOLS = [
     "bppgpu_update_matrices", "bppgpu_update_partials", "bppgpu_root_loglikelihood",
     "bppgpu_root_likelihood_vector", "bppgpu_set_diploid", "bppgpu_root_loglikelihood_diploid",
     "bppgpu_get_clv", "bppgpu_get_pmatrix", "bppgpu_set_pmatrix", "bppgpu_get_scaler",
-    "bppgpu_batch_create", "bppgpu_batch_destroy", "bppgpu_batch_size", "bppgpu_batch_kernel_name",
+    "bppgpu_batch_create", "bppgpu_batch_destroy", "bppgpu_batch_size", "bppgpu_batch_kernel_name", "bppgpu_batch_plan_stats",
     "bppgpu_batch_update_matrices", "bppgpu_batch_update_partials", "bppgpu_batch_root_loglikelihood",
     "bppgpu_batch_full_pass", "bppgpu_batch_stage", "bppgpu_batch_run", "bppgpu_batch_set_waves", "bppgpu_batch_collect",
     "bppgpu_batch_wait_inputs", "bppgpu_batch_flip_indices", "bppgpu_batch_set_branch_lengths",
@@ -106,6 +106,7 @@ def load():
         "bppgpu_batch_destroy": (None, [vp]),
         "bppgpu_batch_size": (u, [vp]),
         "bppgpu_batch_kernel_name": (C.c_char_p, [vp]),
+        "bppgpu_batch_plan_stats": (C.c_int, [vp, C.POINTER(C.c_uint)]),
         "bppgpu_batch_update_matrices": (i, [vp, up, up, dp]),
         "bppgpu_batch_update_partials": (i, [vp, up, opp]),
         "bppgpu_batch_root_loglikelihood": (i, [vp, up, ip, dp]),

@@ -211,6 +211,12 @@ struct bppgpu_batch
   bool plan_valid[2] = {false, false};
   unsigned int plan_key[2] = {0, 0};     // want_root / slots / tip-slot capacity the cached plan was made for
   cudaEvent_t ev_inputs = nullptr;       // recorded behind the last H2D copy of the step's host arrays
+  // class of a cached 4-state plan (plan_class_kernel, read back asynchronously): PLAN_CLASS_* bits once known.
+  // Runs on a cached plan whose loci are all lean (or all scaled one-chunk) launch the specialised kernel.
+  unsigned int * d_class = nullptr, * h_class = nullptr;   // 2 words each (per parity); h_class pinned
+  cudaEvent_t ev_class[2] = {nullptr, nullptr};
+  bool class_pending[2] = {false, false};
+  unsigned int plan_class[2] = {0, 0};
   TileDesc * d_tiles = nullptr;
   unsigned long long * d_tile_blk = nullptr;        // per tile: {block offset, 0}, written by the planner
   unsigned int * d_plan_count = nullptr;
@@ -253,11 +259,13 @@ struct bppgpu_batch
   bool have_m = false, have_o = false;
   std::vector<unsigned int> last_mcounts, last_ocounts;
   unsigned int max_tips = 0;
+  int su_slots = 0;                    // 4 states, trees of more than 16 tips: stack slots the staged op lists need (0 = unknown)
   unsigned int tip_words_rt = 1;       // packed tip words the 4-state kernel stages per cell
   unsigned int wave_pref = 0;          // 0 = automatic
   std::vector<unsigned int> h_tile_first;
   // launch configuration of the tree kernel, resolved once per (shared-memory size)
-  size_t cfg_smem = 0; int cfg_per_sm = 0; unsigned int cfg_key = 0xFFFFFFFFu;
+  size_t cfg_smem[3] = {0, 0, 0}; int cfg_per_sm[3] = {0, 0, 0}; unsigned int cfg_key[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
+  int last_kind = 0;                   // KIND of the last 4-state tree launch (kernel name reporting)
 };
 
 // ------------------------------------------------------------------------------------ helpers
@@ -820,6 +828,35 @@ extern "C" int bppgpu_set_diploid(bppgpu_locus * l, unsigned int unphased, const
 // ------------------------------------------------------------------------------------ batch
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// shared memory of a 4-state launch (S4Layout::bytes) for run-time RL / cells per thread
+static size_t s4_smem_bytes(unsigned RL, unsigned cpt, int slots, unsigned cap, unsigned words)
+{
+  switch (RL * 10 + cpt)
+  {
+    case 11: return S4Layout<1, 1>::bytes(slots, cap, words);
+    case 12: return S4Layout<1, 2>::bytes(slots, cap, words);
+    case 14: return S4Layout<1, 4>::bytes(slots, cap, words);
+    case 21: return S4Layout<2, 1>::bytes(slots, cap, words);
+    case 22: return S4Layout<2, 2>::bytes(slots, cap, words);
+    case 24: return S4Layout<2, 4>::bytes(slots, cap, words);
+    case 41: return S4Layout<4, 1>::bytes(slots, cap, words);
+    case 42: return S4Layout<4, 2>::bytes(slots, cap, words);
+    case 44: return S4Layout<4, 4>::bytes(slots, cap, words);
+    case 81: return S4Layout<8, 1>::bytes(slots, cap, words);
+    case 82: return S4Layout<8, 2>::bytes(slots, cap, words);
+    case 84: return S4Layout<8, 4>::bytes(slots, cap, words);
+    default: return ~(size_t)0;
+  }
+}
+
+// stack slots a full pass over a T-tip tree is given: ceil(log2 T) - 1 covers a balanced tree in Sethi-Ullman order
+static int s4_slots_formula(unsigned maxT)
+{
+  int slots = 1;
+  while ((1u << slots) < maxT) ++slots;
+  return std::min(std::max(slots - 1, 1), 6);
+}
+
 static void batch_launch_cfg(bppgpu_batch * b)
 {
   // all loci of a batch share states / rate_cats (checked at creation)
@@ -840,14 +877,18 @@ static void batch_launch_cfg(bppgpu_batch * b)
   if (b->kernel_kind == 0 && R >= 4 && mean >= 7 * (TREE_NT / 2)) b->cpt = 4;
   if (const char * ev = getenv("BPPGPU_CPT"))                 // tuning knob
     if (b->kernel_kind == 0 && (atoi(ev) == 1 || atoi(ev) == 2 || atoi(ev) == 4)) b->cpt = (unsigned)atoi(ev);
-  // big trees: the packed tip words of every cell are staged in shared memory (two buffers of (words + 1) x 4 bytes per
-  // cell); fewer cells per thread keep that under 40 kB so that lookup tables and stack still fit
+  // big trees: lookup tables, stack slots and the packed tip words of the tile's sites share the SM's shared memory.
+  // Cells per thread give way until the slots a tree of this size typically needs fit: random (coalescent) trees need
+  // ceil(log2 T) - 2 slots or fewer (a balanced tree one more; the run sizes the stack from the staged lists' real
+  // Sethi-Ullman need, tree_s4_slots), and a list that finds no slot leaves the fast path.
   if (b->kernel_kind == 0)
   {
     unsigned maxT = 0;
     for (auto * l : b->loci) maxT = std::max(maxT, l->tips);
     const unsigned words = std::min<unsigned>((maxT + 7) / 8, (unsigned)S4_MAX_TIP_WORDS);
-    while (b->cpt > 1 && 2u * (words + 1u) * b->cpt * TREE_NT * 4u > 40u * 1024u) b->cpt /= 2;
+    const unsigned cap = std::min<unsigned>((unsigned)lut_cap((int)R), std::max(4u, (maxT + 3u) & ~3u));
+    const int est = maxT > 16 ? std::max(s4_slots_formula(maxT) - 1, 1) : s4_slots_formula(maxT);
+    while (b->cpt > 1 && s4_smem_bytes(R, b->cpt, est, cap, words) + 1024 > b->e->smem_optin) b->cpt /= 2;
   }
   b->tile_threads = b->kernel_kind == 0 ? TREE_NT : (b->kernel_kind == 2 ? S20_NT : 128);
 }
@@ -954,6 +995,13 @@ extern "C" bppgpu_batch * bppgpu_batch_create(bppgpu_engine * e, unsigned int n,
   CUDA_CHECK(cudaEventCreate(&b->t0));
   CUDA_CHECK(cudaEventCreate(&b->t1));
   CUDA_CHECK(cudaEventCreateWithFlags(&b->ev_inputs, cudaEventDisableTiming));
+  if (b->kernel_kind == 0)
+  {
+    CUDA_CHECK(cudaMalloc(&b->d_class, 8));
+    CUDA_CHECK(cudaHostAlloc(&b->h_class, 8, cudaHostAllocDefault));
+    b->h_class[0] = b->h_class[1] = 0;
+    for (auto & ev : b->ev_class) CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  }
   b->h_tile_first = tile_first;
   for (unsigned i = 0; i < n; ++i) b->max_tips = std::max(b->max_tips, loci[i]->tips);
   b->tip_words_rt = std::min<unsigned>((b->max_tips + 7) / 8, (unsigned)S4_MAX_TIP_WORDS);
@@ -982,6 +1030,7 @@ extern "C" void bppgpu_batch_destroy(bppgpu_batch * b)
   cudaFree(b->d_rootdot); cudaFree(b->d_rootsc); cudaFree(b->d_site_off);
   cudaFree(b->d_blocks_par[0]); cudaFree(b->d_blocks_par[1]); cudaFree(b->d_tiles); cudaFree(b->d_tile_blk); cudaFree(b->d_block_sums); cudaFree(b->d_counter);
   cudaFreeHost(b->h_out); cudaFreeHost(b->h_in);
+  if (b->d_class) { cudaFree(b->d_class); cudaFreeHost(b->h_class); for (auto & ev : b->ev_class) cudaEventDestroy(ev); }
   if (b->h_model) cudaFreeHost(b->h_model);
   cudaFree(b->d_model); cudaFree(b->d_eig_scratch);
   cudaEventDestroy(b->t0); cudaEventDestroy(b->t1); cudaEventDestroy(b->ev_inputs);
@@ -1003,10 +1052,33 @@ extern "C" const char * bppgpu_batch_kernel_name(bppgpu_batch * b)
 {
   static thread_local char buf[96];
   const bool exact = b->e->math == BPPGPU_MATH_EXACT;
-  if (b->kernel_kind == 0) snprintf(buf, sizeof(buf), "tree_kernel_s4<%u,%s,%u>", b->RL, exact ? "true" : "false", b->cpt);
+  if (b->kernel_kind == 0) snprintf(buf, sizeof(buf), "tree_kernel_s4<%u,%s,%u,%d>", b->RL, exact ? "true" : "false", b->cpt, b->last_kind);
   else if (b->kernel_kind == 2) snprintf(buf, sizeof(buf), b->s20_cat ? (b->s20_scaled ? "tree_kernel_s20t<%u,true>" : "tree_kernel_s20t<%u,false>") : "tree_kernel_s20<%u>", b->RL);
   else snprintf(buf, sizeof(buf), "tree_kernel_generic<%s>", exact ? "true" : "false");
   return buf;
+}
+extern "C" int bppgpu_batch_plan_stats(bppgpu_batch * b, unsigned int out[8])
+{
+  if (!b || b->kernel_kind != 0 || !b->d_blocks || !b->tables_on_device) return BPPGPU_FAILURE;
+  CUDA_CHECK(cudaSetDevice(b->e->device));
+  CUDA_CHECK(cudaStreamSynchronize(b->stream));
+  const unsigned long long * boff = (const unsigned long long *)(b->h_in + b->o_blk_off);
+  for (int k = 0; k < 8; ++k) out[k] = 0;
+  LocusHdr H;
+  for (unsigned i = 0; i < b->n; ++i)
+  {
+    CUDA_CHECK(cudaMemcpy(&H, b->d_blocks + boff[i], sizeof(H), cudaMemcpyDeviceToHost));
+    if (H.flags & HDR_FAST)
+    {
+      out[0]++;
+      if (H.n_chunks == 1 && (H.flags & HDR_SIMPLE)) out[1]++;
+      else if (H.n_chunks == 1 && (H.flags & HDR_NOHBM)) out[2]++;
+    }
+    else out[3]++;
+    out[4] = std::max(out[4], H.n_chunks);
+  }
+  out[5] = (unsigned)b->slots; out[6] = b->cpt; out[7] = (unsigned)b->tree_smem;
+  return BPPGPU_SUCCESS;
 }
 extern "C" void bppgpu_batch_set_waves(bppgpu_batch * b, unsigned int waves)
 {
@@ -1082,6 +1154,36 @@ static bool locus_ops_valid(const bppgpu_locus * l, unsigned count, const bppgpu
     { *bad = i; return false; }
   }
   return true;
+}
+
+// Stack slots the staged lists need when evaluated in Sethi-Ullman order (the planner's order): a tip or a child the
+// list does not produce costs nothing (lookup / load), an inner node needs max(a, b) values alive, one more when both
+// children need the same; one of them is the register X, the rest are stack slots.  Too few slots only send a locus
+// to the slow walker, so this is a sizing hint, not a correctness input.
+static int batch_su_slots(const bppgpu_batch * b, const unsigned int * ocounts, const bppgpu_partial_op * ops)
+{
+  std::vector<unsigned char> need;
+  std::vector<unsigned int> stamp;
+  int worst = 1;
+  size_t o = 0;
+  for (unsigned i = 0; i < b->n; ++i)
+  {
+    const bppgpu_locus * l = b->loci[i];
+    const unsigned nb = l->tips + l->clv_buffers;
+    if (need.size() < nb) { need.resize(nb); stamp.resize(nb, 0xFFFFFFFFu); }
+    for (unsigned k = 0; k < ocounts[i]; ++k)
+    {
+      const bppgpu_partial_op & q = ops[o + k];
+      if (q.parent_clv_index >= nb || q.left_clv_index >= nb || q.right_clv_index >= nb) continue;   // rejected by the validation
+      const int na = stamp[q.left_clv_index] == i ? need[q.left_clv_index] : 0;
+      const int nr = stamp[q.right_clv_index] == i ? need[q.right_clv_index] : 0;
+      const int n = (na == 0 && nr == 0) ? 1 : (na == nr ? na + 1 : std::max(na, nr));
+      need[q.parent_clv_index] = (unsigned char)std::min(n, 250); stamp[q.parent_clv_index] = i;
+      worst = std::max(worst, n);
+    }
+    o += ocounts[i];
+  }
+  return std::max(worst - 1, 1);
 }
 
 static bool batch_validate(const bppgpu_batch * b, const unsigned int * mcounts, const unsigned int * midx,
@@ -1175,6 +1277,7 @@ static int batch_stage(bppgpu_batch * b, const unsigned int * mcounts, const uns
   static const bool check_always = getenv("BPPGPU_CHECK_INDICES") && atoi(getenv("BPPGPU_CHECK_INDICES")) != 0;
   if (!same || check_always)
     if (!batch_validate(b, mcounts, midx, ocounts, ops, rclv, rsc)) return BPPGPU_FAILURE;
+  if (ocounts && ops && b->kernel_kind == 0 && b->max_tips > 16) b->su_slots = batch_su_slots(b, ocounts, ops);
   // the previous step's blob may still be in flight on the stream (a waved step joins alt_stream into it)
   CUDA_CHECK(cudaStreamSynchronize(b->stream));
   if (b->copy_stream) CUDA_CHECK(cudaStreamSynchronize(b->copy_stream));      // tables of a step that never ran
@@ -1421,41 +1524,52 @@ static int tree_s4_slots(bppgpu_batch * b, int wanted, unsigned cap)
   return slots;
 }
 
-template <int RL, bool EXACT, int CPT>
+template <int RL, bool EXACT, int CPT, int KIND>
 static void launch_tree_s4_impl(bppgpu_batch * b, const TreeParams & prm, cudaStream_t st)
 {
   bppgpu_engine * e = b->e;
   const size_t smem = S4Layout<RL, CPT>::bytes(prm.n_slots, prm.lut_cap, prm.tip_words);
-  const unsigned key = (unsigned)(RL * 100 + CPT * 10 + (EXACT ? 1 : 0));
-  if (b->cfg_key != key || b->cfg_smem != smem)
+  b->slots = prm.n_slots; b->tree_smem = smem;
+  const unsigned key = (unsigned)(KIND * 1000 + RL * 100 + CPT * 10 + (EXACT ? 1 : 0));
+  if (b->cfg_key[KIND] != key || b->cfg_smem[KIND] != smem)
   {
-    ensure_max_smem(e, tree_kernel_s4<RL, EXACT, CPT>);
+    ensure_max_smem(e, tree_kernel_s4<RL, EXACT, CPT, KIND>);
     int per_sm = 0;
-    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tree_kernel_s4<RL, EXACT, CPT>, TREE_NT, smem));
+    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tree_kernel_s4<RL, EXACT, CPT, KIND>, TREE_NT, smem));
     if (per_sm < 1) { fatal("tree kernel does not fit on an SM (smem %zu)", smem); return; }
-    b->cfg_key = key; b->cfg_smem = smem; b->cfg_per_sm = per_sm;
+    b->cfg_key[KIND] = key; b->cfg_smem[KIND] = smem; b->cfg_per_sm[KIND] = per_sm;
   }
-  const unsigned grid = std::min<unsigned>(prm.n_tiles, (unsigned)(b->cfg_per_sm * e->sm_count));
-  tree_kernel_s4<RL, EXACT, CPT><<<grid, TREE_NT, smem, st>>>(prm);
+  const unsigned grid = std::min<unsigned>(prm.n_tiles, (unsigned)(b->cfg_per_sm[KIND] * e->sm_count));
+  tree_kernel_s4<RL, EXACT, CPT, KIND><<<grid, TREE_NT, smem, st>>>(prm);
+}
+
+template <int RL, bool EXACT, int CPT>
+static void launch_tree_s4_kind(bppgpu_batch * b, const TreeParams & prm, cudaStream_t st, int kind)
+{
+  if (kind == 1) launch_tree_s4_impl<RL, EXACT, CPT, 1>(b, prm, st);
+  else if (kind == 2) launch_tree_s4_impl<RL, EXACT, CPT, 2>(b, prm, st);
+  else launch_tree_s4_impl<RL, EXACT, CPT, 0>(b, prm, st);
 }
 
 template <int RL>
-static void launch_tree_s4_rl(bppgpu_batch * b, const TreeParams & prm, cudaStream_t st)
+static void launch_tree_s4_rl(bppgpu_batch * b, const TreeParams & prm, cudaStream_t st, int kind)
 {
   const bool exact = b->e->math == BPPGPU_MATH_EXACT;
-  if (b->cpt == 2) { if (exact) launch_tree_s4_impl<RL, true, 2>(b, prm, st); else launch_tree_s4_impl<RL, false, 2>(b, prm, st); }
-  else if (b->cpt == 4) { if (exact) launch_tree_s4_impl<RL, true, 4>(b, prm, st); else launch_tree_s4_impl<RL, false, 4>(b, prm, st); }
-  else { if (exact) launch_tree_s4_impl<RL, true, 1>(b, prm, st); else launch_tree_s4_impl<RL, false, 1>(b, prm, st); }
+  if (b->cpt == 2) { if (exact) launch_tree_s4_kind<RL, true, 2>(b, prm, st, kind); else launch_tree_s4_kind<RL, false, 2>(b, prm, st, kind); }
+  else if (b->cpt == 4) { if (exact) launch_tree_s4_kind<RL, true, 4>(b, prm, st, kind); else launch_tree_s4_kind<RL, false, 4>(b, prm, st, kind); }
+  else { if (exact) launch_tree_s4_kind<RL, true, 1>(b, prm, st, kind); else launch_tree_s4_kind<RL, false, 1>(b, prm, st, kind); }
 }
 
-static int launch_tree_s4(bppgpu_batch * b, const TreeParams & prm, cudaStream_t st)
+// kind: 0 = the kernel with every path; 1 / 2 = lean-only / scaled-only launch for a cached plan of that class
+static int launch_tree_s4(bppgpu_batch * b, const TreeParams & prm, cudaStream_t st, int kind = 0)
 {
+  b->last_kind = kind;
   switch (b->RL)
   {
-    case 1: launch_tree_s4_rl<1>(b, prm, st); break;
-    case 2: launch_tree_s4_rl<2>(b, prm, st); break;
-    case 4: launch_tree_s4_rl<4>(b, prm, st); break;
-    case 8: launch_tree_s4_rl<8>(b, prm, st); break;
+    case 1: launch_tree_s4_rl<1>(b, prm, st, kind); break;
+    case 2: launch_tree_s4_rl<2>(b, prm, st, kind); break;
+    case 4: launch_tree_s4_rl<4>(b, prm, st, kind); break;
+    case 8: launch_tree_s4_rl<8>(b, prm, st, kind); break;
     default: fatal("internal: RL=%u", b->RL); return BPPGPU_FAILURE;
   }
   return BPPGPU_SUCCESS;
@@ -1568,8 +1682,9 @@ static int batch_run(bppgpu_batch * b, bool do_mats, bool do_tree, bool want_roo
   if (b->kernel_kind != 1)
   {
     const unsigned maxT = b->max_tips;
-    slots = 1; while ((1u << slots) < maxT) ++slots;
-    slots = std::min(std::max(slots - 1, 1), 6);
+    slots = s4_slots_formula(maxT);
+    // big 4-state trees: what the staged lists really need (Sethi-Ullman, batch_validate) -- every slot costs 8-36 kB
+    if (b->kernel_kind == 0 && b->su_slots > 0) slots = std::min(slots, b->su_slots);
     // 20 states: a parked X costs 3.4 kB of shared memory per warp and slot, which would push the
     // P-matrices (read through L1) out of the SM; re-reading the child's CLV (an L2 hit) and redoing one
     // DMMA mat-vec is cheaper, so nothing is parked
@@ -1629,7 +1744,10 @@ static int batch_run(bppgpu_batch * b, bool do_mats, bool do_tree, bool want_roo
         e->d_loci, b->d_batch_locus, n, b->d_blocks, d_blk_off, b->RL, fuse_mats ? d_mat_off : nullptr, d_mat_idx, d_mat_bl);
     CUDA_CHECK(cudaGetLastError());
   }
-  if (cacheable && !cached) { b->plan_valid[b->parity] = !persite; b->plan_key[b->parity] = pkey; }
+  if (cacheable && !cached) { b->plan_valid[b->parity] = !persite; b->plan_key[b->parity] = pkey; b->class_pending[b->parity] = false; b->plan_class[b->parity] = 0; }
+  // BPPGPU_S4_KINDS=0: always the kernel with every path
+  static const bool s4_kinds_on = !(getenv("BPPGPU_S4_KINDS") && atoi(getenv("BPPGPU_S4_KINDS")) == 0);
+  static const int s4_kind_force = getenv("BPPGPU_S4_KIND_FORCE") ? atoi(getenv("BPPGPU_S4_KIND_FORCE")) : -1;   // experiments only
   if (!waved && !cached)
   {
     ProfScope ps(e, b->stream, BPPGPU_KERNEL_PLAN);
@@ -1648,6 +1766,31 @@ static int batch_run(bppgpu_batch * b, bool do_mats, bool do_tree, bool want_roo
           e->d_loci, b->d_batch_locus, n, d_op_off, d_ops, d_root_clv, d_root_sc, want_root ? 1 : 0,
           b->d_plan, b->d_plan_count);
     CUDA_CHECK(cudaGetLastError());
+    if (b->kernel_kind == 0 && b->plan_valid[b->parity] && s4_kinds_on)
+    {
+      // class of the plan that will be reused: read back behind the planner, known to the host by the time the
+      // caller collected this step
+      const int par = b->parity;
+      e->launches++;
+      plan_class_kernel<<<1, 256, 0, b->stream>>>(b->d_blocks, d_blk_off, n, b->d_class + par);
+      CUDA_CHECK(cudaGetLastError());
+      CUDA_CHECK(cudaMemcpyAsync(b->h_class + par, b->d_class + par, 4, cudaMemcpyDeviceToHost, b->stream));
+      CUDA_CHECK(cudaEventRecord(b->ev_class[par], b->stream));
+      b->class_pending[par] = true;
+    }
+  }
+  int s4_kind = 0;
+  if (b->kernel_kind == 0 && cached && !waved && s4_kinds_on)
+  {
+    const int par = b->parity;
+    if (b->class_pending[par] && cudaEventQuery(b->ev_class[par]) == cudaSuccess)
+    {
+      b->plan_class[par] = b->h_class[par];
+      b->class_pending[par] = false;
+    }
+    if (!b->class_pending[par])
+      s4_kind = (b->plan_class[par] & PLAN_CLASS_LEAN) ? 1 : ((b->plan_class[par] & PLAN_CLASS_SCALED) ? 2 : 0);
+    if (s4_kind_force >= 0) s4_kind = s4_kind_force;
   }
   if (b->kernel_kind == 2 && b->s20_cat)
   {
@@ -1708,7 +1851,7 @@ static int batch_run(bppgpu_batch * b, bool do_mats, bool do_tree, bool want_roo
     ProfScope ps(e, b->stream, BPPGPU_KERNEL_TREE);
     if (b->kernel_kind == 0)
     {
-      if (!launch_tree_s4(b, prm, b->stream)) return BPPGPU_FAILURE;
+      if (!launch_tree_s4(b, prm, b->stream, s4_kind)) return BPPGPU_FAILURE;
     }
     else if (b->kernel_kind == 2)
     {

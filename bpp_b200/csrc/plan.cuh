@@ -783,4 +783,24 @@ flip_indices_kernel(const LocusDev * __restrict__ loci, const unsigned int * __r
   if (root_clv && lane == 0) { root_clv[bl] = fclv(root_clv[bl]); root_sc[bl] = fsc(root_sc[bl]); }
 }
 
+// Class of a planned batch (4 states): do ALL its loci run the lean one-chunk instantiation (HDR_SIMPLE), or all the
+// scaled one-chunk one (HDR_NOHBM)?  One word per index parity, read back by the host and kept with the cached plan;
+// runs on that plan then launch the kernel that carries only this instantiation (tree_kernel_s4 KIND 1 / 2).
+enum : unsigned { PLAN_CLASS_KNOWN = 1u, PLAN_CLASS_LEAN = 2u, PLAN_CLASS_SCALED = 4u };
+__global__ void __launch_bounds__(256)
+plan_class_kernel(const unsigned char * __restrict__ blocks, const unsigned long long * __restrict__ blk_off, unsigned int n,
+                  unsigned int * __restrict__ cls)
+{
+  unsigned int lean = 1u, scaled = 1u;
+  for (unsigned int i = threadIdx.x; i < n; i += blockDim.x)
+  {
+    const LocusHdr * H = reinterpret_cast<const LocusHdr *>(blocks + blk_off[i]);
+    const bool one = H->n_chunks == 1;
+    lean &= (one && (H->flags & HDR_SIMPLE)) ? 1u : 0u;
+    scaled &= (one && (H->flags & HDR_NOHBM)) ? 1u : 0u;
+  }
+  const int all_lean = __syncthreads_and((int)lean), all_scaled = __syncthreads_and((int)scaled);
+  if (threadIdx.x == 0) *cls = PLAN_CLASS_KNOWN | (all_lean ? PLAN_CLASS_LEAN : 0u) | (all_scaled ? PLAN_CLASS_SCALED : 0u);
+}
+
 }  // namespace bppgpu

@@ -150,9 +150,11 @@ struct S4Layout               // everything in uint4 (16-byte) units
   __host__ __device__ static constexpr unsigned stage_sz(unsigned cap) { return TIPP + cap * RL * 9; }
   __host__ __device__ static constexpr unsigned lut0(unsigned cap) { return STAGE0 + NSTAGE * stage_sz(cap); }
   __host__ __device__ static constexpr unsigned stack0(unsigned cap) { return lut0(cap) + cap * lut_slot_u4(RL); }
-  // after the stack: packed tip words and pattern weights of the current and the next tile,
-  // [2 buffers][W tip words, then the weight][CPT][TREE_NT] u32 (W = the launch's tip_words), filled by 4-byte cp.async
-  __host__ __device__ static constexpr unsigned tips_buf(unsigned words) { return (words + 1) * CPT * TREE_NT; }   // u32 per buffer
+  // after the stack: packed tip words and pattern weights of the current and the next tile, one entry per SITE (the
+  // RL lanes of a site read the same word: a broadcast),
+  // [2 buffers][W tip words, then the weight][CPT][SROW] u32 (W = the launch's tip_words), filled by 4-byte cp.async
+  static constexpr unsigned SROW = TREE_NT / RL;                  // sites per row of TREE_NT cells
+  __host__ __device__ static constexpr unsigned tips_buf(unsigned words) { return (words + 1) * CPT * SROW; }   // u32 per buffer
   __host__ __device__ static constexpr unsigned tips0_u32(int slots, unsigned cap)
   {
     return (stack0(cap) + (unsigned)slots * SLOT) * 4 + (unsigned)slots * CPT * TREE_NT;
@@ -174,9 +176,9 @@ struct TileCtx
   unsigned int cell[CPT];        // clamped cell index
   bool valid[CPT];
   unsigned int tw0[CPT];         // tip word 0 (tips 0..7) of the thread's cells
-  unsigned int tips_s;           // u32 index of this thread's entry in the tile's tip buffer: word w of cell j at
-                                 // tips_s + (w * CPT + j) * TREE_NT, pattern weight at tips_s + wgt_off + j * TREE_NT
-  unsigned int wgt_off;          // = tip_words * CPT * TREE_NT
+  unsigned int tips_s;           // u32 index of this thread's site in the tile's tip buffer: word w of cell j at
+                                 // tips_s + (w * CPT + j) * SROW, pattern weight at tips_s + wgt_off + j * SROW (SROW = TREE_NT / RL)
+  unsigned int wgt_off;          // = tip_words * CPT * SROW
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -259,7 +261,7 @@ __device__ __forceinline__ double tile_fast(const TreeParams & prm, const TileCt
 #pragma unroll
         for (int j = 0; j < CPT; ++j)
         {
-          const unsigned int wa = aword ? s1[tc.tips_s + (aword * CPT + j) * TREE_NT] : tc.tw0[j];
+          const unsigned int wa = aword ? s1[tc.tips_s + (aword * CPT + j) * Lay::SROW] : tc.tw0[j];
           const unsigned int at = base + ((wa >> ash) & amask) * ROWB + j * jst;
           a0[j] = *reinterpret_cast<const double2 *>(sm + at);
           a1[j] = *reinterpret_cast<const double2 *>(sm + at + dh);
@@ -289,7 +291,7 @@ __device__ __forceinline__ double tile_fast(const TreeParams & prm, const TileCt
 #pragma unroll
           for (int j = 0; j < CPT; ++j)
           {
-            const unsigned int wb = bword ? s1[tc.tips_s + (bword * CPT + j) * TREE_NT] : tc.tw0[j];
+            const unsigned int wb = bword ? s1[tc.tips_s + (bword * CPT + j) * Lay::SROW] : tc.tw0[j];
             const unsigned int at = base + ((wb >> bsh) & bmask) * ROWB + j * jst;
             const double2 b0 = *reinterpret_cast<const double2 *>(sm + at);
             const double2 b1 = *reinterpret_cast<const double2 *>(sm + at + dh);
@@ -428,7 +430,7 @@ __device__ __forceinline__ double tile_fast(const TreeParams & prm, const TileCt
         {
           sv = log(term[j]);
           if (SCALED && osc[j]) sv = __dadd_rn(sv, __dmul_rn((double)osc[j], prm.log_threshold));
-          sv = __dmul_rn(sv, (double)s1[tc.tips_s + tc.wgt_off + j * TREE_NT]);
+          sv = __dmul_rn(sv, (double)s1[tc.tips_s + tc.wgt_off + j * Lay::SROW]);
         }
         if (tc.valid[j] && tc.cat == 0)
         {
@@ -628,8 +630,15 @@ __device__ __forceinline__ void build_lut(unsigned int sb, unsigned int lut0)
 // CTAs per SM: 3 / 2 / 1 for 1 / 2 / 4 cells per thread (85 / 128 / 255 registers).  Measured on B200:
 // 2 cells at 2 CTAs beats 3 CTAs at 80 registers (spills) for R = 1; 4 cells win for R >= 4, where the
 // shared-memory pipe is the limit and the P-matrix loads are amortised over twice the cells.
-template <int RL, bool EXACT, int CPT>
-__global__ void __launch_bounds__(TREE_NT, s4_ctas_per_sm(CPT))
+//
+// KIND selects what is compiled in.  0: every path (lean / scaled / HBM-class fast instantiations, chunk-by-chunk
+// restaging, the cell-at-a-time walker) -- the kernel for freshly planned lists, partial updates and big trees.
+// 1 / 2: ONLY the lean (tile_fast MODE 0) or only the scaled (MODE 1) one-chunk instantiation, for launches whose
+// cached plan is known (plan_class_kernel) to hold nothing but HDR_SIMPLE / HDR_NOHBM one-chunk loci: the steady
+// state of full passes (mixing, tau, alpha, qrates moves).  The monolithic kernel pays for the paths it does not
+// take with registers (242, spilling the per-op bases) and instruction-cache footprint.
+template <int RL, bool EXACT, int CPT, int KIND>
+__global__ void __launch_bounds__(TREE_NT, s4_ctas_per_sm_kind(CPT, KIND))
 tree_kernel_s4(const TreeParams prm)
 {
   using Lay = S4Layout<RL, CPT>;
@@ -675,8 +684,8 @@ tree_kernel_s4(const TreeParams prm)
   auto stage_wait = [&](unsigned int, bool fresh) { (void)mphase; if (fresh) { cp_async_commit(); cp_async_wait_all(); __syncthreads(); } };
 #endif
   const unsigned int tips0 = Lay::tips0_u32(prm.n_slots, prm.lut_cap), tips_buf = Lay::tips_buf(prm.tip_words);
-  // packed tip words + pattern weight of the thread's cells of tile d -> tip buffer `tb` (asynchronous; each
-  // thread copies and later reads only its own entries, so the cp.async wait alone orders them)
+  // packed tip words + pattern weight of the sites of tile d -> tip buffer `tb` (asynchronous; the lane of category 0
+  // copies, the site's RL lanes read: every read comes after a CTA barrier that follows the copying lane's wait)
   auto load_tips = [&](const TileDesc & d, unsigned int tb)
   {
 #pragma unroll
@@ -684,10 +693,11 @@ tree_kernel_s4(const TreeParams prm)
     {
       const unsigned int craw = d.cell0 + ptid + j * TREE_NT;
       const unsigned int pat = (craw < d.ncell ? craw : d.ncell - 1) / RL;
-      unsigned int * dst = &s1[tips0 + tb * tips_buf + j * TREE_NT + tid];
+      if (ptid % RL) continue;                         // one lane per site copies
+      unsigned int * dst = &s1[tips0 + tb * tips_buf + j * Lay::SROW + ptid / RL];
       const unsigned int nw = d.tip_words < prm.tip_words ? d.tip_words : prm.tip_words;
-      for (unsigned int w = 0; w < nw; ++w) cp_async4(dst + w * (CPT * TREE_NT), d.tipwords + (size_t)pat * d.tip_words + w);
-      cp_async4(dst + prm.tip_words * (CPT * TREE_NT), d.weights + pat);
+      for (unsigned int w = 0; w < nw; ++w) cp_async4(dst + w * (CPT * Lay::SROW), d.tipwords + (size_t)pat * d.tip_words + w);
+      cp_async4(dst + prm.tip_words * (CPT * Lay::SROW), d.weights + pat);
     }
   };
 
@@ -747,10 +757,10 @@ tree_kernel_s4(const TreeParams prm)
     const LocusHdr * H = reinterpret_cast<const LocusHdr *>(&s4[sb]);
     tc.sb = sb;
     tc.cat = (d.cell0 + ptid) % RL;
-    tc.tips_s = tips0 + tb * tips_buf + tid;
-    tc.wgt_off = prm.tip_words * (CPT * TREE_NT);
+    tc.tips_s = tips0 + tb * tips_buf + ptid / RL;
+    tc.wgt_off = prm.tip_words * (CPT * Lay::SROW);
 #pragma unroll
-    for (int j = 0; j < CPT; ++j) tc.tw0[j] = s1[tc.tips_s + j * TREE_NT];
+    for (int j = 0; j < CPT; ++j) tc.tw0[j] = s1[tc.tips_s + j * Lay::SROW];
 #pragma unroll
     for (int j = 0; j < CPT; ++j)
     {
@@ -760,6 +770,20 @@ tree_kernel_s4(const TreeParams prm)
     }
 
     double site_sum;
+    if constexpr (KIND != 0)
+    {
+      // specialised launch: the host selected it from the class word of the cached plan; a locus of another class
+      // cannot be here (and would poison its lnL instead of computing something wrong)
+      double x[CPT][4];
+      unsigned int psc[CPT];
+      unsigned int wnz = 0;
+#pragma unroll
+      for (int j = 0; j < CPT; ++j) { x[j][0] = x[j][1] = x[j][2] = x[j][3] = 0.0; psc[j] = 0; }
+      site_sum = tile_fast<RL, EXACT, CPT, KIND - 1>(prm, tc, x, psc, wnz);
+      if (H->n_chunks != 1 || !(H->flags & (KIND == 1 ? HDR_SIMPLE : HDR_NOHBM))) site_sum = __longlong_as_double(0x7FF8000000000000ll);
+    }
+    else
+    {
     // another chunk of the current locus -> the stage buffer (synchronously, in place of the one that is there)
     auto restage = [&](unsigned int c)
     {
@@ -812,11 +836,12 @@ tree_kernel_s4(const TreeParams prm)
 #pragma unroll
         for (int j = 0; j < CPT; ++j)
           site_sum += chunk_general<RL, EXACT, CPT>(prm, sb, lut0 | (stack0 << 16), tc.sst1, j, tc.cell[j], tc.valid[j], tc.cat, tc.tw0[j],
-                                                    (d.tip_words > 1 && prm.tip_words > 1) ? s1[tc.tips_s + (CPT + j) * TREE_NT] : 0u,
-                                                    s1[tc.tips_s + tc.wgt_off + j * TREE_NT], xs[j], &pscs[j]);
+                                                    (d.tip_words > 1 && prm.tip_words > 1) ? s1[tc.tips_s + (CPT + j) * Lay::SROW] : 0u,
+                                                    s1[tc.tips_s + tc.wgt_off + j * Lay::SROW], xs[j], &pscs[j]);
       }
     }
 
+    }
     // ---- deterministic tile reduction of the weighted site lnL values
     if (prm.tile_partial)
     {

@@ -487,6 +487,14 @@ class Batch:
     def kernel_name(self):
         return self.L.bppgpu_batch_kernel_name(self.h).decode()
 
+    def plan_stats(self):
+        """Loci per path of the last planned step (4-state batches): see bppgpu_batch_plan_stats."""
+        out = (C.c_uint * 8)()
+        if not self.L.bppgpu_batch_plan_stats(self.h, out):
+            return None
+        keys = ("fast", "lean", "scaled", "walker", "max_chunks", "slots", "cells_per_thread", "smem_bytes")
+        return dict(zip(keys, [int(v) for v in out]))
+
     @property
     def lnl_sum_dev(self):
         return self.L.bppgpu_batch_lnl_sum_dev(self.h)

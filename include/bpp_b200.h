@@ -186,6 +186,12 @@ bppgpu_batch * bppgpu_batch_create(bppgpu_engine * e, unsigned int n_loci, bppgp
 void bppgpu_batch_destroy(bppgpu_batch * b);
 unsigned int bppgpu_batch_size(const bppgpu_batch * b);
 const char * bppgpu_batch_kernel_name(bppgpu_batch * b);      /* tree kernel instantiation the batch launches */
+/* Diagnostics of the last planned step of a 4-state batch (synchronises the batch): how many loci run which path of
+ * the tree kernel.  out[0] = loci on the fast path (stack machine over staged chunks), out[1] = of those, lean
+ * one-chunk loci, out[2] = scaled one-chunk loci, out[3] = loci on the cell-at-a-time walker, out[4] = largest
+ * chunk count, out[5] = stack slots per cell, out[6] = cells per thread, out[7] = shared memory of the launch (bytes).
+ * Returns BPPGPU_FAILURE for other batch kinds or before the first run. */
+int bppgpu_batch_plan_stats(bppgpu_batch * b, unsigned int out[8]);
 
 int  bppgpu_batch_update_matrices(bppgpu_batch * b, const unsigned int * counts,
                                   const unsigned int * pmatrix_indices, const double * branch_lengths);

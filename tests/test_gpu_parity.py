@@ -241,6 +241,9 @@ def test_against_oracle_seeded(eng, cfg):
     w = synth.make_workload("seeded", n_loci=12, seed=4242, lg=lg_tables(), **cfg)
     loci, trees, batch = _load(eng, w)
     lnl, _ = batch.full_pass(trees.full_pass_step())
+    if w.states == 4 and w.rate_cats in (1, 2, 4, 8) and 16 < w.tips <= 128:
+        st = batch.plan_stats()            # big trees up to 128 tips: every locus on the fast path
+        assert st["walker"] == 0 and st["fast"] == w.n_loci, st
     cm = char_map(w.states)
     step = 1 if w.states == 4 else 4
     for i in range(0, w.n_loci, step):
@@ -391,16 +394,28 @@ def test_illegal_state_code_is_fatal(eng):
     l.destroy()
 
 
-def test_staged_run_is_idempotent_and_deterministic(eng):
-    """stage once, run twice: identical bits (fixed-order reductions, no float atomics)."""
-    w = synth.make_workload("idem", n_loci=40, tips=8, sites=300, states=4, rate_cats=4, model="GTR", seed=9)
+@pytest.mark.parametrize("scaling,tips,kind", [(False, 8, 1), (True, 8, 2), (False, 24, 0)])
+def test_staged_run_is_idempotent_and_deterministic(eng, scaling, tips, kind):
+    """stage once, run several times: identical bits (fixed-order reductions, no float atomics).  The first run
+    launches the kernel that carries every path; once the class of the cached plan is known (all loci lean / all
+    scaled one-chunk) the later runs launch the specialised instantiation (KIND 1 / 2), which must reproduce the
+    first run's bits; a batch of multi-chunk trees (24 tips) stays on the general kernel."""
+    w = synth.make_workload("idem", n_loci=40, tips=tips, sites=300, states=4, rate_cats=4, model="GTR", seed=9,
+                            scaling=scaling)
     loci, trees, batch = _load(eng, w)
     batch.stage(trees.full_pass_step())
     batch.run()
     a, ta = batch.collect()
-    batch.run()
-    b, tb = batch.collect()
-    assert np.array_equal(a, b) and ta == tb
+    assert batch.kernel_name.endswith(",0>")
+    for _ in range(3):
+        batch.run()
+        b, tb = batch.collect()
+        assert np.array_equal(a, b) and ta == tb
+    assert batch.kernel_name.endswith(",%d>" % kind), batch.kernel_name
+    cm = char_map(4)
+    for i in range(0, w.n_loci, 8):
+        ref = F.locus_from_workload(w, i, cm).full_pass()
+        assert abs(b[i] - ref) <= LNL_RTOL * abs(ref), (i, b[i], ref)
     _free(loci, batch)
 
 
@@ -497,6 +512,9 @@ def test_frogs_diploid_loci_in_one_batch(eng):
     lnl, total = batch.full_pass(step)
     assert rel_err(lnl, np.array(want)) <= LNL_RTOL
     assert abs(total - (-7320.932289)) < 5e-6
+    # real data (42-60 sequences per locus) stays on the chunk-by-chunk fast path, no locus on the cell-at-a-time walker
+    st = batch.plan_stats()
+    assert st["fast"] == len(loci) and st["walker"] == 0, st
     # and the split form: root-only evaluation of resident CLVs
     assert np.array_equal(batch.root_loglikelihood(np.array(rc)), lnl)
     _free(loci, batch)

@@ -28,8 +28,10 @@ for tips in TIPS:
     prof = {k: round(v["ms"] / max(1, v["launches"]), 3) for k, v in eng.profile().items() if v["launches"]}
     eng.set_profiling(False)
     node_updates = n * (tips - 1)
-    print("R=%d %s tips=%2d loci=%5d: %.3f ms/pass  %.1f M node-updates/s  (%.2f GB/s of CLV writes)  %s %s" % (
-        R, model, tips, n, ms, node_updates / ms / 1e3, node_updates * 1000 * R * 32 / ms / 1e6, batch.kernel_name, prof), flush=True)
+    st = batch.plan_stats() or {}
+    print("R=%d %s tips=%2d loci=%5d: %.3f ms/pass  %.1f M node-updates/s  (%.2f GB/s of CLV writes)  %s %s walker=%s chunks=%s slots=%s smem=%s" % (
+        R, model, tips, n, ms, node_updates / ms / 1e3, node_updates * 1000 * R * 32 / ms / 1e6, batch.kernel_name, prof,
+        st.get("walker"), st.get("max_chunks"), st.get("slots"), st.get("smem_bytes")), flush=True)
     batch.destroy()
     for l in loci:
         l.destroy()
