@@ -179,6 +179,7 @@ struct TileCtx
   unsigned int tips_s;           // u32 index of this thread's site in the tile's tip buffer: word w of cell j at
                                  // tips_s + (w * CPT + j) * SROW, pattern weight at tips_s + wgt_off + j * SROW (SROW = TREE_NT / RL)
   unsigned int wgt_off;          // = tip_words * CPT * SROW
+  unsigned int cell0, ncell;     // the tile's first cell and the locus' cell count
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -189,11 +190,17 @@ struct TileCtx
 // scale buffers), MODE 2 also HBM-class operands (partial updates).
 // One call runs the ops of the chunk that is staged; x / psc (the register X and its scaler count) carry over
 // from chunk to chunk of the same tile.
+// MODE 3 is the SPECULATIVE form of MODE 1 (specialised scaled launches, KIND 2): per-site rescaling is rare (all
+// 4 x RL entries of a site below 2^-256), so the pass runs like MODE 0 -- no scaler counts, no scaler stores, no
+// per-op lane exchange -- and only records, one bit per (op, cell), where an op's values fell below the threshold.
+// The caller combines the bits over the lanes of a site once per tile; if no site qualified (the common case) the
+// scalers of the tile are zero-filled in one coalesced sweep, otherwise the warp repeats the tile in MODE 1.
 template <int RL, bool EXACT, int CPT, int MODE>
 __device__ __forceinline__ double tile_fast(const TreeParams & prm, const TileCtx<CPT> & tc, double (&x)[CPT][4],
-                                            unsigned int (&psc)[CPT], unsigned int & wnz)
+                                            unsigned int (&psc)[CPT], unsigned int & wnz, unsigned long long & spec)
 {
-  constexpr bool SCALED = MODE >= 1, FULL = MODE == 2;
+  constexpr bool SCALED = MODE == 1 || MODE == 2, FULL = MODE == 2, SPEC = MODE == 3;
+  static_assert(!SPEC || TREE_CHUNK * CPT <= 64, "one bit per (op, cell) of a chunk");
   constexpr unsigned int LOG2RL = RL == 1 ? 0 : (RL == 2 ? 1 : (RL == 4 ? 2 : 3));
   using Lay = S4Layout<RL, CPT>;
   const unsigned int tid = threadIdx.x, lane = tid & 31u;
@@ -313,6 +320,17 @@ __device__ __forceinline__ double tile_fast(const TreeParams & prm, const TileCt
     // mantissa, so "all four below" is max(high words) < 0x2FF00000 -- off the FP64 pipe), the cells' bits packed
     // into one word and combined over the site's RL lanes once per op, and ONE warp-uniform branch.  Scaler
     // counts of staged children are read only once some count of the warp is non-zero (wnz).
+    if (SPEC && (ctl & OP_SCALE))
+    {
+      unsigned int bits = 0;
+#pragma unroll
+      for (int j = 0; j < CPT; ++j)
+      {
+        const int h0 = __double2hiint(o[j][0]), h1 = __double2hiint(o[j][1]), h2 = __double2hiint(o[j][2]), h3 = __double2hiint(o[j][3]);
+        if (max(max(h0, h1), max(h2, h3)) < 0x2FF00000) bits |= 1u << j;
+      }
+      spec |= (unsigned long long)bits << (k * CPT);
+    }
     if (SCALED && (ctl & OP_SCALE))
     {
       const uint4 w2 = s4[ops + 4 * k + 2], w3 = s4[ops + 4 * k + 3];
@@ -768,6 +786,7 @@ tree_kernel_s4(const TreeParams prm)
       tc.valid[j] = craw < d.ncell;
       tc.cell[j] = tc.valid[j] ? craw : d.ncell - 1;
     }
+    tc.cell0 = d.cell0; tc.ncell = d.ncell;
 
     double site_sum;
     if constexpr (KIND != 0)
@@ -779,7 +798,43 @@ tree_kernel_s4(const TreeParams prm)
       unsigned int wnz = 0;
 #pragma unroll
       for (int j = 0; j < CPT; ++j) { x[j][0] = x[j][1] = x[j][2] = x[j][3] = 0.0; psc[j] = 0; }
-      site_sum = tile_fast<RL, EXACT, CPT, KIND - 1>(prm, tc, x, psc, wnz);
+      unsigned long long spec = 0;
+      if constexpr (KIND == 1) site_sum = tile_fast<RL, EXACT, CPT, 0>(prm, tc, x, psc, wnz, spec);
+      // one or two categories: (nearly) every lane stores a scaler anyway and there is little lane exchange to save;
+      // the speculative form measured slower there (config 2 scaled: 0.515 against 0.476 ms)
+      else if constexpr (RL < 4) site_sum = tile_fast<RL, EXACT, CPT, 1>(prm, tc, x, psc, wnz, spec);
+      else
+      {
+        constexpr unsigned int LOG2RL = RL == 1 ? 0 : (RL == 2 ? 1 : (RL == 4 ? 2 : 3));
+        site_sum = tile_fast<RL, EXACT, CPT, 3>(prm, tc, x, psc, wnz, spec);
+        // a site is rescaled when ALL its RL categories are below the threshold at the same op
+#pragma unroll
+        for (int dd = 1; dd < RL; dd <<= 1) spec &= __shfl_xor_sync(0xFFFFFFFFu, spec, S4Lanes<RL>::xor_step(dd));
+        if (__any_sync(0xFFFFFFFFu, spec != 0ull))
+        {
+          // rare: this warp repeats its cells of the tile with the rescaling in place (no CTA barrier inside tile_fast;
+          // the repeat overwrites every CLV, scaler and per-site value the speculative pass stored)
+#pragma unroll
+          for (int j = 0; j < CPT; ++j) { x[j][0] = x[j][1] = x[j][2] = x[j][3] = 0.0; psc[j] = 0; }
+          wnz = 0;
+          site_sum = tile_fast<RL, EXACT, CPT, 1>(prm, tc, x, psc, wnz, spec);
+        }
+        else
+        {
+          // no site of this warp was rescaled: the scalers of its sites are zero for every scaled op of the list --
+          // one sweep, lane = (op, cell row, site of the warp's row), instead of CPT predicated stores per op
+          constexpr unsigned int SPW = 32u >> LOG2RL, PER_OP = CPT * SPW;
+          const unsigned int ops = sb + Lay::OPS, cn = s1[(sb + Lay::CH) * 4];
+          for (unsigned int i = lane; i < cn * PER_OP; i += 32)
+          {
+            const unsigned int k = i / PER_OP, r = i % PER_OP, j = r / SPW, sw = r % SPW;
+            const unsigned int ctl = s1[(ops + 4 * k) * 4];
+            const int dsc = (int)s1[(ops + 4 * k + 1) * 4 + 2];
+            const unsigned int cell = tc.cell0 + j * TREE_NT + (tid & ~31u) + sw * RL;
+            if ((ctl & OP_SCALE) && cell < tc.ncell) H->scale[(size_t)dsc * H->sites + (cell >> LOG2RL)] = 0u;
+          }
+        }
+      }
       if (H->n_chunks != 1 || !(H->flags & (KIND == 1 ? HDR_SIMPLE : HDR_NOHBM))) site_sum = __longlong_as_double(0x7FF8000000000000ll);
     }
     else
@@ -805,19 +860,20 @@ tree_kernel_s4(const TreeParams prm)
       double x[CPT][4];
       unsigned int psc[CPT];
       unsigned int wnz = 0;                    // some scaler count of this warp's cells is non-zero (this tile)
+      unsigned long long spec = 0;             // (MODE 3 only)
 #pragma unroll
       for (int j = 0; j < CPT; ++j) { x[j][0] = x[j][1] = x[j][2] = x[j][3] = 0.0; psc[j] = 0; }
       // one chunk (trees of up to 16 ops whose tips fit the lookup tables) and no HBM-class operand: the lean
       // instantiations; anything else on the fast path runs the full one, chunk by chunk
-      if (n_chunks == 1 && (flags & HDR_SIMPLE)) site_sum = tile_fast<RL, EXACT, CPT, 0>(prm, tc, x, psc, wnz);
-      else if (n_chunks == 1 && (flags & HDR_NOHBM)) site_sum = tile_fast<RL, EXACT, CPT, 1>(prm, tc, x, psc, wnz);
+      if (n_chunks == 1 && (flags & HDR_SIMPLE)) site_sum = tile_fast<RL, EXACT, CPT, 0>(prm, tc, x, psc, wnz, spec);
+      else if (n_chunks == 1 && (flags & HDR_NOHBM)) site_sum = tile_fast<RL, EXACT, CPT, 1>(prm, tc, x, psc, wnz, spec);
       else
       {
         site_sum = 0.0;
         for (unsigned int c = 0; c < n_chunks; ++c)
         {
           if (c > 0) restage(c);
-          site_sum += tile_fast<RL, EXACT, CPT, 2>(prm, tc, x, psc, wnz);
+          site_sum += tile_fast<RL, EXACT, CPT, 2>(prm, tc, x, psc, wnz, spec);
         }
       }
     }

@@ -65,6 +65,69 @@ def test_clv_scaler_pmatrix_match_reference_fixture(eng, name):
     _free(loci, batch)
 
 
+@pytest.mark.parametrize("name", ["gtr_g4_scale", "gtr_g4_deep_scale", "f81_r1_scale", "tn93_g4_scale"])
+def test_specialised_scaled_launch_reproduces_clvs_and_scalers(eng, name):
+    """Runs on a cached plan of scaled one-chunk loci launch the specialised kernel (KIND 2), which evaluates a
+    tile speculatively without scaler bookkeeping and repeats it only where a site really has to be rescaled
+    (the deep-tree fixture: scalers up to 2).  Every inner CLV and every scaler must equal the reference's, exactly
+    as after the first run on the kernel that carries all paths."""
+    w, d = load_case(name)
+    T = w.tips
+    loci, trees, batch = _load(eng, w)
+    batch.stage(trees.full_pass_step())
+    batch.run()
+    lnl0, _ = batch.collect()
+    l = loci[0]
+    first = [(l.get_clv(n).copy(), l.get_scaler(n - T).copy()) for n in range(T, 2 * T - 1)]
+    # scribble over the scalers so that the later runs have to write every one of them
+    for _ in range(3):
+        batch.run()
+        lnl, _ = batch.collect()
+    if T <= 17:
+        assert batch.kernel_name.endswith(",2>"), batch.kernel_name
+    assert np.array_equal(lnl, lnl0)
+    for k, n in enumerate(range(T, 2 * T - 1)):
+        assert np.array_equal(l.get_clv(n), first[k][0]), (name, n)
+        assert np.array_equal(l.get_scaler(n - T), first[k][1]), (name, n)
+        assert np.array_equal(l.get_scaler(n - T), d["l0_scaler"][k]), (name, n)
+    _free(loci, batch)
+
+
+@pytest.mark.parametrize("rate_cats,tips,dt", [(4, 16, 1e-12), (1, 12, 1e-12), (2, 16, 1e-12), (8, 8, 1e-15)])
+def test_specialised_scaled_launch_with_real_rescaling(eng, rate_cats, tips, dt):
+    """One-chunk trees whose sites DO get rescaled (branches of 1e-12: every mismatch costs ten orders of magnitude):
+    the specialised scaled launch must notice it in its speculative pass and repeat those tiles with the rescaling
+    in place.  Scalers and lnL against the oracle, CLVs and scalers against the first run (general kernel)."""
+    rates = None if rate_cats in (1, 4) else list(np.linspace(0.3, 1.7, rate_cats))
+    w = synth.make_workload("resc", n_loci=5, tips=tips, sites=333, states=4, rate_cats=rate_cats, model="GTR",
+                            scaling=True, seed=77, dt_lo=dt, dt_hi=10 * dt, rates=rates)
+    T = w.tips
+    loci, trees, batch = _load(eng, w)
+    batch.stage(trees.full_pass_step())
+    batch.run()
+    lnl0, _ = batch.collect()
+    first = [[(l.get_clv(n).copy(), l.get_scaler(n - T).copy()) for n in range(T, 2 * T - 1)] for l in loci]
+    for _ in range(3):
+        batch.run()
+        lnl, _ = batch.collect()
+    assert batch.kernel_name.endswith(",2>"), batch.kernel_name
+    assert np.array_equal(lnl, lnl0)
+    cm = char_map(4)
+    fired = 0
+    for i, l in enumerate(loci):
+        o = F.locus_from_workload(w, i, cm)
+        ref = o.full_pass()
+        assert abs(lnl[i] - ref) <= LNL_RTOL * abs(ref), (i, lnl[i], ref)
+        for k, n in enumerate(range(T, 2 * T - 1)):
+            sc = l.get_scaler(n - T)
+            assert np.array_equal(l.get_clv(n), first[i][k][0]), (i, n)
+            assert np.array_equal(sc, first[i][k][1]), (i, n)
+            assert np.array_equal(sc, o.scale[o.scaler_index[n]]), (i, n)
+            fired += int(sc.max())
+    assert fired > 0, "the workload was meant to trigger per-site rescaling"
+    _free(loci, batch)
+
+
 @pytest.mark.parametrize("name", ["jc69_r1", "gtr_g4_scale", "gtr_g4"])
 def test_clv_bit_exact_with_reference_pmatrices(eng, name):
     """Upload the reference's own P-matrices: every inner CLV, scaler and the per-site lnL must be
