@@ -232,6 +232,10 @@ struct TreeParams
 #define BPPGPU_SCALE_THRESHOLD (1.0 / BPPGPU_SCALE_FACTOR)
 
 // ----------------------------------------------------------------------------- memory helpers
+__device__ __forceinline__ void prefetch_l2(const void * p)
+{
+  asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
+}
 __device__ __forceinline__ void ld256_nc(const double * p, double & a, double & b, double & c, double & d)
 {
   asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];"

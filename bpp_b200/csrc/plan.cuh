@@ -450,7 +450,9 @@ plan_kernel_blocks(const LocusDev * __restrict__ loci, const unsigned int * __re
   const unsigned int wib = threadIdx.x >> 5;
   // every closed chunk holds >= m ops, so a list of n (+1 eval-only) ops needs <= n/m + 1 chunks
   const unsigned int m_ops = (cap / 2 < (unsigned)TREE_CHUNK) ? (cap / 2 ? cap / 2 : 1u) : (unsigned)TREE_CHUNK;
-  const bool small = (n <= SM_RAW) && (L.clv_buffers <= SM_BUF) && (n / m_ops + 1 <= SM_OPS / TREE_CHUNK);
+  // (short lists over big trees too: root-path updates of 48-tip loci used to be turned away here by a limit on the
+  // buffer count that only the serial planner's shared-memory tables once had, and ran on the cell-at-a-time walker)
+  const bool small = (n <= SM_RAW) && (n / m_ops + 1 <= SM_OPS / TREE_CHUNK);
   if (small)
   {
     const uint4 * src = reinterpret_cast<const uint4 *>(o);

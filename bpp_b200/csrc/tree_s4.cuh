@@ -229,6 +229,32 @@ __device__ __forceinline__ double tile_fast(const TreeParams & prm, const TileCt
 
   double site_sum = 0.0;
 
+  // Partial updates (root paths of gene-tree moves): nearly every op has a sibling CLV that lives in HBM, and a
+  // thread would meet those loads one after the other, a DRAM round trip per op with a handful of warps per SM to
+  // hide it.  All of the chunk's HBM-resident operands are requested into L2 up front (no registers involved), so
+  // the loads of ops 2..n overlap the first one's latency.
+#ifndef BPPGPU_S4_L2PREFETCH
+#define BPPGPU_S4_L2PREFETCH 1
+#endif
+  if (FULL && BPPGPU_S4_L2PREFETCH)
+    for (unsigned int k = 0; k < cn; ++k)
+    {
+      const unsigned int ctl = s1[(ops + 4 * k) * 4];
+      const unsigned int akind = (ctl >> OP_AKIND_SHIFT) & 15u, bkind = (ctl >> OP_BKIND_SHIFT) & 15u;
+      if (akind == SRC_HBM)
+      {
+        const size_t off = (size_t)(s1[(ops + 4 * k + 2) * 4] * (sites * RL)) << 5;
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) prefetch_l2(pc[j] + off);
+      }
+      if (bkind == SRC_HBM && !(ctl & OP_BPREV))
+      {
+        const size_t off = (size_t)(s1[(ops + 4 * k + 3) * 4] * (sites * RL)) << 5;
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) prefetch_l2(pc[j] + off);
+      }
+    }
+
   for (unsigned int k = 0; k < cn; ++k)
   {
     const uint4 w0 = s4[ops + 4 * k], w1 = s4[ops + 4 * k + 1];

@@ -228,7 +228,9 @@ def test_device_side_flip_and_cached_plan(eng, name):
 
 @pytest.mark.parametrize("cfg", [dict(tips=8, rate_cats=1, model="JC69", scaling=False),
                                  dict(tips=16, rate_cats=4, model="GTR", scaling=True),
-                                 dict(tips=48, rate_cats=4, model="GTR", scaling=False)])
+                                 dict(tips=48, rate_cats=4, model="GTR", scaling=False),
+                                 dict(tips=100, rate_cats=4, model="GTR", scaling=True),
+                                 dict(tips=128, rate_cats=1, model="JC69", scaling=False)])
 def test_age_moves_across_all_loci_match_the_reference(eng, cfg):
     """The schedule for the most frequent proposal (gene-tree age move, gtree.c:4585, 5437-5467): the SAME move in
     every locus as one batch -- 2-3 P-matrices and the root path's partials per locus, ragged, children outside
@@ -250,6 +252,8 @@ def test_age_moves_across_all_loci_match_the_reference(eng, cfg):
         nodes, ages = engine.propose_ages(trees, rng)
         step = engine.age_move_step(trees, nodes, ages)
         lnl, total = batch.full_pass(step)
+        st = batch.plan_stats()              # root paths stay on the fast path whatever the size of the tree (<= 128 tips)
+        assert st["walker"] == 0 and st["fast"] == w.n_loci, st
         _, ref = rs.age_move_all(0, w.n_loci, nodes, ages, 2)
         assert rel_err(lnl, ref) <= LNL_RTOL
         assert abs(total - lnl.sum()) <= 1e-9 * abs(total)

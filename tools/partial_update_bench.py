@@ -32,7 +32,7 @@ def run(T, n_loci, sites=1000, rate_cats=4, model="GTR", rounds=30, ref_loci=204
     # parity + CPU baseline on a sample (the reference applies the same moves, in the same order)
     cpu = None
     from oracle import refbind
-    if refbind.available():
+    if refbind.available() and not os.environ.get("PU_NO_CPU"):
         from helpers import ref_set_from_workload
         ws = w.subset(ref_loci)
         rs = ref_set_from_workload(ws)
@@ -70,7 +70,7 @@ def run(T, n_loci, sites=1000, rate_cats=4, model="GTR", rounds=30, ref_loci=204
            "ms_per_batch_device": dev_ms, "moves_per_sec_device": n_loci / (dev_ms / 1000.0),
            "node_updates_per_sec_e2e": node_updates / secs, "mean_path_length": node_updates / (rounds * n_loci),
            "per_kernel_ms": {k: v["ms"] / rounds for k, v in prof.items()},
-           "kernel": batch.kernel_name, "cpu_reference": cpu, "max_rel_err_lnl_vs_reference": err,
+           "kernel": batch.kernel_name, "plan_stats": batch.plan_stats(), "cpu_reference": cpu, "max_rel_err_lnl_vs_reference": err,
            "speedup_e2e_vs_reference_all_cores": (n_loci * rounds / secs) / cpu["moves_per_sec"] if cpu else None}
     batch.destroy()
     eng.close()
