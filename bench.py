@@ -315,6 +315,7 @@ def measure(name, n_loci, args, rank, world, local_rank, D, steps, warmup, cpu_s
         batch.run()
         allreduce()
     ms_total = batch.timer_stop_ms()
+    kname = batch.kernel_name                 # the instantiation the timed steps launched (the later stages replan)
     D.barrier()
     launches = eng.launch_count - l0
     prof = eng.profile()
@@ -373,7 +374,6 @@ def measure(name, n_loci, args, rank, world, local_rank, D, steps, warmup, cpu_s
     peak, peak_src = measured_peak()
     tree_ms = prof["tree"]["ms"] / max(1, steps)          # per step (one launch per step on this path)
     b_pass, b_min = w.b_pass(), w.b_min()
-    kname = batch.kernel_name
     achieved_min = b_min * w.n_loci / (tree_ms / 1000.0) / 1e9 if tree_ms > 0 else None
     achieved_can = b_pass * w.n_loci / (tree_ms / 1000.0) / 1e9 if tree_ms > 0 else None
     traffic, traffic_src = (None, None)

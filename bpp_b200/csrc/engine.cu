@@ -1740,8 +1740,13 @@ static int batch_run(bppgpu_batch * b, bool do_mats, bool do_tree, bool want_roo
   if (!waved && cached && b->kernel_kind == 0)
   {
     ProfScope ps(e, b->stream, BPPGPU_KERNEL_PLAN);
-    plan_refresh_blocks<<<(n * 32 + 127) / 128, 128, 0, b->stream>>>(
-        e->d_loci, b->d_batch_locus, n, b->d_blocks, d_blk_off, b->RL, fuse_mats ? d_mat_off : nullptr, d_mat_idx, d_mat_bl);
+    // a CTA per locus for batches of few, big trees; a warp per locus otherwise
+    if (n <= 4096 && b->max_tips > 16)
+      plan_refresh_blocks<4><<<n, 128, 0, b->stream>>>(
+          e->d_loci, b->d_batch_locus, n, b->d_blocks, d_blk_off, b->RL, fuse_mats ? d_mat_off : nullptr, d_mat_idx, d_mat_bl);
+    else
+      plan_refresh_blocks<1><<<(n * 32 + 127) / 128, 128, 0, b->stream>>>(
+          e->d_loci, b->d_batch_locus, n, b->d_blocks, d_blk_off, b->RL, fuse_mats ? d_mat_off : nullptr, d_mat_idx, d_mat_bl);
     CUDA_CHECK(cudaGetLastError());
   }
   if (cacheable && !cached) { b->plan_valid[b->parity] = !persite; b->plan_key[b->parity] = pkey; b->class_pending[b->parity] = false; b->plan_class[b->parity] = 0; }
@@ -1772,7 +1777,8 @@ static int batch_run(bppgpu_batch * b, bool do_mats, bool do_tree, bool want_roo
       // caller collected this step
       const int par = b->parity;
       e->launches++;
-      plan_class_kernel<<<1, 256, 0, b->stream>>>(b->d_blocks, d_blk_off, n, b->d_class + par);
+      CUDA_CHECK(cudaMemsetAsync(b->d_class + par, (int)(PLAN_CLASS_KNOWN | PLAN_CLASS_LEAN | PLAN_CLASS_SCALED), 4, b->stream));   // every byte 0x07
+      plan_class_kernel<<<(n + 255) / 256, 256, 0, b->stream>>>(b->d_blocks, d_blk_off, n, b->d_class + par);
       CUDA_CHECK(cudaGetLastError());
       CUDA_CHECK(cudaMemcpyAsync(b->h_class + par, b->d_class + par, 4, cudaMemcpyDeviceToHost, b->stream));
       CUDA_CHECK(cudaEventRecord(b->ev_class[par], b->stream));

@@ -343,13 +343,14 @@ plan_small_parallel(const LocusDev & L, const RawOp * o, unsigned int n, unsigne
 // planning (srec) or from the block itself (refresh of a cached plan).
 __device__ __forceinline__ void gather_block_matrices(const LocusDev & L, unsigned char * blk, unsigned int chunks0, size_t cb,
                                                       unsigned int n_chunks, unsigned int RL, unsigned int lut_unit,
-                                                      bool hbm_slots, const OpRec * srec)
+                                                      bool hbm_slots, const OpRec * srec, unsigned int c_first = 0,
+                                                      unsigned int c_step = 1)
 {
   const unsigned int lane = threadIdx.x & 31u;
   const unsigned int per = RL * 8;                      // double2 per (op, which) matrix set; RL is a power of two
   const unsigned int per_sh = 31u - (unsigned)__clz((int)per);
   const float inv_lut_unit = 1.0f / (float)lut_unit;
-  for (unsigned int c = 0; c < n_chunks; ++c)
+  for (unsigned int c = c_first; c < n_chunks; c += c_step)       // (several warps of a big locus share the chunks)
   {
     unsigned char * ch = blk + chunks0 + (size_t)c * cb;
     const ChunkHdr hdr = *reinterpret_cast<const ChunkHdr *>(ch);
@@ -725,31 +726,39 @@ plan_kernel_blocks(const LocusDev * __restrict__ loci, const unsigned int * __re
 // to the next with the same lists is the VALUE of the P-matrices.  When the batch still holds the planned blocks
 // of the staged lists (bppgpu_batch_run twice on the same stage, or the other index parity after
 // bppgpu_batch_flip_indices), the planner is skipped: this kernel rebuilds the matrices from the branch lengths
-// (mat_off != nullptr) and copies them into the Pup / tipP areas of the blocks again.  One warp per locus.
+// (mat_off != nullptr) and copies them into the Pup / tipP areas of the blocks again.  WPL warps per locus (1, 2 or
+// 4, all in one CTA): batches of many loci use one -- there are warps enough -- while a few hundred big trees (254
+// matrices x RL categories each at 128 tips) would leave most of the GPU idle behind 250 serial warps, so the
+// host gives each of those a whole CTA: the warps split the matrices, then the chunks.
+template <int WPL>
 __global__ void __launch_bounds__(128)
 plan_refresh_blocks(const LocusDev * __restrict__ loci, const unsigned int * __restrict__ batch_locus,
                     unsigned int n_loci, unsigned char * __restrict__ blocks, const unsigned long long * __restrict__ blk_off,
                     unsigned int RL, const unsigned int * __restrict__ mat_off, const unsigned int * __restrict__ mat_idx,
                     const double * __restrict__ mat_bl)
 {
-  const unsigned int bl = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned int bl = warp / WPL, sub = warp % WPL;
   const unsigned int lane = threadIdx.x & 31u;
-  if (bl >= n_loci) return;
-  const LocusDev & L = loci[batch_locus[bl]];
-  if (mat_off)
+  const bool act = bl < n_loci;                 // (no early return: the warps of a locus meet at a CTA barrier)
+  if (act && mat_off)
   {
+    const LocusDev & L = loci[batch_locus[bl]];
     const unsigned int mfirst = mat_off[bl], mcount = mat_off[bl + 1] - mfirst;
-    for (unsigned int t = lane; t < mcount * RL; t += 32)
+    for (unsigned int t = sub * 32 + lane; t < mcount * RL; t += 32 * WPL)
     {
       const unsigned int n = t % RL, m = t / RL;
       pmatrix_full4(L, mat_idx[mfirst + m], mat_bl[mfirst + m], n);
     }
-    __syncwarp();
   }
+  if (WPL == 1) __syncwarp(); else __syncthreads();      // the matrices of the locus are written (block-scope ordering)
+  if (!act) return;
+  const LocusDev & L = loci[batch_locus[bl]];
   unsigned char * blk = blocks + blk_off[bl];
   const LocusHdr * H = reinterpret_cast<const LocusHdr *>(blk);
   const unsigned int chunks0 = (unsigned int)(sizeof(LocusHdr) + rw_bytes(RL));
-  gather_block_matrices(L, blk, chunks0, chunk_bytes(RL), H->n_chunks, RL, lut_slot_u4((int)RL), (H->flags & HDR_LANEPLAN) != 0, nullptr);
+  gather_block_matrices(L, blk, chunks0, chunk_bytes(RL), H->n_chunks, RL, lut_slot_u4((int)RL), (H->flags & HDR_LANEPLAN) != 0, nullptr,
+                        sub, WPL);
 }
 
 // ---------------------------------------------------------------- device-side index flips
@@ -793,16 +802,23 @@ __global__ void __launch_bounds__(256)
 plan_class_kernel(const unsigned char * __restrict__ blocks, const unsigned long long * __restrict__ blk_off, unsigned int n,
                   unsigned int * __restrict__ cls)
 {
+  // *cls starts as KNOWN | LEAN | SCALED (set by the host on the stream); a CTA that meets a locus of another class
+  // clears the bit -- once: later CTAs see it gone and skip the atomic
+  const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
   unsigned int lean = 1u, scaled = 1u;
-  for (unsigned int i = threadIdx.x; i < n; i += blockDim.x)
+  if (i < n)
   {
     const LocusHdr * H = reinterpret_cast<const LocusHdr *>(blocks + blk_off[i]);
     const bool one = H->n_chunks == 1;
-    lean &= (one && (H->flags & HDR_SIMPLE)) ? 1u : 0u;
-    scaled &= (one && (H->flags & HDR_NOHBM)) ? 1u : 0u;
+    lean = (one && (H->flags & HDR_SIMPLE)) ? 1u : 0u;
+    scaled = (one && (H->flags & HDR_NOHBM)) ? 1u : 0u;
   }
   const int all_lean = __syncthreads_and((int)lean), all_scaled = __syncthreads_and((int)scaled);
-  if (threadIdx.x == 0) *cls = PLAN_CLASS_KNOWN | (all_lean ? PLAN_CLASS_LEAN : 0u) | (all_scaled ? PLAN_CLASS_SCALED : 0u);
+  if (threadIdx.x == 0)
+  {
+    const unsigned int clear = (all_lean ? 0u : PLAN_CLASS_LEAN) | (all_scaled ? 0u : PLAN_CLASS_SCALED);
+    if (clear && (*reinterpret_cast<volatile unsigned int *>(cls) & clear)) atomicAnd(cls, ~clear);
+  }
 }
 
 }  // namespace bppgpu
