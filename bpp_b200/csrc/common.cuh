@@ -96,14 +96,6 @@ __host__ __device__ constexpr int s4_ctas_per_sm(int cpt)
 {
   return cpt == 2 ? BPPGPU_S4_CTAS2 : (TREE_NT > 256 ? 1 : (cpt == 1 ? 3 : 1) * (256 / TREE_NT));
 }
-// specialised 4-state launches (KIND 1 lean / 2 scaled, tree_s4.cuh) carry one instantiation of the op loop only
-#ifndef BPPGPU_S4_KIND_CTAS4
-#define BPPGPU_S4_KIND_CTAS4 1
-#endif
-__host__ __device__ constexpr int s4_ctas_per_sm_kind(int cpt, int kind)
-{
-  return (kind != 0 && cpt == 4) ? BPPGPU_S4_KIND_CTAS4 * (TREE_NT > 256 ? 1 : (256 / TREE_NT)) : s4_ctas_per_sm(cpt);
-}
 constexpr int TREE_CHUNK = 16;      // ops per staged chunk
 constexpr int S4_MAX_TIP_WORDS = 16; // packed tip words (8 tips each) the 4-state fast path stages per cell: 128 tips
 constexpr int PM_STRIDE  = 18;      // doubles per (matrix, cat) in shared memory (16 + 2 pad: the RL

@@ -264,8 +264,8 @@ struct bppgpu_batch
   unsigned int wave_pref = 0;          // 0 = automatic
   std::vector<unsigned int> h_tile_first;
   // launch configuration of the tree kernel, resolved once per (shared-memory size)
-  size_t cfg_smem[3] = {0, 0, 0}; int cfg_per_sm[3] = {0, 0, 0}; unsigned int cfg_key[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
-  int last_kind = 0;                   // KIND of the last 4-state tree launch (kernel name reporting)
+  size_t cfg_smem[2] = {0, 0}; int cfg_per_sm[2] = {0, 0}; unsigned int cfg_key[2] = {0xFFFFFFFFu, 0xFFFFFFFFu};   // [SCALED_ONLY]
+  bool last_scaled_only = false;       // instantiation of the last 4-state tree launch (kernel name reporting)
 };
 
 // ------------------------------------------------------------------------------------ helpers
@@ -1052,7 +1052,7 @@ extern "C" const char * bppgpu_batch_kernel_name(bppgpu_batch * b)
 {
   static thread_local char buf[96];
   const bool exact = b->e->math == BPPGPU_MATH_EXACT;
-  if (b->kernel_kind == 0) snprintf(buf, sizeof(buf), "tree_kernel_s4<%u,%s,%u,%d>", b->RL, exact ? "true" : "false", b->cpt, b->last_kind);
+  if (b->kernel_kind == 0) snprintf(buf, sizeof(buf), "tree_kernel_s4<%u,%s,%u,%s>", b->RL, exact ? "true" : "false", b->cpt, b->last_scaled_only ? "scaled_only" : "all_paths");
   else if (b->kernel_kind == 2) snprintf(buf, sizeof(buf), b->s20_cat ? (b->s20_scaled ? "tree_kernel_s20t<%u,true>" : "tree_kernel_s20t<%u,false>") : "tree_kernel_s20<%u>", b->RL);
   else snprintf(buf, sizeof(buf), "tree_kernel_generic<%s>", exact ? "true" : "false");
   return buf;
@@ -1524,52 +1524,52 @@ static int tree_s4_slots(bppgpu_batch * b, int wanted, unsigned cap)
   return slots;
 }
 
-template <int RL, bool EXACT, int CPT, int KIND>
+template <int RL, bool EXACT, int CPT, bool SCALED_ONLY>
 static void launch_tree_s4_impl(bppgpu_batch * b, const TreeParams & prm, cudaStream_t st)
 {
   bppgpu_engine * e = b->e;
   const size_t smem = S4Layout<RL, CPT>::bytes(prm.n_slots, prm.lut_cap, prm.tip_words);
   b->slots = prm.n_slots; b->tree_smem = smem;
-  const unsigned key = (unsigned)(KIND * 1000 + RL * 100 + CPT * 10 + (EXACT ? 1 : 0));
-  if (b->cfg_key[KIND] != key || b->cfg_smem[KIND] != smem)
+  constexpr int K = SCALED_ONLY ? 1 : 0;
+  const unsigned key = (unsigned)(K * 1000 + RL * 100 + CPT * 10 + (EXACT ? 1 : 0));
+  if (b->cfg_key[K] != key || b->cfg_smem[K] != smem)
   {
-    ensure_max_smem(e, tree_kernel_s4<RL, EXACT, CPT, KIND>);
+    ensure_max_smem(e, tree_kernel_s4<RL, EXACT, CPT, SCALED_ONLY>);
     int per_sm = 0;
-    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tree_kernel_s4<RL, EXACT, CPT, KIND>, TREE_NT, smem));
+    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tree_kernel_s4<RL, EXACT, CPT, SCALED_ONLY>, TREE_NT, smem));
     if (per_sm < 1) { fatal("tree kernel does not fit on an SM (smem %zu)", smem); return; }
-    b->cfg_key[KIND] = key; b->cfg_smem[KIND] = smem; b->cfg_per_sm[KIND] = per_sm;
+    b->cfg_key[K] = key; b->cfg_smem[K] = smem; b->cfg_per_sm[K] = per_sm;
   }
-  const unsigned grid = std::min<unsigned>(prm.n_tiles, (unsigned)(b->cfg_per_sm[KIND] * e->sm_count));
-  tree_kernel_s4<RL, EXACT, CPT, KIND><<<grid, TREE_NT, smem, st>>>(prm);
+  const unsigned grid = std::min<unsigned>(prm.n_tiles, (unsigned)(b->cfg_per_sm[K] * e->sm_count));
+  tree_kernel_s4<RL, EXACT, CPT, SCALED_ONLY><<<grid, TREE_NT, smem, st>>>(prm);
 }
 
 template <int RL, bool EXACT, int CPT>
-static void launch_tree_s4_kind(bppgpu_batch * b, const TreeParams & prm, cudaStream_t st, int kind)
+static void launch_tree_s4_kind(bppgpu_batch * b, const TreeParams & prm, cudaStream_t st, bool scaled_only)
 {
-  if (kind == 1) launch_tree_s4_impl<RL, EXACT, CPT, 1>(b, prm, st);
-  else if (kind == 2) launch_tree_s4_impl<RL, EXACT, CPT, 2>(b, prm, st);
-  else launch_tree_s4_impl<RL, EXACT, CPT, 0>(b, prm, st);
+  if (scaled_only) launch_tree_s4_impl<RL, EXACT, CPT, true>(b, prm, st);
+  else launch_tree_s4_impl<RL, EXACT, CPT, false>(b, prm, st);
 }
 
 template <int RL>
-static void launch_tree_s4_rl(bppgpu_batch * b, const TreeParams & prm, cudaStream_t st, int kind)
+static void launch_tree_s4_rl(bppgpu_batch * b, const TreeParams & prm, cudaStream_t st, bool scaled_only)
 {
   const bool exact = b->e->math == BPPGPU_MATH_EXACT;
-  if (b->cpt == 2) { if (exact) launch_tree_s4_kind<RL, true, 2>(b, prm, st, kind); else launch_tree_s4_kind<RL, false, 2>(b, prm, st, kind); }
-  else if (b->cpt == 4) { if (exact) launch_tree_s4_kind<RL, true, 4>(b, prm, st, kind); else launch_tree_s4_kind<RL, false, 4>(b, prm, st, kind); }
-  else { if (exact) launch_tree_s4_kind<RL, true, 1>(b, prm, st, kind); else launch_tree_s4_kind<RL, false, 1>(b, prm, st, kind); }
+  if (b->cpt == 2) { if (exact) launch_tree_s4_kind<RL, true, 2>(b, prm, st, scaled_only); else launch_tree_s4_kind<RL, false, 2>(b, prm, st, scaled_only); }
+  else if (b->cpt == 4) { if (exact) launch_tree_s4_kind<RL, true, 4>(b, prm, st, scaled_only); else launch_tree_s4_kind<RL, false, 4>(b, prm, st, scaled_only); }
+  else { if (exact) launch_tree_s4_kind<RL, true, 1>(b, prm, st, scaled_only); else launch_tree_s4_kind<RL, false, 1>(b, prm, st, scaled_only); }
 }
 
-// kind: 0 = the kernel with every path; 1 / 2 = lean-only / scaled-only launch for a cached plan of that class
-static int launch_tree_s4(bppgpu_batch * b, const TreeParams & prm, cudaStream_t st, int kind = 0)
+// scaled_only: the specialised launch for a cached plan of scaled one-chunk loci (otherwise the kernel with every path)
+static int launch_tree_s4(bppgpu_batch * b, const TreeParams & prm, cudaStream_t st, bool scaled_only = false)
 {
-  b->last_kind = kind;
+  b->last_scaled_only = scaled_only;
   switch (b->RL)
   {
-    case 1: launch_tree_s4_rl<1>(b, prm, st, kind); break;
-    case 2: launch_tree_s4_rl<2>(b, prm, st, kind); break;
-    case 4: launch_tree_s4_rl<4>(b, prm, st, kind); break;
-    case 8: launch_tree_s4_rl<8>(b, prm, st, kind); break;
+    case 1: launch_tree_s4_rl<1>(b, prm, st, scaled_only); break;
+    case 2: launch_tree_s4_rl<2>(b, prm, st, scaled_only); break;
+    case 4: launch_tree_s4_rl<4>(b, prm, st, scaled_only); break;
+    case 8: launch_tree_s4_rl<8>(b, prm, st, scaled_only); break;
     default: fatal("internal: RL=%u", b->RL); return BPPGPU_FAILURE;
   }
   return BPPGPU_SUCCESS;
@@ -1750,9 +1750,8 @@ static int batch_run(bppgpu_batch * b, bool do_mats, bool do_tree, bool want_roo
     CUDA_CHECK(cudaGetLastError());
   }
   if (cacheable && !cached) { b->plan_valid[b->parity] = !persite; b->plan_key[b->parity] = pkey; b->class_pending[b->parity] = false; b->plan_class[b->parity] = 0; }
-  // BPPGPU_S4_KINDS=0: always the kernel with every path
-  static const bool s4_kinds_on = !(getenv("BPPGPU_S4_KINDS") && atoi(getenv("BPPGPU_S4_KINDS")) == 0);
-  static const int s4_kind_force = getenv("BPPGPU_S4_KIND_FORCE") ? atoi(getenv("BPPGPU_S4_KIND_FORCE")) : -1;   // experiments only
+  // BPPGPU_S4_SCALED_ONLY=0: always the kernel with every path
+  static const bool s4_kinds_on = !(getenv("BPPGPU_S4_SCALED_ONLY") && atoi(getenv("BPPGPU_S4_SCALED_ONLY")) == 0);
   if (!waved && !cached)
   {
     ProfScope ps(e, b->stream, BPPGPU_KERNEL_PLAN);
@@ -1771,11 +1770,16 @@ static int batch_run(bppgpu_batch * b, bool do_mats, bool do_tree, bool want_roo
           e->d_loci, b->d_batch_locus, n, d_op_off, d_ops, d_root_clv, d_root_sc, want_root ? 1 : 0,
           b->d_plan, b->d_plan_count);
     CUDA_CHECK(cudaGetLastError());
-    if (b->kernel_kind == 0 && b->plan_valid[b->parity] && s4_kinds_on)
+  }
+  // Class of a plan that IS being reused (first run on the cached blocks): one small kernel over the block headers,
+  // read back behind it; known to the host once the caller has collected that step, and from then on the runs on
+  // this plan launch the specialised kernel.  Steps that are planned afresh every time (partial updates) never pay.
+  bool s4_scaled_only = false;
+  if (b->kernel_kind == 0 && cached && !waved && s4_kinds_on)
+  {
+    const int par = b->parity;
+    if (b->plan_class[par] == 0 && !b->class_pending[par])
     {
-      // class of the plan that will be reused: read back behind the planner, known to the host by the time the
-      // caller collected this step
-      const int par = b->parity;
       e->launches++;
       CUDA_CHECK(cudaMemsetAsync(b->d_class + par, (int)(PLAN_CLASS_KNOWN | PLAN_CLASS_LEAN | PLAN_CLASS_SCALED), 4, b->stream));   // every byte 0x07
       plan_class_kernel<<<(n + 255) / 256, 256, 0, b->stream>>>(b->d_blocks, d_blk_off, n, b->d_class + par);
@@ -1784,19 +1788,14 @@ static int batch_run(bppgpu_batch * b, bool do_mats, bool do_tree, bool want_roo
       CUDA_CHECK(cudaEventRecord(b->ev_class[par], b->stream));
       b->class_pending[par] = true;
     }
-  }
-  int s4_kind = 0;
-  if (b->kernel_kind == 0 && cached && !waved && s4_kinds_on)
-  {
-    const int par = b->parity;
-    if (b->class_pending[par] && cudaEventQuery(b->ev_class[par]) == cudaSuccess)
+    else if (b->class_pending[par] && cudaEventQuery(b->ev_class[par]) == cudaSuccess)
     {
-      b->plan_class[par] = b->h_class[par];
+      b->plan_class[par] = b->h_class[par] & (PLAN_CLASS_KNOWN | PLAN_CLASS_LEAN | PLAN_CLASS_SCALED);
       b->class_pending[par] = false;
     }
+    // all loci scaled-capable one-chunk lists, and not all of them lean (an unscaled batch is both)
     if (!b->class_pending[par])
-      s4_kind = (b->plan_class[par] & PLAN_CLASS_LEAN) ? 1 : ((b->plan_class[par] & PLAN_CLASS_SCALED) ? 2 : 0);
-    if (s4_kind_force >= 0) s4_kind = s4_kind_force;
+      s4_scaled_only = (b->plan_class[par] & PLAN_CLASS_SCALED) && !(b->plan_class[par] & PLAN_CLASS_LEAN);
   }
   if (b->kernel_kind == 2 && b->s20_cat)
   {
@@ -1857,7 +1856,7 @@ static int batch_run(bppgpu_batch * b, bool do_mats, bool do_tree, bool want_roo
     ProfScope ps(e, b->stream, BPPGPU_KERNEL_TREE);
     if (b->kernel_kind == 0)
     {
-      if (!launch_tree_s4(b, prm, b->stream, s4_kind)) return BPPGPU_FAILURE;
+      if (!launch_tree_s4(b, prm, b->stream, s4_scaled_only)) return BPPGPU_FAILURE;
     }
     else if (b->kernel_kind == 2)
     {

@@ -796,7 +796,8 @@ flip_indices_kernel(const LocusDev * __restrict__ loci, const unsigned int * __r
 
 // Class of a planned batch (4 states): do ALL its loci run the lean one-chunk instantiation (HDR_SIMPLE), or all the
 // scaled one-chunk one (HDR_NOHBM)?  One word per index parity, read back by the host and kept with the cached plan;
-// runs on that plan then launch the kernel that carries only this instantiation (tree_kernel_s4 KIND 1 / 2).
+// runs on a plan that is all scaled (and not all lean) then launch the kernel that carries only that instantiation
+// (tree_kernel_s4<.., SCALED_ONLY = true>).
 enum : unsigned { PLAN_CLASS_KNOWN = 1u, PLAN_CLASS_LEAN = 2u, PLAN_CLASS_SCALED = 4u };
 __global__ void __launch_bounds__(256)
 plan_class_kernel(const unsigned char * __restrict__ blocks, const unsigned long long * __restrict__ blk_off, unsigned int n,

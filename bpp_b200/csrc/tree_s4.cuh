@@ -190,7 +190,7 @@ struct TileCtx
 // scale buffers), MODE 2 also HBM-class operands (partial updates).
 // One call runs the ops of the chunk that is staged; x / psc (the register X and its scaler count) carry over
 // from chunk to chunk of the same tile.
-// MODE 3 is the SPECULATIVE form of MODE 1 (specialised scaled launches, KIND 2): per-site rescaling is rare (all
+// MODE 3 is the SPECULATIVE form of MODE 1 (specialised scaled launches, SCALED_ONLY): per-site rescaling is rare (all
 // 4 x RL entries of a site below 2^-256), so the pass runs like MODE 0 -- no scaler counts, no scaler stores, no
 // per-op lane exchange -- and only records, one bit per (op, cell), where an op's values fell below the threshold.
 // The caller combines the bits over the lanes of a site once per tile; if no site qualified (the common case) the
@@ -675,14 +675,15 @@ __device__ __forceinline__ void build_lut(unsigned int sb, unsigned int lut0)
 // 2 cells at 2 CTAs beats 3 CTAs at 80 registers (spills) for R = 1; 4 cells win for R >= 4, where the
 // shared-memory pipe is the limit and the P-matrix loads are amortised over twice the cells.
 //
-// KIND selects what is compiled in.  0: every path (lean / scaled / HBM-class fast instantiations, chunk-by-chunk
-// restaging, the cell-at-a-time walker) -- the kernel for freshly planned lists, partial updates and big trees.
-// 1 / 2: ONLY the lean (tile_fast MODE 0) or only the scaled (MODE 1) one-chunk instantiation, for launches whose
-// cached plan is known (plan_class_kernel) to hold nothing but HDR_SIMPLE / HDR_NOHBM one-chunk loci: the steady
-// state of full passes (mixing, tau, alpha, qrates moves).  The monolithic kernel pays for the paths it does not
-// take with registers (242, spilling the per-op bases) and instruction-cache footprint.
-template <int RL, bool EXACT, int CPT, int KIND>
-__global__ void __launch_bounds__(TREE_NT, s4_ctas_per_sm_kind(CPT, KIND))
+// SCALED_ONLY = false: the kernel with every path (lean / scaled / HBM-class fast instantiations, chunk-by-chunk
+// restaging, the cell-at-a-time walker): freshly planned lists, partial updates, big trees, and unscaled full passes.
+// SCALED_ONLY = true: ONLY the scaled one-chunk instantiation, in its speculative form, for runs on a cached plan that
+// is known (plan_class_kernel) to hold nothing but HDR_NOHBM one-chunk loci: full passes with scale buffers in the
+// steady state of the mixing / tau / alpha / qrates moves.  (A lean-only launch was built and measured too: 186
+// instead of 242 registers and no stack frame, and not a microsecond faster -- DESIGN.md 4.3 -- so unscaled batches
+// stay on the general kernel.)
+template <int RL, bool EXACT, int CPT, bool SCALED_ONLY>
+__global__ void __launch_bounds__(TREE_NT, s4_ctas_per_sm(CPT))
 tree_kernel_s4(const TreeParams prm)
 {
   using Lay = S4Layout<RL, CPT>;
@@ -815,7 +816,7 @@ tree_kernel_s4(const TreeParams prm)
     tc.cell0 = d.cell0; tc.ncell = d.ncell;
 
     double site_sum;
-    if constexpr (KIND != 0)
+    if constexpr (SCALED_ONLY)
     {
       // specialised launch: the host selected it from the class word of the cached plan; a locus of another class
       // cannot be here (and would poison its lnL instead of computing something wrong)
@@ -825,10 +826,9 @@ tree_kernel_s4(const TreeParams prm)
 #pragma unroll
       for (int j = 0; j < CPT; ++j) { x[j][0] = x[j][1] = x[j][2] = x[j][3] = 0.0; psc[j] = 0; }
       unsigned long long spec = 0;
-      if constexpr (KIND == 1) site_sum = tile_fast<RL, EXACT, CPT, 0>(prm, tc, x, psc, wnz, spec);
       // one or two categories: (nearly) every lane stores a scaler anyway and there is little lane exchange to save;
       // the speculative form measured slower there (config 2 scaled: 0.515 against 0.476 ms)
-      else if constexpr (RL < 4) site_sum = tile_fast<RL, EXACT, CPT, 1>(prm, tc, x, psc, wnz, spec);
+      if constexpr (RL < 4) site_sum = tile_fast<RL, EXACT, CPT, 1>(prm, tc, x, psc, wnz, spec);
       else
       {
         constexpr unsigned int LOG2RL = RL == 1 ? 0 : (RL == 2 ? 1 : (RL == 4 ? 2 : 3));
@@ -861,7 +861,7 @@ tree_kernel_s4(const TreeParams prm)
           }
         }
       }
-      if (H->n_chunks != 1 || !(H->flags & (KIND == 1 ? HDR_SIMPLE : HDR_NOHBM))) site_sum = __longlong_as_double(0x7FF8000000000000ll);
+      if (H->n_chunks != 1 || !(H->flags & HDR_NOHBM)) site_sum = __longlong_as_double(0x7FF8000000000000ll);
     }
     else
     {

@@ -67,7 +67,7 @@ def test_clv_scaler_pmatrix_match_reference_fixture(eng, name):
 
 @pytest.mark.parametrize("name", ["gtr_g4_scale", "gtr_g4_deep_scale", "f81_r1_scale", "tn93_g4_scale"])
 def test_specialised_scaled_launch_reproduces_clvs_and_scalers(eng, name):
-    """Runs on a cached plan of scaled one-chunk loci launch the specialised kernel (KIND 2), which evaluates a
+    """Runs on a cached plan of scaled one-chunk loci launch the specialised kernel (SCALED_ONLY), which evaluates a
     tile speculatively without scaler bookkeeping and repeats it only where a site really has to be rescaled
     (the deep-tree fixture: scalers up to 2).  Every inner CLV and every scaler must equal the reference's, exactly
     as after the first run on the kernel that carries all paths."""
@@ -84,7 +84,7 @@ def test_specialised_scaled_launch_reproduces_clvs_and_scalers(eng, name):
         batch.run()
         lnl, _ = batch.collect()
     if T <= 17:
-        assert batch.kernel_name.endswith(",2>"), batch.kernel_name
+        assert batch.kernel_name.endswith(",scaled_only>"), batch.kernel_name
     assert np.array_equal(lnl, lnl0)
     for k, n in enumerate(range(T, 2 * T - 1)):
         assert np.array_equal(l.get_clv(n), first[k][0]), (name, n)
@@ -110,7 +110,7 @@ def test_specialised_scaled_launch_with_real_rescaling(eng, rate_cats, tips, dt)
     for _ in range(3):
         batch.run()
         lnl, _ = batch.collect()
-    assert batch.kernel_name.endswith(",2>"), batch.kernel_name
+    assert batch.kernel_name.endswith(",scaled_only>"), batch.kernel_name
     assert np.array_equal(lnl, lnl0)
     cm = char_map(4)
     fired = 0
@@ -461,24 +461,24 @@ def test_illegal_state_code_is_fatal(eng):
     l.destroy()
 
 
-@pytest.mark.parametrize("scaling,tips,kind", [(False, 8, 1), (True, 8, 2), (False, 24, 0)])
+@pytest.mark.parametrize("scaling,tips,kind", [(False, 8, "all_paths"), (True, 8, "scaled_only"), (True, 24, "all_paths")])
 def test_staged_run_is_idempotent_and_deterministic(eng, scaling, tips, kind):
-    """stage once, run several times: identical bits (fixed-order reductions, no float atomics).  The first run
-    launches the kernel that carries every path; once the class of the cached plan is known (all loci lean / all
-    scaled one-chunk) the later runs launch the specialised instantiation (KIND 1 / 2), which must reproduce the
-    first run's bits; a batch of multi-chunk trees (24 tips) stays on the general kernel."""
+    """stage once, run several times: identical bits (fixed-order reductions, no float atomics).  The first runs
+    launch the kernel that carries every path; once the class of the cached plan is known (all loci scaled one-chunk
+    lists) the later runs launch the specialised instantiation, which must reproduce the first run's bits; unscaled
+    batches and batches of multi-chunk trees (24 tips) stay on the general kernel."""
     w = synth.make_workload("idem", n_loci=40, tips=tips, sites=300, states=4, rate_cats=4, model="GTR", seed=9,
                             scaling=scaling)
     loci, trees, batch = _load(eng, w)
     batch.stage(trees.full_pass_step())
     batch.run()
     a, ta = batch.collect()
-    assert batch.kernel_name.endswith(",0>")
+    assert batch.kernel_name.endswith(",all_paths>")
     for _ in range(3):
         batch.run()
         b, tb = batch.collect()
         assert np.array_equal(a, b) and ta == tb
-    assert batch.kernel_name.endswith(",%d>" % kind), batch.kernel_name
+    assert batch.kernel_name.endswith(",%s>" % kind), batch.kernel_name
     cm = char_map(4)
     for i in range(0, w.n_loci, 8):
         ref = F.locus_from_workload(w, i, cm).full_pass()

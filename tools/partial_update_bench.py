@@ -18,6 +18,7 @@ from bpp_b200 import engine, synth  # noqa: E402
 
 
 def run(T, n_loci, sites=1000, rate_cats=4, model="GTR", rounds=30, ref_loci=2048):
+    ref_loci = min(ref_loci, n_loci)
     w = synth.make_workload("age%d" % T, n_loci=n_loci, tips=T, sites=sites, states=4, rate_cats=rate_cats,
                             model=model, seed=synth.SEED + T)
     eng = engine.Engine(0)
@@ -80,5 +81,5 @@ def run(T, n_loci, sites=1000, rate_cats=4, model="GTR", rounds=30, ref_loci=204
 if __name__ == "__main__":
     tips = [int(a) for a in sys.argv[1:]] or [8, 16, 48]
     for T in tips:
-        n = 10000 if T <= 16 else 4000
+        n = 10000 if T <= 16 else (4000 if T <= 48 else 1000)
         print(json.dumps(run(T, n)), flush=True)
