@@ -568,6 +568,7 @@ plan_kernel_blocks(const LocusDev * __restrict__ loci, const unsigned int * __re
     unsigned int prev = 0xFFFFFFFFu;        // buffer whose X sits in the register, or none
     unsigned int prev_off = 0;              // global op slot of the op that produced it
     bool root_done = false, fast = true;
+    bool any_reread = false, any_scaled = false;     // an HBML operand / a scaled op: not the lean (scaled-lean) op loop
     unsigned int c_idx = 0, c_nops = 0, c_ntips = 0;
     auto close_chunk = [&]()
     {
@@ -653,6 +654,8 @@ plan_kernel_blocks(const LocusDev * __restrict__ loci, const unsigned int * __re
       const Operand & A = opd[ia];
       const Operand & B = opd[1 - ia];
       if (A.kind == SRC_HBM || B.kind == SRC_HBM || B.kind == SRC_HBML) fast = false;
+      if (A.kind == SRC_HBML) any_reread = true;
+      if (r.psc >= 0) any_scaled = true;
       OpRec q;
       q.ctl = (A.kind << OP_AKIND_SHIFT) | (B.kind << OP_BKIND_SHIFT);
       q.dst_cell = (r.parent - T) * cells_per_buf; q.dsc = r.psc; q.park_off = 0; q.up_pm = 0; q.pad = 0;
@@ -700,7 +703,9 @@ plan_kernel_blocks(const LocusDev * __restrict__ loci, const unsigned int * __re
     H->tipwords = reinterpret_cast<const unsigned int *>(L.tip_codes); H->pmat = L.pmat;
     H->clv_stride = L.clv_stride; H->sites = L.sites; H->nops = cnt; H->tip_words = L.tip_words;
     // chunk by chunk on the fast path as long as every operand is a staged tip, the register or a stack slot
-    H->n_chunks = n_chunks; H->flags = fast ? HDR_FAST : 0u; H->pad0 = 0;
+    H->n_chunks = n_chunks;
+    H->flags = fast ? (HDR_FAST | (any_reread ? 0u : HDR_NOHBM) | ((any_reread || any_scaled) ? 0u : HDR_SIMPLE)) : 0u;
+    H->pad0 = 0;
     for (int j = 0; j < 4; ++j) H->freqs[j] = L.freqs[j];
     plan_count[bl] = cnt;
   }

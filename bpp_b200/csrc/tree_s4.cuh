@@ -889,19 +889,28 @@ tree_kernel_s4(const TreeParams prm)
       unsigned long long spec = 0;             // (MODE 3 only)
 #pragma unroll
       for (int j = 0; j < CPT; ++j) { x[j][0] = x[j][1] = x[j][2] = x[j][3] = 0.0; psc[j] = 0; }
-      // one chunk (trees of up to 16 ops whose tips fit the lookup tables) and no HBM-class operand: the lean
-      // instantiations; anything else on the fast path runs the full one, chunk by chunk
-      if (n_chunks == 1 && (flags & HDR_SIMPLE)) site_sum = tile_fast<RL, EXACT, CPT, 0>(prm, tc, x, psc, wnz, spec);
-      else if (n_chunks == 1 && (flags & HDR_NOHBM)) site_sum = tile_fast<RL, EXACT, CPT, 1>(prm, tc, x, psc, wnz, spec);
+      // no HBM-class operand and no scaler: the lean instantiation; no HBM-class operand: the scaled one; anything
+      // else on the fast path runs the full one.  One chunk for trees of up to 16 ops whose tips fit the lookup
+      // tables, chunk by chunk beyond (X, its scaler count and the parked values carry over)
+      site_sum = 0.0;
+      if (flags & HDR_SIMPLE)
+        for (unsigned int c = 0; c < n_chunks; ++c)
+        {
+          if (c > 0) restage(c);
+          site_sum += tile_fast<RL, EXACT, CPT, 0>(prm, tc, x, psc, wnz, spec);
+        }
+      else if (flags & HDR_NOHBM)
+        for (unsigned int c = 0; c < n_chunks; ++c)
+        {
+          if (c > 0) restage(c);
+          site_sum += tile_fast<RL, EXACT, CPT, 1>(prm, tc, x, psc, wnz, spec);
+        }
       else
-      {
-        site_sum = 0.0;
         for (unsigned int c = 0; c < n_chunks; ++c)
         {
           if (c > 0) restage(c);
           site_sum += tile_fast<RL, EXACT, CPT, 2>(prm, tc, x, psc, wnz, spec);
         }
-      }
     }
     else
     {
