@@ -719,7 +719,22 @@ tree_kernel_s4(const TreeParams prm)
     }
   };
   auto stage_wait = [&](unsigned int buf, bool) { mbar_wait(mbar + buf, mphase[buf]); mphase[buf] ^= 1u; };
+  // chunk c >= 1 of the locus at blk -> stage buffer b, behind a copy of the header and the rate weights (two bulk
+  // copies on the buffer's mbarrier): the chunks of a big tree alternate between the two stage buffers
+  auto chunk_fetch = [&](unsigned int b, unsigned long long blk, unsigned int c)
+  {
+    if (tid == 0)
+    {
+      mbar_expect_tx(mbar + b, stage_sz * 16u);
+      bulk_load(&s4[Lay::STAGE0 + b * stage_sz], prm.blocks + blk, Lay::CH * 16u, mbar + b);
+      bulk_load(&s4[Lay::STAGE0 + b * stage_sz + Lay::CH], prm.blocks + blk + ((size_t)Lay::CH + (size_t)c * Lay::CHUNK) * 16u,
+                (stage_sz - Lay::CH) * 16u, mbar + b);
+    }
+  };
+  constexpr bool PINGPONG = Lay::NSTAGE == 2;
 #else
+  constexpr bool PINGPONG = false;
+  auto chunk_fetch = [&](unsigned int, unsigned long long, unsigned int) {};
   auto stage_fetch = [&](unsigned int buf, unsigned long long blk)
   {
     const uint4 * src = reinterpret_cast<const uint4 *>(prm.blocks + blk);
@@ -784,22 +799,29 @@ tree_kernel_s4(const TreeParams prm)
     // ---- prefetch: tips/weight of tile t+1 -> registers; block of the next locus -> other stage buffer;
     //      descriptor of tile t+2 -> ring
     const unsigned int tb = (t - t_begin) & 1u;          // tip buffer of this tile
+    const unsigned int sb = Lay::STAGE0 + buf * stage_sz;
+    const LocusHdr * H = reinterpret_cast<const LocusHdr *>(&s4[sb]);
+    // a locus of several chunks uses the other stage buffer for its own next chunk (below); the block of the tile
+    // after this one is then requested while the last chunk runs
+    const bool pingpong = PINGPONG && H->n_chunks > 1 && (H->flags & HDR_FAST);
+    unsigned int next_locus = 0xFFFFFFFFu;
+    unsigned long long next_blk = 0;
     if (t + 1 < t_end)
     {
       const unsigned int rn = Lay::RING + ((t + 1) & 3u) * 3;
       const TileDesc dn = *reinterpret_cast<const TileDesc *>(&s4[rn]);
       load_tips(dn, tb ^ 1u);
-      if (Lay::NSTAGE == 2 && dn.locus != d.locus && dn.locus != prefetched_locus)
+      next_locus = dn.locus;
+      next_blk = *reinterpret_cast<const unsigned long long *>(&s4[rn + 2]);
+      if (Lay::NSTAGE == 2 && !pingpong && dn.locus != d.locus && dn.locus != prefetched_locus)
       {
-        stage_fetch(buf ^ 1u, *reinterpret_cast<const unsigned long long *>(&s4[rn + 2]));
+        stage_fetch(buf ^ 1u, next_blk);
         prefetched_locus = dn.locus;
       }
     }
     ring_fetch(t + 2);
     cp_async_commit();
 
-    const unsigned int sb = Lay::STAGE0 + buf * stage_sz;
-    const LocusHdr * H = reinterpret_cast<const LocusHdr *>(&s4[sb]);
     tc.sb = sb;
     tc.cat = (d.cell0 + ptid) % RL;
     tc.tips_s = tips0 + tb * tips_buf + ptid / RL;
@@ -893,22 +915,51 @@ tree_kernel_s4(const TreeParams prm)
       // else on the fast path runs the full one.  One chunk for trees of up to 16 ops whose tips fit the lookup
       // tables, chunk by chunk beyond (X, its scaler count and the parked values carry over)
       site_sum = 0.0;
+      // chunk c >= 1 becomes current: with two stage buffers its copy was started while chunk c-1 ran, so what is
+      // left is one barrier (every warp is done with chunk c-1, its buffer and the lookup tables), the wait for the
+      // copy, the table rebuild and the barrier behind it; otherwise it is staged in place, synchronously
+      auto advance = [&](unsigned int c)
+      {
+        if (pingpong)
+        {
+          __syncthreads();
+          buf ^= 1u;
+          stage_wait(buf, false);
+          tc.sb = Lay::STAGE0 + buf * stage_sz;
+          build_lut<RL, EXACT, CPT>(tc.sb, lut0);
+          __syncthreads();
+          staged_locus = 0xFFFFFFFFu;          // chunk 0 is gone
+        }
+        else restage(c);
+      };
+      // before chunk c runs: start the copy of what comes next into the other buffer (whose last readers passed the
+      // barrier in advance(c), or the end of the previous tile): the locus' next chunk, or after the last one the
+      // block of the next tile (this locus again, or the next one)
+      auto ahead = [&](unsigned int c)
+      {
+        if (!pingpong) return;
+        if (c + 1 < n_chunks) chunk_fetch(buf ^ 1u, blk, c + 1);
+        else if (next_locus != 0xFFFFFFFFu) { stage_fetch(buf ^ 1u, next_blk); prefetched_locus = next_locus; }
+      };
       if (flags & HDR_SIMPLE)
         for (unsigned int c = 0; c < n_chunks; ++c)
         {
-          if (c > 0) restage(c);
+          if (c > 0) advance(c);
+          ahead(c);
           site_sum += tile_fast<RL, EXACT, CPT, 0>(prm, tc, x, psc, wnz, spec);
         }
       else if (flags & HDR_NOHBM)
         for (unsigned int c = 0; c < n_chunks; ++c)
         {
-          if (c > 0) restage(c);
+          if (c > 0) advance(c);
+          ahead(c);
           site_sum += tile_fast<RL, EXACT, CPT, 1>(prm, tc, x, psc, wnz, spec);
         }
       else
         for (unsigned int c = 0; c < n_chunks; ++c)
         {
-          if (c > 0) restage(c);
+          if (c > 0) advance(c);
+          ahead(c);
           site_sum += tile_fast<RL, EXACT, CPT, 2>(prm, tc, x, psc, wnz, spec);
         }
     }
