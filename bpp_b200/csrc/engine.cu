@@ -265,6 +265,8 @@ struct bppgpu_batch
   std::vector<unsigned int> h_tile_first;
   // launch configuration of the tree kernel, resolved once per (shared-memory size)
   size_t cfg_smem[2] = {0, 0}; int cfg_per_sm[2] = {0, 0}; unsigned int cfg_key[2] = {0xFFFFFFFFu, 0xFFFFFFFFu};   // [SCALED_ONLY]
+  unsigned long long overflow_epoch = 0;   // engine dirty_epoch at the last col_overflow check (20 states)
+  bool flip_checked = false;           // bppgpu_batch_flip_indices: the loci have BPP's 2x buffer allocation
   bool last_scaled_only = false;       // instantiation of the last 4-state tree launch (kernel name reporting)
 };
 
@@ -1672,13 +1674,16 @@ static int batch_run(bppgpu_batch * b, bool do_mats, bool do_tree, bool want_roo
   // beyond that the plan falls back to re-reading the child from HBM (still correct)
   int slots = 0;
   unsigned lut_cap_rt = 0;
-  if (b->kernel_kind == 2)
+  if (b->kernel_kind == 2 && b->overflow_epoch != e->dirty_epoch.load())      // (tip states changed since the last look)
+  {
     for (auto * l : b->loci)
       if (l->col_overflow)
       {
         fatal("a locus of this batch has more than 4 distinct ambiguity codes; create the batch after the tip states are set");
         return BPPGPU_FAILURE;
       }
+    b->overflow_epoch = e->dirty_epoch.load();
+  }
   if (b->kernel_kind != 1)
   {
     const unsigned maxT = b->max_tips;
@@ -1981,10 +1986,14 @@ extern "C" int bppgpu_batch_flip_indices(bppgpu_batch * b)
   CUDA_CHECK(cudaSetDevice(e->device));
   if (!b->tables_on_device || !(b->staged_ops || b->staged_mats || b->staged_roots))
   { fatal("bppgpu_batch_flip_indices: no staged step to flip"); return BPPGPU_FAILURE; }
-  for (auto * l : b->loci)
-    if (l->clv_buffers != 2 * (l->tips - 1) || l->prob_matrices != 2 * (2 * l->tips - 2) ||
-        (l->scale_buffers != 0 && l->scale_buffers != 2 * (l->tips - 1)))
-    { fatal("bppgpu_batch_flip_indices: needs BPP's 2x buffer allocation (method.c:4137-4147)"); return BPPGPU_FAILURE; }
+  if (!b->flip_checked)           // the dimensions of a locus never change: checked once per batch, not per proposal
+  {
+    for (auto * l : b->loci)
+      if (l->clv_buffers != 2 * (l->tips - 1) || l->prob_matrices != 2 * (2 * l->tips - 2) ||
+          (l->scale_buffers != 0 && l->scale_buffers != 2 * (l->tips - 1)))
+      { fatal("bppgpu_batch_flip_indices: needs BPP's 2x buffer allocation (method.c:4137-4147)"); return BPPGPU_FAILURE; }
+    b->flip_checked = true;
+  }
   if (b->inputs_pending)
   {
     // staged in waves and never run: bring the whole step to the device first

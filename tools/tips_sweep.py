@@ -12,7 +12,8 @@ eng = engine.Engine(0)
 TIPS = tuple(int(t) for t in sys.argv[3].split(",")) if len(sys.argv) > 3 else (8, 16, 17, 24, 32, 48, 64, 96, 128)
 for tips in TIPS:
     n = max(200, 32000 // tips)
-    w = synth.make_workload("sweep", n_loci=n, tips=tips, sites=1000, states=4, rate_cats=R, model=model, seed=3)
+    rates = None if R in (1, 4) else [0.2 + 1.6 * k / (R - 1) for k in range(R)]
+    w = synth.make_workload("sweep", n_loci=n, tips=tips, sites=1000, states=4, rate_cats=R, model=model, seed=3, rates=rates)
     loci, trees = engine.load_workload(eng, w)
     batch = engine.Batch(eng, loci)
     batch.set_waves(1)
