@@ -163,6 +163,11 @@ struct bppgpu_locus
   unsigned int id = 0;
   unsigned int dtype = 0, model = 0, tips = 0, clv_buffers = 0, states = 0, sites = 0;
   unsigned int rate_matrices = 0, prob_matrices = 0, rate_cats = 0, scale_buffers = 0, attributes = 0;
+  // rate_cats is what the DEVICE holds: 1, 2, 4 or 8 categories for 4- and 20-state loci, so that every category count
+  // up to 8 runs the fast kernels.  user_cats is what the caller created the locus with; the categories beyond it are
+  // copies of category 0 with weight 0 -- they add +0.0 to every site likelihood and, being copies, never change
+  // whether ALL categories of a site are below the scaling threshold -- and the accessors strip them again.
+  unsigned int user_cats = 0;
   LocusDev dev;                        // host copy of the device descriptor
   // sizes of the arena blocks (for release)
   size_t b_clv = 0, b_tipdense = 0, b_codes = 0, b_flags = 0, b_pmat = 0, b_scale = 0, b_weights = 0, b_model = 0;
@@ -592,13 +597,18 @@ extern "C" bppgpu_locus * bppgpu_locus_create(bppgpu_engine * e, unsigned int dt
   if (states < 2 || states > 32) { fatal("unsupported number of states %u", states); return nullptr; }
   if (rate_matrices != 1) { fatal("rate_matrices must be 1 (method.c:4143)"); return nullptr; }
   if (sites == 0 || tips < 2 || rate_cats == 0) { fatal("invalid locus dimensions"); return nullptr; }
+  const unsigned int user_cats = rate_cats;
+  // 3 -> 4, 5..7 -> 8 categories on the device (BPPGPU_PAD_CATS=0: keep the count and take the generic kernel)
+  static const bool pad_cats = !(getenv("BPPGPU_PAD_CATS") && atoi(getenv("BPPGPU_PAD_CATS")) == 0);
+  if (pad_cats && (states == 4 || states == S20) && rate_cats < 8 && (rate_cats & (rate_cats - 1)) != 0)
+    rate_cats = rate_cats < 4 ? 4 : 8;
   std::lock_guard<std::mutex> lock(e->mu);
   CUDA_CHECK(cudaSetDevice(e->device));
   bppgpu_locus * l = new bppgpu_locus();
   l->e = e;
   l->dtype = dtype; l->model = model; l->tips = tips; l->clv_buffers = clv_buffers; l->states = states;
   l->sites = sites; l->rate_matrices = rate_matrices; l->prob_matrices = prob_matrices;
-  l->rate_cats = rate_cats; l->scale_buffers = scale_buffers; l->attributes = attributes;
+  l->rate_cats = rate_cats; l->user_cats = user_cats; l->scale_buffers = scale_buffers; l->attributes = attributes;
   const size_t S = states, R = rate_cats, P = sites;
   const size_t clv_doubles = P * R * S;
   LocusDev & d = l->dev;
@@ -665,7 +675,8 @@ extern "C" bppgpu_locus * bppgpu_locus_create(bppgpu_engine * e, unsigned int dt
   l->h_freqs.assign(S, 0.0);                       // zero like locus.c:826 until pll_set_frequencies
   l->h_subst.assign(S * (S - 1) / 2, 0.0);
   l->h_rates.assign(R, 1.0);
-  l->h_rate_weights.assign(R, 1.0 / (double)R);    // locus.c:845-848
+  l->h_rate_weights.assign(R, 0.0);
+  for (unsigned r = 0; r < user_cats; ++r) l->h_rate_weights[r] = 1.0 / (double)user_cats;    // locus.c:845-848
   l->h_evecs.assign(S * S, 0.0); l->h_ievecs.assign(S * S, 0.0); l->h_evals.assign(S, 0.0);
   l->model_dirty = true, l->e->dirty_epoch++;
   if (!e->free_ids.empty()) { l->id = e->free_ids.back(); e->free_ids.pop_back(); e->loci[l->id] = l; }
@@ -769,11 +780,15 @@ extern "C" void bppgpu_set_subst_params(bppgpu_locus * l, unsigned int idx, cons
 }
 extern "C" void bppgpu_set_category_rates(bppgpu_locus * l, const double * r)
 {
-  l->h_rates.assign(r, r + l->rate_cats); l->model_dirty = true, l->e->dirty_epoch++;
+  l->h_rates.assign(l->rate_cats, r[0]);                     // (padding categories: copies of category 0)
+  std::copy(r, r + l->user_cats, l->h_rates.begin());
+  l->model_dirty = true, l->e->dirty_epoch++;
 }
 extern "C" void bppgpu_set_category_weights(bppgpu_locus * l, const double * w)
 {
-  l->h_rate_weights.assign(w, w + l->rate_cats); l->model_dirty = true, l->e->dirty_epoch++;
+  l->h_rate_weights.assign(l->rate_cats, 0.0);               // (padding categories weigh nothing)
+  std::copy(w, w + l->user_cats, l->h_rate_weights.begin());
+  l->model_dirty = true, l->e->dirty_epoch++;
 }
 extern "C" void bppgpu_set_eigen(bppgpu_locus * l, unsigned int idx, const double * ev, const double * iev, const double * lam)
 {
@@ -2134,24 +2149,25 @@ extern "C" double bppgpu_root_loglikelihood_diploid(bppgpu_locus * l, unsigned i
 extern "C" int bppgpu_get_clv(bppgpu_locus * l, unsigned int clv_index, double * out)
 {
   CUDA_CHECK(cudaSetDevice(l->e->device));
-  const size_t P = l->sites, R = l->rate_cats, S = l->states, nd = P * R * S;
+  const size_t P = l->sites, R = l->rate_cats, U = l->user_cats, S = l->states, nd = P * R * S;
   if (clv_index >= l->tips + l->clv_buffers) { fatal("clv index out of range"); return BPPGPU_FAILURE; }
   CUDA_CHECK(cudaDeviceSynchronize());
   if (clv_index >= l->tips || l->h_tip_dense_flag[clv_index])
   {
     const double * src = clv_index >= l->tips ? l->dev.clv + (size_t)(clv_index - l->tips) * nd : l->dev.tip_dense + (size_t)clv_index * nd;
-    if (l->dev.site_stride == R * S) { CUDA_CHECK(cudaMemcpy(out, src, nd * 8, cudaMemcpyDeviceToHost)); return BPPGPU_SUCCESS; }
-    // category-major on the device: hand it out in the reference's [site][cat][state] order
+    if (l->dev.site_stride == R * S && U == R) { CUDA_CHECK(cudaMemcpy(out, src, nd * 8, cudaMemcpyDeviceToHost)); return BPPGPU_SUCCESS; }
+    // category-major on the device, or more categories there than the caller has: hand it out in the reference's
+    // [site][cat][state] order with the caller's categories
     std::vector<double> raw(nd);
     CUDA_CHECK(cudaMemcpy(raw.data(), src, nd * 8, cudaMemcpyDeviceToHost));
-    for (size_t i = 0; i < P; ++i) for (size_t r = 0; r < R; ++r)
-      memcpy(out + (i * R + r) * S, &raw[i * l->dev.site_stride + r * l->dev.cat_stride], S * 8);
+    for (size_t i = 0; i < P; ++i) for (size_t r = 0; r < U; ++r)
+      memcpy(out + (i * U + r) * S, &raw[i * l->dev.site_stride + r * l->dev.cat_stride], S * 8);
     return BPPGPU_SUCCESS;
   }
   for (size_t i = 0; i < P; ++i)          // expand the packed tip like set_tipclv, locus.c:540-555
   {
     const unsigned int c = get_code(l, clv_index, i);
-    for (size_t r = 0; r < R; ++r) for (size_t j = 0; j < S; ++j) out[(i * R + r) * S + j] = (double)((c >> j) & 1u);
+    for (size_t r = 0; r < U; ++r) for (size_t j = 0; j < S; ++j) out[(i * U + r) * S + j] = (double)((c >> j) & 1u);
   }
   return BPPGPU_SUCCESS;
 }
@@ -2163,8 +2179,8 @@ extern "C" int bppgpu_get_pmatrix(bppgpu_locus * l, unsigned int idx, double * o
   CUDA_CHECK(cudaSetDevice(l->e->device));
   CUDA_CHECK(cudaDeviceSynchronize());
   if (idx >= l->prob_matrices) { fatal("pmatrix index out of range"); return BPPGPU_FAILURE; }
-  const size_t nd = (size_t)l->rate_cats * l->states * l->states;
-  CUDA_CHECK(cudaMemcpy(out, l->dev.pmat + idx * nd, nd * 8, cudaMemcpyDeviceToHost));
+  const size_t ss = (size_t)l->states * l->states, nd = (size_t)l->rate_cats * ss;
+  CUDA_CHECK(cudaMemcpy(out, l->dev.pmat + idx * nd, (size_t)l->user_cats * ss * 8, cudaMemcpyDeviceToHost));   // the caller's categories
   return BPPGPU_SUCCESS;
 }
 
@@ -2173,8 +2189,10 @@ extern "C" int bppgpu_set_pmatrix(bppgpu_locus * l, unsigned int idx, const doub
   CUDA_CHECK(cudaSetDevice(l->e->device));
   CUDA_CHECK(cudaDeviceSynchronize());
   if (idx >= l->prob_matrices) { fatal("pmatrix index out of range"); return BPPGPU_FAILURE; }
-  const size_t nd = (size_t)l->rate_cats * l->states * l->states;
-  CUDA_CHECK(cudaMemcpy(l->dev.pmat + idx * nd, in, nd * 8, cudaMemcpyHostToDevice));
+  const size_t ss = (size_t)l->states * l->states, nd = (size_t)l->rate_cats * ss;
+  CUDA_CHECK(cudaMemcpy(l->dev.pmat + idx * nd, in, (size_t)l->user_cats * ss * 8, cudaMemcpyHostToDevice));
+  for (unsigned r = l->user_cats; r < l->rate_cats; ++r)       // padding categories: copies of category 0
+    CUDA_CHECK(cudaMemcpy(l->dev.pmat + idx * nd + r * ss, in, ss * 8, cudaMemcpyHostToDevice));
   return BPPGPU_SUCCESS;
 }
 

@@ -114,7 +114,11 @@ void bppgpu_engine_reset_profile(bppgpu_engine * e);
 /* ------------------------------------------------------------------ locus (bpp.h:2032-2090)
  * replaces locus_create / locus_destroy (locus.c:622-870, 872).  Same arguments, same meaning;
  * BPP calls it with clv_buffers = 2(T-1), prob_matrices = 2(2T-2), scale_buffers = 2(T-1) or 0,
- * rate_matrices = 1 (method.c:4137-4147). */
+ * rate_matrices = 1 (method.c:4137-4147).
+ * Any rate_cats is accepted.  On the device a 4- or 20-state locus holds 1, 2, 4 or 8 categories (3 is kept as 4,
+ * 5..7 as 8: the extra ones are copies of category 0 with weight 0, which changes neither a site likelihood nor a
+ * scaling decision); every call below takes and returns arrays with the caller's rate_cats.  More than 8
+ * categories, or another state count, run the generic kernel. */
 bppgpu_locus * bppgpu_locus_create(bppgpu_engine * e,
                                    unsigned int dtype, unsigned int model,
                                    unsigned int tips, unsigned int clv_buffers,

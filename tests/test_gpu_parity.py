@@ -128,6 +128,49 @@ def test_specialised_scaled_launch_with_real_rescaling(eng, rate_cats, tips, dt)
     _free(loci, batch)
 
 
+@pytest.mark.parametrize("rate_cats,states,dt", [(5, 4, 0.01), (5, 4, 1e-12), (3, 4, 0.01), (7, 4, 0.01), (3, 20, 0.01)])
+def test_category_counts_that_are_not_powers_of_two(eng, rate_cats, states, dt):
+    """BPP users run 5 rate categories as readily as 4.  The device holds 4 or 8 (the extra ones are copies of category
+    0 with weight 0: +0.0 in every site likelihood, and no influence on whether ALL categories of a site are below the
+    scaling threshold), the accessors speak the caller's count.  lnL, every inner CLV, every scaler (dt = 1e-12: with
+    real rescaling) and the P-matrices against the oracle; set_pmatrix / get_pmatrix round trip."""
+    model = "GTR" if states == 4 else "LG"
+    rates = list(np.linspace(0.3, 1.9, rate_cats))
+    w = synth.make_workload("odd", n_loci=3, tips=11 if states == 4 else 6, sites=150, states=states, rate_cats=rate_cats,
+                            model=model, scaling=True, seed=31, dt_lo=dt, dt_hi=10 * dt, rates=rates, lg=lg_tables())
+    T, R, S = w.tips, rate_cats, states
+    loci, trees, batch = _load(eng, w)
+    lnl, _ = batch.full_pass(trees.full_pass_step())
+    assert batch.kernel_name.startswith("tree_kernel_s4<%d" % (4 if R < 4 else 8)) or states == 20, batch.kernel_name
+    cm = char_map(states)
+    tol = 1e-9 if states == 20 else 1e-11
+    fired = 0
+    for i, l in enumerate(loci):
+        o = F.locus_from_workload(w, i, cm)
+        ref = o.full_pass()
+        assert abs(lnl[i] - ref) <= LNL_RTOL * abs(ref), (i, lnl[i], ref)
+        for n in range(T, 2 * T - 1):
+            got = l.get_clv(n)
+            assert got.size == w.sites * R * S
+            assert rel_err(got.reshape(w.sites, R, S), o.clv[o.clv_index[n]]) < tol, (i, n)
+            sc = l.get_scaler(n - T)
+            assert np.array_equal(sc, o.scale[o.scaler_index[n]]), (i, n)
+            fired += int(sc.max())
+        for n in range(2 * T - 2):
+            pm = l.get_pmatrix(n)
+            assert pm.size == R * S * S
+            assert np.max(np.abs(pm.reshape(R, S, S) - o.pmat[o.pmatrix_index[n]])) < 1e-13
+        probe = np.arange(R * S * S, dtype=np.float64) / (R * S * S)
+        l.set_pmatrix(0, probe)
+        assert np.array_equal(l.get_pmatrix(0), probe)
+    if dt < 1e-6:
+        assert fired > 0, "the workload was meant to trigger per-site rescaling"
+    # a packed tip handed out with the caller's category count
+    tip = loci[0].get_clv(0)
+    assert tip.size == w.sites * R * S
+    _free(loci, batch)
+
+
 @pytest.mark.parametrize("name", ["jc69_r1", "gtr_g4_scale", "gtr_g4"])
 def test_clv_bit_exact_with_reference_pmatrices(eng, name):
     """Upload the reference's own P-matrices: every inner CLV, scaler and the per-site lnL must be
@@ -296,7 +339,11 @@ def engine_pinned(a):
     dict(tips=8, sites=500, states=20, rate_cats=4, model="LG"),                     # config-4 shape
     dict(tips=2, sites=1, states=4, rate_cats=1, model="JC69"),                      # smallest legal locus
     dict(tips=3, sites=257, states=4, rate_cats=2, model="GTR", rates=[0.4, 1.6]),   # ragged last tile
-    dict(tips=7, sites=300, states=4, rate_cats=3, model="GTR", rates=[0.2, 0.9, 1.9]),   # R not a power of 2
+    dict(tips=7, sites=300, states=4, rate_cats=3, model="GTR", rates=[0.2, 0.9, 1.9]),   # R not a power of 2: 4 on the device
+    dict(tips=9, sites=300, states=4, rate_cats=5, model="GTR", scaling=True, rates=[0.1, 0.4, 0.8, 1.3, 2.4]),   # 5 -> 8
+    dict(tips=20, sites=130, states=4, rate_cats=6, model="HKY", rates=list(np.linspace(0.2, 2.0, 6))),           # 6 -> 8, chunks
+    dict(tips=6, sites=90, states=20, rate_cats=3, model="LG", rates=[0.3, 1.0, 1.7]),                            # 20 states, 3 -> 4
+    dict(tips=5, sites=64, states=4, rate_cats=9, model="GTR", rates=list(np.linspace(0.2, 2.0, 9))),             # generic kernel
     dict(tips=33, sites=129, states=4, rate_cats=8, model="GTR", scaling=True, rates=list(np.linspace(0.1, 3, 8))),
     # big trees: serially planned with Sethi-Ullman ordering, several chunks, up to 16 packed tip words per cell
     dict(tips=60, sites=301, states=4, rate_cats=1, model="JC69"),                   # frogs-sized loci
