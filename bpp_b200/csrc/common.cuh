@@ -103,7 +103,7 @@ constexpr int PM_STRIDE  = 18;      // doubles per (matrix, cat) in shared memor
 constexpr int LUT_ROW    = 6;       // doubles per state-mask row of a tip lookup table (4 + 2 pad: the
                                     // one-hot masks 1,2,4,8 and 15 fall into different bank groups)
 constexpr int LUT_CAT    = 16 * LUT_ROW + 2;   // doubles per (tip child, cat) table
-__host__ __device__ constexpr int lut_cap(int RL) { return RL <= 2 ? 32 : (64 / RL); }   // tip children per chunk
+__host__ __device__ constexpr int lut_cap(int RL) { return RL <= 2 ? 32 : 16; }   // tip children per chunk
 // Layout of the tip lookup tables in shared memory (uint4 = 16-byte units; an entry X = P_edge . bits(mask) is two
 // uint4: states 0,1 and states 2,3).
 //   RL <= 2: [slot][cat][mask] with padded rows (LUT_ROW) -- a quarter warp holds 8 or 4 different sites of the same
@@ -114,10 +114,15 @@ __host__ __device__ constexpr int lut_cap(int RL) { return RL <= 2 ? 32 : (64 / 
 //            halves exchanged; the odd site of a quarter warp (lane bit 2) reads B and issues its loads in the
 //            opposite order, so every load instruction of a quarter warp covers eight different 16-byte bank groups,
 //            whatever the masks are.
+//   RL == 8: [slot][mask][cat], ONE table.  A quarter warp is one site x 8 categories, i.e. one row of 256 bytes; the
+//            lanes of categories 4..7 are exactly the lanes with bit 2 set, so instead of a replica their entries are
+//            STORED with the halves exchanged and they fetch in the opposite order: conflict-free at half the space,
+//            which is what lets 16 tip children (a whole 16-tip tree) share a chunk as with 4 categories -- with
+//            5 to 8 categories a 16-tip tree used to take three chunks of 8 table slots.
 __host__ __device__ constexpr unsigned int lut_row_u4(int RL)  { return RL >= 4 ? 2u * (unsigned)RL : (unsigned)(LUT_ROW / 2); }
 __host__ __device__ constexpr unsigned int lut_cat_u4(int RL)  { return RL >= 4 ? 2u : (unsigned)(LUT_CAT / 2); }
-__host__ __device__ constexpr unsigned int lut_rep_u4(int RL)  { return RL >= 4 ? 32u * (unsigned)RL : 0u; }
-__host__ __device__ constexpr unsigned int lut_slot_u4(int RL) { return RL >= 4 ? 64u * (unsigned)RL : (unsigned)RL * (LUT_CAT / 2); }
+__host__ __device__ constexpr unsigned int lut_rep_u4(int RL)  { return RL == 4 ? 32u * (unsigned)RL : 0u; }
+__host__ __device__ constexpr unsigned int lut_slot_u4(int RL) { return RL == 4 ? 64u * (unsigned)RL : (RL == 8 ? 32u * (unsigned)RL : (unsigned)RL * (LUT_CAT / 2)); }
 
 struct ChunkHdr { unsigned int nops, ntips, pad0, pad1; };
 

@@ -439,9 +439,8 @@ plan_kernel_blocks(const LocusDev * __restrict__ loci, const unsigned int * __re
   // small loci (the common case) are planned entirely in shared memory: raw ops, the producer map and
   // the OpRecs under construction; the block in HBM is written once, coalesced, at the end
   // SM_OPS: records of up to 4 chunks (a chunk closes after TREE_CHUNK ops or when its lookup tables are full: a
-  // 31-op list over 16 table slots, i.e. 4 rate categories, can take 4; 8 categories have 8 slots and stay on the
-  // shared-memory path up to 15 ops only -- more would cost the planner its occupancy); the lane-parallel planner
-  // itself handles lists of up to 32 ops
+  // 31-op list over the 16 table slots of 4 or 8 rate categories can take 4); the lane-parallel planner itself
+  // handles lists of up to 32 ops
   constexpr unsigned int SM_OPS = 4 * TREE_CHUNK, SM_RAW = 32, SM_BUF = 64;
   __shared__ __align__(16) RawOp s_raw[4][SM_RAW];
   __shared__ __align__(16) OpRec s_rec[4][SM_OPS];

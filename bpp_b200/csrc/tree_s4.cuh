@@ -213,6 +213,7 @@ __device__ __forceinline__ double tile_fast(const TreeParams & prm, const TileCt
   // per-thread invariants and per-op (warp-uniform) terms, so that a lookup costs shift / and / multiply-add per cell.
   constexpr unsigned int ROWB = lut_row_u4(RL) * 16u, SLOTJ = 2u * TREE_NT * 16u;
   const unsigned char * const sm = reinterpret_cast<const unsigned char *>(s4);
+  static_assert(!(RL == 8 && BPPGPU_S4_PERM), "8 categories: lane bit 2 must be category bit 2");
   const unsigned int hs = (lane >> 2) & 1u, hl = RL >= 4 ? hs : 0u;
   const unsigned int lut_lo = (tc.lut0 + tc.cat * lut_cat_u4(RL) + hl * lut_rep_u4(RL) + hl) * 16u;   // first-fetched half
   const unsigned int stk_lo = (tc.stack0 + tid * 2 + hs) * 16u;
@@ -543,7 +544,8 @@ __device__ __noinline__ double chunk_general(const TreeParams prm, unsigned int 
       if (kind == SRC_TIP_PACKED)
       {
         const unsigned int li = lut_t + off + tipmask(sel, p0) * lut_row_u4(RL);
-        const double2 u = as_d2(s4[li]), w = as_d2(s4[li + 1]);
+        const unsigned int xh = (RL == 8 && cat >= 4) ? 1u : 0u;          // (see lut_slot_u4: stored exchanged)
+        const double2 u = as_d2(s4[li + xh]), w = as_d2(s4[li + (xh ^ 1u)]);
         r.a = u.x; r.b = u.y; r.c = w.x; r.d = w.y; sc = 0;
       }
       else if (kind == SRC_SLOT)
@@ -661,9 +663,10 @@ __device__ __forceinline__ void build_lut(unsigned int sb, unsigned int lut0)
     const Vec4 v = matvec_s4<EXACT>(sb + Lay::TIPP + sc * 9, (double)(mask & 1u), (double)((mask >> 1) & 1u),
                                     (double)((mask >> 2) & 1u), (double)((mask >> 3) & 1u));
     const unsigned int at = lut0 + (sc / RL) * lut_slot_u4(RL) + (sc % RL) * lut_cat_u4(RL) + mask * lut_row_u4(RL);
-    s4[at] = as_u4(v.a, v.b);
-    s4[at + 1] = as_u4(v.c, v.d);
-    if (RL >= 4)                                         // replica B: halves exchanged
+    const unsigned int xh = (RL == 8 && (sc % RL) >= 4) ? 1u : 0u;   // 8 categories: 4..7 stored with the halves exchanged
+    s4[at + xh] = as_u4(v.a, v.b);
+    s4[at + (xh ^ 1u)] = as_u4(v.c, v.d);
+    if (RL == 4)                                         // replica B: halves exchanged
     {
       s4[at + lut_rep_u4(RL)] = as_u4(v.c, v.d);
       s4[at + lut_rep_u4(RL) + 1] = as_u4(v.a, v.b);
