@@ -332,6 +332,7 @@ tree_kernel_s20t(const TreeParams prm, unsigned int * __restrict__ rootsc)
         const unsigned long long v = ((unsigned long long)seq << 32) | m;
         asm volatile("st.relaxed.cluster.shared::cta.u64 [%0], %1;" :: "r"(la), "l"(v) : "memory");
       }
+      __syncwarp();      // tile_check reads the warp's own word too (lane = op x category): ordered within the warp
     };
     auto consume = [&](unsigned int seq) -> unsigned int        // AND of the other categories' bits of op `seq`
     {
