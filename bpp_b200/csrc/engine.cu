@@ -1808,10 +1808,16 @@ static int batch_run(bppgpu_batch * b, bool do_mats, bool do_tree, bool want_roo
       CUDA_CHECK(cudaEventRecord(b->ev_class[par], b->stream));
       b->class_pending[par] = true;
     }
-    else if (b->class_pending[par] && cudaEventQuery(b->ev_class[par]) == cudaSuccess)
+    else if (b->class_pending[par])
     {
-      b->plan_class[par] = b->h_class[par] & (PLAN_CLASS_KNOWN | PLAN_CLASS_LEAN | PLAN_CLASS_SCALED);
-      b->class_pending[par] = false;
+      const cudaError_t q = cudaEventQuery(b->ev_class[par]);
+      if (q == cudaSuccess)
+      {
+        b->plan_class[par] = b->h_class[par] & (PLAN_CLASS_KNOWN | PLAN_CLASS_LEAN | PLAN_CLASS_SCALED);
+        b->class_pending[par] = false;
+      }
+      else if (q == cudaErrorNotReady) (void)cudaGetLastError();      // "not ready" is an answer, not an error to keep
+      else CUDA_CHECK(q);
     }
     // all loci scaled-capable one-chunk lists, and not all of them lean (an unscaled batch is both)
     if (!b->class_pending[par])

@@ -806,19 +806,17 @@ tree_kernel_s4(const TreeParams prm)
     const LocusHdr * H = reinterpret_cast<const LocusHdr *>(&s4[sb]);
     // a locus of several chunks uses the other stage buffer for its own next chunk (below); the block of the tile
     // after this one is then requested while the last chunk runs
-    const bool pingpong = PINGPONG && H->n_chunks > 1 && (H->flags & HDR_FAST);
-    unsigned int next_locus = 0xFFFFFFFFu;
-    unsigned long long next_blk = 0;
+    // (nothing of this is kept in registers across the tile: the one-chunk kernels run at their register cap, and the
+    // chunk loop below reads the flag and the next tile's ring entry again)
     if (t + 1 < t_end)
     {
       const unsigned int rn = Lay::RING + ((t + 1) & 3u) * 3;
       const TileDesc dn = *reinterpret_cast<const TileDesc *>(&s4[rn]);
       load_tips(dn, tb ^ 1u);
-      next_locus = dn.locus;
-      next_blk = *reinterpret_cast<const unsigned long long *>(&s4[rn + 2]);
+      const bool pingpong = PINGPONG && H->n_chunks > 1 && (H->flags & HDR_FAST);
       if (Lay::NSTAGE == 2 && !pingpong && dn.locus != d.locus && dn.locus != prefetched_locus)
       {
-        stage_fetch(buf ^ 1u, next_blk);
+        stage_fetch(buf ^ 1u, *reinterpret_cast<const unsigned long long *>(&s4[rn + 2]));
         prefetched_locus = dn.locus;
       }
     }
@@ -921,6 +919,7 @@ tree_kernel_s4(const TreeParams prm)
       // chunk c >= 1 becomes current: with two stage buffers its copy was started while chunk c-1 ran, so what is
       // left is one barrier (every warp is done with chunk c-1, its buffer and the lookup tables), the wait for the
       // copy, the table rebuild and the barrier behind it; otherwise it is staged in place, synchronously
+      const bool pingpong = PINGPONG && n_chunks > 1;          // (HDR_FAST holds in this branch)
       auto advance = [&](unsigned int c)
       {
         if (pingpong)
@@ -942,7 +941,12 @@ tree_kernel_s4(const TreeParams prm)
       {
         if (!pingpong) return;
         if (c + 1 < n_chunks) chunk_fetch(buf ^ 1u, blk, c + 1);
-        else if (next_locus != 0xFFFFFFFFu) { stage_fetch(buf ^ 1u, next_blk); prefetched_locus = next_locus; }
+        else if (t + 1 < t_end)                    // (ring slot t+1 stays valid through tile t: ring_fetch(t+2) fills another)
+        {
+          const unsigned int rn = Lay::RING + ((t + 1) & 3u) * 3;
+          stage_fetch(buf ^ 1u, *reinterpret_cast<const unsigned long long *>(&s4[rn + 2]));
+          prefetched_locus = reinterpret_cast<const TileDesc *>(&s4[rn])->locus;
+        }
       };
       if (flags & HDR_SIMPLE)
         for (unsigned int c = 0; c < n_chunks; ++c)

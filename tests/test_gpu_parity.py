@@ -526,6 +526,13 @@ def test_staged_run_is_idempotent_and_deterministic(eng, scaling, tips, kind):
         b, tb = batch.collect()
         assert np.array_equal(a, b) and ta == tb
     assert batch.kernel_name.endswith(",%s>" % kind), batch.kernel_name
+    # runs queued back to back without a collect in between (the class of the plan may still be on its way when the
+    # next run is issued: "not ready" must not surface as an error), on a freshly staged copy of the same step
+    batch.stage(trees.full_pass_step())
+    for _ in range(6):
+        batch.run()
+    b, tb = batch.collect()
+    assert np.array_equal(a, b) and ta == tb
     cm = char_map(4)
     for i in range(0, w.n_loci, 8):
         ref = F.locus_from_workload(w, i, cm).full_pass()

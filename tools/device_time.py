@@ -29,5 +29,6 @@ for _ in range(K):
 ms = batch.timer_stop_ms() / K
 prof = eng.profile()
 out, tot = batch.collect()
-print("%s n=%d scaling=%d: %.4f ms/step  %.3f M evals/s  %s  sum %.6f" % (
-    cfg, n, scaling, ms, n / ms / 1e3, {k: round(v["ms"] / max(1, v["launches"]), 4) for k, v in prof.items()}, tot), flush=True)
+print("%s n=%d scaling=%d: %.4f ms/step  %.3f M evals/s  %s  sum %.6f  %s" % (
+    cfg, n, scaling, ms, n / ms / 1e3, {k: round(v["ms"] / max(1, v["launches"]), 4) for k, v in prof.items()}, tot,
+    batch.kernel_name), flush=True)
